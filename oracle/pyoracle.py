@@ -1,0 +1,169 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes access to the CPU oracle.
+
+Two back ends with the same call signatures:
+  * ``Oracle("port")``      -> oracle/liboracle.so      (C restatement, wt_oracle.c)
+  * ``Oracle("reference")`` -> oracle/_ref/libwtref.so  (the unmodified reference
+    hot path compiled from /root/reference/src by oracle/Makefile)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+``--impl reference`` legs may import this module; the product package
+(wiggletools_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+OPS = {
+    "sum": 0, "mult": 1, "product": 1, "mean": 2, "var": 3, "stddev": 4, "entropy": 5,
+    "CV": 6, "cv": 6, "min": 7, "max": 8, "median": 9, "ttest": 16, "wilcoxon": 17, "mwu": 17,
+}
+
+
+class CTrack(C.Structure):
+    _fields_ = [("chrom", C.c_void_p), ("start", C.c_void_p), ("end", C.c_void_p),
+                ("value", C.c_void_p), ("n", C.c_int64), ("default_value", C.c_double)]
+
+
+class COut(C.Structure):
+    _fields_ = [("chrom", C.c_void_p), ("start", C.c_void_p), ("end", C.c_void_p),
+                ("value", C.c_void_p), ("cap", C.c_int64)]
+
+
+class Track:
+    """One genome track: parallel arrays sorted by (chrom index, start)."""
+
+    def __init__(self, chrom, start, end, value, default=0.0):
+        self.chrom = np.ascontiguousarray(chrom, dtype=np.int32)
+        self.start = np.ascontiguousarray(start, dtype=np.int32)
+        self.end = np.ascontiguousarray(end, dtype=np.int32)
+        self.value = np.ascontiguousarray(value, dtype=np.float64)
+        self.default = float(default)
+        assert len(self.chrom) == len(self.start) == len(self.end) == len(self.value)
+
+    def __len__(self):
+        return len(self.start)
+
+    def c(self):
+        return CTrack(self.chrom.ctypes.data, self.start.ctypes.data, self.end.ctypes.data,
+                      self.value.ctypes.data, len(self), self.default)
+
+
+def build(ref=None):
+    """(Re)build liboracle.so, and _ref/ when the reference tree is present."""
+    subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
+    if ref is None:
+        ref = os.path.isdir("/root/reference/src")
+    if ref:
+        subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+
+
+class Segments:
+    def __init__(self, chrom, start, end, value, default=None):
+        self.chrom, self.start, self.end, self.value, self.default = chrom, start, end, value, default
+
+    def __len__(self):
+        return len(self.start)
+
+
+class Oracle:
+    def __init__(self, kind="port"):
+        self.kind = kind
+        if kind == "port":
+            path, self.p = os.path.join(HERE, "liboracle.so"), "wto_"
+        elif kind == "reference":
+            path, self.p = os.path.join(HERE, "_ref", "libwtref.so"), "wtref_"
+        else:
+            raise ValueError(kind)
+        if not os.path.exists(path):
+            raise FileNotFoundError(path + " (run `make -C oracle` / `make -C oracle ref`)")
+        self.lib = C.CDLL(path)
+        f = self._f("reduce")
+        f.restype = C.c_int64
+        f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        f = self._f("setcompare")
+        f.restype = C.c_int64
+        f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        f = self._f("auc")
+        f.restype = C.c_double
+        f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        f = self._f("pearson")
+        f.restype = C.c_double
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        f = self._f("rows")
+        f.restype = C.c_int64
+        f.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        f = self._f("tdist_Q")
+        f.restype = C.c_double
+        f.argtypes = [C.c_double, C.c_double]
+
+    def _f(self, name):
+        return getattr(self.lib, self.p + name)
+
+    @staticmethod
+    def _names(names):
+        arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        return arr
+
+    @staticmethod
+    def _tracks(tracks):
+        arr = (CTrack * len(tracks))(*[t.c() for t in tracks])
+        return arr
+
+    @staticmethod
+    def _out(cap):
+        chrom = np.empty(cap, np.int32)
+        start = np.empty(cap, np.int32)
+        end = np.empty(cap, np.int32)
+        value = np.empty(cap, np.float64)
+        o = COut(chrom.ctypes.data, start.ctypes.data, end.ctypes.data, value.ctypes.data, cap)
+        return o, (chrom, start, end, value)
+
+    @staticmethod
+    def _cap(tracks):
+        return 2 * sum(len(t) for t in tracks) + 16
+
+    def reduce(self, op, tracks, names=("chr1",), strict=False):
+        cap = self._cap(tracks)
+        o, arrs = self._out(cap)
+        ct, cn = self._tracks(tracks), self._names(names)
+        dflt = C.c_double(0)
+        n = self._f("reduce")(OPS[op], len(tracks), C.addressof(ct), int(strict), len(names),
+                              C.addressof(cn), C.addressof(o), C.addressof(dflt))
+        assert n <= cap
+        return Segments(*[a[:n].copy() for a in arrs], default=dflt.value)
+
+    def setcompare(self, op, set1, set2, names=("chr1",)):
+        cap = self._cap(list(set1) + list(set2))
+        o, arrs = self._out(cap)
+        c1, c2, cn = self._tracks(set1), self._tracks(set2), self._names(names)
+        n = self._f("setcompare")(OPS[op], len(set1), C.addressof(c1), len(set2), C.addressof(c2),
+                                  len(names), C.addressof(cn), C.addressof(o))
+        assert n <= cap
+        return Segments(*[a[:n].copy() for a in arrs])
+
+    def auc(self, op, tracks, names=("chr1",), strict=False):
+        ct, cn = self._tracks(tracks), self._names(names)
+        return self._f("auc")(OPS[op], len(tracks), C.addressof(ct), int(strict), len(names), C.addressof(cn))
+
+    def pearson(self, x, y, names=("chr1",)):
+        cx, cy, cn = x.c(), y.c(), self._names(names)
+        return self._f("pearson")(C.addressof(cx), C.addressof(cy), len(names), C.addressof(cn))
+
+    def rows(self, tracks, names=("chr1",), strict=False):
+        cap = self._cap(tracks)
+        o, arrs = self._out(cap)
+        vals = np.empty((cap, len(tracks)), np.float64)
+        inplay = np.empty((cap, len(tracks)), np.int8)
+        ct, cn = self._tracks(tracks), self._names(names)
+        n = self._f("rows")(len(tracks), C.addressof(ct), int(strict), len(names), C.addressof(cn),
+                            C.addressof(o), vals.ctypes.data, inplay.ctypes.data)
+        assert n <= cap
+        seg = Segments(*[a[:n].copy() for a in arrs])
+        return seg, vals[:n].copy(), inplay[:n].copy()
+
+    def tdist_Q(self, t, nu):
+        return self._f("tdist_Q")(t, nu)
