@@ -1,0 +1,158 @@
+/* wiggletools_b200 -- C ABI of the B200 interval-stream reduction engine.
+ *
+ * This is the drop-in boundary for ONE hot path of Ensembl/WiggleTools:
+ *   N sorted (chrom,start,end,value) tracks -> union-breakpoint segments
+ *   (Multiplexer / Multiset) -> per-segment N-wide statistic -> optional
+ *   whole-genome scalars (AUC, Pearson).
+ *
+ * Two layers are exported by libwiggletools_b200.so:
+ *
+ *  (1) the batch engine (wb200_*): plain pointers and sizes, one call per
+ *      chromosome shard.  This is what a binding (ctypes / cgo / JNI) uses.
+ *  (2) the reference's own operator API for the path (newMultiplexer,
+ *      popMultiplexer, newMultiset, SumReduction ... MWUReduction,
+ *      AUCIntegrator, PearsonIntegrator) with the reference's struct layouts,
+ *      declared in include/wiggletools_dropin.h, so that the unmodified
+ *      src/commandParser.c and writers link against it.
+ *
+ * Conventions (all from the reference): coordinates are 1-based half-open
+ * [start,end) int32 (src/wigReader.c:123-124); values are double; tracks are
+ * sorted, non-overlapping within a track (newMultiplexer runs inputs through
+ * NonOverlappingWiggleIterator, src/multiplexer.c:163).
+ *
+ * Errors: every function returns 0 on success or a negative WB200_E* code and
+ * records a message readable with wb200_last_error().  There is no CPU
+ * fallback: without a CUDA device the create call fails.
+ */
+#ifndef WIGGLETOOLS_B200_H
+#define WIGGLETOOLS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Statistic computed per union segment.  Each replaces the reference
+ * constructor + pop function cited. */
+enum wb200_op {
+	WB200_SUM     = 0,  /* SumReduction      src/reducers.c:259-307 */
+	WB200_PRODUCT = 1,  /* ProductReduction  src/reducers.c:313-361 */
+	WB200_MEAN    = 2,  /* MeanReduction     src/reducers.c:367-422 */
+	WB200_VAR     = 3,  /* VarianceReduction src/reducers.c:428-505 */
+	WB200_STDDEV  = 4,  /* StdDevReduction   src/reducers.c:511-589 */
+	WB200_ENTROPY = 5,  /* EntropyReduction  src/reducers.c:640-666 (runs the stddev pop, :665) */
+	WB200_CV      = 6,  /* CVReduction       src/reducers.c:672-750 */
+	WB200_MIN     = 7,  /* MinReduction      src/reducers.c:192-253 */
+	WB200_MAX     = 8,  /* MaxReduction      src/reducers.c:125-186 */
+	WB200_MEDIAN  = 9,  /* MedianReduction   src/reducers.c:780-834 */
+	WB200_TTEST   = 16, /* TTestReduction    src/setComparisons.c:35-131 (over a Multiset of 2) */
+	WB200_MWU     = 17  /* MWUReduction      src/setComparisons.c:269-390 */
+};
+
+enum wb200_error {
+	WB200_OK = 0,
+	WB200_ENODEV = -1,     /* no CUDA device / driver */
+	WB200_ECUDA = -2,      /* CUDA runtime error (message has the detail) */
+	WB200_EINVAL = -3,     /* bad argument (op, counts, unsorted input ...) */
+	WB200_ENOMEM = -4,     /* device or pinned-host allocation failed */
+	WB200_ECAPACITY = -5,  /* caller-provided output capacity too small */
+	WB200_EUNSUPPORTED = -6
+};
+
+#define WB200_MAX_TRACKS 1023  /* per set; cover counters are 10-bit fields */
+
+typedef struct wb200_ctx wb200_ctx;
+
+/* One track restricted to one chromosome (host or device pointers, depending
+ * on the call).  Mirrors the fields a WiggleIterator streams
+ * (src/wiggleIterator.h:21-35: start, finish, value, default_value). */
+typedef struct wb200_track {
+	const int32_t *start;
+	const int32_t *end;
+	const double *value;
+	int64_t n;
+	double default_value;
+} wb200_track;
+
+/* Segments of one chromosome.  For *_host calls the arrays are owned by the
+ * context (pinned host memory) and stay valid until the next call on it. */
+typedef struct wb200_segments {
+	int32_t *start;
+	int32_t *end;
+	double *value;
+	int64_t n;
+	double default_value;  /* the reducer's derived default (constructor semantics) */
+	double auc;            /* sum over segments of (end-start)*value, NaN skipped (AUCPop, src/statistics.c:103-120) */
+} wb200_segments;
+
+/* Timing / accounting of the last call (for bench.py). */
+typedef struct wb200_stats {
+	int64_t intervals;       /* I: input intervals consumed */
+	int64_t segments;        /* S: segments emitted */
+	int64_t windows;
+	int64_t slow_segments;   /* segments evaluated by the row path inside the fast kernel */
+	int32_t kernels;         /* kernel launches issued by the call */
+	int32_t fast_path;       /* 1 if the fixed-point scan path was used */
+	float ms_count;          /* device time of the count kernel(s) */
+	float ms_emit;           /* device time of the emit kernel(s) */
+	float ms_total;          /* device time of the whole call (events on the call's stream) */
+	int64_t h2d_bytes, d2h_bytes;
+} wb200_stats;
+
+/* -- lifetime ------------------------------------------------------------ */
+/* device: CUDA ordinal.  Fails (NULL, message via wb200_last_error(NULL)) when
+ * no device is usable. */
+wb200_ctx *wb200_create(int device);
+void wb200_destroy(wb200_ctx *ctx);
+const char *wb200_last_error(const wb200_ctx *ctx);
+const wb200_stats *wb200_last_stats(const wb200_ctx *ctx);
+/* Use an externally owned stream (e.g. torch's current stream) for all work. */
+int wb200_set_stream(wb200_ctx *ctx, void *cuda_stream);
+/* Tuning knobs: window size in bp (power of two, 0 = automatic). */
+int wb200_set_window(wb200_ctx *ctx, int window_bp);
+
+/* Pinned host memory for staging (cudaHostAlloc). */
+void *wb200_host_alloc(int64_t bytes);
+void wb200_host_free(void *p);
+
+/* -- the hot path, host buffers (end-to-end entry) ----------------------- */
+/* Replaces: newMultiplexer(iters,count,strict) + <op>Reduction(multi) + the
+ * consumer loop, for one chromosome (src/multiplexer.c:157-169,
+ * src/reducers.c, src/wiggleIterator.c:62-65).  For WB200_TTEST / WB200_MWU
+ * the first nset1 tracks are set A and the rest set B (newMultiset of two
+ * multiplexers, src/multiSet.c:115-128); otherwise pass nset1 = ntracks.
+ * H2D staging, kernels and D2H of the result all happen inside the call. */
+int wb200_reduce_host(wb200_ctx *ctx, int op, int ntracks, int nset1, int strict,
+                      const wb200_track *tracks, wb200_segments *out);
+
+/* -- the hot path, device-resident buffers ------------------------------- */
+/* d_start/d_end/d_value: all tracks of the chromosome concatenated; h_off[i]
+ * .. h_off[i+1] is track i (host array of ntracks+1 offsets).  Positions lie in
+ * [pos_lo, pos_hi].  Output arrays (device) must hold out_cap segments; an
+ * upper bound is min(2*I+1, pos_hi-pos_lo+1).  *n_out receives S. */
+int wb200_reduce_device(wb200_ctx *ctx, int op, int ntracks, int nset1, int strict,
+                        const int32_t *d_start, const int32_t *d_end, const double *d_value,
+                        const int64_t *h_off, const double *h_defaults,
+                        int32_t pos_lo, int32_t pos_hi,
+                        int32_t *d_out_start, int32_t *d_out_end, double *d_out_value,
+                        int64_t out_cap, int64_t *n_out, double *default_out, double *auc_out);
+
+/* -- whole-genome scalars ------------------------------------------------ */
+/* Pearson correlation of two tracks over one chromosome shard: returns the six
+ * running moments so that shards (chromosomes, GPUs) can be merged exactly as
+ * the reference's sequential update would (PearsonPop, src/statistics.c:414-458).
+ * moments = {count, sum_X, sum_Y, T_XX, T_XY, T_YY}. */
+int wb200_pearson_host(wb200_ctx *ctx, const wb200_track *x, const wb200_track *y, double moments[6]);
+/* Fold shard b into a (the sequential update applied to pre-reduced shards). */
+void wb200_pearson_merge(double a[6], const double b[6]);
+double wb200_pearson_result(const double moments[6]);
+
+/* Student-t upper tail used by WB200_TTEST (stands where the reference calls
+ * gsl_cdf_tdist_Q, src/setComparisons.c:117); exported for tests. */
+double wb200_tdist_Q(double t, double nu);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

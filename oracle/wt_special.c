@@ -42,12 +42,30 @@ static double wt_betacf(double a, double b, double x) {
 	return h;
 }
 
+
+/* ln B(a,b) = lgamma(a)+lgamma(b)-lgamma(a+b).  With b = 1/2 and large a the
+ * lgamma difference cancels catastrophically; use the asymptotic series of
+ * ln[Gamma(a+1/2)/Gamma(a)] there. */
+static double wt_lbeta(double a, double b) {
+	if (b == 0.5 && a >= 20.0) {
+		double r = 1.0 / a, r2 = r * r;
+		double ratio = 0.5 * log(a) - r / 8 + r * r2 / 192 - r * r2 * r2 / 640 + 17 * r * r2 * r2 * r2 / 14336;
+		return 0.5723649429247001 - ratio; /* ln sqrt(pi) */
+	}
+	if (a == 0.5 && b >= 20.0) {
+		double r = 1.0 / b, r2 = r * r;
+		double ratio = 0.5 * log(b) - r / 8 + r * r2 / 192 - r * r2 * r2 / 640 + 17 * r * r2 * r2 * r2 / 14336;
+		return 0.5723649429247001 - ratio;
+	}
+	return lgamma(a) + lgamma(b) - lgamma(a + b);
+}
+
 /* I_x(a,b) given both x and xc = 1-x (passed separately so neither suffers
  * cancellation). */
 static double wt_incbeta(double a, double b, double x, double xc) {
 	if (x <= 0.0) return 0.0;
 	if (xc <= 0.0) return 1.0;
-	double lbt = lgamma(a + b) - lgamma(a) - lgamma(b) + a * log(x) + b * log(xc);
+	double lbt = -wt_lbeta(a, b) + a * (xc < 0.5 ? log1p(-xc) : log(x)) + b * (x < 0.5 ? log1p(-x) : log(xc));
 	double bt = exp(lbt);
 	if (x < (a + 1.0) / (a + b + 2.0))
 		return bt * wt_betacf(a, b, x) / a;

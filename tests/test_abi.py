@@ -1,0 +1,44 @@
+"""CPU tests of the C-ABI boundary: the library builds, loads, exports every
+symbol include/wiggletools_b200.h declares, and refuses to run without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from wiggletools_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(wb200_[A-Za-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    syms = declared_symbols("wiggletools_b200.h")
+    assert syms, "no declarations parsed"
+    assert set(syms) == set(_lib.EXPORTS)
+    for s in syms:
+        assert hasattr(lib, s), "missing export " + s
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = _lib.load()
+    assert not lib.wb200_create(0)
+    msg = lib.wb200_last_error(None).decode()
+    assert "no CPU fallback" in msg
+
+
+def test_product_never_touches_the_oracle():
+    for d, _, files in os.walk(os.path.join(ROOT, "wiggletools_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+                text = open(os.path.join(d, f)).read()
+                assert "pyoracle" not in text and "liboracle" not in text and "libwtref" not in text, f

@@ -1,0 +1,194 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI
+(wb200_reduce_host / wb200_pearson_host), against the CPU oracle on the same
+seeded inputs and against the committed fixtures generated from the compiled
+reference.  Coordinates must be bit-identical; fp64 values within RTOL=1e-10
+relative (most are bit-identical and asserted so where the algorithm guarantees
+it)."""
+import math
+
+import numpy as np
+import pytest
+
+from wiggletools_b200 import api
+from wiggletools_b200.synth import make_tracks
+from oracle.pyoracle import Track as OTrack
+from util import GOLDEN_NAMES, REDUCE_OPS, RTOL, assert_segments, golden_tracks, load_golden, same_float
+
+pytestmark = pytest.mark.gpu
+
+NAMES = ["chr1", "chr10", "chr2"]
+
+
+def both(tr, defaults=None):
+    o = [OTrack(t["chrom"], t["start"], t["end"], t["value"], default=(defaults[i] if defaults else 0.0)) for i, t in enumerate(tr)]
+    g = [api.Track(t["chrom"], t["start"], t["end"], t["value"], default=(defaults[i] if defaults else 0.0)) for i, t in enumerate(tr)]
+    return o, g
+
+
+def test_committed_golden_fixtures(engine):
+    z, cases = load_golden()
+    for case in cases:
+        tracks = golden_tracks(z, case, cls=api.Track)
+        for op in REDUCE_OPS:
+            for strict in (0, 1):
+                key = "%s/%s/%d" % (case, op, strict)
+                r = engine.reduce(op, tracks, GOLDEN_NAMES, strict=bool(strict))
+                assert_segments(r, z[key + "/chrom"], z[key + "/start"], z[key + "/end"], z[key + "/value"], what=key)
+                assert same_float(r.default, float(z[key + "/default"])), key
+        want = float(z[case + "/auc_mean"])
+        got = engine.auc("mean", tracks, GOLDEN_NAMES)
+        assert math.isclose(got, want, rel_tol=RTOL), (case, got, want)
+        if len(tracks) >= 2:
+            got, want = engine.pearson(tracks[0], tracks[1], GOLDEN_NAMES), float(z[case + "/pearson01"])
+            assert same_float(got, want) or math.isclose(got, want, rel_tol=1e-9), (case, got, want)
+        if len(tracks) >= 6:
+            for op in ("ttest", "wilcoxon"):
+                key = "%s/%s" % (case, op)
+                r = engine.setcompare(op, tracks[:3], tracks[3:], GOLDEN_NAMES)
+                assert_segments(r, z[key + "/chrom"], z[key + "/start"], z[key + "/end"], z[key + "/value"], what=key)
+
+
+@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("n", [1, 2, 5, 33])
+def test_random_vs_oracle(engine, port, seed, n):
+    kw = dict(nan_prob=0.02 if seed % 2 else 0.0, neg=(seed == 2), align=(1 if seed < 3 else 10))
+    tr = make_tracks(n, [30000, 9000, 18000], seed=200 + seed, max_len=40, max_gap=30, **kw)
+    defaults = None if seed < 2 else [float(i % 3) for i in range(n)]
+    o, g = both(tr, defaults)
+    for op in REDUCE_OPS:
+        for strict in (False, True):
+            want = port.reduce(op, o, NAMES, strict)
+            got = engine.reduce(op, g, NAMES, strict=strict)
+            # every statistic here follows the reference's operation order exactly
+            # (row path), or is an exact integer sum (fast path): bit-identical
+            assert_segments(got, want.chrom, want.start, want.end, want.value, exact=True, what="%s strict=%d" % (op, strict))
+            assert same_float(got.default, want.default)
+    if n >= 6:
+        for op in ("ttest", "wilcoxon"):
+            want = port.setcompare(op, o[:3], o[3:], NAMES)
+            got = engine.setcompare(op, g[:3], g[3:], NAMES)
+            assert_segments(got, want.chrom, want.start, want.end, want.value, what=op)
+    if n >= 2:
+        want, got = port.pearson(o[0], o[1], NAMES), engine.pearson(g[0], g[1], NAMES)
+        assert same_float(got, want) or math.isclose(got, want, rel_tol=1e-9), (got, want)
+    want, got = port.auc("mean", o, NAMES), engine.auc("mean", g, NAMES)
+    assert same_float(got, want) or math.isclose(got, want, rel_tol=RTOL)
+
+
+def test_general_doubles_within_tolerance(engine, port):
+    """Values with full 53-bit mantissas and a wide dynamic range: the
+    fixed-point path must fall back per segment where it cannot be exact."""
+    rng = np.random.default_rng(7)
+    tr = make_tracks(12, [40000], seed=9, max_len=60, max_gap=20)
+    for i, t in enumerate(tr):
+        t["value"] = rng.lognormal(0.0, 3.0 if i % 2 else 0.5, len(t["value"]))
+    tr[3]["value"][::17] = np.inf
+    tr[4]["value"][::13] = 1e300
+    tr[5]["value"][::11] = 1e-300
+    o, g = both(tr)
+    for op in ("sum", "mean"):
+        want = port.reduce(op, o, ["chr1"])
+        got = engine.reduce(op, g, ["chr1"])
+        assert_segments(got, want.chrom, want.start, want.end, want.value, rtol=RTOL, what=op)
+    st = engine.last_stats[-1]
+    assert st["fast_path"] == 1 and st["slow_segments"] > 0
+
+
+@pytest.mark.parametrize("window", [256, 1024, 4096, 8192])
+def test_window_size_does_not_change_results(port, window):
+    tr = make_tracks(9, [70000, 5000], seed=31, max_len=300, max_gap=2500)
+    # long intervals spanning many windows, and long empty stretches
+    tr[0]["start"] = np.array([10, 30000], np.int32); tr[0]["end"] = np.array([25000, 69000], np.int32)
+    tr[0]["value"] = np.array([2.5, 7.0]); tr[0]["chrom"] = np.zeros(2, np.int32)
+    o, g = both(tr)
+    eng = api.Engine(0, window=window)
+    for op in ("mean", "max", "var", "median"):
+        for strict in (False, True):
+            want = port.reduce(op, o, ["chr1", "chr2"], strict)
+            got = eng.reduce(op, g, ["chr1", "chr2"], strict=strict)
+            assert_segments(got, want.chrom, want.start, want.end, want.value, exact=True, what="%s w=%d" % (op, window))
+    eng.close()
+
+
+def test_edge_cases(engine, port):
+    names = ["chr1", "chr2"]
+    e = np.empty(0)
+    cases = {
+        "all_empty": [dict(chrom=e, start=e, end=e, value=e)] * 3,
+        "one_empty": [dict(chrom=[0, 0], start=[5, 9], end=[7, 12], value=[1.0, 2.0]), dict(chrom=e, start=e, end=e, value=e)],
+        "abutting": [dict(chrom=[0, 0, 0], start=[1, 4, 9], end=[4, 9, 20], value=[1.0, 1.0, 3.0]),
+                     dict(chrom=[0, 0], start=[4, 9], end=[9, 10], value=[5.0, 6.0])],
+        "identical": [dict(chrom=[0, 1], start=[100, 7], end=[200, 9], value=[2.0, 4.0])] * 4,
+        "disjoint_chroms": [dict(chrom=[0], start=[3], end=[8], value=[1.5]), dict(chrom=[1], start=[3], end=[8], value=[2.5])],
+        "window_edges": [dict(chrom=[0, 0, 0], start=[1, 4097, 8193], end=[4097, 8193, 8194], value=[1.0, 2.0, 3.0]),
+                         dict(chrom=[0, 0], start=[4096, 4098], end=[4097, 12289], value=[4.0, 8.0])],
+        "big_coords": [dict(chrom=[0, 0], start=[2147400000, 2147480000], end=[2147450000, 2147483000], value=[1.0, 2.0]),
+                       dict(chrom=[0], start=[2147449999], end=[2147480001], value=[0.5])],
+    }
+    for name, tr in cases.items():
+        o, g = both(tr)
+        for op in ("sum", "mean", "min", "var", "median"):
+            for strict in (False, True):
+                want = port.reduce(op, o, names, strict)
+                got = engine.reduce(op, g, names, strict=strict)
+                assert_segments(got, want.chrom, want.start, want.end, want.value, exact=True, what="%s %s" % (name, op))
+                assert same_float(got.default, want.default)
+
+
+def test_arity_errors(engine):
+    t = api.Track([0], [1], [2], [1.0])
+    with pytest.raises(api.WB200Error):
+        engine.setcompare("ttest", [t, t], [t, t, t])
+    with pytest.raises(api.WB200Error):
+        engine.reduce("mean", [])
+
+
+def test_many_tracks(engine, port):
+    tr = make_tracks(300, [6000], seed=77, max_len=50, max_gap=40)
+    o, g = both(tr)
+    for op in ("mean", "stddev", "median", "max"):
+        want = port.reduce(op, o, ["chr1"])
+        got = engine.reduce(op, g, ["chr1"])
+        assert_segments(got, want.chrom, want.start, want.end, want.value, exact=True, what=op)
+    want = port.setcompare("wilcoxon", o[:120], o[120:], ["chr1"])
+    got = engine.setcompare("wilcoxon", g[:120], g[120:], ["chr1"])
+    assert_segments(got, want.chrom, want.start, want.end, want.value, what="wilcoxon")
+    want = port.setcompare("ttest", o[:120], o[120:], ["chr1"])
+    got = engine.setcompare("ttest", g[:120], g[120:], ["chr1"])
+    assert_segments(got, want.chrom, want.start, want.end, want.value, what="ttest")
+
+
+def test_mirror_protocol(engine, port):
+    """The Python mirror of newMultiplexer / MeanReduction / pop()."""
+    tr = make_tracks(4, [3000], seed=5, max_len=30, max_gap=30)
+    o, g = both(tr)
+    want = port.reduce("mean", o, ["chr1"])
+    wi = api.MeanReduction(api.Multiplexer(g, names=["chr1"]), engine=engine)
+    k = 0
+    while not wi.done:
+        assert (wi.chrom, wi.start, wi.finish, wi.value) == ("chr1", want.start[k], want.end[k], want.value[k])
+        wi.pop()
+        k += 1
+    assert k == len(want)
+
+
+def test_full_scale_properties(engine):
+    """Size-independent properties at a size the oracle cannot check quickly:
+    linearity (sum(x,x) == 2*x on x's own segmentation), mean*N == sum, segment
+    tiling, and idempotence of mean over identical tracks."""
+    tr = make_tracks(6, [3_000_000], seed=123)
+    g = [api.Track(t["chrom"], t["start"], t["end"], t["value"]) for t in tr]
+    s = engine.reduce("sum", g, ["chr1"])
+    m = engine.reduce("mean", g, ["chr1"])
+    assert np.array_equal(s.start, m.start) and np.array_equal(s.end, m.end)
+    assert np.array_equal(m.value * 6, s.value)
+    assert (s.end > s.start).all() and (s.start[1:] >= s.end[:-1]).all()
+    one = engine.reduce("sum", [g[0], g[0]], ["chr1"])
+    assert np.array_equal(one.start, g[0].start) and np.array_equal(one.value, 2 * g[0].value)
+    same = engine.reduce("mean", [g[1]] * 5, ["chr1"])
+    assert np.array_equal(same.value, g[1].value)
+    mx, mn = engine.reduce("max", g, ["chr1"]), engine.reduce("min", g, ["chr1"])
+    assert (mx.value >= mn.value).all() and (mx.value * 6 >= s.value).all()
+    # AUC of the sum == sum of the tracks' own AUCs (integers here: exact)
+    total = sum(float(((t.end - t.start) * t.value).sum()) for t in g)
+    assert math.isclose(s.auc, total, rel_tol=1e-12)

@@ -1,0 +1,77 @@
+"""ctypes loader for libwiggletools_b200.so (the C ABI in include/wiggletools_b200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C
+wiggletools_b200/csrc``.  There is no fallback: a missing library or a missing
+CUDA device raises.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libwiggletools_b200.so")
+
+
+class CTrack(C.Structure):
+    _fields_ = [("start", C.c_void_p), ("end", C.c_void_p), ("value", C.c_void_p),
+                ("n", C.c_int64), ("default_value", C.c_double)]
+
+
+class CSegments(C.Structure):
+    _fields_ = [("start", C.c_void_p), ("end", C.c_void_p), ("value", C.c_void_p),
+                ("n", C.c_int64), ("default_value", C.c_double), ("auc", C.c_double)]
+
+
+class CStats(C.Structure):
+    _fields_ = [("intervals", C.c_int64), ("segments", C.c_int64), ("windows", C.c_int64),
+                ("slow_segments", C.c_int64), ("kernels", C.c_int32), ("fast_path", C.c_int32),
+                ("ms_count", C.c_float), ("ms_emit", C.c_float), ("ms_total", C.c_float),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and declare its signatures."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "wiggletools_b200: %s is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C wiggletools_b200/csrc`; there is no CPU fallback" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.wb200_create.restype = C.c_void_p
+    lib.wb200_create.argtypes = [C.c_int]
+    lib.wb200_destroy.argtypes = [C.c_void_p]
+    lib.wb200_last_error.restype = C.c_char_p
+    lib.wb200_last_error.argtypes = [C.c_void_p]
+    lib.wb200_last_stats.restype = C.POINTER(CStats)
+    lib.wb200_last_stats.argtypes = [C.c_void_p]
+    lib.wb200_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.wb200_set_window.argtypes = [C.c_void_p, C.c_int]
+    lib.wb200_host_alloc.restype = C.c_void_p
+    lib.wb200_host_alloc.argtypes = [C.c_int64]
+    lib.wb200_host_free.argtypes = [C.c_void_p]
+    lib.wb200_reduce_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.wb200_reduce_device.argtypes = [
+        C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.wb200_pearson_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.wb200_pearson_merge.argtypes = [C.c_void_p, C.c_void_p]
+    lib.wb200_pearson_result.restype = C.c_double
+    lib.wb200_pearson_result.argtypes = [C.c_void_p]
+    lib.wb200_tdist_Q.restype = C.c_double
+    lib.wb200_tdist_Q.argtypes = [C.c_double, C.c_double]
+    _lib = lib
+    return lib
+
+
+# every symbol include/wiggletools_b200.h declares
+EXPORTS = [
+    "wb200_create", "wb200_destroy", "wb200_last_error", "wb200_last_stats", "wb200_set_stream",
+    "wb200_set_window", "wb200_host_alloc", "wb200_host_free", "wb200_reduce_host",
+    "wb200_reduce_device", "wb200_pearson_host", "wb200_pearson_merge", "wb200_pearson_result",
+    "wb200_tdist_Q",
+]

@@ -1,0 +1,257 @@
+"""Host-side mirror (Python) of the WiggleTools operator interface for the
+merge+reduce hot path, on top of the C ABI (include/wiggletools_b200.h).
+
+Reference interface mirrored (file:line under /root/reference/src):
+  newMultiplexer(iters, count, strict)      multiplexer.c:157-169 -> Multiplexer(tracks, strict)
+  newMultiset(multis, 2)                    multiSet.c:115-128    -> Multiset(mux_a, mux_b)
+  Sum/Product/Mean/.../MedianReduction      reducers.c            -> SumReduction(mux) ...
+  TTestReduction / MWUReduction             setComparisons.c      -> TTestReduction(mset) ...
+  AUCIntegrator                             statistics.c:103-127  -> AUCIntegrator(reduction)
+  consumer loop while(!wi->done){...;pop}   wiggleIterator.c:57-65 -> WiggleIterator.pop()/.done
+
+All arithmetic happens in the CUDA library; this module only slices tracks by
+chromosome (the reference visits chromosomes in strcmp order, multiplexer.c:50-74)
+and wraps results.  Coordinates are 1-based half-open, as inside the reference.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+OPS = {
+    "sum": 0, "mult": 1, "product": 1, "mean": 2, "var": 3, "stddev": 4, "entropy": 5,
+    "CV": 6, "cv": 6, "min": 7, "max": 8, "median": 9, "ttest": 16, "wilcoxon": 17, "mwu": 17,
+}
+
+
+class WB200Error(RuntimeError):
+    pass
+
+
+class Track:
+    """One genome track: parallel arrays sorted by chromosome (strcmp order of the
+    names they index) then start; intervals do not overlap within a track."""
+
+    def __init__(self, chrom, start, end, value, default=0.0):
+        self.chrom = np.ascontiguousarray(chrom, dtype=np.int32)
+        self.start = np.ascontiguousarray(start, dtype=np.int32)
+        self.end = np.ascontiguousarray(end, dtype=np.int32)
+        self.value = np.ascontiguousarray(value, dtype=np.float64)
+        self.default = float(default)
+        n = len(self.start)
+        if not (len(self.chrom) == len(self.end) == len(self.value) == n):
+            raise ValueError("track arrays differ in length")
+        # chromosome runs: {chrom index: (lo, hi)}
+        self.runs = {}
+        if n:
+            cut = np.flatnonzero(np.diff(self.chrom)) + 1
+            lo = np.concatenate(([0], cut))
+            hi = np.concatenate((cut, [n]))
+            for a, b in zip(lo, hi):
+                c = int(self.chrom[a])
+                if c in self.runs:
+                    raise ValueError("track is not sorted by chromosome")
+                self.runs[c] = (int(a), int(b))
+
+    def __len__(self):
+        return len(self.start)
+
+
+class Segments:
+    """Result records: chrom index, start, end (exclusive), value."""
+
+    def __init__(self, chrom, start, end, value, default=float("nan"), auc=0.0):
+        self.chrom, self.start, self.end, self.value = chrom, start, end, value
+        self.default, self.auc = default, auc
+
+    def __len__(self):
+        return len(self.start)
+
+
+class Engine:
+    """One CUDA context of the engine (one per process/GPU)."""
+
+    def __init__(self, device=0, window=0):
+        self.lib = _lib.load()
+        self.ctx = self.lib.wb200_create(device)
+        if not self.ctx:
+            raise WB200Error(self.lib.wb200_last_error(None).decode())
+        if window:
+            self._check(self.lib.wb200_set_window(self.ctx, window))
+        self.last_stats = []
+
+    def close(self):
+        if self.ctx:
+            self.lib.wb200_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise WB200Error("wb200 error %d: %s" % (rc, self.lib.wb200_last_error(self.ctx).decode()))
+
+    def stats(self):
+        s = self.lib.wb200_last_stats(self.ctx).contents
+        return {k: getattr(s, k) for k, _ in s._fields_}
+
+    # -- one chromosome, host arrays ---------------------------------------
+    def reduce_chrom(self, op, tracks, nset1=None, strict=False):
+        """tracks: list of (start, end, value, default) numpy arrays of ONE chromosome."""
+        n = len(tracks)
+        arr = (_lib.CTrack * n)()
+        keep = []
+        for i, (s, e, v, d) in enumerate(tracks):
+            s = np.ascontiguousarray(s, np.int32); e = np.ascontiguousarray(e, np.int32)
+            v = np.ascontiguousarray(v, np.float64)
+            keep.append((s, e, v))
+            arr[i] = _lib.CTrack(s.ctypes.data, e.ctypes.data, v.ctypes.data, len(s), float(d))
+        out = _lib.CSegments()
+        code = OPS[op] if isinstance(op, str) else int(op)
+        self._check(self.lib.wb200_reduce_host(self.ctx, code, n, n if nset1 is None else nset1,
+                                               int(bool(strict)), C.addressof(arr), C.addressof(out)))
+        m = out.n
+        if m:
+            start = np.ctypeslib.as_array(C.cast(out.start, C.POINTER(C.c_int32)), (m,)).copy()
+            end = np.ctypeslib.as_array(C.cast(out.end, C.POINTER(C.c_int32)), (m,)).copy()
+            value = np.ctypeslib.as_array(C.cast(out.value, C.POINTER(C.c_double)), (m,)).copy()
+        else:
+            start = np.empty(0, np.int32); end = np.empty(0, np.int32); value = np.empty(0, np.float64)
+        self.last_stats.append(self.stats())
+        return start, end, value, out.default_value, out.auc
+
+    # -- whole genome -------------------------------------------------------
+    def reduce(self, op, tracks, names=("chr1",), strict=False, nset1=None):
+        """<op> over N genome tracks: segments of every chromosome, in the
+        reference's visiting order (ascending strcmp of the names)."""
+        self.last_stats = []
+        present = sorted({c for t in tracks for c in t.runs}, key=lambda c: names[c].encode())
+        cs, ss, es, vs = [], [], [], []
+        auc = 0.0
+        dflt = float("nan")
+        for c in present:
+            per = []
+            for t in tracks:
+                lo, hi = t.runs.get(c, (0, 0))
+                per.append((t.start[lo:hi], t.end[lo:hi], t.value[lo:hi], t.default))
+            s, e, v, dflt, a = self.reduce_chrom(op, per, nset1=nset1, strict=strict)
+            cs.append(np.full(len(s), c, np.int32)); ss.append(s); es.append(e); vs.append(v)
+            auc += a   # chromosome partials are folded in visiting order
+        if not present:
+            # defaults only: constructor semantics still apply
+            per = [(np.empty(0, np.int32), np.empty(0, np.int32), np.empty(0), t.default) for t in tracks]
+            _, _, _, dflt, _ = self.reduce_chrom(op, per, nset1=nset1, strict=strict)
+            return Segments(np.empty(0, np.int32), np.empty(0, np.int32), np.empty(0, np.int32), np.empty(0), dflt, 0.0)
+        return Segments(np.concatenate(cs), np.concatenate(ss), np.concatenate(es), np.concatenate(vs), dflt, auc)
+
+    def setcompare(self, op, set1, set2, names=("chr1",)):
+        return self.reduce(op, list(set1) + list(set2), names, nset1=len(set1))
+
+    def pearson(self, x, y, names=("chr1",)):
+        """Pearson correlation of two tracks over the genome (PearsonIntegrator,
+        src/statistics.c:414-465): per-chromosome moments from the GPU, folded in
+        visiting order with the pairwise form of the reference's update."""
+        present = sorted(set(x.runs) | set(y.runs), key=lambda c: names[c].encode())
+        total = (C.c_double * 6)(0, 0, 0, 0, 0, 0)
+        for c in present:
+            keep, ct = [], []
+            for t in (x, y):
+                lo, hi = t.runs.get(c, (0, 0))
+                s, e, v = t.start[lo:hi], t.end[lo:hi], t.value[lo:hi]
+                keep.append((s, e, v))
+                ct.append(_lib.CTrack(s.ctypes.data, e.ctypes.data, v.ctypes.data, len(s), t.default))
+            m = (C.c_double * 6)()
+            self._check(self.lib.wb200_pearson_host(self.ctx, C.addressof(ct[0]), C.addressof(ct[1]), C.addressof(m)))
+            self.lib.wb200_pearson_merge(C.addressof(total), C.addressof(m))
+        return self.lib.wb200_pearson_result(C.addressof(total))
+
+    def auc(self, op, tracks, names=("chr1",), strict=False):
+        return self.reduce(op, tracks, names, strict).auc
+
+
+_default_engine = None
+
+
+def default_engine():
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine(0)
+    return _default_engine
+
+
+# ---------------------------------------------------------------------------
+# Mirror of the reference's object protocol
+# ---------------------------------------------------------------------------
+class Multiplexer:
+    """newMultiplexer(iters, count, strict): multiplexer.c:157-169."""
+
+    def __init__(self, tracks, strict=False, names=("chr1",)):
+        self.tracks, self.strict, self.names = list(tracks), bool(strict), tuple(names)
+        self.count = len(self.tracks)
+
+
+class Multiset:
+    """newMultiset(multis, count): multiSet.c:115-128 (two sets)."""
+
+    def __init__(self, *multis):
+        if len(multis) != 2:
+            raise WB200Error("set comparisons take exactly two multiplexers")
+        self.multis = multis
+        self.count = 2
+
+
+class WiggleIterator:
+    """The consumer protocol of src/wiggleIterator.c:20-65: the constructor pops
+    once, so the first record is readable on return; loop ``while not wi.done``."""
+
+    def __init__(self, seg, names):
+        self._seg, self._names, self._k = seg, names, 0
+        self.default_value = seg.default
+        self.chrom = None
+        self.start = self.finish = 0
+        self.value = float("nan")
+        self.done = False
+        self.pop()
+
+    def pop(self):
+        if self.done:
+            return
+        if self._k >= len(self._seg):
+            self.done = True
+            return
+        k = self._k
+        self.chrom = self._names[self._seg.chrom[k]]
+        self.start = int(self._seg.start[k]); self.finish = int(self._seg.end[k])
+        self.value = float(self._seg.value[k])
+        self._k += 1
+
+
+def _reduction(op):
+    def ctor(multi, engine=None):
+        eng = engine or default_engine()
+        if isinstance(multi, Multiset):
+            a, b = multi.multis
+            seg = eng.setcompare(op, a.tracks, b.tracks, a.names)
+            return WiggleIterator(seg, a.names)
+        seg = eng.reduce(op, multi.tracks, multi.names, strict=multi.strict)
+        return WiggleIterator(seg, multi.names)
+    return ctor
+
+
+SumReduction = _reduction("sum")
+ProductReduction = _reduction("mult")
+MeanReduction = _reduction("mean")
+VarianceReduction = _reduction("var")
+StdDevReduction = _reduction("stddev")
+EntropyReduction = _reduction("entropy")
+CVReduction = _reduction("cv")
+MinReduction = _reduction("min")
+MaxReduction = _reduction("max")
+MedianReduction = _reduction("median")
+TTestReduction = _reduction("ttest")
+MWUReduction = _reduction("wilcoxon")

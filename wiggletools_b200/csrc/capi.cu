@@ -1,0 +1,493 @@
+// wiggletools_b200 -- host side of the C ABI declared in include/wiggletools_b200.h.
+// Owns the CUDA context objects (stream, growable device/pinned buffers),
+// stages host tracks to HBM, sequences the kernels of engine.cu and returns
+// segments.  No CPU implementation of the path lives here: without a device
+// wb200_create() fails.
+#include "../../include/wiggletools_b200.h"
+#include "engine.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace wb;
+
+namespace {
+
+std::string g_last_error;  // for failures before a context exists
+
+struct DevBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+	cudaError_t ensure(size_t bytes) {
+		if (bytes <= cap) return cudaSuccess;
+		if (p) cudaFree(p);
+		p = nullptr; cap = 0;
+		size_t want = bytes + bytes / 8 + 256;
+		cudaError_t e = cudaMalloc(&p, want);
+		if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+		if (e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+	template <class T> T *as() const { return (T *) p; }
+};
+
+struct HostBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+	cudaError_t ensure(size_t bytes) {
+		if (bytes <= cap) return cudaSuccess;
+		if (p) cudaFreeHost(p);
+		p = nullptr; cap = 0;
+		size_t want = bytes + bytes / 8 + 256;
+		cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+		if (e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+	template <class T> T *as() const { return (T *) p; }
+};
+
+} // namespace
+
+struct wb200_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	bool own_stream = true;
+	int sms = 148;
+	int window_bp = 0;
+	std::string err;
+	wb200_stats stats{};
+	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+	DevBuf in_start, in_end, in_value, off, dflt, dflt_fx, cursor, wcount, woff, aucp, small, moments;
+	DevBuf out_start, out_end, out_value;
+	HostBuf h_small, h_meta, h_start, h_end, h_value;
+};
+
+namespace {
+
+int fail(wb200_ctx *ctx, int code, const std::string &msg) {
+	if (ctx) ctx->err = msg; else g_last_error = msg;
+	return code;
+}
+
+int cuda_fail(wb200_ctx *ctx, cudaError_t e, const char *what) {
+	return fail(ctx, e == cudaErrorMemoryAllocation ? WB200_ENOMEM : WB200_ECUDA,
+	            std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call); } while (0)
+
+// Derived default_value of each reducer's output: what the reference's
+// constructors compute from the inputs' defaults (src/reducers.c:170-186,
+// 237-253, 294-307, 348-361, 404-422, 481-505, 565-589, 640-666, 727-750,
+// 815-834; set comparisons return NaN, src/setComparisons.c:130,389).
+double derived_default(int op, int n, const double *d) {
+	double sum = 0;
+	switch (op) {
+	case OP_SUM:
+		for (int i = 0; i < n; i++) { if (std::isnan(d[i])) return NAN; sum += d[i]; }
+		return sum;
+	case OP_PRODUCT: {
+		double p = 1;
+		for (int i = 0; i < n; i++) { if (std::isnan(d[i])) return NAN; p *= d[i]; }
+		return p;
+	}
+	case OP_MEAN: {
+		for (int i = 0; i < n; i++) { if (std::isnan(d[i])) return NAN; sum += d[i]; }
+		float f = (float) (sum / n);
+		return f;
+	}
+	case OP_VAR: case OP_STDDEV: {
+		for (int i = 0; i < n; i++) { if (std::isnan(d[i])) return NAN; sum += d[i]; }
+		double mean = sum / n, err = 0;
+		for (int i = 0; i < n; i++) err += (d[i] - mean) * (d[i] - mean);
+		return op == OP_VAR ? err / n : std::sqrt(err / n);
+	}
+	case OP_ENTROPY: {
+		int count = 0;
+		for (int i = 0; i < n; i++) { if (std::isnan(d[i])) return NAN; if (d[i] != 0) count++; }
+		double p = count / n;   // integer division, as in the reference
+		return p ? -p * std::log(p) - (1 - p) * std::log(1 - p) : 0;
+	}
+	case OP_CV: {
+		for (int i = 0; i < n; i++) { if (std::isnan(d[i])) return NAN; sum += d[i]; }
+		double mean = sum / n, err = 0;
+		for (int i = 0; i < n; i++) err += (mean - d[i]) * (mean - d[i]);
+		float f = (float) (std::sqrt(err / n) / mean);
+		return f;
+	}
+	case OP_MAX: case OP_MIN: {
+		double m = d[0];
+		if (std::isnan(m)) return m;
+		for (int i = 1; i < n; i++) {
+			if (std::isnan(d[i])) return NAN;
+			if (op == OP_MAX ? d[i] > m : d[i] < m) m = d[i];
+		}
+		return m;
+	}
+	case OP_MEDIAN: {
+		std::vector<double> v(d, d + n);
+		for (int i = 0; i < n; i++) if (std::isnan(v[i])) return NAN;
+		std::sort(v.begin(), v.end());
+		float f = (float) v[n / 2];
+		return f;
+	}
+	}
+	return NAN;
+}
+
+bool valid_op(int op) {
+	return (op >= OP_SUM && op <= OP_MEDIAN) || op == OP_TTEST || op == OP_MWU;
+}
+
+int ceil_log2(long long v) { int l = 0; while ((1ll << l) < v) l++; return l; }
+
+// Core: inputs already resident on the device.
+int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
+               const int32_t *d_start, const int32_t *d_end, const double *d_value,
+               const int64_t *h_off, const double *h_dflt, int32_t pos_lo, int32_t pos_hi,
+               int32_t *d_out_start, int32_t *d_out_end, double *d_out_value, int64_t out_cap,
+               int64_t *n_out, double *default_out, double *auc_out, double *moments_out = nullptr) {
+	if (!valid_op(op) && !(op == OP_PEARSON && moments_out && N == 2)) return fail(ctx, WB200_EINVAL, "unknown op");
+	if (N < 1) return fail(ctx, WB200_EINVAL, "need at least one track");
+	const bool setop = op >= OP_TTEST;
+	if (!setop) n1 = N;
+	const int n2 = N - n1;
+	if (n1 > MAX_TRACKS || n2 > MAX_TRACKS) return fail(ctx, WB200_EUNSUPPORTED, "more than 1023 tracks in a set");
+	// the reference's arity checks (it prints and exit(1)s; here: an error code)
+	if (op == OP_TTEST && (n1 < 3 || n2 < 3))
+		return fail(ctx, WB200_EINVAL, "The t-test function only works for two sets with enough elements to compute variance");
+	if (op == OP_MWU && (n1 < 1 || n2 < 1))
+		return fail(ctx, WB200_EINVAL, "The Mann-Whitney U function only works for two non-empty sets");
+	if (pos_hi < pos_lo) pos_hi = pos_lo;
+	const int64_t I = h_off[N];
+	for (int i = 0; i < N; i++)
+		if (h_off[i + 1] < h_off[i] || h_off[i + 1] - h_off[i] > INT32_MAX)
+			return fail(ctx, WB200_EINVAL, "bad track offsets");
+
+	cudaStream_t s = ctx->stream;
+	wb200_stats &st = ctx->stats;
+	st = wb200_stats{};
+	st.intervals = I;
+
+	// window size
+	int wlog = 12;
+	if (ctx->window_bp > 0) wlog = ceil_log2(ctx->window_bp);
+	else {
+		const char *env = getenv("WB200_WINDOW");
+		if (env && atoi(env) > 0) wlog = ceil_log2(atoi(env));
+		else {
+			double density = 2.0 * (double) I / ((double) pos_hi - pos_lo + 1.0);
+			if (density > 0.6) wlog = 11;
+		}
+	}
+	wlog = std::min(13, std::max(8, wlog));
+	const int64_t span = (int64_t) pos_hi - pos_lo;
+	const int nw = (int) (span >> wlog) + 1;
+
+	Job job{};
+	job.start = d_start; job.end = d_end; job.value = d_value;
+	job.N = N; job.n1 = n1; job.strict = strict ? 1 : 0; job.op = op;
+	job.p0 = pos_lo; job.wlog = wlog; job.nw = nw;
+	job.strip = (int) std::min<int64_t>(64, std::max<int64_t>(4, nw / ((int64_t) ctx->sms * 8)));
+	job.out_start = d_out_start; job.out_end = d_out_end; job.out_value = d_out_value; job.out_cap = out_cap;
+
+	// small tables
+	CK(ctx->off.ensure((N + 1) * sizeof(int64_t)));
+	CK(ctx->dflt.ensure(N * sizeof(double)));
+	CK(ctx->dflt_fx.ensure(N * sizeof(int64_t)));
+	CK(ctx->h_meta.ensure((size_t) (N + 1) * 8 + (size_t) N * 16));
+	int64_t *hm_off = ctx->h_meta.as<int64_t>();
+	double *hm_dflt = (double *) (hm_off + N + 1);
+	int64_t *hm_fx = (int64_t *) (hm_dflt + N);
+	memcpy(hm_off, h_off, (N + 1) * sizeof(int64_t));
+	memcpy(hm_dflt, h_dflt, N * sizeof(double));
+	CK(ctx->cursor.ensure((size_t) nw * N * sizeof(int32_t)));
+	CK(ctx->wcount.ensure((size_t) nw * sizeof(uint32_t)));
+	CK(ctx->woff.ensure((size_t) (nw + 1) * sizeof(int64_t)));
+	CK(ctx->aucp.ensure((size_t) nw * sizeof(double)));
+	CK(ctx->small.ensure(128));
+	CK(ctx->h_small.ensure(128));
+	if (moments_out) { CK(ctx->moments.ensure((size_t) nw * 6 * sizeof(double))); job.moments = ctx->moments.as<double>(); }
+	job.off = ctx->off.as<int64_t>(); job.dflt = ctx->dflt.as<double>(); job.dflt_fx = ctx->dflt_fx.as<int64_t>();
+	job.cursor = ctx->cursor.as<int32_t>(); job.wcount = ctx->wcount.as<uint32_t>(); job.woff = ctx->woff.as<int64_t>();
+	job.auc_partial = ctx->aucp.as<double>();
+	// small: [0..1] sample result, [2] auc, [3] slow count
+	double *d_small = ctx->small.as<double>();
+	job.slow_count = (unsigned long long *) (d_small + 3);
+
+	CK(cudaEventRecord(ctx->ev[0], s));
+	CK(cudaMemcpyAsync(ctx->off.p, hm_off, (N + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+	CK(cudaMemcpyAsync(ctx->dflt.p, hm_dflt, N * sizeof(double), cudaMemcpyHostToDevice, s));
+	CK(cudaMemsetAsync(d_small, 0, 128, s));
+	st.kernels = 0;
+
+	// fixed-point fast path for sum / mean
+	job.fast = 0;
+	if ((op == OP_SUM || op == OP_MEAN) && I > 0) {
+		bool ok = true;
+		for (int i = 0; i < N; i++) if (!std::isfinite(h_dflt[i])) ok = false;
+		if (ok) {
+			int64_t stride = std::max<int64_t>(1, I / (1 << 16));
+			CK(launch_sample_maxabs(d_value, I, stride, d_small, s));
+			st.kernels++;
+			CK(cudaMemcpyAsync(ctx->h_small.p, d_small, 16, cudaMemcpyDeviceToHost, s));
+			CK(cudaStreamSynchronize(s));
+			double maxabs = ctx->h_small.as<double>()[0];
+			for (int i = 0; i < N; i++) maxabs = std::max(maxabs, std::fabs(h_dflt[i]));
+			int emax = 0;
+			if (maxabs > 0) { std::frexp(maxabs, &emax); }   // maxabs < 2^emax
+			// format: |m| < 2^mbits; two 32-bit limbs when that is enough for
+			// float32-grade inputs (24-bit mantissas), else three.
+			const int l2n = ceil_log2(2 * (int64_t) N);
+			const int lw = 32 - l2n;
+			const int cap2 = 29 - l2n + lw;
+			const int cap3 = std::min(29 - l2n + 2 * lw, 62 - ceil_log2(N + 1));
+			const char *env = getenv("WB200_LIMBS");
+			int limbs = (env && atoi(env) == 3) ? 3 : ((env && atoi(env) == 2) ? 2 : (cap2 >= 40 ? 2 : 3));
+			int mbits = limbs == 2 ? cap2 : cap3;
+			job.fx_mbits = mbits;
+			job.fx_q = emax + 2 - mbits;           // two bits of headroom above the sampled maximum
+			job.fx_q = std::max(-1000, std::min(1000, job.fx_q));
+			const double inv = std::ldexp(1.0, -job.fx_q), lim = std::ldexp(1.0, mbits);
+			long long base = 0;
+			for (int i = 0; i < N && ok; i++) {
+				double t = h_dflt[i] * inv;
+				if (!(std::fabs(t) < lim) || t != std::rint(t)) ok = false;
+				else { hm_fx[i] = (int64_t) t; base += hm_fx[i]; }
+			}
+			if (ok) {
+				job.fast = 1;
+				job.fx_base = base;
+				CK(cudaMemcpyAsync(ctx->dflt_fx.p, hm_fx, N * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+			}
+		}
+	}
+	if (op == OP_MWU) {
+		// integer division in both moments, src/setComparisons.c:386-387
+		job.mwu_mu = (double) (n1 * n2 / 2);
+		job.mwu_sigma = std::sqrt((double) (n1 * n2 * (n1 + n2 + 1) / 12));
+	}
+
+	size_t need = window_smem_bytes(wlog, N, true, op);
+	if (need > 227 * 1024) return fail(ctx, WB200_EUNSUPPORTED, "window does not fit shared memory; lower WB200_WINDOW");
+
+	CK(cudaEventRecord(ctx->ev[1], s));
+	CK(launch_count(job, s));
+	CK(launch_scan_counts(job.wcount, ctx->woff.as<int64_t>(), nw, s));
+	CK(cudaEventRecord(ctx->ev[2], s));
+	CK(launch_emit(job, s));
+	CK(launch_reduce_auc(job.auc_partial, nw, d_small + 2, s));
+	if (moments_out) { CK(launch_reduce_moments(job.moments, nw, d_small + 4, s)); st.kernels++; }
+	CK(cudaEventRecord(ctx->ev[3], s));
+	st.kernels += 4;
+
+	// S, AUC, slow-path count
+	int64_t *h_small = ctx->h_small.as<int64_t>();
+	CK(cudaMemcpyAsync(h_small, ctx->woff.as<int64_t>() + nw, 8, cudaMemcpyDeviceToHost, s));
+	CK(cudaMemcpyAsync(h_small + 2, d_small + 2, 64, cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+	const int64_t S = h_small[0];
+	st.segments = S;
+	st.windows = nw;
+	st.fast_path = job.fast;
+	st.slow_segments = h_small[3];
+	cudaEventElapsedTime(&st.ms_count, ctx->ev[1], ctx->ev[2]);
+	cudaEventElapsedTime(&st.ms_emit, ctx->ev[2], ctx->ev[3]);
+	cudaEventElapsedTime(&st.ms_total, ctx->ev[0], ctx->ev[3]);
+	if (n_out) *n_out = S;
+	if (auc_out) memcpy(auc_out, h_small + 2, 8);
+	if (default_out) *default_out = setop ? NAN : derived_default(op, N, h_dflt);
+	if (moments_out) { memcpy(moments_out, h_small + 4, 6 * sizeof(double)); return WB200_OK; }
+	if (S > out_cap) return fail(ctx, WB200_ECAPACITY, "output capacity too small");
+	return WB200_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+wb200_ctx *wb200_create(int device) {
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0) {
+		g_last_error = std::string("wiggletools_b200: no usable CUDA device (") +
+		               (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+		               "); this engine has no CPU fallback";
+		return nullptr;
+	}
+	if (device < 0 || device >= count) { g_last_error = "wiggletools_b200: bad device ordinal"; return nullptr; }
+	if ((e = cudaSetDevice(device)) != cudaSuccess) { g_last_error = cudaGetErrorString(e); return nullptr; }
+	wb200_ctx *ctx = new wb200_ctx();
+	ctx->device = device;
+	cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, device);
+	if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+		g_last_error = cudaGetErrorString(e);
+		delete ctx;
+		return nullptr;
+	}
+	for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+	return ctx;
+}
+
+void wb200_destroy(wb200_ctx *ctx) {
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	DevBuf *d[] = {&ctx->in_start, &ctx->in_end, &ctx->in_value, &ctx->off, &ctx->dflt, &ctx->dflt_fx, &ctx->cursor,
+	               &ctx->wcount, &ctx->woff, &ctx->aucp, &ctx->small, &ctx->moments, &ctx->out_start, &ctx->out_end, &ctx->out_value};
+	for (auto *b : d) b->release();
+	HostBuf *h[] = {&ctx->h_small, &ctx->h_meta, &ctx->h_start, &ctx->h_end, &ctx->h_value};
+	for (auto *b : h) b->release();
+	for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+	if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+const char *wb200_last_error(const wb200_ctx *ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+const wb200_stats *wb200_last_stats(const wb200_ctx *ctx) { return &ctx->stats; }
+
+int wb200_set_stream(wb200_ctx *ctx, void *cuda_stream) {
+	if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+	ctx->stream = (cudaStream_t) cuda_stream;
+	ctx->own_stream = false;
+	return WB200_OK;
+}
+
+int wb200_set_window(wb200_ctx *ctx, int window_bp) {
+	if (window_bp < 0 || (window_bp & (window_bp - 1))) return fail(ctx, WB200_EINVAL, "window must be a power of two");
+	ctx->window_bp = window_bp;
+	return WB200_OK;
+}
+
+void *wb200_host_alloc(int64_t bytes) {
+	void *p = nullptr;
+	if (cudaHostAlloc(&p, (size_t) bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+	return p;
+}
+
+void wb200_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int wb200_reduce_device(wb200_ctx *ctx, int op, int ntracks, int nset1, int strict,
+                        const int32_t *d_start, const int32_t *d_end, const double *d_value,
+                        const int64_t *h_off, const double *h_defaults, int32_t pos_lo, int32_t pos_hi,
+                        int32_t *d_out_start, int32_t *d_out_end, double *d_out_value,
+                        int64_t out_cap, int64_t *n_out, double *default_out, double *auc_out) {
+	if (!ctx) return WB200_EINVAL;
+	cudaSetDevice(ctx->device);
+	return run_device(ctx, op, ntracks, nset1, strict, d_start, d_end, d_value, h_off, h_defaults, pos_lo, pos_hi,
+	                  d_out_start, d_out_end, d_out_value, out_cap, n_out, default_out, auc_out);
+}
+
+int wb200_reduce_host(wb200_ctx *ctx, int op, int ntracks, int nset1, int strict,
+                      const wb200_track *tracks, wb200_segments *out) {
+	if (!ctx || !tracks || !out) return WB200_EINVAL;
+	cudaSetDevice(ctx->device);
+	const int N = ntracks;
+	if (N < 1) return fail(ctx, WB200_EINVAL, "need at least one track");
+	std::vector<int64_t> off(N + 1, 0);
+	std::vector<double> dflt(N);
+	int64_t lo = INT32_MAX, hi = 1;
+	for (int i = 0; i < N; i++) {
+		off[i + 1] = off[i] + tracks[i].n;
+		dflt[i] = tracks[i].default_value;
+		if (tracks[i].n > 0) {
+			lo = std::min<int64_t>(lo, tracks[i].start[0]);
+			hi = std::max<int64_t>(hi, tracks[i].end[tracks[i].n - 1]);
+		}
+	}
+	const int64_t I = off[N];
+	if (lo > hi) lo = hi;
+	cudaStream_t s = ctx->stream;
+	CK(ctx->in_start.ensure(std::max<int64_t>(1, I) * sizeof(int32_t)));
+	CK(ctx->in_end.ensure(std::max<int64_t>(1, I) * sizeof(int32_t)));
+	CK(ctx->in_value.ensure(std::max<int64_t>(1, I) * sizeof(double)));
+	for (int i = 0; i < N; i++) {
+		if (!tracks[i].n) continue;
+		CK(cudaMemcpyAsync(ctx->in_start.as<int32_t>() + off[i], tracks[i].start, tracks[i].n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+		CK(cudaMemcpyAsync(ctx->in_end.as<int32_t>() + off[i], tracks[i].end, tracks[i].n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+		CK(cudaMemcpyAsync(ctx->in_value.as<double>() + off[i], tracks[i].value, tracks[i].n * sizeof(double), cudaMemcpyHostToDevice, s));
+	}
+	const int64_t cap = std::max<int64_t>(1, std::min<int64_t>(2 * I + 1, hi - lo + 1));
+	CK(ctx->out_start.ensure(cap * sizeof(int32_t)));
+	CK(ctx->out_end.ensure(cap * sizeof(int32_t)));
+	CK(ctx->out_value.ensure(cap * sizeof(double)));
+	int64_t S = 0;
+	double dv = NAN, auc = 0;
+	int rc = run_device(ctx, op, N, nset1, strict, ctx->in_start.as<int32_t>(), ctx->in_end.as<int32_t>(),
+	                    ctx->in_value.as<double>(), off.data(), dflt.data(), (int32_t) lo, (int32_t) hi,
+	                    ctx->out_start.as<int32_t>(), ctx->out_end.as<int32_t>(), ctx->out_value.as<double>(),
+	                    cap, &S, &dv, &auc);
+	if (rc != WB200_OK) return rc;
+	CK(ctx->h_start.ensure(std::max<int64_t>(1, S) * sizeof(int32_t)));
+	CK(ctx->h_end.ensure(std::max<int64_t>(1, S) * sizeof(int32_t)));
+	CK(ctx->h_value.ensure(std::max<int64_t>(1, S) * sizeof(double)));
+	if (S > 0) {
+		CK(cudaMemcpyAsync(ctx->h_start.p, ctx->out_start.p, S * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+		CK(cudaMemcpyAsync(ctx->h_end.p, ctx->out_end.p, S * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+		CK(cudaMemcpyAsync(ctx->h_value.p, ctx->out_value.p, S * sizeof(double), cudaMemcpyDeviceToHost, s));
+	}
+	CK(cudaStreamSynchronize(s));
+	ctx->stats.h2d_bytes = I * 16;
+	ctx->stats.d2h_bytes = S * 16;
+	out->start = ctx->h_start.as<int32_t>();
+	out->end = ctx->h_end.as<int32_t>();
+	out->value = ctx->h_value.as<double>();
+	out->n = S;
+	out->default_value = dv;
+	out->auc = auc;
+	return WB200_OK;
+}
+
+
+int wb200_pearson_host(wb200_ctx *ctx, const wb200_track *x, const wb200_track *y, double moments[6]) {
+	if (!ctx || !x || !y || !moments) return WB200_EINVAL;
+	cudaSetDevice(ctx->device);
+	const wb200_track *tr[2] = {x, y};
+	int64_t off[3] = {0, x->n, x->n + y->n};
+	double dflt[2] = {x->default_value, y->default_value};
+	int64_t lo = INT32_MAX, hi = 1;
+	for (int i = 0; i < 2; i++)
+		if (tr[i]->n > 0) {
+			lo = std::min<int64_t>(lo, tr[i]->start[0]);
+			hi = std::max<int64_t>(hi, tr[i]->end[tr[i]->n - 1]);
+		}
+	if (lo > hi) lo = hi;
+	const int64_t I = off[2];
+	cudaStream_t s = ctx->stream;
+	CK(ctx->in_start.ensure(std::max<int64_t>(1, I) * sizeof(int32_t)));
+	CK(ctx->in_end.ensure(std::max<int64_t>(1, I) * sizeof(int32_t)));
+	CK(ctx->in_value.ensure(std::max<int64_t>(1, I) * sizeof(double)));
+	for (int i = 0; i < 2; i++) {
+		if (!tr[i]->n) continue;
+		CK(cudaMemcpyAsync(ctx->in_start.as<int32_t>() + off[i], tr[i]->start, tr[i]->n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+		CK(cudaMemcpyAsync(ctx->in_end.as<int32_t>() + off[i], tr[i]->end, tr[i]->n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+		CK(cudaMemcpyAsync(ctx->in_value.as<double>() + off[i], tr[i]->value, tr[i]->n * sizeof(double), cudaMemcpyHostToDevice, s));
+	}
+	int rc = run_device(ctx, OP_PEARSON, 2, 2, 0, ctx->in_start.as<int32_t>(), ctx->in_end.as<int32_t>(),
+	                    ctx->in_value.as<double>(), off, dflt, (int32_t) lo, (int32_t) hi,
+	                    nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, moments);
+	ctx->stats.h2d_bytes = I * 16;
+	ctx->stats.d2h_bytes = 48;
+	return rc;
+}
+
+// Shard merge for the Pearson moments {n, sum_X, sum_Y, T_XX, T_XY, T_YY}: the
+// pairwise form of the reference's sequential update (src/statistics.c:443-456,
+// derivation in technical-supplement.tex:14-74) applied to two pre-reduced
+// shards: T(a+b) = T(a) + T(b) + n_a n_b/(n_a+n_b) * dX * dY.
+void wb200_pearson_merge(double a[6], const double b[6]) { merge6(a, b); }
+
+// PearsonPop's final expression (src/statistics.c:420-421): NaN unless T_XX*T_YY != 0
+double wb200_pearson_result(const double m[6]) {
+	if (m[3] * m[5] != 0) return m[4] / std::sqrt(m[3] * m[5]);
+	return NAN;
+}
+
+} // extern "C"

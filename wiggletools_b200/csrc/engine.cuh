@@ -1,0 +1,89 @@
+// wiggletools_b200 -- device-side job description shared by the kernels
+// (engine.cu) and the host C ABI (capi.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace wb {
+
+constexpr int THREADS = 256;           // threads per CTA in the window kernels
+constexpr int WARPS = THREADS / 32;
+constexpr int MAX_TRACKS = 1023;       // per set: 10-bit cover fields
+
+// Cover word layout (one int32 per breakpoint slot): the prefix sum over slots
+// gives, for the segment that starts at the slot,
+//   bits  0.. 9  tracks of set A in play   (all tracks for a plain multiplexer)
+//   bits 10..19  tracks of set B in play
+//   bits 20..31  tracks in play whose value is not exactly representable in
+//                the fixed-point accumulator ("poison": NaN, Inf, out of range)
+constexpr int COV_B_SHIFT = 10;
+constexpr int COV_P_SHIFT = 20;
+constexpr int COV_MASK = 1023;
+
+enum Op : int {
+	OP_SUM = 0, OP_PRODUCT = 1, OP_MEAN = 2, OP_VAR = 3, OP_STDDEV = 4, OP_ENTROPY = 5,
+	OP_CV = 6, OP_MIN = 7, OP_MAX = 8, OP_MEDIAN = 9, OP_TTEST = 16, OP_MWU = 17,
+	OP_PEARSON = 32   // internal: 2-track moments (PearsonPop, src/statistics.c:414-458)
+};
+
+struct Job {
+	// inputs: all tracks of one chromosome, concatenated
+	const int32_t *start;
+	const int32_t *end;
+	const double *value;
+	const int64_t *off;     // [N+1] device
+	const double *dflt;     // [N] device: default_value per track
+	const int64_t *dflt_fx; // [N] device: fixed-point defaults (fast path)
+	int N;                  // tracks
+	int n1;                 // tracks in set A (== N for a plain multiplexer)
+	int strict;
+	int op;
+	// windowing
+	int64_t p0;             // position of window 0, slot 0
+	int wlog;               // log2(window size in bp)
+	int nw;                 // number of windows
+	int strip;              // windows per count-kernel strip
+	// scratch
+	int32_t *cursor;        // [nw * N] first interval of track i with end >= window start
+	uint32_t *wcount;       // [nw] segments emitted by each window
+	const int64_t *woff;    // [nw + 1] exclusive scan of wcount
+	// outputs
+	int32_t *out_start;
+	int32_t *out_end;
+	double *out_value;
+	int64_t out_cap;
+	double *auc_partial;    // [nw] per-window sum of (end-start)*value (NaN skipped), or null
+	unsigned long long *slow_count; // segments that took the row path
+	double *moments;        // [nw * 6] per-window Pearson moments (OP_PEARSON), or null
+	// fixed-point fast path (sum / mean)
+	int fast;               // 1: scan path enabled for this op
+	int fx_q;               // value = m * 2^fx_q
+	int fx_mbits;           // |m| < 2^fx_mbits
+	int64_t fx_base;        // sum of fixed-point defaults (all tracks absent)
+	double mwu_mu, mwu_sigma; // MWU normal approximation moments (host-computed, integer division quirk)
+};
+
+// Pearson moments m = {n, sum_X, sum_Y, T_XX, T_XY, T_YY}; fold shard b into a.
+// Pairwise form of the reference's sequential update (src/statistics.c:443-456).
+__host__ __device__ inline void merge6(double *a, const double *b) {
+	if (b[0] == 0) return;
+	if (a[0] == 0) { for (int k = 0; k < 6; k++) a[k] = b[k]; return; }
+	const double n = a[0] + b[0];
+	const double dx = a[1] / a[0] - b[1] / b[0], dy = a[2] / a[0] - b[2] / b[0];
+	const double w = a[0] * b[0] / n;
+	a[3] += b[3] + w * dx * dx;
+	a[4] += b[4] + w * dx * dy;
+	a[5] += b[5] + w * dy * dy;
+	a[0] = n; a[1] += b[1]; a[2] += b[2];
+}
+
+// launch helpers implemented in engine.cu
+size_t window_smem_bytes(int wlog, int N, bool emit, int op);
+cudaError_t launch_count(const Job &job, cudaStream_t s);
+cudaError_t launch_scan_counts(const uint32_t *wcount, int64_t *woff, int nw, cudaStream_t s);
+cudaError_t launch_emit(const Job &job, cudaStream_t s);
+cudaError_t launch_sample_maxabs(const double *value, int64_t n, int64_t stride, double *out2, cudaStream_t s);
+cudaError_t launch_reduce_auc(const double *partial, int nw, double *out, cudaStream_t s);
+cudaError_t launch_reduce_moments(const double *moments, int nw, double *out6, cudaStream_t s);
+
+} // namespace wb
