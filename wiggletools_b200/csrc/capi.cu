@@ -156,7 +156,7 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
                int64_t *n_out, double *default_out, double *auc_out, double *moments_out = nullptr) {
 	if (!valid_op(op) && !(op == OP_PEARSON && moments_out && N == 2)) return fail(ctx, WB200_EINVAL, "unknown op");
 	if (N < 1) return fail(ctx, WB200_EINVAL, "need at least one track");
-	const bool setop = op >= OP_TTEST;
+	const bool setop = (op == OP_TTEST || op == OP_MWU);
 	if (!setop) n1 = N;
 	const int n2 = N - n1;
 	if (n1 > MAX_TRACKS || n2 > MAX_TRACKS) return fail(ctx, WB200_EUNSUPPORTED, "more than 1023 tracks in a set");

@@ -509,7 +509,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	__syncthreads();
 
 	// ---- phase 4/5: scan over slots, keep, emit --------------------------
-	const bool setop = job.op >= OP_TTEST;
+	const bool setop = (job.op == OP_TTEST || job.op == OP_MWU);
 	const bool sorted_op = (job.op == OP_MEDIAN || job.op == OP_MWU);
 	int carry_cov = 0;
 	long long carry_sum = 0;
