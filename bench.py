@@ -28,6 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from wiggletools_b200.synth import sorted_chroms  # noqa: E402
+from wiggletools_b200.shard import lpt_assign  # noqa: E402
 
 N_TRACKS = int(os.environ.get("WB200_BENCH_TRACKS", 64))
 SCALE = float(os.environ.get("WB200_BENCH_SCALE", 1.0))   # <1 shrinks every chromosome (development only)
@@ -38,18 +39,6 @@ def genome():
     names, lengths = sorted_chroms()
     lengths = [max(10000, int(l * SCALE)) for l in lengths]
     return names, lengths
-
-
-def shard_chromosomes(lengths, world):
-    """LPT bin packing of chromosomes onto ranks (by length ~ interval count)."""
-    order = sorted(range(len(lengths)), key=lambda i: -lengths[i])
-    load = [0] * world
-    owner = [0] * len(lengths)
-    for i in order:
-        r = min(range(world), key=lambda k: load[k])
-        owner[i] = r
-        load[r] += lengths[i]
-    return owner
 
 
 # ---------------------------------------------------------------------------
@@ -219,7 +208,7 @@ def main():
     lib.wb200_set_stream(ctx, C.c_void_p(stream.cuda_stream))
 
     names, lengths = genome()
-    owner = shard_chromosomes(lengths, world)
+    owner = lpt_assign(lengths, world)
     mine = [i for i in range(len(lengths)) if owner[i] == rank]
 
     # resident inputs and outputs for this rank's chromosomes

@@ -76,6 +76,10 @@ class Oracle:
             path, self.p = os.path.join(HERE, "liboracle.so"), "wto_"
         elif kind == "reference":
             path, self.p = os.path.join(HERE, "_ref", "libwtref.so"), "wtref_"
+        elif kind == "dropin":
+            # ref_harness.c bound to libwiggletools_b200.so's drop-in API: the
+            # thing under test driven through the reference's own call sequence
+            path, self.p = os.path.join(HERE, "_ref", "libwtdropin.so"), "wtref_"
         else:
             raise ValueError(kind)
         if not os.path.exists(path):
@@ -93,12 +97,13 @@ class Oracle:
         f = self._f("pearson")
         f.restype = C.c_double
         f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
-        f = self._f("rows")
-        f.restype = C.c_int64
-        f.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-        f = self._f("tdist_Q")
-        f.restype = C.c_double
-        f.argtypes = [C.c_double, C.c_double]
+        if kind != "dropin":
+            f = self._f("rows")
+            f.restype = C.c_int64
+            f.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+            f = self._f("tdist_Q")
+            f.restype = C.c_double
+            f.argtypes = [C.c_double, C.c_double]
 
     def _f(self, name):
         return getattr(self.lib, self.p + name)

@@ -22,11 +22,23 @@
 #include <string.h>
 #include <math.h>
 
+#ifdef WB200_DROPIN
+/* Same harness, compiled against the GPU library's drop-in API instead of the
+ * reference objects (oracle/_ref/libwtdropin.so): the parity tests then drive
+ * newMultiplexer / MeanReduction / ... of libwiggletools_b200.so exactly the
+ * way they drive the reference. */
+#include "wiggletools_dropin.h"
+#define bool char
+#define true 1
+#define false 0
+#else
 #include "wiggleIterator.h"   /* reference header: struct wiggleIterator_st */
 #include "multiplexer.h"
 #include "multiSet.h"
+#endif
 
 /* ---- 1. stubs for absent third-party readers --------------------------- */
+#ifndef WB200_DROPIN
 static void wtref_absent(const char *what) {
 	fprintf(stderr, "oracle/_ref: %s needs a library that is not in this image\n", what);
 	exit(1);
@@ -36,6 +48,7 @@ WiggleIterator *BigBedReader(char *f, bool h) { (void)f; (void)h; wtref_absent("
 WiggleIterator *BamReader(char *f, bool h, bool r) { (void)f; (void)h; (void)r; wtref_absent("BamReader"); return NULL; }
 WiggleIterator *BcfReader(char *f, bool h) { (void)f; (void)h; wtref_absent("BcfReader"); return NULL; }
 void libBigWigInit(int n) { (void)n; }
+#endif
 
 /* ---- 2. in-memory source ------------------------------------------------ */
 typedef struct {
@@ -193,6 +206,7 @@ double wtref_pearson(const wt_track *x, const wt_track *y, int nnames, char **na
 	return *(double *) wi->data;
 }
 
+#ifndef WB200_DROPIN
 /* Raw multiplexer rows (what mWigWriter sees): values[count] + inplay[count]
  * per segment; row_values/row_inplay hold cap*count entries. */
 int64_t wtref_rows(int ntracks, const wt_track *tracks, int strict, int nnames, char **names,
@@ -224,6 +238,9 @@ int64_t wtref_reduce_compressed(int op, int ntracks, const wt_track *tracks, int
 	return drain(wi, names, nnames, out);
 }
 
+#endif /* !WB200_DROPIN */
+
+#ifndef WB200_DROPIN
 double wtref_tdist_Q(double t, double nu);
 double gsl_cdf_tdist_Q(double, double);
 double wtref_tdist_Q(double t, double nu) { return gsl_cdf_tdist_Q(t, nu); }
@@ -234,3 +251,4 @@ int wtref_cli(int argc, char **argv) {
 	rollYourOwn(argc, argv);
 	return 0;
 }
+#endif /* !WB200_DROPIN */

@@ -42,3 +42,17 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
                 text = open(os.path.join(d, f)).read()
                 assert "pyoracle" not in text and "liboracle" not in text and "libwtref" not in text, f
+
+
+def test_dropin_symbols_exported():
+    """Every function include/wiggletools_dropin.h declares is exported."""
+    text = open(os.path.join(ROOT, "include", "wiggletools_dropin.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    body = text[text.index("-- multiplexer.c") if "-- multiplexer.c" in text else 0:]
+    names = set(re.findall(r"\b([A-Za-z][A-Za-z0-9]*)\s*\(", text)) - {"void", "defined", "pop", "seek"}
+    names = {n for n in names if n[0].isupper() or n.startswith(("new", "pop", "seek", "run", "destroy"))}
+    names |= {"pop", "seek"}
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    assert len(names) >= 30
+    for n in sorted(names):
+        assert hasattr(lib, n), "missing drop-in export " + n

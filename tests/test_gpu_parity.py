@@ -192,3 +192,64 @@ def test_full_scale_properties(engine):
     # AUC of the sum == sum of the tracks' own AUCs (integers here: exact)
     total = sum(float(((t.end - t.start) * t.value).sum()) for t in g)
     assert math.isclose(s.auc, total, rel_tol=1e-12)
+
+
+# ---------------------------------------------------------------------------
+# the drop-in boundary: the reference's own API exported by the GPU library
+# ---------------------------------------------------------------------------
+def test_dropin_api_matches_oracle(port):
+    """newMultiplexer / <op>Reduction / newMultiset / TTest / MWU / AUCIntegrator /
+    PearsonIntegrator of libwiggletools_b200.so, driven by the same C harness
+    that drives the compiled reference (oracle/ref_harness.c)."""
+    import os
+    from oracle.pyoracle import Oracle
+    if not os.path.exists(os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "libwtdropin.so")):
+        pytest.skip("oracle/_ref/libwtdropin.so not built")
+    drop = Oracle("dropin")
+    for seed, n in ((0, 3), (1, 7), (3, 12)):
+        kw = dict(nan_prob=0.02 if seed % 2 else 0.0, align=(1 if seed < 3 else 10))
+        tr = make_tracks(n, [20000, 6000, 9000], seed=300 + seed, max_len=40, max_gap=30, **kw)
+        defaults = None if seed < 1 else [float(i % 3) for i in range(n)]
+        o, _ = both(tr, defaults)
+        for op in REDUCE_OPS:
+            for strict in (False, True):
+                want, got = port.reduce(op, o, NAMES, strict), drop.reduce(op, o, NAMES, strict)
+                assert_segments(got, want.chrom, want.start, want.end, want.value, exact=True, what="dropin %s" % op)
+                assert same_float(got.default, want.default), op
+        if n >= 6:
+            for op in ("ttest", "wilcoxon"):
+                want, got = port.setcompare(op, o[:3], o[3:], NAMES), drop.setcompare(op, o[:3], o[3:], NAMES)
+                assert_segments(got, want.chrom, want.start, want.end, want.value, what="dropin " + op)
+        want, got = port.pearson(o[0], o[1], NAMES), drop.pearson(o[0], o[1], NAMES)
+        assert same_float(got, want) or math.isclose(got, want, rel_tol=1e-9)
+        want, got = port.auc("mean", o, NAMES), drop.auc("mean", o, NAMES)
+        assert same_float(got, want) or math.isclose(got, want, rel_tol=RTOL)
+
+
+def test_dropin_cli_config1(tmp_path):
+    """BASELINE.json configs[0]: `wiggletools mean fixedStep variableStep` through
+    the reference's unmodified parser/readers/writer linked against the GPU
+    library (oracle/_ref/wiggletools_b200).  The .wig twins of the .bw fixtures
+    are written here from their values (test/fixedStep.wig, test/variableStep.wig)."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "wiggletools_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/wiggletools_b200 not built (needs /root/reference at build time)")
+    f, v = tmp_path / "fixedStep.wig", tmp_path / "variableStep.wig"
+    f.write_text("fixedStep chrom=chr1 start=1 step=1 span=1\n" + "".join("%d\n" % i for i in range(10)))
+    v.write_text("variableStep chrom=chr1 span=1\n" + "".join("%d\t%d\n" % (p, x) for p, x in zip((1, 2, 4, 6, 8), (1, 2, 3, 4, 5))))
+
+    def run(*args):
+        return subprocess.run([exe] + list(args), capture_output=True, text=True, check=True, cwd=tmp_path).stdout
+
+    out = run("mean", "fixedStep.wig", "variableStep.wig").split("\n")
+    assert out[0] == "fixedStep chrom=chr1 start=1 step=1"
+    assert [float(x) for x in out[1:11]] == [.5, 1.5, 1, 3, 2, 4.5, 3, 6, 4, 4.5]
+    bg = run("write_bg", "-", "var", "fixedStep.wig", "variableStep.wig").strip().split("\n")
+    assert [float(l.split("\t")[3]) for l in bg] == [.25, .25, .5, 0, 2, .25, 4.5, 1, 8, 10.125]
+    assert run("AUC", "mean", "fixedStep.wig", "variableStep.wig").strip() == "30.000000"
+    assert run("pearson", "fixedStep.wig", "variableStep.wig").strip() == "-0.028968"   # test/expected/pearson.txt
+    # sum x x == scale 2 x (test/test.py:76), via the reference's own isZero/diff chain
+    assert subprocess.run([exe, "do", "isZero", "diff", "sum", "fixedStep.wig", "fixedStep.wig", ":", "scale", "2", "fixedStep.wig"],
+                          cwd=tmp_path).returncode == 0

@@ -1,0 +1,450 @@
+// wiggletools_b200 -- the reference's operator API for the merge+reduce path,
+// implemented on top of the batch engine (see include/wiggletools_dropin.h).
+//
+// The reference is a lazy pull graph: newMultiplexer() + MeanReduction() build
+// iterators and every pop() advances a heap sweep by one segment
+// (multiplexer.c:98-128, reducers.c:367-402).  Here a reduction is BATCH per
+// chromosome: on demand the input iterators are drained for the next
+// chromosome (strcmp order, multiplexer.c:50-74) into SoA arrays, one
+// wb200_reduce_host() call computes all of the chromosome's segments on the
+// GPU, and pop() then walks the result buffer.
+#include "../../include/wiggletools_dropin.h"
+#include "../../include/wiggletools_b200.h"
+
+#include <cmath>
+#include <cstddef>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <set>
+#include <string>
+#include <vector>
+
+// layouts the reference's callers rely on
+static_assert(offsetof(wiggleIterator_st, value) == 16 && offsetof(wiggleIterator_st, done) == 32 &&
+              offsetof(wiggleIterator_st, data) == 40 && offsetof(wiggleIterator_st, pop) == 48 &&
+              offsetof(wiggleIterator_st, overlaps) == 64 && offsetof(wiggleIterator_st, default_value) == 72 &&
+              offsetof(wiggleIterator_st, append) == 80 && sizeof(wiggleIterator_st) == 88, "WiggleIterator layout");
+static_assert(offsetof(multiplexer_st, values) == 16 && offsetof(multiplexer_st, count) == 32 &&
+              offsetof(multiplexer_st, inplay) == 40 && offsetof(multiplexer_st, iters) == 48 &&
+              offsetof(multiplexer_st, done) == 56 && offsetof(multiplexer_st, strict) == 57 &&
+              offsetof(multiplexer_st, pop) == 64 && offsetof(multiplexer_st, data) == 96 &&
+              sizeof(multiplexer_st) == 104, "Multiplexer layout");
+static_assert(offsetof(multiset_st, values) == 16 && offsetof(multiset_st, count) == 24 &&
+              offsetof(multiset_st, inplay) == 32 && offsetof(multiset_st, multis) == 40 &&
+              offsetof(multiset_st, done) == 48 && sizeof(multiset_st) == 72, "Multiset layout");
+
+namespace {
+
+wb200_ctx *g_ctx = nullptr;
+
+wb200_ctx *engine() {
+	if (!g_ctx) {
+		const char *dev = getenv("WB200_DEVICE");
+		g_ctx = wb200_create(dev ? atoi(dev) : 0);
+		if (!g_ctx) {
+			fprintf(stderr, "%s\n", wb200_last_error(nullptr));
+			exit(1);
+		}
+	}
+	return g_ctx;
+}
+
+// one stable char* per chromosome name for the life of the process
+char *intern(const char *name) {
+	static std::set<std::string> names;
+	return const_cast<char *>(names.insert(name).first->c_str());
+}
+
+void die(const char *msg) {
+	fprintf(stderr, "wiggletools_b200: %s\n", msg);
+	exit(1);
+}
+
+void gpu_multiplexer_pop(Multiplexer *);
+void gpu_multiplexer_seek(Multiplexer *, const char *, int, int);
+
+bool is_gpu_multiplexer(const Multiplexer *m) { return m->pop == &gpu_multiplexer_pop; }
+
+// ---------------------------------------------------------------------------
+// batch reduction behind a WiggleIterator
+// ---------------------------------------------------------------------------
+struct Reducer {
+	int op = 0;
+	int n1 = 0;
+	bool strict = false;
+	bool pearson = false;
+	std::vector<WiggleIterator *> iters;
+	// staged inputs of the current chromosome
+	std::vector<std::vector<int32_t>> s, e;
+	std::vector<std::vector<double>> v;
+	// results of the current chromosome
+	std::vector<int32_t> rs, re;
+	std::vector<double> rv;
+	size_t k = 0;
+	char *chrom = nullptr;
+	double auc = 0;            // running whole-genome AUC (device partials, chromosome order)
+	double moments[6] = {0, 0, 0, 0, 0, 0};
+
+	// Drain every input positioned on the strcmp-smallest chromosome
+	// (multiplexer.c:50-74) and run the engine on it.  false = inputs exhausted.
+	bool next_chromosome() {
+		const size_t n = iters.size();
+		const char *best = nullptr;
+		for (WiggleIterator *it : iters)
+			if (!it->done && (!best || strcmp(it->chrom, best) < 0)) best = it->chrom;
+		if (!best) return false;
+		chrom = intern(best);
+		s.resize(n); e.resize(n); v.resize(n);
+		std::vector<wb200_track> tracks(n);
+		for (size_t i = 0; i < n; i++) {
+			WiggleIterator *it = iters[i];
+			s[i].clear(); e[i].clear(); v[i].clear();
+			while (!it->done && strcmp(it->chrom, chrom) == 0) {
+				s[i].push_back(it->start);
+				e[i].push_back(it->finish);
+				v[i].push_back(it->value);
+				pop(it);
+			}
+			tracks[i].start = s[i].data(); tracks[i].end = e[i].data(); tracks[i].value = v[i].data();
+			tracks[i].n = (int64_t) s[i].size();
+			tracks[i].default_value = it->default_value;
+		}
+		rs.clear(); re.clear(); rv.clear(); k = 0;
+		if (pearson) {
+			double m[6];
+			if (wb200_pearson_host(engine(), &tracks[0], &tracks[1], m) != WB200_OK) die(wb200_last_error(engine()));
+			wb200_pearson_merge(moments, m);
+			return true;
+		}
+		wb200_segments out;
+		if (wb200_reduce_host(engine(), op, (int) n, n1, strict ? 1 : 0, tracks.data(), &out) != WB200_OK)
+			die(wb200_last_error(engine()));
+		rs.assign(out.start, out.start + out.n);
+		re.assign(out.end, out.end + out.n);
+		rv.assign(out.value, out.value + out.n);
+		auc += out.auc;
+		return true;
+	}
+};
+
+void reducer_pop(WiggleIterator *wi) {
+	Reducer *r = (Reducer *) wi->data;
+	while (r->k >= r->rs.size())
+		if (!r->next_chromosome()) { wi->done = true; return; }
+	wi->chrom = r->chrom;
+	wi->start = r->rs[r->k];
+	wi->finish = r->re[r->k];
+	wi->value = r->rv[r->k];
+	r->k++;
+}
+
+void reducer_seek(WiggleIterator *wi, const char *chrom, int start, int finish) {
+	// WiggleReducerSeek (reducers.c:25-29): seek every input, then pop
+	Reducer *r = (Reducer *) wi->data;
+	for (WiggleIterator *it : r->iters) seek(it, chrom, start, finish);
+	r->rs.clear(); r->re.clear(); r->rv.clear(); r->k = 0;
+	pop(wi);
+}
+
+double host_default(int op, const std::vector<WiggleIterator *> &iters) {
+	// the constructors' derived default_value: ask the engine (empty job, same
+	// code path as the real one, no kernels needed for zero intervals)
+	std::vector<wb200_track> tr(iters.size());
+	for (size_t i = 0; i < iters.size(); i++) { tr[i] = wb200_track{nullptr, nullptr, nullptr, 0, iters[i]->default_value}; }
+	wb200_segments out;
+	if (wb200_reduce_host(engine(), op, (int) tr.size(), (int) tr.size(), 0, tr.data(), &out) != WB200_OK)
+		die(wb200_last_error(engine()));
+	return out.default_value;
+}
+
+WiggleIterator *make_reduction(int op, Multiplexer *multi) {
+	if (!is_gpu_multiplexer(multi))
+		die("reducers run on multiplexers built by newMultiplexer(); a custom multiplexer (apply/mwrite) as reducer input is not supported");
+	Reducer *r = new Reducer();
+	r->op = op;
+	r->strict = multi->strict;
+	r->iters.assign(multi->iters, multi->iters + multi->count);
+	r->n1 = multi->count;
+	double dflt = host_default(op, r->iters);
+	return newWiggleIterator(r, &reducer_pop, &reducer_seek, dflt, false);
+}
+
+WiggleIterator *make_setcompare(int op, Multiset *ms) {
+	Reducer *r = new Reducer();
+	r->op = op;
+	for (int m = 0; m < 2; m++) {
+		if (!is_gpu_multiplexer(ms->multis[m])) die("set comparisons need multiplexers built by newMultiplexer()");
+		r->iters.insert(r->iters.end(), ms->multis[m]->iters, ms->multis[m]->iters + ms->multis[m]->count);
+	}
+	r->n1 = ms->multis[0]->count;
+	return newWiggleIterator(r, &reducer_pop, &reducer_seek, NAN, false);
+}
+
+// ---------------------------------------------------------------------------
+// a GPU-backed Multiplexer is a description of the inputs; rows are not served
+// ---------------------------------------------------------------------------
+void gpu_multiplexer_pop(Multiplexer *) {
+	die("this Multiplexer is batch (GPU): per-row values[]/inplay[] are not materialised, "
+	    "so mwrite / paste / raw popMultiplexer are not available on it");
+}
+
+void gpu_multiplexer_seek(Multiplexer *multi, const char *chrom, int start, int finish) {
+	for (int i = 0; i < multi->count; i++) seek(multi->iters[i], chrom, start, finish);
+}
+
+// ---------------------------------------------------------------------------
+// generic pieces restated from the reference (not on the hot path)
+// ---------------------------------------------------------------------------
+struct UnaryData { WiggleIterator *iter; };
+
+void union_pop(WiggleIterator *wi) {
+	// merge overlapping records of one source (unaryOps.c:60-86)
+	WiggleIterator *iter = ((UnaryData *) wi->data)->iter;
+	if (iter->done) { wi->done = true; return; }
+	int count = 0;
+	while (!iter->done) {
+		if (!count) {
+			wi->chrom = iter->chrom; wi->start = iter->start; wi->finish = iter->finish; wi->value = iter->value;
+		} else if (wi->chrom == iter->chrom && wi->finish > iter->start) {
+			if (iter->finish > wi->finish) wi->finish = iter->finish;
+		} else
+			break;
+		count++;
+		pop(iter);
+	}
+	wi->done = (count == 0);
+}
+
+void unary_seek(WiggleIterator *wi, const char *chrom, int start, int finish) {
+	seek(((UnaryData *) wi->data)->iter, chrom, start, finish);
+	wi->done = false;
+	pop(wi);
+}
+
+struct SelectData { Multiplexer *multi; int index; };
+
+void select_pop(WiggleIterator *wi) {
+	// SelectReductionPop (reducers.c:40-65), generic over any multiplexer
+	if (wi->done) return;
+	SelectData *d = (SelectData *) wi->data;
+	Multiplexer *multi = d->multi;
+	if (multi->done) { wi->done = true; return; }
+	while (multi->inplay[d->index]) {
+		popMultiplexer(multi);
+		if (multi->done) { wi->done = true; return; }
+	}
+	wi->value = multi->values[d->index];
+	wi->chrom = multi->chrom; wi->start = multi->start; wi->finish = multi->finish;
+	popMultiplexer(multi);
+}
+
+void select_seek(WiggleIterator *wi, const char *chrom, int start, int finish) {
+	seekMultiplexer(((SelectData *) wi->data)->multi, chrom, start, finish);
+	pop(wi);
+}
+
+struct StatData { double res; WiggleIterator *source; Reducer *gpu; };
+
+void auc_pop(WiggleIterator *wi) {
+	// AUCPop (statistics.c:103-120): pass records through, integrate len*value.
+	// When the source is one of our reductions the integral is the engine's own
+	// (per-chromosome partials computed on the device, folded in order).
+	StatData *d = (StatData *) wi->data;
+	if (d->source->done) {
+		if (d->gpu) d->res = d->gpu->auc;
+		wi->done = true;
+		return;
+	}
+	wi->chrom = d->source->chrom; wi->start = d->source->start; wi->finish = d->source->finish;
+	wi->value = d->source->value;
+	if (!d->gpu && !std::isnan(wi->value)) d->res += (wi->finish - wi->start) * wi->value;
+	pop(d->source);
+}
+
+void stat_seek(WiggleIterator *wi, const char *chrom, int start, int finish) {
+	StatData *d = (StatData *) wi->data;
+	seek(d->source, chrom, start, finish);
+	if (d->gpu) d->gpu->auc = 0;
+	d->res = 0;
+	pop(wi);
+}
+
+struct PearsonData { double res; Reducer *r; };
+
+void pearson_pop(WiggleIterator *wi) {
+	// PearsonPop (statistics.c:414-458) as a batch: no records are passed
+	// through; the result is ready when the iterator reports done.
+	PearsonData *d = (PearsonData *) wi->data;
+	while (d->r->next_chromosome()) {}
+	d->res = wb200_pearson_result(d->r->moments);
+	wi->done = true;
+}
+
+void pearson_seek(WiggleIterator *wi, const char *chrom, int start, int finish) {
+	PearsonData *d = (PearsonData *) wi->data;
+	for (WiggleIterator *it : d->r->iters) seek(it, chrom, start, finish);
+	for (double &m : d->r->moments) m = 0;
+	pop(wi);
+}
+
+} // namespace
+
+extern "C" {
+
+// -- wiggleIterator.c ---------------------------------------------------------
+WiggleIterator *newWiggleIterator(void *data, void (*popFunction)(WiggleIterator *),
+                                  void (*seekFunction)(WiggleIterator *, const char *, int, int),
+                                  double default_value, wt_bool overlapping) {
+	WiggleIterator *wi = (WiggleIterator *) calloc(1, sizeof(WiggleIterator));
+	wi->data = data;
+	wi->pop = popFunction;
+	wi->seek = seekFunction;
+	wi->value = 1;            // default for non-valued bed tracks (wiggleIterator.c:26)
+	wi->overlaps = overlapping;
+	wi->default_value = default_value;
+	pop(wi);                  // eager first record (wiggleIterator.c:32)
+	return wi;
+}
+
+void pop(WiggleIterator *wi) { if (!wi->done) wi->pop(wi); }
+void runWiggleIterator(WiggleIterator *wi) { while (!wi->done) wi->pop(wi); }
+void seek(WiggleIterator *wi, const char *chrom, int start, int finish) { wi->done = 0; wi->seek(wi, chrom, start, finish); }
+void destroyWiggleIterator(WiggleIterator *wi) { free(wi->data); free(wi); }
+
+WiggleIterator *UnionWiggleIterator(WiggleIterator *i) {
+	UnaryData *d = (UnaryData *) calloc(1, sizeof(UnaryData));
+	d->iter = i;
+	return newWiggleIterator(d, &union_pop, &unary_seek, i->default_value, 0);
+}
+
+WiggleIterator *NonOverlappingWiggleIterator(WiggleIterator *i) { return i->overlaps ? UnionWiggleIterator(i) : i; }
+
+// -- multiplexer.c --------------------------------------------------------------
+void popMultiplexer(Multiplexer *multi) { if (!multi->done) multi->pop(multi); }
+void runMultiplexer(Multiplexer *multi) { while (!multi->done) multi->pop(multi); }
+void seekMultiplexer(Multiplexer *multi, const char *chrom, int start, int finish) {
+	multi->done = 0;
+	multi->seek(multi, chrom, start, finish);
+}
+
+Multiplexer *newCoreMultiplexer(void *data, int count, void (*popf)(Multiplexer *),
+                                void (*seekf)(Multiplexer *, const char *, int, int)) {
+	Multiplexer *m = (Multiplexer *) calloc(1, sizeof(Multiplexer));
+	m->count = count;
+	m->values = (double *) calloc(count, sizeof(double));
+	m->default_values = (double *) calloc(count, sizeof(double));
+	m->inplay = (wt_bool *) calloc(count, sizeof(wt_bool));
+	m->pop = popf;
+	m->seek = seekf;
+	m->data = data;
+	return m;
+}
+
+Multiplexer *newMultiplexer(WiggleIterator **iters, int count, wt_bool strict) {
+	Multiplexer *m = newCoreMultiplexer(nullptr, count, &gpu_multiplexer_pop, &gpu_multiplexer_seek);
+	m->strict = strict;
+	m->iters = (WiggleIterator **) calloc(count, sizeof(WiggleIterator *));
+	for (int i = 0; i < count; i++) {
+		m->iters[i] = NonOverlappingWiggleIterator(iters[i]);
+		m->default_values[i] = m->values[i] = m->iters[i]->default_value;
+	}
+	// The reference pops once here (:167).  A batch multiplexer has no rows to
+	// show; it stays not-done until a reduction or integrator consumes it.
+	return m;
+}
+
+// -- multiSet.c -------------------------------------------------------------------
+Multiset *newMultiset(Multiplexer **multis, int count) {
+	Multiset *ms = (Multiset *) calloc(1, sizeof(Multiset));
+	ms->count = count;
+	ms->multis = multis;   // kept, not copied (multiSet.c:118)
+	ms->inplay = (wt_bool *) calloc(count, sizeof(wt_bool));
+	ms->values = (double **) calloc(count, sizeof(double *));
+	for (int i = 0; i < count; i++) ms->values[i] = multis[i]->values;
+	return ms;
+}
+
+void popMultiset(Multiset *) { die("a Multiset is batch (GPU): consume it with TTestReduction / MWUReduction"); }
+
+void seekMultiset(Multiset *ms, const char *chrom, int start, int finish) {
+	ms->done = 0;
+	for (int i = 0; i < ms->count; i++) seekMultiplexer(ms->multis[i], chrom, start, finish);
+}
+
+// -- reducers.c ---------------------------------------------------------------------
+WiggleIterator *SumReduction(Multiplexer *m) { return make_reduction(WB200_SUM, m); }
+WiggleIterator *ProductReduction(Multiplexer *m) { return make_reduction(WB200_PRODUCT, m); }
+WiggleIterator *MeanReduction(Multiplexer *m) { return make_reduction(WB200_MEAN, m); }
+WiggleIterator *VarianceReduction(Multiplexer *m) { return make_reduction(WB200_VAR, m); }
+WiggleIterator *StdDevReduction(Multiplexer *m) { return make_reduction(WB200_STDDEV, m); }
+WiggleIterator *EntropyReduction(Multiplexer *m) { return make_reduction(WB200_ENTROPY, m); }
+WiggleIterator *CVReduction(Multiplexer *m) { return make_reduction(WB200_CV, m); }
+WiggleIterator *MinReduction(Multiplexer *m) { return make_reduction(WB200_MIN, m); }
+WiggleIterator *MaxReduction(Multiplexer *m) { return make_reduction(WB200_MAX, m); }
+WiggleIterator *MedianReduction(Multiplexer *m) { return make_reduction(WB200_MEDIAN, m); }
+
+WiggleIterator *SelectReduction(Multiplexer *multi, int index) {
+	if (is_gpu_multiplexer(multi)) die("select needs multiplexer rows; not available on a batch (GPU) multiplexer");
+	SelectData *d = (SelectData *) calloc(1, sizeof(SelectData));
+	d->multi = multi;
+	d->index = index;
+	return newWiggleIterator(d, &select_pop, &select_seek, multi->default_values[index], 0);
+}
+
+WiggleIterator *FillInReduction(Multiplexer *multi, wt_bool trim) {
+	if (multi->count != 2) {
+		printf("The fill in operator can only work on 2 iterators! Got %i\n", multi->count);
+		exit(1);
+	}
+	(void) trim;
+	die("fillIn needs multiplexer rows; not available on a batch (GPU) multiplexer yet");
+	return nullptr;
+}
+
+// -- setComparisons.c -------------------------------------------------------------------
+WiggleIterator *TTestReduction(Multiset *ms) {
+	if (ms->count != 2 || ms->multis[0]->count < 3 || ms->multis[1]->count < 3) {
+		puts("The t-test function only works for two sets with enough elements to compute variance");
+		exit(1);
+	}
+	return make_setcompare(WB200_TTEST, ms);
+}
+
+WiggleIterator *MWUReduction(Multiset *ms) {
+	if (ms->count != 2 || ms->multis[0]->count == 0 || ms->multis[1]->count == 0) {
+		puts("The Mann-Whitney U function only works for two non-empty sets");
+		exit(1);
+	}
+	return make_setcompare(WB200_MWU, ms);
+}
+
+WiggleIterator *FTestReduction(Multiset *) {
+	die("ftest is not provided: the reference implementation is defective (setComparisons.c:183,199 loop on the wrong index)");
+	return nullptr;
+}
+
+// -- statistics.c ---------------------------------------------------------------------------
+WiggleIterator *AUCIntegrator(WiggleIterator *wi) {
+	StatData *d = (StatData *) calloc(1, sizeof(StatData));
+	d->source = NonOverlappingWiggleIterator(wi);
+	d->gpu = (d->source->pop == &reducer_pop) ? (Reducer *) d->source->data : nullptr;
+	WiggleIterator *res = newWiggleIterator(d, &auc_pop, &stat_seek, wi->default_value, 0);
+	res->append = wi;   // newStatisticIterator (statistics.c:45-49)
+	return res;
+}
+
+WiggleIterator *PearsonIntegrator(Multiplexer *multi) {
+	if (!is_gpu_multiplexer(multi) || multi->count != 2) die("pearson takes a multiplexer of exactly two iterators");
+	PearsonData *d = (PearsonData *) calloc(1, sizeof(PearsonData));
+	d->res = NAN;
+	d->r = new Reducer();
+	d->r->pearson = true;
+	d->r->iters.assign(multi->iters, multi->iters + 2);
+	d->r->n1 = 2;
+	WiggleIterator *res = newWiggleIterator(d, &pearson_pop, &pearson_seek, multi->iters[1]->default_value, 0);
+	res->append = multi->iters[1];
+	return res;
+}
+
+} // extern "C"
