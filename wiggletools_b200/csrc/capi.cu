@@ -208,7 +208,7 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 	int64_t *hm_fx = (int64_t *) (hm_dflt + N);
 	memcpy(hm_off, h_off, (N + 1) * sizeof(int64_t));
 	memcpy(hm_dflt, h_dflt, N * sizeof(double));
-	CK(ctx->cursor.ensure((size_t) nw * N * sizeof(int32_t)));
+	CK(ctx->cursor.ensure((size_t) (nw + 1) * N * sizeof(int32_t)));
 	CK(ctx->wcount.ensure((size_t) nw * sizeof(uint32_t)));
 	CK(ctx->woff.ensure((size_t) (nw + 1) * sizeof(int64_t)));
 	CK(ctx->aucp.ensure((size_t) nw * sizeof(double)));

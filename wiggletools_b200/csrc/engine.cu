@@ -40,45 +40,82 @@ namespace wb {
 #define FULL 0xffffffffu
 
 // ---------------------------------------------------------------------------
-// shared-memory layout
+// shared-memory layouts
 // ---------------------------------------------------------------------------
-struct Layout {
-	int words;       // bitmap words
-	int slots;       // W + 1 breakpoint slots (slot 0 = state carried into the window)
-	size_t off_bitmap, off_wprefix, off_cov, off_limb, off_bpos, off_cur, off_nxt, off_misc, off_rows, total;
-};
+// Arrays scanned by thread-owned contiguous chunks (V = 2^k entries per thread)
+// are stored with one pad word per 32: pidx(p) = p + (p >> 5), which makes the
+// chunked accesses bank-conflict free for every power-of-two V.
+__host__ __device__ __forceinline__ int pidx(int p) { return p + (p >> 5); }
 
-__host__ __device__ inline Layout make_layout(int wlog, int N, bool emit, int limbs, int rowbuf) {
-	Layout L;
-	int W = 1 << wlog;
-	L.words = W / 32;
-	L.slots = W + 1;
-	size_t o = 0;
-	L.off_misc = o;    o += 1024;                                  // scalars + warp totals
-	L.off_bitmap = o;  o += (size_t) L.words * 4;
-	L.off_wprefix = o; o += (size_t) L.words * 4;
-	L.off_cov = o;     o += (size_t) (L.slots + 3) / 4 * 16;
-	L.off_limb = o;    if (emit) o += (size_t) limbs * ((L.slots + 3) / 4 * 16);
-	L.off_bpos = o;    if (emit) o += (size_t) (L.slots + 8) / 8 * 16;
-	L.off_cur = o;     o += (size_t) (N + 3) / 4 * 16;
-	L.off_nxt = o;     o += (size_t) (N + 3) / 4 * 16;
-	L.off_rows = o;    o += (size_t) rowbuf;
-	L.total = o;
+constexpr int ITRACK_CAP = 2048;     // flat (track,interval) items per window handled in one pass
+
+struct Misc {                        // scalars and per-thread scan bases
+	int nb;                          // breakpoints in the window
+	int next_bp;                     // first breakpoint at or after the window end
+	int base_cov;                    // count kernel: cover carried into the window
+	int total_items;                 // flat item count T
+	int kept;                        // count kernel: kept segments
+	int pad[3];
+	long long wsum[WARPS];           // warp totals (value scan / slow counter)
+	int wcov[WARPS];                 // warp totals (cover scan)
+	int wkeep[WARPS];                // warp totals (compaction)
+	double wauc[WARPS];
+	double wmom[WARPS][6];           // Pearson moments per warp
+	int tb_cov[THREADS];             // per-thread exclusive scan bases
+	int kbase[THREADS];
+	long long tb_val[THREADS];
+};
+constexpr int MISC_BYTES = 5120;
+static_assert(sizeof(Misc) <= MISC_BYTES, "Misc must fit its shared-memory slot");
+
+struct CountLayout { size_t off_cur, off_nxt, off_toff, off_tn, off_covp, off_ev, total; };
+
+__host__ __device__ inline CountLayout make_count_layout(int wlog, int N) {
+	CountLayout L;
+	const int W = 1 << wlog;
+	size_t o = MISC_BYTES;
+	const size_t nn = (size_t) (N + 3) / 4 * 16;
+	L.off_cur = o;  o += nn;
+	L.off_nxt = o;  o += nn;
+	L.off_tn = o;   o += nn;
+	L.off_toff = o; o += 2 * nn;
+	L.off_covp = o; o += (size_t) (W + W / 32 + 4) * 4;
+	L.off_ev = o;   o += (size_t) W;
+	L.total = (o + 15) / 16 * 16;
 	return L;
 }
 
-struct Misc {               // lives at off_misc
-	int nb;                 // breakpoints in the window
-	int next_bp;            // first breakpoint at or after the window end
-	int kept;               // running count of emitted segments
-	int pad;
-	long long wsum[WARPS];  // warp totals (value scan)
-	int wcov[WARPS];        // warp totals (cover scan)
-	int wkeep[WARPS];       // warp totals (compaction)
-	double wauc[WARPS];
-	double wmom[WARPS][6];  // Pearson moments per warp
+struct EmitLayout {
+	int words, slots, pslots;        // bitmap words; W+1 slots; padded slot count
+	size_t off_cur, off_nxt, off_pre, off_toff, off_tn, off_tmd, off_bitmap, off_wprefix, off_cov, off_limb,
+	       off_klocal, off_bpos, off_itrack, off_rows, total;
 };
-static_assert(sizeof(Misc) <= 1024, "Misc must fit its shared-memory slot");
+
+__host__ __device__ inline EmitLayout make_emit_layout(int wlog, int N, int limbs, int rowbuf) {
+	EmitLayout L;
+	const int W = 1 << wlog;
+	L.words = W / 32;
+	L.slots = W + 1;
+	L.pslots = (pidx(W + 1) + 8) / 4 * 4;
+	size_t o = MISC_BYTES;
+	const size_t nn = (size_t) (N + 4) / 4 * 16;
+	L.off_cur = o;     o += nn;
+	L.off_nxt = o;     o += nn;
+	L.off_pre = o;     o += nn;
+	L.off_tn = o;      o += nn;
+	L.off_toff = o;    o += 2 * nn;
+	L.off_tmd = o;     o += 2 * nn;
+	L.off_bitmap = o;  o += (size_t) L.words * 4;
+	L.off_wprefix = o; o += (size_t) L.words * 4;
+	L.off_cov = o;     o += (size_t) L.pslots * 4;
+	L.off_limb = o;    o += (size_t) limbs * L.pslots * 4;
+	L.off_klocal = o;  o += (size_t) L.pslots * 2;
+	L.off_bpos = o;    o += (size_t) (L.slots + 8) / 8 * 16;
+	L.off_itrack = o;  o += (size_t) ITRACK_CAP * 2;
+	L.off_rows = (o + 15) / 16 * 16; o = L.off_rows + (size_t) rowbuf;
+	L.total = (o + 15) / 16 * 16;
+	return L;
+}
 
 // ---------------------------------------------------------------------------
 // small device helpers
@@ -363,56 +400,101 @@ __device__ double warp_sorted_eval(const Row &r, SortKey *buf, int P /*pow2 >= N
 }
 
 // ---------------------------------------------------------------------------
-// the window pipeline
+// block-wide scans (one value per thread)
 // ---------------------------------------------------------------------------
-template <bool EMIT, int LIMBS>
-__device__ void process_window(const Job &job, int w, unsigned char *smem, const Layout &L,
-                               int lw /*limb width*/, double inv_scale, double lim, double scale) {
-	Misc *misc = (Misc *) (smem + L.off_misc);
-	uint32_t *bitmap = (uint32_t *) (smem + L.off_bitmap);
-	uint32_t *wprefix = (uint32_t *) (smem + L.off_wprefix);
-	int32_t *cov = (int32_t *) (smem + L.off_cov);
-	uint32_t *limb = (uint32_t *) (smem + L.off_limb);
-	uint16_t *bpos = (uint16_t *) (smem + L.off_bpos);
+// Exclusive scan of an (int, long long) pair per thread; totals returned to all.
+__device__ __forceinline__ void block_scan2(Misc *misc, int c, long long a, int &ec, long long &ea, int &tc, long long &ta) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int ic = c; long long ia = a;
+	for (int d = 1; d < 32; d <<= 1) {
+		int vc = __shfl_up_sync(FULL, ic, d);
+		long long va = __shfl_up_sync(FULL, ia, d);
+		if (lane >= d) { ic += vc; ia += va; }
+	}
+	if (lane == 31) { misc->wcov[warp] = ic; misc->wsum[warp] = ia; }
+	__syncthreads();
+	int bc = 0; long long ba = 0; tc = 0; ta = 0;
+#pragma unroll
+	for (int k = 0; k < WARPS; k++) {
+		int kc = misc->wcov[k]; long long ka = misc->wsum[k];
+		if (k < warp) { bc += kc; ba += ka; }
+		tc += kc; ta += ka;
+	}
+	ec = bc + ic - c; ea = ba + ia - a;
+	__syncthreads();
+}
+
+__device__ __forceinline__ void block_scan1(Misc *misc, int c, int &ec, int &tc) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int ic = c;
+	for (int d = 1; d < 32; d <<= 1) { int vc = __shfl_up_sync(FULL, ic, d); if (lane >= d) ic += vc; }
+	if (lane == 31) misc->wkeep[warp] = ic;
+	__syncthreads();
+	int bc = 0; tc = 0;
+#pragma unroll
+	for (int k = 0; k < WARPS; k++) { int kc = misc->wkeep[k]; if (k < warp) bc += kc; tc += kc; }
+	ec = bc + ic - c;
+	__syncthreads();
+}
+
+__device__ __forceinline__ bool keep_rule(const Job &job, bool setop, int c) {
+	const int covA = c & COV_MASK, covB = (c >> COV_B_SHIFT) & COV_MASK;
+	if (setop) return covA > 0 && covB > 0;            // src/setComparisons.c:48-54
+	if (job.strict) return covA == job.N;              // src/multiplexer.c:123-128
+	return covA > 0;                                   // gaps are skipped, :112-115
+}
+
+// ---------------------------------------------------------------------------
+// count kernel: segments per window + the per-window cursor table
+// ---------------------------------------------------------------------------
+// Position-indexed: one packed cover delta per base pair of the window
+// (atomicAdd, native 32-bit) and a byte flag "an interval starts or ends here".
+// One pass over the window's intervals, then a chunked prefix scan over the W
+// positions.  One CTA walks a strip of consecutive windows so that each track's
+// cursor is chained from window to window (binary search only at strip start).
+template <int VLOG>
+__device__ void count_window(const Job &job, int w, unsigned char *smem, const CountLayout &L) {
+	constexpr int V = 1 << VLOG, W = THREADS << VLOG;
+	Misc *misc = (Misc *) smem;
 	int32_t *cur = (int32_t *) (smem + L.off_cur);
 	int32_t *nxt = (int32_t *) (smem + L.off_nxt);
-	const int limb_stride = (L.slots + 3) / 4 * 4;
-
+	const int32_t *tn = (const int32_t *) (smem + L.off_tn);
+	const long long *toff = (const long long *) (smem + L.off_toff);
+	int32_t *covp = (int32_t *) (smem + L.off_covp);
+	unsigned char *ev = smem + L.off_ev;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int N = job.N;
-	const int W = 1 << job.wlog;
 	const long long w0 = job.p0 + ((long long) w << job.wlog);
 	const long long w1 = w0 + W;
+	const bool setop = (job.op == OP_TTEST || job.op == OP_MWU);
 
-	// ---- phase 0: clear the bitmap --------------------------------------
-	for (int t = tid; t < L.words; t += THREADS) bitmap[t] = 0;
-	if (tid == 0) { misc->next_bp = INT_MAX; misc->kept = 0; }
+	{
+		uint4 z = make_uint4(0, 0, 0, 0);
+		uint4 *zc = (uint4 *) covp;
+		for (int t = tid; t < (W + W / 32 + 4) / 4; t += THREADS) zc[t] = z;
+		uint4 *ze = (uint4 *) ev;
+		for (int t = tid; t < W / 16; t += THREADS) ze[t] = z;
+		if (tid == 0) { misc->base_cov = 0; misc->kept = 0; }
+	}
 	__syncthreads();
 
-	// ---- phase 1: mark breakpoints; find where each track leaves the window
 	for (int i = warp; i < N; i += WARPS) {
-		const long long o = job.off[i];
-		const int n = (int) (job.off[i + 1] - o);
+		const long long o = toff[i];
+		const int n = tn[i];
+		const int f = (i < job.n1) ? 1 : (1 << COV_B_SHIFT);
 		int j0 = cur[i];
 		while (true) {
-			int j = j0 + lane;
-			bool valid = j < n;
+			const int j = j0 + lane;
+			const bool valid = j < n;
 			int s = 0, e = 0;
 			if (valid) { s = job.start[o + j]; e = job.end[o + j]; }
-			bool stop = !valid || (long long) e >= w1;
-			unsigned bal = __ballot_sync(FULL, stop);
-			int Lst = bal ? __ffs(bal) - 1 : 32;
-			if (lane < Lst) {
-				// interval ends inside the window (w0 <= e < w1)
-				if ((long long) s >= w0) { int x = (int) (s - w0); atomicOr(&bitmap[x >> 5], 1u << (x & 31)); }
-				int x = (int) (e - w0); atomicOr(&bitmap[x >> 5], 1u << (x & 31));
-			} else if (lane == Lst && valid) {
-				// first interval reaching the window end: its start may still be ours
-				if ((long long) s < w1) {
-					if ((long long) s >= w0) { int x = (int) (s - w0); atomicOr(&bitmap[x >> 5], 1u << (x & 31)); }
-					atomicMin(&misc->next_bp, e);
-				} else
-					atomicMin(&misc->next_bp, s);
+			const bool stop = !valid || (long long) e >= w1;
+			const unsigned bal = __ballot_sync(FULL, stop);
+			const int Lst = bal ? __ffs(bal) - 1 : 32;
+			if (lane < Lst || (lane == Lst && valid && (long long) s < w1)) {
+				if ((long long) s >= w0) { const int x = (int) (s - w0); atomicAdd(&covp[pidx(x)], f); ev[x] = 1; }
+				else atomicAdd(&misc->base_cov, f);                       // spans the window start
+				if (lane < Lst) { const int x = (int) (e - w0); atomicAdd(&covp[pidx(x)], -f); ev[x] = 1; }
 			}
 			if (bal) { if (lane == 0) nxt[i] = j0 + Lst; break; }
 			j0 += 32;
@@ -420,34 +502,163 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	}
 	__syncthreads();
 
-	// ---- phase 2: rank the breakpoints ----------------------------------
-	{
-		// L.words <= THREADS for every supported window size
-		int pc = (tid < L.words) ? __popc(bitmap[tid]) : 0;
-		int inc = pc;
-		for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += v; }
-		if (lane == 31) misc->wcov[warp] = inc;
+	const int p0 = tid * V;
+	int local = 0;
+#pragma unroll
+	for (int q = 0; q < V; q++) local += covp[pidx(p0 + q)];
+	int ec, tc;
+	block_scan1(misc, local, ec, tc);
+	int running = misc->base_cov + ec, kept = 0;
+#pragma unroll
+	for (int q = 0; q < V; q++) {
+		running += covp[pidx(p0 + q)];
+		if (ev[p0 + q]) kept += keep_rule(job, setop, running) ? 1 : 0;
+	}
+	for (int d = 16; d > 0; d >>= 1) kept += __shfl_down_sync(FULL, kept, d);
+	if (lane == 0 && kept) atomicAdd(&misc->kept, kept);
+	__syncthreads();
+	if (tid == 0) job.wcount[w] = (uint32_t) misc->kept;
+	for (int i = tid; i < N; i += THREADS) job.cursor[(size_t) w * N + i] = cur[i];
+}
+
+template <int VLOG>
+__global__ void __launch_bounds__(THREADS) count_kernel(const Job job) {
+	extern __shared__ __align__(16) unsigned char smem[];
+	const CountLayout L = make_count_layout(job.wlog, job.N);
+	int32_t *cur = (int32_t *) (smem + L.off_cur);
+	int32_t *nxt = (int32_t *) (smem + L.off_nxt);
+	int32_t *tn = (int32_t *) (smem + L.off_tn);
+	long long *toff = (long long *) (smem + L.off_toff);
+	const int wbeg = blockIdx.x * job.strip;
+	const int wend = min(job.nw, wbeg + job.strip);
+	if (wbeg >= wend) return;
+	const long long w0 = job.p0 + ((long long) wbeg << job.wlog);
+	for (int i = threadIdx.x; i < job.N; i += THREADS) {
+		const long long o = job.off[i];
+		const int n = (int) (job.off[i + 1] - o);
+		toff[i] = o; tn[i] = n;
+		cur[i] = lower_bound_ge(job.end + o, n, w0);
+	}
+	__syncthreads();
+	for (int w = wbeg; w < wend; w++) {
+		count_window<VLOG>(job, w, smem, L);
 		__syncthreads();
-		int base = 0;
-		for (int k = 0; k < warp; k++) base += misc->wcov[k];
-		if (tid < L.words) wprefix[tid] = 1 + base + inc - pc;   // slot of the word's first set bit
-		if (tid == THREADS - 1) misc->nb = base + inc;
+		for (int i = threadIdx.x; i < job.N; i += THREADS) cur[i] = nxt[i];
+		__syncthreads();
+	}
+	// the cursor row after the last window (row nw) closes the table for emit
+	if (wend == job.nw)
+		for (int i = threadIdx.x; i < job.N; i += THREADS) job.cursor[(size_t) job.nw * job.N + i] = cur[i];
+}
+
+// ---------------------------------------------------------------------------
+// emit kernel: the window pipeline with values
+// ---------------------------------------------------------------------------
+template <int LIMBS>
+__device__ void emit_window(const Job &job, int w, unsigned char *smem, const EmitLayout &L,
+                            int lw, double inv_scale, double lim, double scale) {
+	Misc *misc = (Misc *) smem;
+	int32_t *cur = (int32_t *) (smem + L.off_cur);
+	int32_t *nxt = (int32_t *) (smem + L.off_nxt);
+	int32_t *pre = (int32_t *) (smem + L.off_pre);
+	const int32_t *tn = (const int32_t *) (smem + L.off_tn);
+	const long long *toff = (const long long *) (smem + L.off_toff);
+	const long long *tmd = (const long long *) (smem + L.off_tmd);
+	uint32_t *bitmap = (uint32_t *) (smem + L.off_bitmap);
+	uint32_t *wprefix = (uint32_t *) (smem + L.off_wprefix);
+	int32_t *cov = (int32_t *) (smem + L.off_cov);
+	uint32_t *limb = (uint32_t *) (smem + L.off_limb);
+	uint16_t *klocal = (uint16_t *) (smem + L.off_klocal);
+	uint16_t *bpos = (uint16_t *) (smem + L.off_bpos);
+	uint16_t *itrack = (uint16_t *) (smem + L.off_itrack);
+	const int ls = L.pslots;                      // limb array stride
+
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int N = job.N;
+	const int W = 1 << job.wlog;
+	const long long w0 = job.p0 + ((long long) w << job.wlog);
+	const long long w1 = w0 + W;
+	const bool setop = (job.op == OP_TTEST || job.op == OP_MWU);
+	const bool fast = job.fast != 0;
+
+	// ---- cursors of this window and the next; flat item index ----------------
+	int run = 0;   // carry of the per-track length scan
+	for (int base = 0; base < N; base += THREADS) {
+		const int i = base + tid;
+		int len = 0;
+		if (i < N) {
+			const int c = job.cursor[(size_t) w * N + i];
+			const int x = job.cursor[(size_t) (w + 1) * N + i];
+			cur[i] = c; nxt[i] = x;
+			len = max(0, min(x, tn[i] - 1) - c + 1);
+		}
+		int ec, tc;
+		block_scan1(misc, len, ec, tc);
+		if (i < N) pre[i] = run + ec;
+		run += tc;
+	}
+	const int T = run;
+	const bool flat = T <= ITRACK_CAP;
+	for (int t = tid; t < L.words; t += THREADS) bitmap[t] = 0;
+	if (tid == 0) misc->next_bp = INT_MAX;
+	__syncthreads();
+	if (flat)
+		for (int i = tid; i < N; i += THREADS) {
+			const int b = pre[i], len = max(0, min(nxt[i], tn[i] - 1) - cur[i] + 1);
+			for (int q = 0; q < len; q++) itrack[b + q] = (uint16_t) i;
+		}
+	__syncthreads();
+
+	// ---- phase 1: mark breakpoints ------------------------------------------
+	auto mark_item = [&](int i, int j) {
+		const long long o = toff[i];
+		const int s = job.start[o + j], e = job.end[o + j];
+		if (j < nxt[i]) {
+			// interval ends inside the window (w0 <= e < w1)
+			if ((long long) s >= w0) { const int x = (int) (s - w0); atomicOr(&bitmap[x >> 5], 1u << (x & 31)); }
+			const int x = (int) (e - w0); atomicOr(&bitmap[x >> 5], 1u << (x & 31));
+		} else if ((long long) s < w1) {
+			// first interval reaching the window end; its start is still ours
+			if ((long long) s >= w0) { const int x = (int) (s - w0); atomicOr(&bitmap[x >> 5], 1u << (x & 31)); }
+			atomicMin(&misc->next_bp, e);
+		} else
+			atomicMin(&misc->next_bp, s);
+	};
+	if (flat) {
+		for (int k = tid; k < T; k += THREADS) { const int i = itrack[k]; mark_item(i, cur[i] + k - pre[i]); }
+	} else {
+		for (int i = warp; i < N; i += WARPS) {
+			const int jl = min(nxt[i], tn[i] - 1);
+			for (int j = cur[i] + lane; j <= jl; j += 32) mark_item(i, j);
+		}
+	}
+	__syncthreads();
+
+	// ---- phase 2: rank the breakpoints ----------------------------------------
+	{
+		const int pc = (tid < L.words) ? __popc(bitmap[tid]) : 0;   // L.words <= THREADS
+		int ec, tc;
+		block_scan1(misc, pc, ec, tc);
+		if (tid < L.words) wprefix[tid] = 1 + ec;                   // slot of the word's first set bit
+		if (tid == 0) misc->nb = tc;
 		__syncthreads();
 	}
 	const int nb = misc->nb;
-	for (int t = tid; t <= nb; t += THREADS) {
-		cov[t] = 0;
-		if (EMIT) {
+	int vlog = 0;
+	while ((THREADS << vlog) < nb + 1) vlog++;
+	const int V = 1 << vlog;
+	{
+		const int top = pidx(nb) + 1;
+		for (int t = tid; t < top; t += THREADS) {
+			cov[t] = 0;
 #pragma unroll
-			for (int l = 0; l < LIMBS; l++) limb[l * limb_stride + t] = 0;
+			for (int l = 0; l < LIMBS; l++) limb[l * ls + t] = 0;
 		}
-	}
-	if (EMIT) {
 		if (tid < L.words) {
 			uint32_t bits = bitmap[tid];
 			int slot = (int) wprefix[tid];
 			while (bits) {
-				int bit = __ffs(bits) - 1;
+				const int bit = __ffs(bits) - 1;
 				bits &= bits - 1;
 				bpos[slot++] = (uint16_t) (tid * 32 + bit);
 			}
@@ -455,118 +666,113 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	}
 	__syncthreads();
 
-	// ---- phase 3: events -> cover deltas (and fixed-point value deltas) --
-	const bool fast = EMIT && job.fast;
-	for (int i = warp; i < N; i += WARPS) {
-		const long long o = job.off[i];
-		const int n = (int) (job.off[i + 1] - o);
-		const int jl = nxt[i];
-		const int field = (i < job.n1) ? 1 : (1 << COV_B_SHIFT);
-		long long md = 0;
-		if (fast) md = job.dflt_fx[i];
-		for (int j0 = cur[i]; j0 <= jl; j0 += 32) {
-			int j = j0 + lane;
-			if (j > jl || j >= n) continue;
-			int s = job.start[o + j], e = job.end[o + j];
-			bool inside = j < jl;
-			if (!inside && (long long) s >= w1) continue;
-			int cd = field;
-			long long d = 0;
-			if (fast) {
-				long long m;
-				if (to_fixed(job.value[o + j], inv_scale, lim, m)) d = m - md;
-				else cd += (1 << COV_P_SHIFT);
-			}
-			int ss = ((long long) s >= w0) ? slot_of(bitmap, wprefix, (int) (s - w0)) : 0;
-			atomicAdd(&cov[ss], cd);
-			if (fast && d != 0) {
-				if (LIMBS == 2) {
-					atomicAdd(&limb[ss], (uint32_t) (d & ((1ll << lw) - 1)));
-					atomicAdd(&limb[limb_stride + ss], (uint32_t) (d >> lw));
-				} else {
-					atomicAdd(&limb[ss], (uint32_t) (d & ((1ll << lw) - 1)));
-					atomicAdd(&limb[limb_stride + ss], (uint32_t) ((d >> lw) & ((1ll << lw) - 1)));
-					atomicAdd(&limb[2 * limb_stride + ss], (uint32_t) (d >> (2 * lw)));
-				}
-			}
-			if (inside) {
-				int se = slot_of(bitmap, wprefix, (int) (e - w0));
-				atomicAdd(&cov[se], -cd);
-				if (fast && d != 0) {
-					long long nd = -d;
-					if (LIMBS == 2) {
-						atomicAdd(&limb[se], (uint32_t) (nd & ((1ll << lw) - 1)));
-						atomicAdd(&limb[limb_stride + se], (uint32_t) (nd >> lw));
-					} else {
-						atomicAdd(&limb[se], (uint32_t) (nd & ((1ll << lw) - 1)));
-						atomicAdd(&limb[limb_stride + se], (uint32_t) ((nd >> lw) & ((1ll << lw) - 1)));
-						atomicAdd(&limb[2 * limb_stride + se], (uint32_t) (nd >> (2 * lw)));
-					}
-				}
-			}
+	// ---- phase 3: events -> cover deltas and fixed-point value deltas ---------
+	auto add_value = [&](int slot, long long d) {
+		const int ps = pidx(slot);
+		if (LIMBS == 2) {
+			atomicAdd(&limb[ps], (uint32_t) (d & ((1ll << lw) - 1)));
+			atomicAdd(&limb[ls + ps], (uint32_t) (d >> lw));
+		} else {
+			atomicAdd(&limb[ps], (uint32_t) (d & ((1ll << lw) - 1)));
+			atomicAdd(&limb[ls + ps], (uint32_t) ((d >> lw) & ((1ll << lw) - 1)));
+			atomicAdd(&limb[2 * ls + ps], (uint32_t) (d >> (2 * lw)));
+		}
+	};
+	auto event_item = [&](int i, int j) {
+		const long long o = toff[i];
+		const int s = job.start[o + j], e = job.end[o + j];
+		const bool inside = j < nxt[i];
+		if (!inside && (long long) s >= w1) return;
+		int cd = (i < job.n1) ? 1 : (1 << COV_B_SHIFT);
+		long long d = 0;
+		if (fast) {
+			long long m;
+			if (to_fixed(job.value[o + j], inv_scale, lim, m)) d = m - tmd[i];
+			else cd += (1 << COV_P_SHIFT);
+		}
+		const int ss = ((long long) s >= w0) ? slot_of(bitmap, wprefix, (int) (s - w0)) : 0;
+		atomicAdd(&cov[pidx(ss)], cd);
+		if (fast && d != 0) add_value(ss, d);
+		if (inside) {
+			const int se = slot_of(bitmap, wprefix, (int) (e - w0));
+			atomicAdd(&cov[pidx(se)], -cd);
+			if (fast && d != 0) add_value(se, -d);
+		}
+	};
+	if (flat) {
+		for (int k = tid; k < T; k += THREADS) { const int i = itrack[k]; event_item(i, cur[i] + k - pre[i]); }
+	} else {
+		for (int i = warp; i < N; i += WARPS) {
+			const int jl = min(nxt[i], tn[i] - 1);
+			for (int j = cur[i] + lane; j <= jl; j += 32) event_item(i, j);
 		}
 	}
 	__syncthreads();
 
-	// ---- phase 4/5: scan over slots, keep, emit --------------------------
-	const bool setop = (job.op == OP_TTEST || job.op == OP_MWU);
+	// ---- phase 4: chunked prefix scan over the slots --------------------------
+	// thread t owns slots [t*V, t*V+V); local inclusive prefixes are written back
+	// in place, the per-thread bases stay in shared memory (tb_cov / tb_val).
+	auto load_val = [&](int ps) -> long long {
+		if (LIMBS == 2)
+			return (long long) (unsigned long long) limb[ps] + ((long long) (int32_t) limb[ls + ps] << lw);
+		return (long long) (unsigned long long) limb[ps] + ((long long) (unsigned long long) limb[ls + ps] << lw)
+		     + ((long long) (int32_t) limb[2 * ls + ps] << (2 * lw));
+	};
+	const int r0 = tid << vlog;
+	{
+		int c = 0; long long a = 0;
+		for (int q = 0; q < V; q++) {
+			const int r = r0 + q;
+			if (r > nb) break;
+			const int ps = pidx(r);
+			c += cov[ps];
+			cov[ps] = c;
+			if (fast) {
+				a += load_val(ps);
+				limb[ps] = (uint32_t) a;              // from here on limb[0..1] hold the raw int64 prefix
+				limb[ls + ps] = (uint32_t) ((unsigned long long) a >> 32);
+			}
+		}
+		int ec, tc; long long ea, ta;
+		block_scan2(misc, c, a, ec, ea, tc, ta);
+		misc->tb_cov[tid] = ec;
+		misc->tb_val[tid] = ea;
+		int kept = 0;
+		for (int q = 0; q < V; q++) {
+			const int r = r0 + q;
+			if (r > nb) break;
+			const int ps = pidx(r);
+			klocal[ps] = (uint16_t) kept;
+			if (r >= 1 && keep_rule(job, setop, cov[ps] + ec)) kept++;
+		}
+		int ek, tk;
+		block_scan1(misc, kept, ek, tk);
+		misc->kbase[tid] = ek;
+	}
+	__syncthreads();
+
+	// ---- phase 5: emit, one slot per thread (coalesced stores) -----------------
 	const bool sorted_op = (job.op == OP_MEDIAN || job.op == OP_MWU);
-	int carry_cov = 0;
-	long long carry_sum = 0;
-	int kept_total = 0;
-	double auc = 0;
-	const long long out_base = EMIT ? job.woff[w] : 0;
+	const bool pearson = (job.op == OP_PEARSON);
+	const long long out_base = job.woff[w];
 	const int next_bp = misc->next_bp;
 	Row row; row.job = &job; row.cur = cur; row.nxt = nxt; row.b = 0;
 	unsigned long long slow = 0;
+	double auc = 0;
 	double mom[6] = {0, 0, 0, 0, 0, 0};
-	const bool pearson = (job.op == OP_PEARSON);
 
-	for (int base = 0; base <= nb; base += THREADS) {
+	for (int base = 1; base <= nb; base += THREADS) {
 		const int r = base + tid;
-		int c = (r <= nb) ? cov[r] : 0;
-		long long a = 0;
-		if (fast && r <= nb) {
-			if (LIMBS == 2)
-				a = (long long) (unsigned long long) limb[r] + ((long long) (int32_t) limb[limb_stride + r] << lw);
-			else
-				a = (long long) (unsigned long long) limb[r] + ((long long) (unsigned long long) limb[limb_stride + r] << lw)
-				  + ((long long) (int32_t) limb[2 * limb_stride + r] << (2 * lw));
-		}
-		// inclusive warp scans
-		for (int d = 1; d < 32; d <<= 1) {
-			int vc = __shfl_up_sync(FULL, c, d);
-			long long va = __shfl_up_sync(FULL, a, d);
-			if (lane >= d) { c += vc; a += va; }
-		}
-		if (lane == 31) { misc->wcov[warp] = c; misc->wsum[warp] = a; }
-		__syncthreads();
-		int bc = carry_cov; long long ba = carry_sum;
-		int tc = 0; long long ta = 0;
-		for (int k = 0; k < WARPS; k++) {
-			int kc = misc->wcov[k]; long long ka = misc->wsum[k];
-			if (k < warp) { bc += kc; ba += ka; }
-			tc += kc; ta += ka;
-		}
-		c += bc; a += ba;
-		carry_cov += tc; carry_sum += ta;
-
-		// state after slot r = state of the segment starting at breakpoint r
-		const int covA = c & COV_MASK, covB = (c >> COV_B_SHIFT) & COV_MASK, poison = c >> COV_P_SHIFT;
 		bool keep = false;
-		if (r >= 1 && r <= nb) {
-			if (setop) keep = covA > 0 && covB > 0;          // src/setComparisons.c:48-54
-			else if (job.strict) keep = covA == N;           // src/multiplexer.c:123-128
-			else keep = covA > 0;                            // gaps are skipped, :112-115
+		int c = 0, ps = 0, owner = 0;
+		if (r <= nb) {
+			ps = pidx(r);
+			owner = r >> vlog;
+			c = cov[ps] + misc->tb_cov[owner];
+			keep = keep_rule(job, setop, c);
 		}
-		unsigned kb = __ballot_sync(FULL, keep);
-		if (lane == 0) misc->wkeep[warp] = __popc(kb);
-		__syncthreads();
-		int kprefix = kept_total, ktot = 0;
-		for (int k = 0; k < WARPS; k++) { int kk = misc->wkeep[k]; if (k < warp) kprefix += kk; ktot += kk; }
-		kept_total += ktot;
-
-		if (EMIT && pearson) {
+		const unsigned kb = __ballot_sync(FULL, keep);
+		if (pearson) {
 			if (keep) {
 				const int bs = (int) (w0 + bpos[r]);
 				const int be = (r < nb) ? (int) (w0 + bpos[r + 1]) : next_bp;
@@ -577,124 +783,101 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 				double one[6] = {len, X * len, Y * len, 0, 0, 0};
 				merge6(mom, one);
 			}
-		} else if (EMIT) {
-			if (!sorted_op) {
-				if (keep) {
-					const long long oi = out_base + kprefix + __popc(kb & ((1u << lane) - 1u));
-					const int bs = (int) (w0 + bpos[r]);
-					const int be = (r < nb) ? (int) (w0 + bpos[r + 1]) : next_bp;
-					double v;
-					if (fast && poison == 0) {
-						v = (double) (a + job.fx_base) * scale;
-						if (job.op == OP_MEAN) v = v / N;
-					} else {
-						row.b = bs;
-						v = row_eval(row);
-						slow++;
-					}
+		} else if (!sorted_op) {
+			if (keep) {
+				const long long oi = out_base + misc->kbase[owner] + klocal[ps];
+				const int bs = (int) (w0 + bpos[r]);
+				const int be = (r < nb) ? (int) (w0 + bpos[r + 1]) : next_bp;
+				double v;
+				if (fast && (c >> COV_P_SHIFT) == 0) {
+					const long long a = (long long) (((unsigned long long) limb[ls + ps] << 32) | limb[ps]) + misc->tb_val[owner];
+					v = (double) (a + job.fx_base) * scale;
+					if (job.op == OP_MEAN) v = v / N;
+				} else {
+					row.b = bs;
+					v = row_eval(row);
+					slow++;
+				}
+				if (oi < job.out_cap) {
+					job.out_start[oi] = bs;
+					job.out_end[oi] = be;
+					job.out_value[oi] = v;
+				}
+				if (!isnan(v)) auc += (double) (be - bs) * v;
+			}
+		} else {
+			// one warp per kept segment, in lane order
+			int P = 1; while (P < N) P <<= 1;
+			SortKey *buf = (SortKey *) (smem + L.off_rows) + (size_t) warp * P;
+			unsigned todo = kb;
+			while (todo) {
+				const int src = __ffs(todo) - 1;
+				todo &= todo - 1;
+				const int rr = base + warp * 32 + src;
+				const int bs = (int) (w0 + bpos[rr]);
+				const int be = (rr < nb) ? (int) (w0 + bpos[rr + 1]) : next_bp;
+				row.b = bs;
+				const double v = warp_sorted_eval(row, buf, P);
+				if (lane == 0) {
+					const long long oi = out_base + misc->kbase[rr >> vlog] + klocal[pidx(rr)];
 					if (oi < job.out_cap) {
 						job.out_start[oi] = bs;
 						job.out_end[oi] = be;
 						job.out_value[oi] = v;
 					}
 					if (!isnan(v)) auc += (double) (be - bs) * v;
-				}
-			} else {
-				// one warp per kept segment, in lane order
-				SortKey *buf = (SortKey *) (smem + L.off_rows) + (size_t) warp * (L.total - L.off_rows) / WARPS / sizeof(SortKey);
-				int P = 1; while (P < N) P <<= 1;
-				unsigned todo = kb;
-				while (todo) {
-					int src = __ffs(todo) - 1;
-					todo &= todo - 1;
-					int rr = base + warp * 32 + src;
-					const int bs = (int) (w0 + bpos[rr]);
-					const int be = (rr < nb) ? (int) (w0 + bpos[rr + 1]) : next_bp;
-					row.b = bs;
-					double v = warp_sorted_eval(row, buf, P);
-					const long long oi = out_base + kprefix + __popc(kb & ((1u << src) - 1u));
-					if (lane == 0) {
-						if (oi < job.out_cap) {
-							job.out_start[oi] = bs;
-							job.out_end[oi] = be;
-							job.out_value[oi] = v;
-						}
-						if (!isnan(v)) auc += (double) (be - bs) * v;
-						slow++;
-					}
+					slow++;
 				}
 			}
 		}
-		__syncthreads();
 	}
 
-	if (!EMIT) {
-		if (tid == 0) job.wcount[w] = (uint32_t) kept_total;
-		for (int i = tid; i < N; i += THREADS) job.cursor[(size_t) w * N + i] = cur[i];
-	} else {
-		// deterministic block reduction of the AUC partial and slow-path count
+	// deterministic block reduction of the AUC partial / slow-path count / moments
+	for (int d = 16; d > 0; d >>= 1) {
+		auc += __shfl_down_sync(FULL, auc, d);
+		slow += __shfl_down_sync(FULL, slow, d);
+	}
+	if (pearson) {
 		for (int d = 16; d > 0; d >>= 1) {
-			auc += __shfl_down_sync(FULL, auc, d);
-			slow += __shfl_down_sync(FULL, slow, d);
+			double other[6];
+			for (int k = 0; k < 6; k++) other[k] = __shfl_down_sync(FULL, mom[k], d);
+			if (lane + d < 32) merge6(mom, other);
 		}
-		if (pearson) {
-			for (int d = 16; d > 0; d >>= 1) {
-				double other[6];
-				for (int k = 0; k < 6; k++) other[k] = __shfl_down_sync(FULL, mom[k], d);
-				if (lane + d < 32) merge6(mom, other);
-			}
-			if (lane == 0) for (int k = 0; k < 6; k++) misc->wmom[warp][k] = mom[k];
-		}
-		if (lane == 0) { misc->wauc[warp] = auc; misc->wsum[warp] = (long long) slow; }
-		__syncthreads();
-		if (tid == 0 && pearson && job.moments) {
+		if (lane == 0) for (int k = 0; k < 6; k++) misc->wmom[warp][k] = mom[k];
+	}
+	__syncthreads();   // all reads of tb_*/kbase done before misc->wsum is reused
+	if (lane == 0) { misc->wauc[warp] = auc; misc->wsum[warp] = (long long) slow; }
+	__syncthreads();
+	if (tid == 0) {
+		if (pearson && job.moments) {
 			double t[6] = {0, 0, 0, 0, 0, 0};
 			for (int k = 0; k < WARPS; k++) merge6(t, misc->wmom[k]);
 			for (int k = 0; k < 6; k++) job.moments[(size_t) w * 6 + k] = t[k];
 		}
-		if (tid == 0) {
-			double t = 0; long long sl = 0;
-			for (int k = 0; k < WARPS; k++) { t += misc->wauc[k]; sl += misc->wsum[k]; }
-			if (job.auc_partial) job.auc_partial[w] = t;
-			if (sl && job.slow_count) atomicAdd(job.slow_count, (unsigned long long) sl);
-		}
+		double t = 0; long long sl = 0;
+		for (int k = 0; k < WARPS; k++) { t += misc->wauc[k]; sl += misc->wsum[k]; }
+		if (job.auc_partial) job.auc_partial[w] = t;
+		if (sl && job.slow_count) atomicAdd(job.slow_count, (unsigned long long) sl);
 	}
 	__syncthreads();
-}
-
-// count kernel: one CTA per strip of consecutive windows; cursors are found by
-// binary search at the strip start and then chained from window to window.
-__global__ void __launch_bounds__(THREADS) count_kernel(const Job job) {
-	extern __shared__ __align__(16) unsigned char smem[];
-	const Layout L = make_layout(job.wlog, job.N, false, 0, 0);
-	int32_t *cur = (int32_t *) (smem + L.off_cur);
-	int32_t *nxt = (int32_t *) (smem + L.off_nxt);
-	const int wbeg = blockIdx.x * job.strip;
-	const int wend = min(job.nw, wbeg + job.strip);
-	if (wbeg >= wend) return;
-	const long long w0 = job.p0 + ((long long) wbeg << job.wlog);
-	for (int i = threadIdx.x; i < job.N; i += THREADS) {
-		const long long o = job.off[i];
-		cur[i] = lower_bound_ge(job.end + o, (int) (job.off[i + 1] - o), w0);
-	}
-	__syncthreads();
-	for (int w = wbeg; w < wend; w++) {
-		process_window<false, 2>(job, w, smem, L, 0, 0.0, 0.0, 0.0);
-		for (int i = threadIdx.x; i < job.N; i += THREADS) cur[i] = nxt[i];
-		__syncthreads();
-	}
 }
 
 template <int LIMBS>
 __global__ void __launch_bounds__(THREADS) emit_kernel(const Job job, int lw, double inv_scale, double lim, double scale, int rowbuf) {
 	extern __shared__ __align__(16) unsigned char smem[];
-	const Layout L = make_layout(job.wlog, job.N, true, LIMBS, rowbuf);
-	int32_t *cur = (int32_t *) (smem + L.off_cur);
-	for (int w = blockIdx.x; w < job.nw; w += gridDim.x) {
-		for (int i = threadIdx.x; i < job.N; i += THREADS) cur[i] = job.cursor[(size_t) w * job.N + i];
-		__syncthreads();
-		process_window<true, LIMBS>(job, w, smem, L, lw, inv_scale, lim, scale);
+	const EmitLayout L = make_emit_layout(job.wlog, job.N, LIMBS, rowbuf);
+	int32_t *tn = (int32_t *) (smem + L.off_tn);
+	long long *toff = (long long *) (smem + L.off_toff);
+	long long *tmd = (long long *) (smem + L.off_tmd);
+	for (int i = threadIdx.x; i < job.N; i += THREADS) {
+		const long long o = job.off[i];
+		toff[i] = o;
+		tn[i] = (int) (job.off[i + 1] - o);
+		tmd[i] = job.fast ? job.dflt_fx[i] : 0;
 	}
+	__syncthreads();
+	for (int w = blockIdx.x; w < job.nw; w += gridDim.x)
+		emit_window<LIMBS>(job, w, smem, L, lw, inv_scale, lim, scale);
 }
 
 // exclusive scan of the per-window counts (single CTA; nw is small)
@@ -754,16 +937,30 @@ static int row_buffer_bytes(int N, int op) {
 }
 
 size_t window_smem_bytes(int wlog, int N, bool emit, int op) {
-	return make_layout(wlog, N, emit, 3, emit ? row_buffer_bytes(N, op) : 0).total;
+	if (!emit) return make_count_layout(wlog, N).total;
+	return make_emit_layout(wlog, N, 3, row_buffer_bytes(N, op)).total;
+}
+
+template <int VLOG>
+static cudaError_t launch_count_v(const Job &job, cudaStream_t s) {
+	size_t smem = make_count_layout(job.wlog, job.N).total;
+	cudaError_t e = cudaFuncSetAttribute(count_kernel<VLOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+	if (e != cudaSuccess) return e;
+	int strips = (job.nw + job.strip - 1) / job.strip;
+	count_kernel<VLOG><<<strips, THREADS, smem, s>>>(job);
+	return cudaGetLastError();
 }
 
 cudaError_t launch_count(const Job &job, cudaStream_t s) {
-	size_t smem = make_layout(job.wlog, job.N, false, 0, 0).total;
-	cudaError_t e = cudaFuncSetAttribute(count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-	if (e != cudaSuccess) return e;
-	int strips = (job.nw + job.strip - 1) / job.strip;
-	count_kernel<<<strips, THREADS, smem, s>>>(job);
-	return cudaGetLastError();
+	switch (job.wlog) {           // window = THREADS << VLOG base pairs
+	case 8: return launch_count_v<0>(job, s);
+	case 9: return launch_count_v<1>(job, s);
+	case 10: return launch_count_v<2>(job, s);
+	case 11: return launch_count_v<3>(job, s);
+	case 12: return launch_count_v<4>(job, s);
+	case 13: return launch_count_v<5>(job, s);
+	}
+	return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_scan_counts(const uint32_t *wcount, int64_t *woff, int nw, cudaStream_t s) {
@@ -779,7 +976,7 @@ cudaError_t launch_emit(const Job &job, cudaStream_t s) {
 	if (job.fast && job.fx_mbits > 29 - l2n + lw) limbs = 3;
 	double inv_scale = ldexp(1.0, -job.fx_q), scale = ldexp(1.0, job.fx_q), lim = ldexp(1.0, job.fx_mbits);
 	int rowbuf = row_buffer_bytes(job.N, job.op);
-	size_t smem = make_layout(job.wlog, job.N, true, limbs, rowbuf).total;
+	size_t smem = make_emit_layout(job.wlog, job.N, limbs, rowbuf).total;
 	int dev = 0, sms = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -44,7 +44,7 @@ struct Job {
 	int nw;                 // number of windows
 	int strip;              // windows per count-kernel strip
 	// scratch
-	int32_t *cursor;        // [nw * N] first interval of track i with end >= window start
+	int32_t *cursor;        // [(nw+1) * N] first interval of track i with end >= window start (row nw: end of data)
 	uint32_t *wcount;       // [nw] segments emitted by each window
 	const int64_t *woff;    // [nw + 1] exclusive scan of wcount
 	// outputs
