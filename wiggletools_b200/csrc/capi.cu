@@ -177,17 +177,17 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 	st.intervals = I;
 
 	// window size
-	int wlog = 12;
+	int wlog = 11;
 	if (ctx->window_bp > 0) wlog = ceil_log2(ctx->window_bp);
 	else {
 		const char *env = getenv("WB200_WINDOW");
 		if (env && atoi(env) > 0) wlog = ceil_log2(atoi(env));
 		else {
 			double density = 2.0 * (double) I / ((double) pos_hi - pos_lo + 1.0);
-			if (density > 0.6) wlog = 11;
+			if (density > 0.6) wlog = 10;
 		}
 	}
-	wlog = std::min(13, std::max(8, wlog));
+	wlog = std::min(12, std::max(10, wlog));
 	const int64_t span = (int64_t) pos_hi - pos_lo;
 	const int nw = (int) (span >> wlog) + 1;
 

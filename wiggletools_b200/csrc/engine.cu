@@ -40,78 +40,64 @@ namespace wb {
 #define FULL 0xffffffffu
 
 // ---------------------------------------------------------------------------
-// shared-memory layouts
+// shared-memory layout
 // ---------------------------------------------------------------------------
-// Arrays scanned by thread-owned contiguous chunks (V = 2^k entries per thread)
-// are stored with one pad word per 32: pidx(p) = p + (p >> 5), which makes the
-// chunked accesses bank-conflict free for every power-of-two V.
-__host__ __device__ __forceinline__ int pidx(int p) { return p + (p >> 5); }
+// A window of W = THREADS << VLOG base pairs is owned by one CTA; thread t owns
+// the V = 2^VLOG consecutive positions [t*V, t*V+V).  Per position the window
+// keeps a packed cover delta, the fixed-point value delta in 32-bit limbs and a
+// byte flag "an interval starts or ends here".  The 32-bit arrays are read back
+// by their owner with 128-bit loads; phys() rotates each thread's vectors so
+// that those loads (and the scattered atomics) are bank-conflict free.
+template <int VLOG>
+__device__ __forceinline__ int phys(int p) {
+	if (VLOG < 2) return p;
+	constexpr int LV = VLOG - 2, NV = 1 << (VLOG >= 2 ? VLOG - 2 : 0);
+	const int t = p >> VLOG, o = p & ((1 << VLOG) - 1);
+	const int q = (o >> 2) ^ ((t >> (3 - LV)) & (NV - 1));
+	return (t << VLOG) | (q << 2) | (o & 3);
+}
 
-constexpr int ITRACK_CAP = 2048;     // flat (track,interval) items per window handled in one pass
-
-struct Misc {                        // scalars and per-thread scan bases
-	int nb;                          // breakpoints in the window
+struct Misc {                        // scalars, warp totals
 	int next_bp;                     // first breakpoint at or after the window end
-	int base_cov;                    // count kernel: cover carried into the window
-	int total_items;                 // flat item count T
-	int kept;                        // count kernel: kept segments
-	int pad[3];
+	int base_cov;                    // packed cover carried into the window
+	int kept;                        // kept segments of the window
+	int nbp;                         // breakpoints of the window
+	unsigned long long base_val;     // fixed-point value carried into the window
+	long long out_base;              // output offset of the window
 	long long wsum[WARPS];           // warp totals (value scan / slow counter)
 	int wcov[WARPS];                 // warp totals (cover scan)
-	int wkeep[WARPS];                // warp totals (compaction)
+	int wkeep[WARPS];                // warp totals (counts scan)
 	double wauc[WARPS];
 	double wmom[WARPS][6];           // Pearson moments per warp
-	int tb_cov[THREADS];             // per-thread exclusive scan bases
-	int kbase[THREADS];
-	long long tb_val[THREADS];
 };
-constexpr int MISC_BYTES = 5120;
+constexpr int MISC_BYTES = 1024;
 static_assert(sizeof(Misc) <= MISC_BYTES, "Misc must fit its shared-memory slot");
 
-struct CountLayout { size_t off_cur, off_nxt, off_toff, off_tn, off_covp, off_ev, total; };
+constexpr uint16_t BK_KEEP = 0x8000, BK_SLOW = 0x4000, BK_IDX = 0x3fff;
 
-__host__ __device__ inline CountLayout make_count_layout(int wlog, int N) {
-	CountLayout L;
-	const int W = 1 << wlog;
+struct Layout {
+	size_t off_cur, off_nxt, off_tn, off_toff, off_tmd, off_cov, off_limb, off_ev, off_rows, total;
+	// after the scan the position arrays are dead; the dense breakpoint list aliases them:
+	size_t off_bpos, off_bkid, off_bval;
+};
+
+__host__ __device__ inline Layout make_layout(int wlog, int N, bool emit, int limbs, int rowbuf) {
+	Layout L;
+	const size_t W = (size_t) 1 << wlog;
 	size_t o = MISC_BYTES;
-	const size_t nn = (size_t) (N + 3) / 4 * 16;
+	const size_t nn = (size_t) (N + 4) / 4 * 16;
 	L.off_cur = o;  o += nn;
 	L.off_nxt = o;  o += nn;
 	L.off_tn = o;   o += nn;
 	L.off_toff = o; o += 2 * nn;
-	L.off_covp = o; o += (size_t) (W + W / 32 + 4) * 4;
-	L.off_ev = o;   o += (size_t) W;
-	L.total = (o + 15) / 16 * 16;
-	return L;
-}
-
-struct EmitLayout {
-	int words, slots, pslots;        // bitmap words; W+1 slots; padded slot count
-	size_t off_cur, off_nxt, off_pre, off_toff, off_tn, off_tmd, off_bitmap, off_wprefix, off_cov, off_limb,
-	       off_klocal, off_bpos, off_itrack, off_rows, total;
-};
-
-__host__ __device__ inline EmitLayout make_emit_layout(int wlog, int N, int limbs, int rowbuf) {
-	EmitLayout L;
-	const int W = 1 << wlog;
-	L.words = W / 32;
-	L.slots = W + 1;
-	L.pslots = (pidx(W + 1) + 8) / 4 * 4;
-	size_t o = MISC_BYTES;
-	const size_t nn = (size_t) (N + 4) / 4 * 16;
-	L.off_cur = o;     o += nn;
-	L.off_nxt = o;     o += nn;
-	L.off_pre = o;     o += nn;
-	L.off_tn = o;      o += nn;
-	L.off_toff = o;    o += 2 * nn;
-	L.off_tmd = o;     o += 2 * nn;
-	L.off_bitmap = o;  o += (size_t) L.words * 4;
-	L.off_wprefix = o; o += (size_t) L.words * 4;
-	L.off_cov = o;     o += (size_t) L.pslots * 4;
-	L.off_limb = o;    o += (size_t) limbs * L.pslots * 4;
-	L.off_klocal = o;  o += (size_t) L.pslots * 2;
-	L.off_bpos = o;    o += (size_t) (L.slots + 8) / 8 * 16;
-	L.off_itrack = o;  o += (size_t) ITRACK_CAP * 2;
+	L.off_tmd = o;  o += emit ? 2 * nn : 0;
+	L.off_cov = o;  o += 4 * W;
+	L.off_limb = o; o += emit ? (size_t) limbs * 4 * W : 0;
+	L.off_ev = o;   o += W + 16;
+	// dense list: value[W] fp64 | pos[W+8] u16 | kid[W] u16  (12W+16 <= 4W + 8W + W+16)
+	L.off_bval = L.off_cov;
+	L.off_bpos = L.off_bval + 8 * W;
+	L.off_bkid = L.off_bpos + 2 * W + 16;
 	L.off_rows = (o + 15) / 16 * 16; o = L.off_rows + (size_t) rowbuf;
 	L.total = (o + 15) / 16 * 16;
 	return L;
@@ -120,10 +106,6 @@ __host__ __device__ inline EmitLayout make_emit_layout(int wlog, int N, int limb
 // ---------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ int slot_of(const uint32_t *bitmap, const uint32_t *wprefix, int x) {
-	uint32_t w = bitmap[x >> 5];
-	return (int) wprefix[x >> 5] + __popc(w & ((1u << (x & 31)) - 1u));
-}
 
 // first j in [0,n) with a[j] >= key (a ascending)
 __device__ __forceinline__ int lower_bound_ge(const int32_t *a, int n, long long key) {
@@ -445,313 +427,242 @@ __device__ __forceinline__ bool keep_rule(const Job &job, bool setop, int c) {
 }
 
 // ---------------------------------------------------------------------------
-// count kernel: segments per window + the per-window cursor table
+// the window pipeline
 // ---------------------------------------------------------------------------
-// Position-indexed: one packed cover delta per base pair of the window
-// (atomicAdd, native 32-bit) and a byte flag "an interval starts or ends here".
-// One pass over the window's intervals, then a chunked prefix scan over the W
-// positions.  One CTA walks a strip of consecutive windows so that each track's
-// cursor is chained from window to window (binary search only at strip start).
-template <int VLOG>
-__device__ void count_window(const Job &job, int w, unsigned char *smem, const CountLayout &L) {
+// EMIT = false: count the window's segments (and chain the cursors).
+// EMIT = true : same sweep with values, then write the segments.
+//
+//  1. events : 8-lane groups walk one track each from its cursor; every interval
+//              adds +delta at its start position and -delta at its end position
+//              (native 32-bit shared atomics: packed cover counters and the
+//              fixed-point value in limbs) and flags both positions.  Intervals
+//              that began before the window feed the carried-in state.
+//  2. scan   : each thread pulls its V positions into registers (128-bit loads),
+//              prefix-sums them, and one block scan stitches the threads: the
+//              state after every position = cover set + exact value sum of the
+//              segment that starts there.
+//  3. compact: flagged positions (breakpoints) are written as a dense list over
+//              the now-dead position arrays; kept ones carry their output rank.
+//  4. emit   : one breakpoint per thread, coalesced 16 B/segment stores.
+template <bool EMIT, int VLOG, int LIMBS>
+__device__ void process_window(const Job &job, int w, unsigned char *smem, const Layout &L,
+                               int lw, double inv_scale, double lim, double scale) {
 	constexpr int V = 1 << VLOG, W = THREADS << VLOG;
 	Misc *misc = (Misc *) smem;
 	int32_t *cur = (int32_t *) (smem + L.off_cur);
 	int32_t *nxt = (int32_t *) (smem + L.off_nxt);
 	const int32_t *tn = (const int32_t *) (smem + L.off_tn);
 	const long long *toff = (const long long *) (smem + L.off_toff);
-	int32_t *covp = (int32_t *) (smem + L.off_covp);
-	unsigned char *ev = smem + L.off_ev;
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int N = job.N;
-	const long long w0 = job.p0 + ((long long) w << job.wlog);
-	const long long w1 = w0 + W;
-	const bool setop = (job.op == OP_TTEST || job.op == OP_MWU);
-
-	{
-		uint4 z = make_uint4(0, 0, 0, 0);
-		uint4 *zc = (uint4 *) covp;
-		for (int t = tid; t < (W + W / 32 + 4) / 4; t += THREADS) zc[t] = z;
-		uint4 *ze = (uint4 *) ev;
-		for (int t = tid; t < W / 16; t += THREADS) ze[t] = z;
-		if (tid == 0) { misc->base_cov = 0; misc->kept = 0; }
-	}
-	__syncthreads();
-
-	for (int i = warp; i < N; i += WARPS) {
-		const long long o = toff[i];
-		const int n = tn[i];
-		const int f = (i < job.n1) ? 1 : (1 << COV_B_SHIFT);
-		int j0 = cur[i];
-		while (true) {
-			const int j = j0 + lane;
-			const bool valid = j < n;
-			int s = 0, e = 0;
-			if (valid) { s = job.start[o + j]; e = job.end[o + j]; }
-			const bool stop = !valid || (long long) e >= w1;
-			const unsigned bal = __ballot_sync(FULL, stop);
-			const int Lst = bal ? __ffs(bal) - 1 : 32;
-			if (lane < Lst || (lane == Lst && valid && (long long) s < w1)) {
-				if ((long long) s >= w0) { const int x = (int) (s - w0); atomicAdd(&covp[pidx(x)], f); ev[x] = 1; }
-				else atomicAdd(&misc->base_cov, f);                       // spans the window start
-				if (lane < Lst) { const int x = (int) (e - w0); atomicAdd(&covp[pidx(x)], -f); ev[x] = 1; }
-			}
-			if (bal) { if (lane == 0) nxt[i] = j0 + Lst; break; }
-			j0 += 32;
-		}
-	}
-	__syncthreads();
-
-	const int p0 = tid * V;
-	int local = 0;
-#pragma unroll
-	for (int q = 0; q < V; q++) local += covp[pidx(p0 + q)];
-	int ec, tc;
-	block_scan1(misc, local, ec, tc);
-	int running = misc->base_cov + ec, kept = 0;
-#pragma unroll
-	for (int q = 0; q < V; q++) {
-		running += covp[pidx(p0 + q)];
-		if (ev[p0 + q]) kept += keep_rule(job, setop, running) ? 1 : 0;
-	}
-	for (int d = 16; d > 0; d >>= 1) kept += __shfl_down_sync(FULL, kept, d);
-	if (lane == 0 && kept) atomicAdd(&misc->kept, kept);
-	__syncthreads();
-	if (tid == 0) job.wcount[w] = (uint32_t) misc->kept;
-	for (int i = tid; i < N; i += THREADS) job.cursor[(size_t) w * N + i] = cur[i];
-}
-
-template <int VLOG>
-__global__ void __launch_bounds__(THREADS) count_kernel(const Job job) {
-	extern __shared__ __align__(16) unsigned char smem[];
-	const CountLayout L = make_count_layout(job.wlog, job.N);
-	int32_t *cur = (int32_t *) (smem + L.off_cur);
-	int32_t *nxt = (int32_t *) (smem + L.off_nxt);
-	int32_t *tn = (int32_t *) (smem + L.off_tn);
-	long long *toff = (long long *) (smem + L.off_toff);
-	const int wbeg = blockIdx.x * job.strip;
-	const int wend = min(job.nw, wbeg + job.strip);
-	if (wbeg >= wend) return;
-	const long long w0 = job.p0 + ((long long) wbeg << job.wlog);
-	for (int i = threadIdx.x; i < job.N; i += THREADS) {
-		const long long o = job.off[i];
-		const int n = (int) (job.off[i + 1] - o);
-		toff[i] = o; tn[i] = n;
-		cur[i] = lower_bound_ge(job.end + o, n, w0);
-	}
-	__syncthreads();
-	for (int w = wbeg; w < wend; w++) {
-		count_window<VLOG>(job, w, smem, L);
-		__syncthreads();
-		for (int i = threadIdx.x; i < job.N; i += THREADS) cur[i] = nxt[i];
-		__syncthreads();
-	}
-	// the cursor row after the last window (row nw) closes the table for emit
-	if (wend == job.nw)
-		for (int i = threadIdx.x; i < job.N; i += THREADS) job.cursor[(size_t) job.nw * job.N + i] = cur[i];
-}
-
-// ---------------------------------------------------------------------------
-// emit kernel: the window pipeline with values
-// ---------------------------------------------------------------------------
-template <int LIMBS>
-__device__ void emit_window(const Job &job, int w, unsigned char *smem, const EmitLayout &L,
-                            int lw, double inv_scale, double lim, double scale) {
-	Misc *misc = (Misc *) smem;
-	int32_t *cur = (int32_t *) (smem + L.off_cur);
-	int32_t *nxt = (int32_t *) (smem + L.off_nxt);
-	int32_t *pre = (int32_t *) (smem + L.off_pre);
-	const int32_t *tn = (const int32_t *) (smem + L.off_tn);
-	const long long *toff = (const long long *) (smem + L.off_toff);
 	const long long *tmd = (const long long *) (smem + L.off_tmd);
-	uint32_t *bitmap = (uint32_t *) (smem + L.off_bitmap);
-	uint32_t *wprefix = (uint32_t *) (smem + L.off_wprefix);
 	int32_t *cov = (int32_t *) (smem + L.off_cov);
 	uint32_t *limb = (uint32_t *) (smem + L.off_limb);
-	uint16_t *klocal = (uint16_t *) (smem + L.off_klocal);
-	uint16_t *bpos = (uint16_t *) (smem + L.off_bpos);
-	uint16_t *itrack = (uint16_t *) (smem + L.off_itrack);
-	const int ls = L.pslots;                      // limb array stride
+	unsigned char *ev = smem + L.off_ev;
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int N = job.N;
-	const int W = 1 << job.wlog;
 	const long long w0 = job.p0 + ((long long) w << job.wlog);
 	const long long w1 = w0 + W;
 	const bool setop = (job.op == OP_TTEST || job.op == OP_MWU);
-	const bool fast = job.fast != 0;
+	const bool fast = EMIT && job.fast != 0;
 
-	// ---- cursors of this window and the next; flat item index ----------------
-	int run = 0;   // carry of the per-track length scan
-	for (int base = 0; base < N; base += THREADS) {
-		const int i = base + tid;
-		int len = 0;
-		if (i < N) {
-			const int c = job.cursor[(size_t) w * N + i];
-			const int x = job.cursor[(size_t) (w + 1) * N + i];
-			cur[i] = c; nxt[i] = x;
-			len = max(0, min(x, tn[i] - 1) - c + 1);
-		}
-		int ec, tc;
-		block_scan1(misc, len, ec, tc);
-		if (i < N) pre[i] = run + ec;
-		run += tc;
-	}
-	const int T = run;
-	const bool flat = T <= ITRACK_CAP;
-	for (int t = tid; t < L.words; t += THREADS) bitmap[t] = 0;
-	if (tid == 0) misc->next_bp = INT_MAX;
-	__syncthreads();
-	if (flat)
-		for (int i = tid; i < N; i += THREADS) {
-			const int b = pre[i], len = max(0, min(nxt[i], tn[i] - 1) - cur[i] + 1);
-			for (int q = 0; q < len; q++) itrack[b + q] = (uint16_t) i;
-		}
-	__syncthreads();
-
-	// ---- phase 1: mark breakpoints ------------------------------------------
-	auto mark_item = [&](int i, int j) {
-		const long long o = toff[i];
-		const int s = job.start[o + j], e = job.end[o + j];
-		if (j < nxt[i]) {
-			// interval ends inside the window (w0 <= e < w1)
-			if ((long long) s >= w0) { const int x = (int) (s - w0); atomicOr(&bitmap[x >> 5], 1u << (x & 31)); }
-			const int x = (int) (e - w0); atomicOr(&bitmap[x >> 5], 1u << (x & 31));
-		} else if ((long long) s < w1) {
-			// first interval reaching the window end; its start is still ours
-			if ((long long) s >= w0) { const int x = (int) (s - w0); atomicOr(&bitmap[x >> 5], 1u << (x & 31)); }
-			atomicMin(&misc->next_bp, e);
-		} else
-			atomicMin(&misc->next_bp, s);
-	};
-	if (flat) {
-		for (int k = tid; k < T; k += THREADS) { const int i = itrack[k]; mark_item(i, cur[i] + k - pre[i]); }
-	} else {
-		for (int i = warp; i < N; i += WARPS) {
-			const int jl = min(nxt[i], tn[i] - 1);
-			for (int j = cur[i] + lane; j <= jl; j += 32) mark_item(i, j);
-		}
-	}
-	__syncthreads();
-
-	// ---- phase 2: rank the breakpoints ----------------------------------------
+	// ---- clear the position arrays -------------------------------------------
 	{
-		const int pc = (tid < L.words) ? __popc(bitmap[tid]) : 0;   // L.words <= THREADS
-		int ec, tc;
-		block_scan1(misc, pc, ec, tc);
-		if (tid < L.words) wprefix[tid] = 1 + ec;                   // slot of the word's first set bit
-		if (tid == 0) misc->nb = tc;
-		__syncthreads();
+		const uint4 z = make_uint4(0, 0, 0, 0);
+		uint4 *zc = (uint4 *) cov;
+		constexpr int n16 = (EMIT ? (1 + LIMBS) : 1) * W / 4;     // cov and limbs are contiguous
+		for (int t = tid; t < n16; t += THREADS) zc[t] = z;
+		uint4 *ze = (uint4 *) ev;
+		for (int t = tid; t < W / 16; t += THREADS) ze[t] = z;
+		if (tid == 0) { misc->next_bp = INT_MAX; misc->base_cov = 0; misc->base_val = 0; }
 	}
-	const int nb = misc->nb;
-	int vlog = 0;
-	while ((THREADS << vlog) < nb + 1) vlog++;
-	const int V = 1 << vlog;
+	__syncthreads();
+
+	// ---- 1. events --------------------------------------------------------------
 	{
-		const int top = pidx(nb) + 1;
-		for (int t = tid; t < top; t += THREADS) {
-			cov[t] = 0;
+		const int gid = tid >> 3, gl = tid & 7, gsh = (lane >> 3) << 3;
+		int in_cov = 0, my_next = INT_MAX;
+		long long in_val = 0;
+		for (int rb = 0; rb < N; rb += THREADS / 8) {
+			const int i = rb + gid;
+			bool done = i >= N;
+			long long o = 0, md = 0;
+			int n = 0, j0 = 0, f = 0;
+			if (!done) {
+				o = toff[i]; n = tn[i]; j0 = cur[i];
+				f = (i < job.n1) ? 1 : (1 << COV_B_SHIFT);
+				if (fast) md = tmd[i];
+			}
+			while (true) {
+				const int j = j0 + gl;
+				const bool valid = !done && j < n;
+				int s = 0, e = 0;
+				double val = 0;
+				if (valid) {
+					s = job.start[o + j]; e = job.end[o + j];
+					if (fast) val = job.value[o + j];
+				}
+				const bool stop = !valid || (long long) e >= w1;
+				const unsigned gb = (__ballot_sync(FULL, stop) >> gsh) & 0xffu;
+				const int Lst = gb ? __ffs(gb) - 1 : 8;
+				const bool inside = gl < Lst;                        // w0 <= e < w1
+				if (valid && (inside || (gl == Lst && (long long) s < w1))) {
+					int cd = f;
+					long long d = 0;
+					if (fast) {
+						long long m;
+						if (to_fixed(val, inv_scale, lim, m)) d = m - md;
+						else cd += (1 << COV_P_SHIFT);
+					}
+					if ((long long) s >= w0) {
+						const int x = (int) (s - w0), ph = phys<VLOG>(x);
+						atomicAdd(&cov[ph], cd);
+						ev[x] = 1;
+						if (fast && d != 0) {
+							atomicAdd(&limb[ph], (uint32_t) (d & ((1ll << lw) - 1)));
+							if (LIMBS == 2) atomicAdd(&limb[W + ph], (uint32_t) (d >> lw));
+							else {
+								atomicAdd(&limb[W + ph], (uint32_t) ((d >> lw) & ((1ll << lw) - 1)));
+								atomicAdd(&limb[2 * W + ph], (uint32_t) (d >> (2 * lw)));
+							}
+						}
+					} else { in_cov += cd; in_val += d; }            // began before the window
+					if (inside) {
+						const int x = (int) (e - w0), ph = phys<VLOG>(x);
+						atomicAdd(&cov[ph], -cd);
+						ev[x] = 1;
+						if (fast && d != 0) {
+							const long long nd = -d;
+							atomicAdd(&limb[ph], (uint32_t) (nd & ((1ll << lw) - 1)));
+							if (LIMBS == 2) atomicAdd(&limb[W + ph], (uint32_t) (nd >> lw));
+							else {
+								atomicAdd(&limb[W + ph], (uint32_t) ((nd >> lw) & ((1ll << lw) - 1)));
+								atomicAdd(&limb[2 * W + ph], (uint32_t) (nd >> (2 * lw)));
+							}
+						}
+					}
+				}
+				if (!done && gb) {
+					// the track leaves the window at interval j0+Lst
+					if (gl == Lst && valid) my_next = min(my_next, (long long) s < w1 ? e : s);
+					if (gl == 0) nxt[i] = j0 + Lst;
+					done = true;
+				}
+				j0 += 8;
+				if (__all_sync(FULL, done)) break;
+			}
+		}
+		// carried-in state and the look-ahead breakpoint: one shared atomic per warp
+		my_next = __reduce_min_sync(FULL, my_next);
+		in_cov = __reduce_add_sync(FULL, in_cov);
+		for (int d = 16; d > 0; d >>= 1) in_val += __shfl_down_sync(FULL, in_val, d);
+		if (lane == 0) {
+			if (my_next != INT_MAX) atomicMin(&misc->next_bp, my_next);
+			if (in_cov) atomicAdd(&misc->base_cov, in_cov);
+			if (fast && in_val) atomicAdd(&misc->base_val, (unsigned long long) in_val);
+		}
+	}
+	__syncthreads();
+
+	// ---- 2. scan: this thread's V positions, in registers -------------------------
+	int c_run[V];
+	long long a_run[V];
+	unsigned evbits = 0;
+	{
+		const int p0 = tid << VLOG;
+		int cv[V]; uint32_t l0[V], l1[V], l2[V];
+		if (VLOG >= 2) {
+			constexpr int NV = V / 4, LV = VLOG - 2;
+			const int swz = (tid >> (3 - LV)) & (NV - 1);
 #pragma unroll
-			for (int l = 0; l < LIMBS; l++) limb[l * ls + t] = 0;
-		}
-		if (tid < L.words) {
-			uint32_t bits = bitmap[tid];
-			int slot = (int) wprefix[tid];
-			while (bits) {
-				const int bit = __ffs(bits) - 1;
-				bits &= bits - 1;
-				bpos[slot++] = (uint16_t) (tid * 32 + bit);
+			for (int q = 0; q < NV; q++) {
+				const int pq = p0 + ((q ^ swz) << 2);
+				const int4 x = *(const int4 *) (cov + pq);
+				cv[4 * q] = x.x; cv[4 * q + 1] = x.y; cv[4 * q + 2] = x.z; cv[4 * q + 3] = x.w;
+				if (fast) {
+					const uint4 y = *(const uint4 *) (limb + pq);
+					l0[4 * q] = y.x; l0[4 * q + 1] = y.y; l0[4 * q + 2] = y.z; l0[4 * q + 3] = y.w;
+					const uint4 z = *(const uint4 *) (limb + W + pq);
+					l1[4 * q] = z.x; l1[4 * q + 1] = z.y; l1[4 * q + 2] = z.z; l1[4 * q + 3] = z.w;
+					if (LIMBS == 3) {
+						const uint4 u = *(const uint4 *) (limb + 2 * W + pq);
+						l2[4 * q] = u.x; l2[4 * q + 1] = u.y; l2[4 * q + 2] = u.z; l2[4 * q + 3] = u.w;
+					}
+				}
 			}
-		}
-	}
-	__syncthreads();
-
-	// ---- phase 3: events -> cover deltas and fixed-point value deltas ---------
-	auto add_value = [&](int slot, long long d) {
-		const int ps = pidx(slot);
-		if (LIMBS == 2) {
-			atomicAdd(&limb[ps], (uint32_t) (d & ((1ll << lw) - 1)));
-			atomicAdd(&limb[ls + ps], (uint32_t) (d >> lw));
 		} else {
-			atomicAdd(&limb[ps], (uint32_t) (d & ((1ll << lw) - 1)));
-			atomicAdd(&limb[ls + ps], (uint32_t) ((d >> lw) & ((1ll << lw) - 1)));
-			atomicAdd(&limb[2 * ls + ps], (uint32_t) (d >> (2 * lw)));
-		}
-	};
-	auto event_item = [&](int i, int j) {
-		const long long o = toff[i];
-		const int s = job.start[o + j], e = job.end[o + j];
-		const bool inside = j < nxt[i];
-		if (!inside && (long long) s >= w1) return;
-		int cd = (i < job.n1) ? 1 : (1 << COV_B_SHIFT);
-		long long d = 0;
-		if (fast) {
-			long long m;
-			if (to_fixed(job.value[o + j], inv_scale, lim, m)) d = m - tmd[i];
-			else cd += (1 << COV_P_SHIFT);
-		}
-		const int ss = ((long long) s >= w0) ? slot_of(bitmap, wprefix, (int) (s - w0)) : 0;
-		atomicAdd(&cov[pidx(ss)], cd);
-		if (fast && d != 0) add_value(ss, d);
-		if (inside) {
-			const int se = slot_of(bitmap, wprefix, (int) (e - w0));
-			atomicAdd(&cov[pidx(se)], -cd);
-			if (fast && d != 0) add_value(se, -d);
-		}
-	};
-	if (flat) {
-		for (int k = tid; k < T; k += THREADS) { const int i = itrack[k]; event_item(i, cur[i] + k - pre[i]); }
-	} else {
-		for (int i = warp; i < N; i += WARPS) {
-			const int jl = min(nxt[i], tn[i] - 1);
-			for (int j = cur[i] + lane; j <= jl; j += 32) event_item(i, j);
-		}
-	}
-	__syncthreads();
-
-	// ---- phase 4: chunked prefix scan over the slots --------------------------
-	// thread t owns slots [t*V, t*V+V); local inclusive prefixes are written back
-	// in place, the per-thread bases stay in shared memory (tb_cov / tb_val).
-	auto load_val = [&](int ps) -> long long {
-		if (LIMBS == 2)
-			return (long long) (unsigned long long) limb[ps] + ((long long) (int32_t) limb[ls + ps] << lw);
-		return (long long) (unsigned long long) limb[ps] + ((long long) (unsigned long long) limb[ls + ps] << lw)
-		     + ((long long) (int32_t) limb[2 * ls + ps] << (2 * lw));
-	};
-	const int r0 = tid << vlog;
-	{
-		int c = 0; long long a = 0;
-		for (int q = 0; q < V; q++) {
-			const int r = r0 + q;
-			if (r > nb) break;
-			const int ps = pidx(r);
-			c += cov[ps];
-			cov[ps] = c;
-			if (fast) {
-				a += load_val(ps);
-				limb[ps] = (uint32_t) a;              // from here on limb[0..1] hold the raw int64 prefix
-				limb[ls + ps] = (uint32_t) ((unsigned long long) a >> 32);
+#pragma unroll
+			for (int q = 0; q < V; q++) {
+				cv[q] = cov[p0 + q];
+				if (fast) { l0[q] = limb[p0 + q]; l1[q] = limb[W + p0 + q]; if (LIMBS == 3) l2[q] = limb[2 * W + p0 + q]; }
 			}
+		}
+#pragma unroll
+		for (int q = 0; q < V; q++) if (ev[p0 + q]) evbits |= 1u << q;
+		int c = 0; long long a = 0;
+#pragma unroll
+		for (int q = 0; q < V; q++) {
+			c += cv[q];
+			c_run[q] = c;
+			if (fast) {
+				if (LIMBS == 2) a += (long long) (unsigned long long) l0[q] + ((long long) (int32_t) l1[q] << lw);
+				else a += (long long) (unsigned long long) l0[q] + ((long long) (unsigned long long) l1[q] << lw)
+				        + ((long long) (int32_t) l2[q] << (2 * lw));
+			}
+			a_run[q] = a;
 		}
 		int ec, tc; long long ea, ta;
-		block_scan2(misc, c, a, ec, ea, tc, ta);
-		misc->tb_cov[tid] = ec;
-		misc->tb_val[tid] = ea;
-		int kept = 0;
+		block_scan2(misc, c, a, ec, ea, tc, ta);          // its barriers also fence the loads above
+		ec += misc->base_cov;
+		ea += (long long) misc->base_val;
+#pragma unroll
+		for (int q = 0; q < V; q++) { c_run[q] += ec; a_run[q] += ea; }
+	}
+
+	// breakpoints and kept segments of this thread; one packed block scan for both
+	int nbp_l = __popc(evbits), kept_l = 0;
+#pragma unroll
+	for (int q = 0; q < V; q++) if ((evbits >> q) & 1) kept_l += keep_rule(job, setop, c_run[q]) ? 1 : 0;
+	int epack, tpack;
+	block_scan1(misc, nbp_l | (kept_l << 16), epack, tpack);
+	const int nbp = tpack & 0xffff, kept_total = tpack >> 16;
+
+	if (!EMIT) {
+		if (tid == 0) job.wcount[w] = (uint32_t) kept_total;
+		for (int i = tid; i < N; i += THREADS) job.cursor[(size_t) w * N + i] = cur[i];
+		return;
+	}
+
+	// ---- 3. compact the breakpoints over the dead position arrays --------------------
+	double *bval = (double *) (smem + L.off_bval);
+	uint16_t *bpos = (uint16_t *) (smem + L.off_bpos);
+	uint16_t *bkid = (uint16_t *) (smem + L.off_bkid);
+	const bool row_op = !(job.op == OP_SUM || job.op == OP_MEAN) || !fast;
+	{
+		int rank = epack & 0xffff, kidx = epack >> 16;
+		const int p0 = tid << VLOG;
+#pragma unroll
 		for (int q = 0; q < V; q++) {
-			const int r = r0 + q;
-			if (r > nb) break;
-			const int ps = pidx(r);
-			klocal[ps] = (uint16_t) kept;
-			if (r >= 1 && keep_rule(job, setop, cov[ps] + ec)) kept++;
+			if ((evbits >> q) & 1) {
+				bpos[rank] = (uint16_t) (p0 + q);
+				uint16_t kd = 0;
+				if (keep_rule(job, setop, c_run[q])) {
+					kd = BK_KEEP | (uint16_t) kidx;
+					if (row_op || (c_run[q] >> COV_P_SHIFT) != 0) kd |= BK_SLOW;
+					else {
+						double v = (double) (a_run[q] + job.fx_base) * scale;
+						if (job.op == OP_MEAN) v = v / N;
+						bval[rank] = v;
+					}
+					kidx++;
+				}
+				bkid[rank] = kd;
+				rank++;
+			}
 		}
-		int ek, tk;
-		block_scan1(misc, kept, ek, tk);
-		misc->kbase[tid] = ek;
 	}
 	__syncthreads();
 
-	// ---- phase 5: emit, one slot per thread (coalesced stores) -----------------
+	// ---- 4. emit, one breakpoint per thread (coalesced stores) ---------------------------
 	const bool sorted_op = (job.op == OP_MEDIAN || job.op == OP_MWU);
 	const bool pearson = (job.op == OP_PEARSON);
 	const long long out_base = job.woff[w];
@@ -761,21 +672,15 @@ __device__ void emit_window(const Job &job, int w, unsigned char *smem, const Em
 	double auc = 0;
 	double mom[6] = {0, 0, 0, 0, 0, 0};
 
-	for (int base = 1; base <= nb; base += THREADS) {
+	for (int base = 0; base < nbp; base += THREADS) {
 		const int r = base + tid;
-		bool keep = false;
-		int c = 0, ps = 0, owner = 0;
-		if (r <= nb) {
-			ps = pidx(r);
-			owner = r >> vlog;
-			c = cov[ps] + misc->tb_cov[owner];
-			keep = keep_rule(job, setop, c);
-		}
-		const unsigned kb = __ballot_sync(FULL, keep);
+		uint16_t kd = 0;
+		if (r < nbp) kd = bkid[r];
+		const bool keep = (kd & BK_KEEP) != 0;
 		if (pearson) {
 			if (keep) {
 				const int bs = (int) (w0 + bpos[r]);
-				const int be = (r < nb) ? (int) (w0 + bpos[r + 1]) : next_bp;
+				const int be = (r + 1 < nbp) ? (int) (w0 + bpos[r + 1]) : next_bp;
 				double X, Y;
 				row.b = bs;
 				row.get(0, X); row.get(1, Y);
@@ -785,19 +690,12 @@ __device__ void emit_window(const Job &job, int w, unsigned char *smem, const Em
 			}
 		} else if (!sorted_op) {
 			if (keep) {
-				const long long oi = out_base + misc->kbase[owner] + klocal[ps];
+				const long long oi = out_base + (kd & BK_IDX);
 				const int bs = (int) (w0 + bpos[r]);
-				const int be = (r < nb) ? (int) (w0 + bpos[r + 1]) : next_bp;
+				const int be = (r + 1 < nbp) ? (int) (w0 + bpos[r + 1]) : next_bp;
 				double v;
-				if (fast && (c >> COV_P_SHIFT) == 0) {
-					const long long a = (long long) (((unsigned long long) limb[ls + ps] << 32) | limb[ps]) + misc->tb_val[owner];
-					v = (double) (a + job.fx_base) * scale;
-					if (job.op == OP_MEAN) v = v / N;
-				} else {
-					row.b = bs;
-					v = row_eval(row);
-					slow++;
-				}
+				if (kd & BK_SLOW) { row.b = bs; v = row_eval(row); slow++; }
+				else v = bval[r];
 				if (oi < job.out_cap) {
 					job.out_start[oi] = bs;
 					job.out_end[oi] = be;
@@ -809,17 +707,17 @@ __device__ void emit_window(const Job &job, int w, unsigned char *smem, const Em
 			// one warp per kept segment, in lane order
 			int P = 1; while (P < N) P <<= 1;
 			SortKey *buf = (SortKey *) (smem + L.off_rows) + (size_t) warp * P;
-			unsigned todo = kb;
+			unsigned todo = __ballot_sync(FULL, keep);
 			while (todo) {
 				const int src = __ffs(todo) - 1;
 				todo &= todo - 1;
 				const int rr = base + warp * 32 + src;
 				const int bs = (int) (w0 + bpos[rr]);
-				const int be = (rr < nb) ? (int) (w0 + bpos[rr + 1]) : next_bp;
+				const int be = (rr + 1 < nbp) ? (int) (w0 + bpos[rr + 1]) : next_bp;
 				row.b = bs;
 				const double v = warp_sorted_eval(row, buf, P);
 				if (lane == 0) {
-					const long long oi = out_base + misc->kbase[rr >> vlog] + klocal[pidx(rr)];
+					const long long oi = out_base + (bkid[rr] & BK_IDX);
 					if (oi < job.out_cap) {
 						job.out_start[oi] = bs;
 						job.out_end[oi] = be;
@@ -845,7 +743,6 @@ __device__ void emit_window(const Job &job, int w, unsigned char *smem, const Em
 		}
 		if (lane == 0) for (int k = 0; k < 6; k++) misc->wmom[warp][k] = mom[k];
 	}
-	__syncthreads();   // all reads of tb_*/kbase done before misc->wsum is reused
 	if (lane == 0) { misc->wauc[warp] = auc; misc->wsum[warp] = (long long) slow; }
 	__syncthreads();
 	if (tid == 0) {
@@ -862,10 +759,41 @@ __device__ void emit_window(const Job &job, int w, unsigned char *smem, const Em
 	__syncthreads();
 }
 
-template <int LIMBS>
+// count kernel: one CTA walks a strip of consecutive windows so that each
+// track's cursor is chained from window to window (binary search only at the
+// strip start); writes the per-window segment counts and the cursor table.
+template <int VLOG>
+__global__ void __launch_bounds__(THREADS) count_kernel(const Job job) {
+	extern __shared__ __align__(16) unsigned char smem[];
+	const Layout L = make_layout(job.wlog, job.N, false, 0, 0);
+	int32_t *cur = (int32_t *) (smem + L.off_cur);
+	int32_t *nxt = (int32_t *) (smem + L.off_nxt);
+	int32_t *tn = (int32_t *) (smem + L.off_tn);
+	long long *toff = (long long *) (smem + L.off_toff);
+	const int wbeg = blockIdx.x * job.strip;
+	const int wend = min(job.nw, wbeg + job.strip);
+	if (wbeg >= wend) return;
+	const long long w0 = job.p0 + ((long long) wbeg << job.wlog);
+	for (int i = threadIdx.x; i < job.N; i += THREADS) {
+		const long long o = job.off[i];
+		const int n = (int) (job.off[i + 1] - o);
+		toff[i] = o; tn[i] = n;
+		cur[i] = lower_bound_ge(job.end + o, n, w0);
+	}
+	__syncthreads();
+	for (int w = wbeg; w < wend; w++) {
+		process_window<false, VLOG, 2>(job, w, smem, L, 0, 0.0, 0.0, 0.0);
+		__syncthreads();
+		for (int i = threadIdx.x; i < job.N; i += THREADS) cur[i] = nxt[i];
+		__syncthreads();
+	}
+}
+
+template <int VLOG, int LIMBS>
 __global__ void __launch_bounds__(THREADS) emit_kernel(const Job job, int lw, double inv_scale, double lim, double scale, int rowbuf) {
 	extern __shared__ __align__(16) unsigned char smem[];
-	const EmitLayout L = make_emit_layout(job.wlog, job.N, LIMBS, rowbuf);
+	const Layout L = make_layout(job.wlog, job.N, true, LIMBS, rowbuf);
+	int32_t *cur = (int32_t *) (smem + L.off_cur);
 	int32_t *tn = (int32_t *) (smem + L.off_tn);
 	long long *toff = (long long *) (smem + L.off_toff);
 	long long *tmd = (long long *) (smem + L.off_tmd);
@@ -875,9 +803,11 @@ __global__ void __launch_bounds__(THREADS) emit_kernel(const Job job, int lw, do
 		tn[i] = (int) (job.off[i + 1] - o);
 		tmd[i] = job.fast ? job.dflt_fx[i] : 0;
 	}
-	__syncthreads();
-	for (int w = blockIdx.x; w < job.nw; w += gridDim.x)
-		emit_window<LIMBS>(job, w, smem, L, lw, inv_scale, lim, scale);
+	for (int w = blockIdx.x; w < job.nw; w += gridDim.x) {
+		for (int i = threadIdx.x; i < job.N; i += THREADS) cur[i] = job.cursor[(size_t) w * job.N + i];
+		__syncthreads();
+		process_window<true, VLOG, LIMBS>(job, w, smem, L, lw, inv_scale, lim, scale);
+	}
 }
 
 // exclusive scan of the per-window counts (single CTA; nw is small)
@@ -937,13 +867,12 @@ static int row_buffer_bytes(int N, int op) {
 }
 
 size_t window_smem_bytes(int wlog, int N, bool emit, int op) {
-	if (!emit) return make_count_layout(wlog, N).total;
-	return make_emit_layout(wlog, N, 3, row_buffer_bytes(N, op)).total;
+	return make_layout(wlog, N, emit, 3, emit ? row_buffer_bytes(N, op) : 0).total;
 }
 
 template <int VLOG>
 static cudaError_t launch_count_v(const Job &job, cudaStream_t s) {
-	size_t smem = make_count_layout(job.wlog, job.N).total;
+	size_t smem = make_layout(job.wlog, job.N, false, 0, 0).total;
 	cudaError_t e = cudaFuncSetAttribute(count_kernel<VLOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 	if (e != cudaSuccess) return e;
 	int strips = (job.nw + job.strip - 1) / job.strip;
@@ -953,18 +882,30 @@ static cudaError_t launch_count_v(const Job &job, cudaStream_t s) {
 
 cudaError_t launch_count(const Job &job, cudaStream_t s) {
 	switch (job.wlog) {           // window = THREADS << VLOG base pairs
-	case 8: return launch_count_v<0>(job, s);
-	case 9: return launch_count_v<1>(job, s);
 	case 10: return launch_count_v<2>(job, s);
 	case 11: return launch_count_v<3>(job, s);
 	case 12: return launch_count_v<4>(job, s);
-	case 13: return launch_count_v<5>(job, s);
 	}
 	return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_scan_counts(const uint32_t *wcount, int64_t *woff, int nw, cudaStream_t s) {
 	scan_counts_kernel<<<1, 1024, 0, s>>>(wcount, woff, nw);
+	return cudaGetLastError();
+}
+
+template <int VLOG, int LIMBS>
+static cudaError_t launch_emit_v(const Job &job, int lw, double inv_scale, double lim, double scale, int rowbuf, cudaStream_t s) {
+	size_t smem = make_layout(job.wlog, job.N, true, LIMBS, rowbuf).total;
+	int dev = 0, sms = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	cudaError_t e = cudaFuncSetAttribute(emit_kernel<VLOG, LIMBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+	if (e != cudaSuccess) return e;
+	int per = 1;
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, emit_kernel<VLOG, LIMBS>, THREADS, smem);
+	int grid = min(job.nw, sms * max(per, 1));
+	emit_kernel<VLOG, LIMBS><<<grid, THREADS, smem, s>>>(job, lw, inv_scale, lim, scale, rowbuf);
 	return cudaGetLastError();
 }
 
@@ -976,28 +917,15 @@ cudaError_t launch_emit(const Job &job, cudaStream_t s) {
 	if (job.fast && job.fx_mbits > 29 - l2n + lw) limbs = 3;
 	double inv_scale = ldexp(1.0, -job.fx_q), scale = ldexp(1.0, job.fx_q), lim = ldexp(1.0, job.fx_mbits);
 	int rowbuf = row_buffer_bytes(job.N, job.op);
-	size_t smem = make_emit_layout(job.wlog, job.N, limbs, rowbuf).total;
-	int dev = 0, sms = 148;
-	cudaGetDevice(&dev);
-	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-	cudaError_t e;
-	int grid;
-	if (limbs == 2) {
-		e = cudaFuncSetAttribute(emit_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-		if (e != cudaSuccess) return e;
-		int per = 1;
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, emit_kernel<2>, THREADS, smem);
-		grid = min(job.nw, sms * max(per, 1));
-		emit_kernel<2><<<grid, THREADS, smem, s>>>(job, lw, inv_scale, lim, scale, rowbuf);
-	} else {
-		e = cudaFuncSetAttribute(emit_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-		if (e != cudaSuccess) return e;
-		int per = 1;
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, emit_kernel<3>, THREADS, smem);
-		grid = min(job.nw, sms * max(per, 1));
-		emit_kernel<3><<<grid, THREADS, smem, s>>>(job, lw, inv_scale, lim, scale, rowbuf);
+#define WB_EMIT(V) (limbs == 2 ? launch_emit_v<V, 2>(job, lw, inv_scale, lim, scale, rowbuf, s) \
+                               : launch_emit_v<V, 3>(job, lw, inv_scale, lim, scale, rowbuf, s))
+	switch (job.wlog) {
+	case 10: return WB_EMIT(2);
+	case 11: return WB_EMIT(3);
+	case 12: return WB_EMIT(4);
 	}
-	return cudaGetLastError();
+#undef WB_EMIT
+	return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_sample_maxabs(const double *value, int64_t n, int64_t stride, double *out2, cudaStream_t s) {
