@@ -64,7 +64,7 @@ struct wb200_ctx {
 	std::string err;
 	wb200_stats stats{};
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-	DevBuf in_start, in_end, in_value, off, dflt, dflt_fx, cursor, wcount, woff, aucp, small, moments;
+	DevBuf in_start, in_end, in_value, off, dflt, dflt_fx, cursor, wcount, woff, aucp, small, moments, slow_list;
 	DevBuf out_start, out_end, out_value;
 	HostBuf h_small, h_meta, h_start, h_end, h_value;
 };
@@ -153,7 +153,7 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
                const int32_t *d_start, const int32_t *d_end, const double *d_value,
                const int64_t *h_off, const double *h_dflt, int32_t pos_lo, int32_t pos_hi,
                int32_t *d_out_start, int32_t *d_out_end, double *d_out_value, int64_t out_cap,
-               int64_t *n_out, double *default_out, double *auc_out, double *moments_out = nullptr) {
+               int64_t *n_out, double *default_out, double *auc_out, double *moments_out = nullptr, bool force_row = false) {
 	if (!valid_op(op) && !(op == OP_PEARSON && moments_out && N == 2)) return fail(ctx, WB200_EINVAL, "unknown op");
 	if (N < 1) return fail(ctx, WB200_EINVAL, "need at least one track");
 	const bool setop = (op == OP_TTEST || op == OP_MWU);
@@ -177,14 +177,14 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 	st.intervals = I;
 
 	// window size
-	int wlog = 11;
+	int wlog = 12;
 	if (ctx->window_bp > 0) wlog = ceil_log2(ctx->window_bp);
 	else {
 		const char *env = getenv("WB200_WINDOW");
 		if (env && atoi(env) > 0) wlog = ceil_log2(atoi(env));
 		else {
 			double density = 2.0 * (double) I / ((double) pos_hi - pos_lo + 1.0);
-			if (density > 0.6) wlog = 10;
+			if (density > 0.6) wlog = 11;
 		}
 	}
 	wlog = std::min(12, std::max(10, wlog));
@@ -221,6 +221,7 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 	// small: [0..1] sample result, [2] auc, [3] slow count
 	double *d_small = ctx->small.as<double>();
 	job.slow_count = (unsigned long long *) (d_small + 3);
+	job.auc_fix = d_small + 10;
 
 	CK(cudaEventRecord(ctx->ev[0], s));
 	CK(cudaMemcpyAsync(ctx->off.p, hm_off, (N + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
@@ -230,7 +231,7 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 
 	// fixed-point fast path for sum / mean
 	job.fast = 0;
-	if ((op == OP_SUM || op == OP_MEAN) && I > 0) {
+	if ((op == OP_SUM || op == OP_MEAN) && I > 0 && !force_row) {
 		bool ok = true;
 		for (int i = 0; i < N; i++) if (!std::isfinite(h_dflt[i])) ok = false;
 		if (ok) {
@@ -269,6 +270,11 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 			}
 		}
 	}
+	if (job.fast) {
+		job.slow_cap = std::max<int64_t>(1 << 16, out_cap / 8);
+		CK(ctx->slow_list.ensure((size_t) job.slow_cap * sizeof(long long)));
+		job.slow_list = ctx->slow_list.as<long long>();
+	}
 	if (op == OP_MWU) {
 		// integer division in both moments, src/setComparisons.c:386-387
 		job.mwu_mu = (double) (n1 * n2 / 2);
@@ -294,6 +300,20 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 	CK(cudaMemcpyAsync(h_small + 2, d_small + 2, 64, cudaMemcpyDeviceToHost, s));
 	CK(cudaStreamSynchronize(s));
 	const int64_t S = h_small[0];
+	if (job.fast && h_small[3] > 0) {
+		// segments the fixed-point path could not represent exactly
+		if (h_small[3] > job.slow_cap || S > out_cap)
+			return run_device(ctx, op, N, n1, strict, d_start, d_end, d_value, h_off, h_dflt, pos_lo, pos_hi,
+			                  d_out_start, d_out_end, d_out_value, out_cap, n_out, default_out, auc_out, moments_out, true);
+		CK(launch_fixup(job, h_small[3], s));
+		st.kernels++;
+		CK(cudaMemcpyAsync(h_small + 10, d_small + 10, 8, cudaMemcpyDeviceToHost, s));
+		CK(cudaStreamSynchronize(s));
+		double a, f;
+		memcpy(&a, h_small + 2, 8); memcpy(&f, h_small + 10, 8);
+		a += f;
+		memcpy(h_small + 2, &a, 8);
+	}
 	st.segments = S;
 	st.windows = nw;
 	st.fast_path = job.fast;
@@ -341,7 +361,7 @@ void wb200_destroy(wb200_ctx *ctx) {
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	DevBuf *d[] = {&ctx->in_start, &ctx->in_end, &ctx->in_value, &ctx->off, &ctx->dflt, &ctx->dflt_fx, &ctx->cursor,
-	               &ctx->wcount, &ctx->woff, &ctx->aucp, &ctx->small, &ctx->moments, &ctx->out_start, &ctx->out_end, &ctx->out_value};
+	               &ctx->wcount, &ctx->woff, &ctx->aucp, &ctx->small, &ctx->moments, &ctx->slow_list, &ctx->out_start, &ctx->out_end, &ctx->out_value};
 	for (auto *b : d) b->release();
 	HostBuf *h[] = {&ctx->h_small, &ctx->h_meta, &ctx->h_start, &ctx->h_end, &ctx->h_value};
 	for (auto *b : h) b->release();

@@ -220,7 +220,7 @@ struct Row {
 
 // Per-segment statistic computed exactly as the reference's pop functions do:
 // same loop order over tracks, same float/double conversions, same NaN rules.
-__device__ double row_eval(const Row &r) {
+__device__ __noinline__ double row_eval(const Row &r) {
 	const Job &job = *r.job;
 	const int N = job.N;
 	double x;
@@ -321,7 +321,7 @@ __device__ __forceinline__ bool key_less(const SortKey &a, const SortKey &b) {
 	return a.ord < b.ord;      // stable: glibc qsort is a merge sort at these sizes
 }
 
-__device__ double warp_sorted_eval(const Row &r, SortKey *buf, int P /*pow2 >= N*/) {
+__device__ __noinline__ double warp_sorted_eval(const Row &r, SortKey *buf, int P /*pow2 >= N*/) {
 	const Job &job = *r.job;
 	const int N = job.N, lane = threadIdx.x & 31;
 	bool nan = false;
@@ -444,7 +444,9 @@ __device__ __forceinline__ bool keep_rule(const Job &job, bool setop, int c) {
 //  3. compact: flagged positions (breakpoints) are written as a dense list over
 //              the now-dead position arrays; kept ones carry their output rank.
 //  4. emit   : one breakpoint per thread, coalesced 16 B/segment stores.
-template <bool EMIT, int VLOG, int LIMBS>
+enum { MODE_COUNT = 0, MODE_FAST = 1, MODE_ROW = 2 };
+
+template <int MODE, int VLOG, int LIMBS>
 __device__ void process_window(const Job &job, int w, unsigned char *smem, const Layout &L,
                                int lw, double inv_scale, double lim, double scale) {
 	constexpr int V = 1 << VLOG, W = THREADS << VLOG;
@@ -463,7 +465,8 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	const long long w0 = job.p0 + ((long long) w << job.wlog);
 	const long long w1 = w0 + W;
 	const bool setop = (job.op == OP_TTEST || job.op == OP_MWU);
-	const bool fast = EMIT && job.fast != 0;
+	constexpr bool EMIT = MODE != MODE_COUNT;
+	constexpr bool fast = MODE == MODE_FAST;      // fixed-point value path (sum / mean)
 
 	// ---- clear the position arrays -------------------------------------------
 	{
@@ -566,7 +569,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	// ---- 2. scan: this thread's V positions, in registers -------------------------
 	int c_run[V];
 	long long a_run[V];
-	unsigned evbits = 0;
+	unsigned evbits = 0, keepbits = 0;
 	{
 		const int p0 = tid << VLOG;
 		int cv[V]; uint32_t l0[V], l1[V], l2[V];
@@ -596,8 +599,17 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 				if (fast) { l0[q] = limb[p0 + q]; l1[q] = limb[W + p0 + q]; if (LIMBS == 3) l2[q] = limb[2 * W + p0 + q]; }
 			}
 		}
+		if (V >= 4) {
+			// flags are 0/1 bytes: gather one bit per byte, four positions per word
 #pragma unroll
-		for (int q = 0; q < V; q++) if (ev[p0 + q]) evbits |= 1u << q;
+			for (int q = 0; q < V / 4; q++) {
+				const uint32_t wd = ((const uint32_t *) (ev + p0))[q];
+				evbits |= (((wd & 0x01010101u) * 0x01020408u) >> 24 & 0xfu) << (4 * q);
+			}
+		} else {
+#pragma unroll
+			for (int q = 0; q < V; q++) if (ev[p0 + q]) evbits |= 1u << q;
+		}
 		int c = 0; long long a = 0;
 #pragma unroll
 		for (int q = 0; q < V; q++) {
@@ -615,13 +627,15 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 		ec += misc->base_cov;
 		ea += (long long) misc->base_val;
 #pragma unroll
-		for (int q = 0; q < V; q++) { c_run[q] += ec; a_run[q] += ea; }
+		for (int q = 0; q < V; q++) {
+			c_run[q] += ec; a_run[q] += ea;
+			if (keep_rule(job, setop, c_run[q])) keepbits |= 1u << q;
+		}
+		keepbits &= evbits;
 	}
 
 	// breakpoints and kept segments of this thread; one packed block scan for both
-	int nbp_l = __popc(evbits), kept_l = 0;
-#pragma unroll
-	for (int q = 0; q < V; q++) if ((evbits >> q) & 1) kept_l += keep_rule(job, setop, c_run[q]) ? 1 : 0;
+	const int nbp_l = __popc(evbits), kept_l = __popc(keepbits);
 	int epack, tpack;
 	block_scan1(misc, nbp_l | (kept_l << 16), epack, tpack);
 	const int nbp = tpack & 0xffff, kept_total = tpack >> 16;
@@ -633,10 +647,10 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	}
 
 	// ---- 3. compact the breakpoints over the dead position arrays --------------------
-	double *bval = (double *) (smem + L.off_bval);
+	long long *bval = (long long *) (smem + L.off_bval);   // exact fixed-point sum of the segment
 	uint16_t *bpos = (uint16_t *) (smem + L.off_bpos);
 	uint16_t *bkid = (uint16_t *) (smem + L.off_bkid);
-	const bool row_op = !(job.op == OP_SUM || job.op == OP_MEAN) || !fast;
+	constexpr bool row_op = MODE == MODE_ROW;
 	{
 		int rank = epack & 0xffff, kidx = epack >> 16;
 		const int p0 = tid << VLOG;
@@ -645,17 +659,12 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 			if ((evbits >> q) & 1) {
 				bpos[rank] = (uint16_t) (p0 + q);
 				uint16_t kd = 0;
-				if (keep_rule(job, setop, c_run[q])) {
-					kd = BK_KEEP | (uint16_t) kidx;
+				if ((keepbits >> q) & 1) {
+					kd = BK_KEEP | (uint16_t) kidx++;
 					if (row_op || (c_run[q] >> COV_P_SHIFT) != 0) kd |= BK_SLOW;
-					else {
-						double v = (double) (a_run[q] + job.fx_base) * scale;
-						if (job.op == OP_MEAN) v = v / N;
-						bval[rank] = v;
-					}
-					kidx++;
 				}
 				bkid[rank] = kd;
+				bval[rank] = a_run[q];
 				rank++;
 			}
 		}
@@ -663,69 +672,108 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	__syncthreads();
 
 	// ---- 4. emit, one breakpoint per thread (coalesced stores) ---------------------------
-	const bool sorted_op = (job.op == OP_MEDIAN || job.op == OP_MWU);
-	const bool pearson = (job.op == OP_PEARSON);
 	const long long out_base = job.woff[w];
 	const int next_bp = misc->next_bp;
-	Row row; row.job = &job; row.cur = cur; row.nxt = nxt; row.b = 0;
 	unsigned long long slow = 0;
 	double auc = 0;
-	double mom[6] = {0, 0, 0, 0, 0, 0};
 
-	for (int base = 0; base < nbp; base += THREADS) {
-		const int r = base + tid;
-		uint16_t kd = 0;
-		if (r < nbp) kd = bkid[r];
-		const bool keep = (kd & BK_KEEP) != 0;
-		if (pearson) {
-			if (keep) {
-				const int bs = (int) (w0 + bpos[r]);
-				const int be = (r + 1 < nbp) ? (int) (w0 + bpos[r + 1]) : next_bp;
-				double X, Y;
-				row.b = bs;
-				row.get(0, X); row.get(1, Y);
-				const double len = (double) (be - bs);
-				double one[6] = {len, X * len, Y * len, 0, 0, 0};
-				merge6(mom, one);
-			}
-		} else if (!sorted_op) {
-			if (keep) {
-				const long long oi = out_base + (kd & BK_IDX);
-				const int bs = (int) (w0 + bpos[r]);
-				const int be = (r + 1 < nbp) ? (int) (w0 + bpos[r + 1]) : next_bp;
-				double v;
-				if (kd & BK_SLOW) { row.b = bs; v = row_eval(row); slow++; }
-				else v = bval[r];
-				if (oi < job.out_cap) {
-					job.out_start[oi] = bs;
-					job.out_end[oi] = be;
-					job.out_value[oi] = v;
+	if (MODE == MODE_FAST) {
+		for (int base = 0; base < nbp; base += THREADS) {
+			const int r = base + tid;
+			if (r >= nbp) break;
+			const uint16_t kd = bkid[r];
+			if (!(kd & BK_KEEP)) continue;
+			const long long oi = out_base + (kd & BK_IDX);
+			const int bs = (int) (w0 + bpos[r]);
+			const int be = (r + 1 < nbp) ? (int) (w0 + bpos[r + 1]) : next_bp;
+			double v = (double) (bval[r] + job.fx_base) * scale;   // correctly rounded exact sum
+			if (job.op == OP_MEAN) v = v / N;
+			if (oi < job.out_cap) {
+				job.out_start[oi] = bs;
+				job.out_end[oi] = be;
+				job.out_value[oi] = v;
+				if (kd & BK_SLOW) {
+					// an input was not representable: the fix-up kernel recomputes this
+					// segment with the reference's own operation order
+					const unsigned long long k = atomicAdd(job.slow_count, 1ull);
+					if (k < (unsigned long long) job.slow_cap) job.slow_list[k] = oi;
 				}
-				if (!isnan(v)) auc += (double) (be - bs) * v;
 			}
-		} else {
-			// one warp per kept segment, in lane order
-			int P = 1; while (P < N) P <<= 1;
-			SortKey *buf = (SortKey *) (smem + L.off_rows) + (size_t) warp * P;
-			unsigned todo = __ballot_sync(FULL, keep);
-			while (todo) {
-				const int src = __ffs(todo) - 1;
-				todo &= todo - 1;
-				const int rr = base + warp * 32 + src;
-				const int bs = (int) (w0 + bpos[rr]);
-				const int be = (rr + 1 < nbp) ? (int) (w0 + bpos[rr + 1]) : next_bp;
-				row.b = bs;
-				const double v = warp_sorted_eval(row, buf, P);
-				if (lane == 0) {
-					const long long oi = out_base + (bkid[rr] & BK_IDX);
+			if (!(kd & BK_SLOW) && !isnan(v)) auc += (double) (be - bs) * v;
+		}
+	} else {
+		const bool sorted_op = (job.op == OP_MEDIAN || job.op == OP_MWU);
+		const bool pearson = (job.op == OP_PEARSON);
+		Row row; row.job = &job; row.cur = cur; row.nxt = nxt; row.b = 0;
+		Mom mom = {0, 0, 0, 0, 0, 0};
+		for (int base = 0; base < nbp; base += THREADS) {
+			const int r = base + tid;
+			uint16_t kd = 0;
+			if (r < nbp) kd = bkid[r];
+			const bool keep = (kd & BK_KEEP) != 0;
+			if (pearson) {
+				if (keep) {
+					const int bs = (int) (w0 + bpos[r]);
+					const int be = (r + 1 < nbp) ? (int) (w0 + bpos[r + 1]) : next_bp;
+					double X, Y;
+					row.b = bs;
+					row.get(0, X); row.get(1, Y);
+					const double len = (double) (be - bs);
+					Mom one = {len, X * len, Y * len, 0, 0, 0};
+					merge_mom(mom, one);
+				}
+			} else if (!sorted_op) {
+				if (keep) {
+					const long long oi = out_base + (kd & BK_IDX);
+					const int bs = (int) (w0 + bpos[r]);
+					const int be = (r + 1 < nbp) ? (int) (w0 + bpos[r + 1]) : next_bp;
+					row.b = bs;
+					const double v = row_eval(row);
+					slow++;
 					if (oi < job.out_cap) {
 						job.out_start[oi] = bs;
 						job.out_end[oi] = be;
 						job.out_value[oi] = v;
 					}
 					if (!isnan(v)) auc += (double) (be - bs) * v;
-					slow++;
 				}
+			} else {
+				// one warp per kept segment, in lane order
+				int P = 1; while (P < N) P <<= 1;
+				SortKey *buf = (SortKey *) (smem + L.off_rows) + (size_t) warp * P;
+				unsigned todo = __ballot_sync(FULL, keep);
+				while (todo) {
+					const int src = __ffs(todo) - 1;
+					todo &= todo - 1;
+					const int rr = base + warp * 32 + src;
+					const int bs = (int) (w0 + bpos[rr]);
+					const int be = (rr + 1 < nbp) ? (int) (w0 + bpos[rr + 1]) : next_bp;
+					row.b = bs;
+					const double v = warp_sorted_eval(row, buf, P);
+					if (lane == 0) {
+						const long long oi = out_base + (bkid[rr] & BK_IDX);
+						if (oi < job.out_cap) {
+							job.out_start[oi] = bs;
+							job.out_end[oi] = be;
+							job.out_value[oi] = v;
+						}
+						if (!isnan(v)) auc += (double) (be - bs) * v;
+						slow++;
+					}
+				}
+			}
+		}
+		if (pearson) {
+			for (int d = 16; d > 0; d >>= 1) {
+				Mom other;
+				other.n = __shfl_down_sync(FULL, mom.n, d); other.sx = __shfl_down_sync(FULL, mom.sx, d);
+				other.sy = __shfl_down_sync(FULL, mom.sy, d); other.txx = __shfl_down_sync(FULL, mom.txx, d);
+				other.txy = __shfl_down_sync(FULL, mom.txy, d); other.tyy = __shfl_down_sync(FULL, mom.tyy, d);
+				if (lane + d < 32) merge_mom(mom, other);
+			}
+			if (lane == 0) {
+				double *wm = misc->wmom[warp];
+				wm[0] = mom.n; wm[1] = mom.sx; wm[2] = mom.sy; wm[3] = mom.txx; wm[4] = mom.txy; wm[5] = mom.tyy;
 			}
 		}
 	}
@@ -735,18 +783,10 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 		auc += __shfl_down_sync(FULL, auc, d);
 		slow += __shfl_down_sync(FULL, slow, d);
 	}
-	if (pearson) {
-		for (int d = 16; d > 0; d >>= 1) {
-			double other[6];
-			for (int k = 0; k < 6; k++) other[k] = __shfl_down_sync(FULL, mom[k], d);
-			if (lane + d < 32) merge6(mom, other);
-		}
-		if (lane == 0) for (int k = 0; k < 6; k++) misc->wmom[warp][k] = mom[k];
-	}
 	if (lane == 0) { misc->wauc[warp] = auc; misc->wsum[warp] = (long long) slow; }
 	__syncthreads();
 	if (tid == 0) {
-		if (pearson && job.moments) {
+		if (MODE == MODE_ROW && job.op == OP_PEARSON && job.moments) {
 			double t[6] = {0, 0, 0, 0, 0, 0};
 			for (int k = 0; k < WARPS; k++) merge6(t, misc->wmom[k]);
 			for (int k = 0; k < 6; k++) job.moments[(size_t) w * 6 + k] = t[k];
@@ -782,15 +822,18 @@ __global__ void __launch_bounds__(THREADS) count_kernel(const Job job) {
 	}
 	__syncthreads();
 	for (int w = wbeg; w < wend; w++) {
-		process_window<false, VLOG, 2>(job, w, smem, L, 0, 0.0, 0.0, 0.0);
+		process_window<MODE_COUNT, VLOG, 2>(job, w, smem, L, 0, 0.0, 0.0, 0.0);
 		__syncthreads();
 		for (int i = threadIdx.x; i < job.N; i += THREADS) cur[i] = nxt[i];
 		__syncthreads();
 	}
+	// the cursor row after the last window (row nw) closes the table for the fix-up kernel
+	if (wend == job.nw)
+		for (int i = threadIdx.x; i < job.N; i += THREADS) job.cursor[(size_t) job.nw * job.N + i] = cur[i];
 }
 
-template <int VLOG, int LIMBS>
-__global__ void __launch_bounds__(THREADS) emit_kernel(const Job job, int lw, double inv_scale, double lim, double scale, int rowbuf) {
+template <int MODE, int VLOG, int LIMBS>
+__global__ void __launch_bounds__(THREADS, MODE == MODE_FAST ? 3 : 1) emit_kernel(const Job job, int lw, double inv_scale, double lim, double scale, int rowbuf) {
 	extern __shared__ __align__(16) unsigned char smem[];
 	const Layout L = make_layout(job.wlog, job.N, true, LIMBS, rowbuf);
 	int32_t *cur = (int32_t *) (smem + L.off_cur);
@@ -801,12 +844,12 @@ __global__ void __launch_bounds__(THREADS) emit_kernel(const Job job, int lw, do
 		const long long o = job.off[i];
 		toff[i] = o;
 		tn[i] = (int) (job.off[i + 1] - o);
-		tmd[i] = job.fast ? job.dflt_fx[i] : 0;
+		tmd[i] = MODE == MODE_FAST ? job.dflt_fx[i] : 0;
 	}
 	for (int w = blockIdx.x; w < job.nw; w += gridDim.x) {
 		for (int i = threadIdx.x; i < job.N; i += THREADS) cur[i] = job.cursor[(size_t) w * job.N + i];
 		__syncthreads();
-		process_window<true, VLOG, LIMBS>(job, w, smem, L, lw, inv_scale, lim, scale);
+		process_window<MODE, VLOG, LIMBS>(job, w, smem, L, lw, inv_scale, lim, scale);
 	}
 }
 
@@ -894,18 +937,18 @@ cudaError_t launch_scan_counts(const uint32_t *wcount, int64_t *woff, int nw, cu
 	return cudaGetLastError();
 }
 
-template <int VLOG, int LIMBS>
+template <int MODE, int VLOG, int LIMBS>
 static cudaError_t launch_emit_v(const Job &job, int lw, double inv_scale, double lim, double scale, int rowbuf, cudaStream_t s) {
 	size_t smem = make_layout(job.wlog, job.N, true, LIMBS, rowbuf).total;
 	int dev = 0, sms = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-	cudaError_t e = cudaFuncSetAttribute(emit_kernel<VLOG, LIMBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+	cudaError_t e = cudaFuncSetAttribute(emit_kernel<MODE, VLOG, LIMBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 	if (e != cudaSuccess) return e;
 	int per = 1;
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, emit_kernel<VLOG, LIMBS>, THREADS, smem);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, emit_kernel<MODE, VLOG, LIMBS>, THREADS, smem);
 	int grid = min(job.nw, sms * max(per, 1));
-	emit_kernel<VLOG, LIMBS><<<grid, THREADS, smem, s>>>(job, lw, inv_scale, lim, scale, rowbuf);
+	emit_kernel<MODE, VLOG, LIMBS><<<grid, THREADS, smem, s>>>(job, lw, inv_scale, lim, scale, rowbuf);
 	return cudaGetLastError();
 }
 
@@ -917,8 +960,9 @@ cudaError_t launch_emit(const Job &job, cudaStream_t s) {
 	if (job.fast && job.fx_mbits > 29 - l2n + lw) limbs = 3;
 	double inv_scale = ldexp(1.0, -job.fx_q), scale = ldexp(1.0, job.fx_q), lim = ldexp(1.0, job.fx_mbits);
 	int rowbuf = row_buffer_bytes(job.N, job.op);
-#define WB_EMIT(V) (limbs == 2 ? launch_emit_v<V, 2>(job, lw, inv_scale, lim, scale, rowbuf, s) \
-                               : launch_emit_v<V, 3>(job, lw, inv_scale, lim, scale, rowbuf, s))
+#define WB_EMIT(V) (!job.fast ? launch_emit_v<MODE_ROW, V, 2>(job, lw, inv_scale, lim, scale, rowbuf, s) \
+                  : limbs == 2 ? launch_emit_v<MODE_FAST, V, 2>(job, lw, inv_scale, lim, scale, rowbuf, s) \
+                               : launch_emit_v<MODE_FAST, V, 3>(job, lw, inv_scale, lim, scale, rowbuf, s))
 	switch (job.wlog) {
 	case 10: return WB_EMIT(2);
 	case 11: return WB_EMIT(3);
@@ -926,6 +970,31 @@ cudaError_t launch_emit(const Job &job, cudaStream_t s) {
 	}
 #undef WB_EMIT
 	return cudaErrorInvalidValue;
+}
+
+// Segments of the fast path whose inputs were not representable in fixed point
+// (NaN, Inf, out of range): recompute them exactly as the reference does.  The
+// cursor rows of the window that holds the segment start bound the search.
+__global__ void fixup_kernel(const Job job, long long count) {
+	const long long k = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= count) return;
+	const long long oi = job.slow_list[k];
+	const int bs = job.out_start[oi];
+	const int w = (int) (((long long) bs - job.p0) >> job.wlog);
+	Row row;
+	row.job = &job;
+	row.cur = job.cursor + (size_t) w * job.N;
+	row.nxt = job.cursor + (size_t) (w + 1) * job.N;
+	row.b = bs;
+	const double v = row_eval(row);
+	job.out_value[oi] = v;
+	if (!isnan(v) && job.auc_fix) atomicAdd(job.auc_fix, (double) (job.out_end[oi] - bs) * v);
+}
+
+cudaError_t launch_fixup(const Job &job, long long count, cudaStream_t s) {
+	if (count <= 0) return cudaSuccess;
+	fixup_kernel<<<(unsigned) ((count + 127) / 128), 128, 0, s>>>(job, count);
+	return cudaGetLastError();
 }
 
 cudaError_t launch_sample_maxabs(const double *value, int64_t n, int64_t stride, double *out2, cudaStream_t s) {

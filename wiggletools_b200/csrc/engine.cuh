@@ -55,6 +55,9 @@ struct Job {
 	double *auc_partial;    // [nw] per-window sum of (end-start)*value (NaN skipped), or null
 	unsigned long long *slow_count; // segments that took the row path
 	double *moments;        // [nw * 6] per-window Pearson moments (OP_PEARSON), or null
+	long long *slow_list;   // fast path: output indices of segments to recompute (fix-up kernel)
+	long long slow_cap;
+	double *auc_fix;        // AUC contribution of the fixed-up segments
 	// fixed-point fast path (sum / mean)
 	int fast;               // 1: scan path enabled for this op
 	int fx_q;               // value = m * 2^fx_q
@@ -77,11 +80,26 @@ __host__ __device__ inline void merge6(double *a, const double *b) {
 	a[0] = n; a[1] += b[1]; a[2] += b[2];
 }
 
+// register-friendly form of the same merge (no arrays)
+struct Mom { double n, sx, sy, txx, txy, tyy; };
+__host__ __device__ inline void merge_mom(Mom &a, const Mom &b) {
+	if (b.n == 0) return;
+	if (a.n == 0) { a = b; return; }
+	const double n = a.n + b.n;
+	const double dx = a.sx / a.n - b.sx / b.n, dy = a.sy / a.n - b.sy / b.n;
+	const double w = a.n * b.n / n;
+	a.txx += b.txx + w * dx * dx;
+	a.txy += b.txy + w * dx * dy;
+	a.tyy += b.tyy + w * dy * dy;
+	a.n = n; a.sx += b.sx; a.sy += b.sy;
+}
+
 // launch helpers implemented in engine.cu
 size_t window_smem_bytes(int wlog, int N, bool emit, int op);
 cudaError_t launch_count(const Job &job, cudaStream_t s);
 cudaError_t launch_scan_counts(const uint32_t *wcount, int64_t *woff, int nw, cudaStream_t s);
 cudaError_t launch_emit(const Job &job, cudaStream_t s);
+cudaError_t launch_fixup(const Job &job, long long count, cudaStream_t s);
 cudaError_t launch_sample_maxabs(const double *value, int64_t n, int64_t stride, double *out2, cudaStream_t s);
 cudaError_t launch_reduce_auc(const double *partial, int nw, double *out, cudaStream_t s);
 cudaError_t launch_reduce_moments(const double *moments, int nw, double *out6, cudaStream_t s);
