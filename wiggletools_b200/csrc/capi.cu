@@ -64,7 +64,7 @@ struct wb200_ctx {
 	std::string err;
 	wb200_stats stats{};
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-	DevBuf in_start, in_end, in_value, off, dflt, dflt_fx, cursor, wcount, woff, aucp, small, moments, slow_list;
+	DevBuf in_start, in_end, in_value, off, dflt, dflt_fx, cursor, state, aucp, small, moments, slow_list;
 	DevBuf out_start, out_end, out_value;
 	HostBuf h_small, h_meta, h_start, h_end, h_value;
 };
@@ -195,7 +195,6 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 	job.start = d_start; job.end = d_end; job.value = d_value;
 	job.N = N; job.n1 = n1; job.strict = strict ? 1 : 0; job.op = op;
 	job.p0 = pos_lo; job.wlog = wlog; job.nw = nw;
-	job.strip = (int) std::min<int64_t>(64, std::max<int64_t>(4, nw / ((int64_t) ctx->sms * 8)));
 	job.out_start = d_out_start; job.out_end = d_out_end; job.out_value = d_out_value; job.out_cap = out_cap;
 
 	// small tables
@@ -209,19 +208,20 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 	memcpy(hm_off, h_off, (N + 1) * sizeof(int64_t));
 	memcpy(hm_dflt, h_dflt, N * sizeof(double));
 	CK(ctx->cursor.ensure((size_t) (nw + 1) * N * sizeof(int32_t)));
-	CK(ctx->wcount.ensure((size_t) nw * sizeof(uint32_t)));
-	CK(ctx->woff.ensure((size_t) (nw + 1) * sizeof(int64_t)));
+	CK(ctx->state.ensure((size_t) nw * sizeof(unsigned long long)));
 	CK(ctx->aucp.ensure((size_t) nw * sizeof(double)));
 	CK(ctx->small.ensure(128));
 	CK(ctx->h_small.ensure(128));
 	if (moments_out) { CK(ctx->moments.ensure((size_t) nw * 6 * sizeof(double))); job.moments = ctx->moments.as<double>(); }
 	job.off = ctx->off.as<int64_t>(); job.dflt = ctx->dflt.as<double>(); job.dflt_fx = ctx->dflt_fx.as<int64_t>();
-	job.cursor = ctx->cursor.as<int32_t>(); job.wcount = ctx->wcount.as<uint32_t>(); job.woff = ctx->woff.as<int64_t>();
+	job.cursor = ctx->cursor.as<int32_t>(); job.state = ctx->state.as<unsigned long long>();
 	job.auc_partial = ctx->aucp.as<double>();
 	// small: [0..1] sample result, [2] auc, [3] slow count
 	double *d_small = ctx->small.as<double>();
 	job.slow_count = (unsigned long long *) (d_small + 3);
 	job.auc_fix = d_small + 10;
+	job.total = (long long *) (d_small + 11);
+	job.ticket = (unsigned int *) (d_small + 12);
 
 	CK(cudaEventRecord(ctx->ev[0], s));
 	CK(cudaMemcpyAsync(ctx->off.p, hm_off, (N + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
@@ -285,18 +285,20 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 	if (need > 227 * 1024) return fail(ctx, WB200_EUNSUPPORTED, "window does not fit shared memory; lower WB200_WINDOW");
 
 	CK(cudaEventRecord(ctx->ev[1], s));
-	CK(launch_count(job, s));
-	CK(launch_scan_counts(job.wcount, ctx->woff.as<int64_t>(), nw, s));
+	int64_t max_len = 0;
+	for (int i = 0; i < N; i++) max_len = std::max<int64_t>(max_len, h_off[i + 1] - h_off[i]);
+	CK(cudaMemsetAsync(ctx->state.p, 0, (size_t) nw * sizeof(unsigned long long), s));
+	CK(launch_cursor(job, max_len, s));
 	CK(cudaEventRecord(ctx->ev[2], s));
 	CK(launch_emit(job, s));
 	CK(launch_reduce_auc(job.auc_partial, nw, d_small + 2, s));
 	if (moments_out) { CK(launch_reduce_moments(job.moments, nw, d_small + 4, s)); st.kernels++; }
 	CK(cudaEventRecord(ctx->ev[3], s));
-	st.kernels += 4;
+	st.kernels += 3;
 
 	// S, AUC, slow-path count
 	int64_t *h_small = ctx->h_small.as<int64_t>();
-	CK(cudaMemcpyAsync(h_small, ctx->woff.as<int64_t>() + nw, 8, cudaMemcpyDeviceToHost, s));
+	CK(cudaMemcpyAsync(h_small, d_small + 11, 8, cudaMemcpyDeviceToHost, s));
 	CK(cudaMemcpyAsync(h_small + 2, d_small + 2, 64, cudaMemcpyDeviceToHost, s));
 	CK(cudaStreamSynchronize(s));
 	const int64_t S = h_small[0];
@@ -361,7 +363,7 @@ void wb200_destroy(wb200_ctx *ctx) {
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	DevBuf *d[] = {&ctx->in_start, &ctx->in_end, &ctx->in_value, &ctx->off, &ctx->dflt, &ctx->dflt_fx, &ctx->cursor,
-	               &ctx->wcount, &ctx->woff, &ctx->aucp, &ctx->small, &ctx->moments, &ctx->slow_list, &ctx->out_start, &ctx->out_end, &ctx->out_value};
+	               &ctx->state, &ctx->aucp, &ctx->small, &ctx->moments, &ctx->slow_list, &ctx->out_start, &ctx->out_end, &ctx->out_value};
 	for (auto *b : d) b->release();
 	HostBuf *h[] = {&ctx->h_small, &ctx->h_meta, &ctx->h_start, &ctx->h_end, &ctx->h_value};
 	for (auto *b : h) b->release();

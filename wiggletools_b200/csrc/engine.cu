@@ -64,6 +64,8 @@ struct Misc {                        // scalars, warp totals
 	int nbp;                         // breakpoints of the window
 	unsigned long long base_val;     // fixed-point value carried into the window
 	long long out_base;              // output offset of the window
+	int ticket;                      // window index drawn by this CTA
+	int pad0;
 	long long wsum[WARPS];           // warp totals (value scan / slow counter)
 	int wcov[WARPS];                 // warp totals (cover scan)
 	int wkeep[WARPS];                // warp totals (counts scan)
@@ -419,6 +421,10 @@ __device__ __forceinline__ void block_scan1(Misc *misc, int c, int &ec, int &tc)
 	__syncthreads();
 }
 
+constexpr unsigned long long LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_VALUE = (1ull << 62) - 1;
+__device__ __forceinline__ unsigned long long ld_volatile(const unsigned long long *p) { return *(const volatile unsigned long long *) p; }
+__device__ __forceinline__ void st_volatile(unsigned long long *p, unsigned long long v) { *(volatile unsigned long long *) p = v; }
+
 __device__ __forceinline__ bool keep_rule(const Job &job, bool setop, int c) {
 	const int covA = c & COV_MASK, covB = (c >> COV_B_SHIFT) & COV_MASK;
 	if (setop) return covA > 0 && covB > 0;            // src/setComparisons.c:48-54
@@ -444,7 +450,7 @@ __device__ __forceinline__ bool keep_rule(const Job &job, bool setop, int c) {
 //  3. compact: flagged positions (breakpoints) are written as a dense list over
 //              the now-dead position arrays; kept ones carry their output rank.
 //  4. emit   : one breakpoint per thread, coalesced 16 B/segment stores.
-enum { MODE_COUNT = 0, MODE_FAST = 1, MODE_ROW = 2 };
+enum { MODE_FAST = 1, MODE_ROW = 2 };
 
 template <int MODE, int VLOG, int LIMBS>
 __device__ void process_window(const Job &job, int w, unsigned char *smem, const Layout &L,
@@ -465,7 +471,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	const long long w0 = job.p0 + ((long long) w << job.wlog);
 	const long long w1 = w0 + W;
 	const bool setop = (job.op == OP_TTEST || job.op == OP_MWU);
-	constexpr bool EMIT = MODE != MODE_COUNT;
+	constexpr bool EMIT = true;
 	constexpr bool fast = MODE == MODE_FAST;      // fixed-point value path (sum / mean)
 
 	// ---- clear the position arrays -------------------------------------------
@@ -640,11 +646,9 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	block_scan1(misc, nbp_l | (kept_l << 16), epack, tpack);
 	const int nbp = tpack & 0xffff, kept_total = tpack >> 16;
 
-	if (!EMIT) {
-		if (tid == 0) job.wcount[w] = (uint32_t) kept_total;
-		for (int i = tid; i < N; i += THREADS) job.cursor[(size_t) w * N + i] = cur[i];
-		return;
-	}
+	// publish this window's segment count so that later windows can start their
+	// look-back while we compact (single-pass chained scan over windows)
+	if (tid == 0) st_volatile(&job.state[w], LB_AGG | (unsigned long long) kept_total);
 
 	// ---- 3. compact the breakpoints over the dead position arrays --------------------
 	long long *bval = (long long *) (smem + L.off_bval);   // exact fixed-point sum of the segment
@@ -671,8 +675,36 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	}
 	__syncthreads();
 
+	// ---- output offset: decoupled look-back over the preceding windows --------------------
+	// Windows are drawn from a global ticket counter, so every predecessor has been
+	// started by a resident CTA and will publish; lane l inspects window w-1-l.
+	if (warp == 0) {
+		unsigned long long sum = 0;
+		int p = w - 1;
+		while (true) {
+			const int idx = p - lane;
+			unsigned long long st;
+			do {
+				st = idx >= 0 ? ld_volatile(&job.state[idx]) : LB_PREFIX;   // before window 0: prefix 0
+			} while (__any_sync(FULL, (st >> 62) == 0));
+			const unsigned pm = __ballot_sync(FULL, (st >> 62) == 2);
+			const int first = pm ? __ffs(pm) - 1 : 32;
+			unsigned long long v = (lane <= first) ? (st & LB_VALUE) : 0;
+			for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(FULL, v, d);
+			sum += __shfl_sync(FULL, v, 0);
+			if (pm) break;
+			p -= 32;
+		}
+		if (lane == 0) {
+			misc->out_base = (long long) sum;
+			st_volatile(&job.state[w], LB_PREFIX | (sum + (unsigned long long) kept_total));
+			if (w == job.nw - 1) *job.total = (long long) (sum + (unsigned long long) kept_total);
+		}
+	}
+	__syncthreads();
+
 	// ---- 4. emit, one breakpoint per thread (coalesced stores) ---------------------------
-	const long long out_base = job.woff[w];
+	const long long out_base = misc->out_base;
 	const int next_bp = misc->next_bp;
 	unsigned long long slow = 0;
 	double auc = 0;
@@ -799,37 +831,21 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	__syncthreads();
 }
 
-// count kernel: one CTA walks a strip of consecutive windows so that each
-// track's cursor is chained from window to window (binary search only at the
-// strip start); writes the per-window segment counts and the cursor table.
-template <int VLOG>
-__global__ void __launch_bounds__(THREADS) count_kernel(const Job job) {
-	extern __shared__ __align__(16) unsigned char smem[];
-	const Layout L = make_layout(job.wlog, job.N, false, 0, 0);
-	int32_t *cur = (int32_t *) (smem + L.off_cur);
-	int32_t *nxt = (int32_t *) (smem + L.off_nxt);
-	int32_t *tn = (int32_t *) (smem + L.off_tn);
-	long long *toff = (long long *) (smem + L.off_toff);
-	const int wbeg = blockIdx.x * job.strip;
-	const int wend = min(job.nw, wbeg + job.strip);
-	if (wbeg >= wend) return;
-	const long long w0 = job.p0 + ((long long) wbeg << job.wlog);
-	for (int i = threadIdx.x; i < job.N; i += THREADS) {
-		const long long o = job.off[i];
-		const int n = (int) (job.off[i + 1] - o);
-		toff[i] = o; tn[i] = n;
-		cur[i] = lower_bound_ge(job.end + o, n, w0);
-	}
-	__syncthreads();
-	for (int w = wbeg; w < wend; w++) {
-		process_window<MODE_COUNT, VLOG, 2>(job, w, smem, L, 0, 0.0, 0.0, 0.0);
-		__syncthreads();
-		for (int i = threadIdx.x; i < job.N; i += THREADS) cur[i] = nxt[i];
-		__syncthreads();
-	}
-	// the cursor row after the last window (row nw) closes the table for the fix-up kernel
-	if (wend == job.nw)
-		for (int i = threadIdx.x; i < job.N; i += THREADS) job.cursor[(size_t) job.nw * job.N + i] = cur[i];
+// cursor kernel: cursor[w][i] = first interval of track i whose end reaches the
+// start of window w.  One thread per interval: interval j is that cursor for every
+// window whose start lies in (end[j-1], end[j]] -- usually none or one.  Reads the
+// end coordinates once (4 B/interval); row nw closes the table.
+__global__ void __launch_bounds__(256) cursor_kernel(const Job job) {
+	const int i = blockIdx.y;
+	const long long o = job.off[i];
+	const int n = (int) (job.off[i + 1] - o);
+	const long long j = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (j > n) return;
+	const long long e_prev = j > 0 ? (long long) job.end[o + j - 1] : LLONG_MIN / 2;
+	const long long e = j < n ? (long long) job.end[o + j] : LLONG_MAX / 2;
+	long long wlo = e_prev < job.p0 ? 0 : ((e_prev - job.p0) >> job.wlog) + 1;
+	long long whi = e < job.p0 ? -1 : min((long long) job.nw, (e - job.p0) >> job.wlog);
+	for (long long w = wlo; w <= whi; w++) job.cursor[(size_t) w * job.N + i] = (int32_t) j;
 }
 
 template <int MODE, int VLOG, int LIMBS>
@@ -846,34 +862,18 @@ __global__ void __launch_bounds__(THREADS, MODE == MODE_FAST ? 3 : 1) emit_kerne
 		tn[i] = (int) (job.off[i + 1] - o);
 		tmd[i] = MODE == MODE_FAST ? job.dflt_fx[i] : 0;
 	}
-	for (int w = blockIdx.x; w < job.nw; w += gridDim.x) {
+	Misc *misc = (Misc *) smem;
+	while (true) {
+		// windows are handed out in order: the look-back only ever waits on windows
+		// that a resident CTA has already started
+		if (threadIdx.x == 0) misc->ticket = (int) atomicAdd(job.ticket, 1u);
+		__syncthreads();
+		const int w = misc->ticket;
+		if (w >= job.nw) break;
 		for (int i = threadIdx.x; i < job.N; i += THREADS) cur[i] = job.cursor[(size_t) w * job.N + i];
 		__syncthreads();
 		process_window<MODE, VLOG, LIMBS>(job, w, smem, L, lw, inv_scale, lim, scale);
 	}
-}
-
-// exclusive scan of the per-window counts (single CTA; nw is small)
-__global__ void __launch_bounds__(1024) scan_counts_kernel(const uint32_t *wcount, int64_t *woff, int nw) {
-	__shared__ long long wtot[32];
-	__shared__ long long carry_s;
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	if (tid == 0) carry_s = 0;
-	__syncthreads();
-	for (int base = 0; base < nw; base += 1024) {
-		int i = base + tid;
-		long long v = (i < nw) ? wcount[i] : 0, inc = v;
-		for (int d = 1; d < 32; d <<= 1) { long long t = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += t; }
-		if (lane == 31) wtot[warp] = inc;
-		__syncthreads();
-		long long b = carry_s;
-		for (int k = 0; k < warp; k++) b += wtot[k];
-		if (i < nw) woff[i] = b + inc - v;
-		__syncthreads();
-		if (tid == 1023) carry_s = b + inc;
-		__syncthreads();
-	}
-	if (tid == 0) woff[nw] = carry_s;
 }
 
 // max |v| over a strided sample of the values, and the largest exponent seen:
@@ -913,27 +913,9 @@ size_t window_smem_bytes(int wlog, int N, bool emit, int op) {
 	return make_layout(wlog, N, emit, 3, emit ? row_buffer_bytes(N, op) : 0).total;
 }
 
-template <int VLOG>
-static cudaError_t launch_count_v(const Job &job, cudaStream_t s) {
-	size_t smem = make_layout(job.wlog, job.N, false, 0, 0).total;
-	cudaError_t e = cudaFuncSetAttribute(count_kernel<VLOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-	if (e != cudaSuccess) return e;
-	int strips = (job.nw + job.strip - 1) / job.strip;
-	count_kernel<VLOG><<<strips, THREADS, smem, s>>>(job);
-	return cudaGetLastError();
-}
-
-cudaError_t launch_count(const Job &job, cudaStream_t s) {
-	switch (job.wlog) {           // window = THREADS << VLOG base pairs
-	case 10: return launch_count_v<2>(job, s);
-	case 11: return launch_count_v<3>(job, s);
-	case 12: return launch_count_v<4>(job, s);
-	}
-	return cudaErrorInvalidValue;
-}
-
-cudaError_t launch_scan_counts(const uint32_t *wcount, int64_t *woff, int nw, cudaStream_t s) {
-	scan_counts_kernel<<<1, 1024, 0, s>>>(wcount, woff, nw);
+cudaError_t launch_cursor(const Job &job, int64_t max_track_len, cudaStream_t s) {
+	dim3 grid((unsigned) ((max_track_len + 1 + 255) / 256), (unsigned) job.N);
+	cursor_kernel<<<grid, 256, 0, s>>>(job);
 	return cudaGetLastError();
 }
 

@@ -42,11 +42,11 @@ struct Job {
 	int64_t p0;             // position of window 0, slot 0
 	int wlog;               // log2(window size in bp)
 	int nw;                 // number of windows
-	int strip;              // windows per count-kernel strip
 	// scratch
 	int32_t *cursor;        // [(nw+1) * N] first interval of track i with end >= window start (row nw: end of data)
-	uint32_t *wcount;       // [nw] segments emitted by each window
-	const int64_t *woff;    // [nw + 1] exclusive scan of wcount
+	unsigned long long *state; // [nw] look-back words: 2 flag bits | segments (aggregate or inclusive prefix)
+	unsigned int *ticket;   // window ticket counter
+	long long *total;       // S, written by the last window
 	// outputs
 	int32_t *out_start;
 	int32_t *out_end;
@@ -96,8 +96,7 @@ __host__ __device__ inline void merge_mom(Mom &a, const Mom &b) {
 
 // launch helpers implemented in engine.cu
 size_t window_smem_bytes(int wlog, int N, bool emit, int op);
-cudaError_t launch_count(const Job &job, cudaStream_t s);
-cudaError_t launch_scan_counts(const uint32_t *wcount, int64_t *woff, int nw, cudaStream_t s);
+cudaError_t launch_cursor(const Job &job, int64_t max_track_len, cudaStream_t s);
 cudaError_t launch_emit(const Job &job, cudaStream_t s);
 cudaError_t launch_fixup(const Job &job, long long count, cudaStream_t s);
 cudaError_t launch_sample_maxabs(const double *value, int64_t n, int64_t stride, double *out2, cudaStream_t s);
