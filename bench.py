@@ -9,7 +9,7 @@ dominant kernel and the reference's CPU path timed beside it.
 
 A step = one pass of the hot path over the whole synthetic genome (24 hg38-like
 chromosomes, 3.1 Gbp, 64 tracks of ~1.2e7 intervals): per chromosome one
-wb200_reduce_device call (count kernel, scan, emit kernel) on inputs resident in
+wb200_reduce_device call (cursor kernel, single-pass emit kernel) on inputs resident in
 HBM.  With N GPUs the chromosomes are sharded across ranks (no data-path
 collective); the whole-genome AUC scalar is all-reduced over NCCL.
 """
@@ -149,7 +149,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    cores = min(os.cpu_count() or 1, 32)
+    cores = os.cpu_count() or 1
     mbp = 8.0 * (64.0 / N_TRACKS) ** 2          # ~1 s per step per core at N=64
     times = []
     for i in range(args.warmup + args.steps):
@@ -287,10 +287,15 @@ def main():
     t_emit = sum(r[3] for r in per_launch) / 1e3
     t_count = sum(r[2] for r in per_launch) / 1e3
     achieved = by / t_emit / 1e9 if t_emit > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu capture
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("emit_kernel_dram_bytes_per_algorithmic_byte")
     roofline = {"bound": "hbm", "kernel": "emit_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_step": by / args.steps,
-                "emit_ms_per_step": 1e3 * t_emit / args.steps, "count_ms_per_step": 1e3 * t_count / args.steps,
+                "frac": achieved / peak, "traffic": (traffic * by / len(per_launch)) if traffic else None,
+                "peak_source": peak_src, "algorithmic_bytes_per_step": by / args.steps,
+                "algorithmic_bytes_per_launch": by / max(1, len(per_launch)),
+                "emit_ms_per_step": 1e3 * t_emit / args.steps, "cursor_ms_per_step": 1e3 * t_count / args.steps,
                 "path_frac": (by / (t_emit + t_count) / 1e9) / peak if t_emit + t_count > 0 else 0.0}
     launches = sum(r[4] for r in per_launch)
     seg_local = sum(sh["S"] for sh in shards)
@@ -309,7 +314,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cores = min(os.cpu_count() or 1, 32)
+        cores = os.cpu_count() or 1
         cpu = cpu_reference_sample(N_TRACKS, 12.0 * (64.0 / N_TRACKS) ** 2, cores)
 
     if rank == 0:

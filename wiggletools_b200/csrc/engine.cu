@@ -31,6 +31,7 @@
 // per-window cursor table) and emit_kernel (steps 1-5 with values), with a
 // scan of the per-window counts in between.
 #include "engine.cuh"
+#include <cuda_pipeline.h>
 #include <cfloat>
 #include <climits>
 #include <cmath>
@@ -64,7 +65,7 @@ struct Misc {                        // scalars, warp totals
 	int nbp;                         // breakpoints of the window
 	unsigned long long base_val;     // fixed-point value carried into the window
 	long long out_base;              // output offset of the window
-	int ticket;                      // window index drawn by this CTA
+	int ticket, ticket1, ticket2;    // window indices drawn by this CTA (current, next, after next)
 	int pad0;
 	long long wsum[WARPS];           // warp totals (value scan / slow counter)
 	int wcov[WARPS];                 // warp totals (cover scan)
@@ -78,7 +79,7 @@ static_assert(sizeof(Misc) <= MISC_BYTES, "Misc must fit its shared-memory slot"
 constexpr uint16_t BK_KEEP = 0x8000, BK_SLOW = 0x4000, BK_IDX = 0x3fff;
 
 struct Layout {
-	size_t off_cur, off_nxt, off_tn, off_toff, off_tmd, off_cov, off_limb, off_ev, off_rows, total;
+	size_t off_cur, off_cur2, off_nxt, off_tn, off_toff, off_tmd, off_cov, off_limb, off_ev, off_rows, total;
 	// after the scan the position arrays are dead; the dense breakpoint list aliases them:
 	size_t off_bpos, off_bkid, off_bval;
 };
@@ -89,6 +90,7 @@ __host__ __device__ inline Layout make_layout(int wlog, int N, bool emit, int li
 	size_t o = MISC_BYTES;
 	const size_t nn = (size_t) (N + 4) / 4 * 16;
 	L.off_cur = o;  o += nn;
+	L.off_cur2 = o; o += nn;
 	L.off_nxt = o;  o += nn;
 	L.off_tn = o;   o += nn;
 	L.off_toff = o; o += 2 * nn;
@@ -425,11 +427,13 @@ constexpr unsigned long long LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_VAL
 __device__ __forceinline__ unsigned long long ld_volatile(const unsigned long long *p) { return *(const volatile unsigned long long *) p; }
 __device__ __forceinline__ void st_volatile(unsigned long long *p, unsigned long long v) { *(volatile unsigned long long *) p = v; }
 
-__device__ __forceinline__ bool keep_rule(const Job &job, bool setop, int c) {
-	const int covA = c & COV_MASK, covB = (c >> COV_B_SHIFT) & COV_MASK;
-	if (setop) return covA > 0 && covB > 0;            // src/setComparisons.c:48-54
-	if (job.strict) return covA == job.N;              // src/multiplexer.c:123-128
-	return covA > 0;                                   // gaps are skipped, :112-115
+// A segment is emitted when enough tracks cover it: any track (gaps are skipped,
+// src/multiplexer.c:112-115), all N under `strict` (:123-128), or at least one of
+// each set for the set comparisons (src/setComparisons.c:48-54).  thr = 1, N, 0.
+__device__ __forceinline__ bool keep_rule(int thr, int c) {
+	const int covA = c & COV_MASK;
+	if (thr) return covA >= thr;
+	return covA > 0 && ((c >> COV_B_SHIFT) & COV_MASK) > 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -453,11 +457,10 @@ __device__ __forceinline__ bool keep_rule(const Job &job, bool setop, int c) {
 enum { MODE_FAST = 1, MODE_ROW = 2 };
 
 template <int MODE, int VLOG, int LIMBS>
-__device__ void process_window(const Job &job, int w, unsigned char *smem, const Layout &L,
+__device__ void process_window(const Job &job, int w, unsigned char *smem, const Layout &L, int32_t *cur,
                                int lw, double inv_scale, double lim, double scale) {
 	constexpr int V = 1 << VLOG, W = THREADS << VLOG;
 	Misc *misc = (Misc *) smem;
-	int32_t *cur = (int32_t *) (smem + L.off_cur);
 	int32_t *nxt = (int32_t *) (smem + L.off_nxt);
 	const int32_t *tn = (const int32_t *) (smem + L.off_tn);
 	const long long *toff = (const long long *) (smem + L.off_toff);
@@ -471,6 +474,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	const long long w0 = job.p0 + ((long long) w << job.wlog);
 	const long long w1 = w0 + W;
 	const bool setop = (job.op == OP_TTEST || job.op == OP_MWU);
+	const int thr = setop ? 0 : (job.strict ? N : 1);
 	constexpr bool EMIT = true;
 	constexpr bool fast = MODE == MODE_FAST;      // fixed-point value path (sum / mean)
 
@@ -635,7 +639,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 #pragma unroll
 		for (int q = 0; q < V; q++) {
 			c_run[q] += ec; a_run[q] += ea;
-			if (keep_rule(job, setop, c_run[q])) keepbits |= 1u << q;
+			if (keep_rule(thr, c_run[q])) keepbits |= 1u << q;
 		}
 		keepbits &= evbits;
 	}
@@ -710,6 +714,8 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	double auc = 0;
 
 	if (MODE == MODE_FAST) {
+		const bool npow2 = (N & (N - 1)) == 0;
+		const double inv_n = 1.0 / N;
 		for (int base = 0; base < nbp; base += THREADS) {
 			const int r = base + tid;
 			if (r >= nbp) break;
@@ -719,7 +725,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 			const int bs = (int) (w0 + bpos[r]);
 			const int be = (r + 1 < nbp) ? (int) (w0 + bpos[r + 1]) : next_bp;
 			double v = (double) (bval[r] + job.fx_base) * scale;   // correctly rounded exact sum
-			if (job.op == OP_MEAN) v = v / N;
+			if (job.op == OP_MEAN) v = npow2 ? v * inv_n : v / N;  // 1/N is exact for a power of two
 			if (oi < job.out_cap) {
 				job.out_start[oi] = bs;
 				job.out_end[oi] = be;
@@ -863,16 +869,32 @@ __global__ void __launch_bounds__(THREADS, MODE == MODE_FAST ? 3 : 1) emit_kerne
 		tmd[i] = MODE == MODE_FAST ? job.dflt_fx[i] : 0;
 	}
 	Misc *misc = (Misc *) smem;
-	while (true) {
-		// windows are handed out in order: the look-back only ever waits on windows
-		// that a resident CTA has already started
-		if (threadIdx.x == 0) misc->ticket = (int) atomicAdd(job.ticket, 1u);
+	int32_t *ca = cur, *cb = (int32_t *) (smem + L.off_cur2);   // current / next cursor rows
+	// Windows are handed out in order by a ticket counter: the look-back only ever
+	// waits on windows that a resident CTA has already drawn.  Each CTA runs two
+	// tickets ahead so that the next window's cursor row is already in shared
+	// memory (cp.async) when the current one finishes.
+	// The first two windows of every CTA are assigned statically (the whole grid is
+	// resident: it is sized by occupancy), interleaved across CTAs so that no window
+	// waits behind a CTA's second window at start-up; later ones come from the counter.
+	int w = blockIdx.x, w1 = blockIdx.x + gridDim.x;
+	if (w < job.nw)
+		for (int i = threadIdx.x; i < job.N; i += THREADS) ca[i] = job.cursor[(size_t) w * job.N + i];
+	__syncthreads();
+	while (w < job.nw) {
+		unsigned t2 = 0;
+		if (threadIdx.x == 0) t2 = atomicAdd(job.ticket, 1u) + 2u * gridDim.x;   // consumed two windows from now
+		if (w1 < job.nw)
+			for (int i = threadIdx.x; i < job.N; i += THREADS)
+				__pipeline_memcpy_async(&cb[i], &job.cursor[(size_t) w1 * job.N + i], 4);
+		__pipeline_commit();
+		process_window<MODE, VLOG, LIMBS>(job, w, smem, L, ca, lw, inv_scale, lim, scale);
+		__pipeline_wait_prior(0);
+		if (threadIdx.x == 0) misc->ticket2 = (int) t2;
 		__syncthreads();
-		const int w = misc->ticket;
-		if (w >= job.nw) break;
-		for (int i = threadIdx.x; i < job.N; i += THREADS) cur[i] = job.cursor[(size_t) w * job.N + i];
+		w = w1; w1 = misc->ticket2;
+		{ int32_t *t = ca; ca = cb; cb = t; }
 		__syncthreads();
-		process_window<MODE, VLOG, LIMBS>(job, w, smem, L, lw, inv_scale, lim, scale);
 	}
 }
 
