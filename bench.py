@@ -146,18 +146,29 @@ def cpu_reference_sample(n_tracks, mbp_per_core, cores):
 
 
 def run_reference_arm(args):
+    """`--impl reference`: the UNMODIFIED reference (oracle/_ref) on this box's host
+    cores, with the reference's own scale-out model (independent processes on
+    independent genome regions).  The process count that gives the reference its
+    best throughput is picked during the warm-up steps (memory bandwidth makes
+    "all cores" slower than a subset on large hosts)."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    ncpu = os.cpu_count() or 1
     mbp = 8.0 * (64.0 / N_TRACKS) ** 2          # ~1 s per step per core at N=64
-    times = []
-    for i in range(args.warmup + args.steps):
-        r = cpu_reference_sample(N_TRACKS, mbp, cores)
-        if i >= args.warmup:
-            times.append(r)
+    candidates = sorted({ncpu, max(1, ncpu // 2), max(1, ncpu // 4)}, reverse=True)
+    best, tried = None, []
+    for i in range(max(1, args.warmup)):
+        c = candidates[min(i, len(candidates) - 1)]
+        r = cpu_reference_sample(N_TRACKS, mbp, c)
+        tried.append((c, r["value"]))
+        if best is None or r["value"] > best[1]:
+            best = (c, r["value"])
+    cores = best[0]
+    times = [cpu_reference_sample(N_TRACKS, mbp, cores) for _ in range(args.steps)]
     value = float(np.mean([t["value"] for t in times]))
     cb = dict(times[-1]); cb["value"] = value
+    cb["sample"] += "; process counts tried in warm-up: " + ", ".join("%d -> %.0f Mbp/s" % t for t in tried)
     names, lengths = genome()
     line = {"impl": "reference", "metric": "Mbp/s, mean over %d tracks" % N_TRACKS, "value": value, "unit": "Mbp/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -314,7 +325,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
+        cores = max(1, (os.cpu_count() or 1) // 4)     # the reference scales best on a subset of a large host
         cpu = cpu_reference_sample(N_TRACKS, 12.0 * (64.0 / N_TRACKS) ** 2, cores)
 
     if rank == 0:
