@@ -126,6 +126,14 @@ void wb200_host_free(void *p);
 int wb200_reduce_host(wb200_ctx *ctx, int op, int ntracks, int nset1, int strict,
                       const wb200_track *tracks, wb200_segments *out);
 
+/* Same, for several chromosome shards in one call: tracks[c*ntracks + i] is track
+ * i on shard c, out[c] receives shard c's segments (all valid until the next
+ * call on the context).  H2D staging of shard c+1, the kernels of shard c and the
+ * D2H of shard c-1 overlap on three streams with double-buffered device memory;
+ * results are bit-identical to nshards calls of wb200_reduce_host. */
+int wb200_reduce_host_batch(wb200_ctx *ctx, int op, int nshards, int ntracks, int nset1, int strict,
+                            const wb200_track *tracks, wb200_segments *out);
+
 /* -- the hot path, device-resident buffers ------------------------------- */
 /* d_start/d_end/d_value: all tracks of the chromosome concatenated; h_off[i]
  * .. h_off[i+1] is track i (host array of ntracks+1 offsets).  Positions lie in

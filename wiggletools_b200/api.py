@@ -125,29 +125,62 @@ class Engine:
         self.last_stats.append(self.stats())
         return start, end, value, out.default_value, out.auc
 
+    # -- several chromosomes, pipelined ----------------------------------------
+    def reduce_shards(self, op, shards, nset1=None, strict=False):
+        """shards: list (one per chromosome) of lists of (start, end, value, default).
+        One wb200_reduce_host_batch call: staging, kernels and read-back of
+        consecutive chromosomes overlap."""
+        nsh, n = len(shards), len(shards[0])
+        arr = (_lib.CTrack * (nsh * n))()
+        keep = []
+        for c, per in enumerate(shards):
+            for i, (s, e, v, d) in enumerate(per):
+                s = np.ascontiguousarray(s, np.int32); e = np.ascontiguousarray(e, np.int32)
+                v = np.ascontiguousarray(v, np.float64)
+                keep.append((s, e, v))
+                arr[c * n + i] = _lib.CTrack(s.ctypes.data, e.ctypes.data, v.ctypes.data, len(s), float(d))
+        out = (_lib.CSegments * nsh)()
+        code = OPS[op] if isinstance(op, str) else int(op)
+        self._check(self.lib.wb200_reduce_host_batch(self.ctx, code, nsh, n, n if nset1 is None else nset1,
+                                                     int(bool(strict)), C.addressof(arr), C.addressof(out)))
+        res = []
+        for c in range(nsh):
+            m = out[c].n
+            if m:
+                start = np.ctypeslib.as_array(C.cast(out[c].start, C.POINTER(C.c_int32)), (m,)).copy()
+                end = np.ctypeslib.as_array(C.cast(out[c].end, C.POINTER(C.c_int32)), (m,)).copy()
+                value = np.ctypeslib.as_array(C.cast(out[c].value, C.POINTER(C.c_double)), (m,)).copy()
+            else:
+                start = np.empty(0, np.int32); end = np.empty(0, np.int32); value = np.empty(0, np.float64)
+            res.append((start, end, value, out[c].default_value, out[c].auc))
+        self.last_stats = [self.stats()]
+        return res
+
     # -- whole genome -------------------------------------------------------
     def reduce(self, op, tracks, names=("chr1",), strict=False, nset1=None):
         """<op> over N genome tracks: segments of every chromosome, in the
         reference's visiting order (ascending strcmp of the names)."""
         self.last_stats = []
         present = sorted({c for t in tracks for c in t.runs}, key=lambda c: names[c].encode())
-        cs, ss, es, vs = [], [], [], []
-        auc = 0.0
-        dflt = float("nan")
-        for c in present:
-            per = []
-            for t in tracks:
-                lo, hi = t.runs.get(c, (0, 0))
-                per.append((t.start[lo:hi], t.end[lo:hi], t.value[lo:hi], t.default))
-            s, e, v, dflt, a = self.reduce_chrom(op, per, nset1=nset1, strict=strict)
-            cs.append(np.full(len(s), c, np.int32)); ss.append(s); es.append(e); vs.append(v)
-            auc += a   # chromosome partials are folded in visiting order
         if not present:
             # defaults only: constructor semantics still apply
             per = [(np.empty(0, np.int32), np.empty(0, np.int32), np.empty(0), t.default) for t in tracks]
             _, _, _, dflt, _ = self.reduce_chrom(op, per, nset1=nset1, strict=strict)
             return Segments(np.empty(0, np.int32), np.empty(0, np.int32), np.empty(0, np.int32), np.empty(0), dflt, 0.0)
-        return Segments(np.concatenate(cs), np.concatenate(ss), np.concatenate(es), np.concatenate(vs), dflt, auc)
+        shards = []
+        for c in present:
+            per = []
+            for t in tracks:
+                lo, hi = t.runs.get(c, (0, 0))
+                per.append((t.start[lo:hi], t.end[lo:hi], t.value[lo:hi], t.default))
+            shards.append(per)
+        res = self.reduce_shards(op, shards, nset1=nset1, strict=strict)
+        cs = [np.full(len(r[0]), c, np.int32) for c, r in zip(present, res)]
+        auc = 0.0
+        for r in res:
+            auc += r[4]   # chromosome partials are folded in visiting order
+        return Segments(np.concatenate(cs), np.concatenate([r[0] for r in res]), np.concatenate([r[1] for r in res]),
+                        np.concatenate([r[2] for r in res]), res[-1][3], auc)
 
     def setcompare(self, op, set1, set2, names=("chr1",)):
         return self.reduce(op, list(set1) + list(set2), names, nset1=len(set1))

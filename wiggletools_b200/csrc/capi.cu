@@ -67,6 +67,11 @@ struct wb200_ctx {
 	DevBuf in_start, in_end, in_value, off, dflt, dflt_fx, cursor, state, aucp, small, moments, slow_list;
 	DevBuf out_start, out_end, out_value;
 	HostBuf h_small, h_meta, h_start, h_end, h_value;
+	// batch pipeline (wb200_reduce_host_batch)
+	cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+	DevBuf bin_start[2], bin_end[2], bin_value[2], bout_start[2], bout_end[2], bout_value[2];
+	HostBuf h_arena;
+	std::vector<cudaEvent_t> pipe_events;
 };
 
 namespace {
@@ -365,7 +370,14 @@ void wb200_destroy(wb200_ctx *ctx) {
 	DevBuf *d[] = {&ctx->in_start, &ctx->in_end, &ctx->in_value, &ctx->off, &ctx->dflt, &ctx->dflt_fx, &ctx->cursor,
 	               &ctx->state, &ctx->aucp, &ctx->small, &ctx->moments, &ctx->slow_list, &ctx->out_start, &ctx->out_end, &ctx->out_value};
 	for (auto *b : d) b->release();
-	HostBuf *h[] = {&ctx->h_small, &ctx->h_meta, &ctx->h_start, &ctx->h_end, &ctx->h_value};
+	for (int k = 0; k < 2; k++) {
+		ctx->bin_start[k].release(); ctx->bin_end[k].release(); ctx->bin_value[k].release();
+		ctx->bout_start[k].release(); ctx->bout_end[k].release(); ctx->bout_value[k].release();
+	}
+	for (auto ev : ctx->pipe_events) cudaEventDestroy(ev);
+	if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+	if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+	HostBuf *h[] = {&ctx->h_small, &ctx->h_meta, &ctx->h_start, &ctx->h_end, &ctx->h_value, &ctx->h_arena};
 	for (auto *b : h) b->release();
 	for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
 	if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -467,6 +479,130 @@ int wb200_reduce_host(wb200_ctx *ctx, int op, int ntracks, int nset1, int strict
 	return WB200_OK;
 }
 
+
+
+int wb200_reduce_host_batch(wb200_ctx *ctx, int op, int nshards, int ntracks, int nset1, int strict,
+                            const wb200_track *tracks, wb200_segments *out) {
+	if (!ctx || !tracks || !out || nshards < 0) return WB200_EINVAL;
+	cudaSetDevice(ctx->device);
+	const int N = ntracks;
+	if (N < 1) return fail(ctx, WB200_EINVAL, "need at least one track");
+	if (!ctx->s_h2d) CK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+	if (!ctx->s_d2h) CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+	while ((int) ctx->pipe_events.size() < 3 * nshards) {
+		cudaEvent_t e;
+		CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		ctx->pipe_events.push_back(e);
+	}
+	cudaEvent_t *ev_h2d = ctx->pipe_events.data(), *ev_comp = ev_h2d + nshards, *ev_d2h = ev_comp + nshards;
+	cudaStream_t s = ctx->stream;
+
+	struct Shard { std::vector<int64_t> off; std::vector<double> dflt; int64_t I, lo, hi, cap, S, arena_off; double dv, auc; };
+	std::vector<Shard> sh(nshards);
+	int64_t est = 0;
+	for (int c = 0; c < nshards; c++) {
+		Shard &h = sh[c];
+		h.off.assign(N + 1, 0); h.dflt.resize(N);
+		h.lo = INT32_MAX; h.hi = 1;
+		for (int i = 0; i < N; i++) {
+			const wb200_track &t = tracks[(size_t) c * N + i];
+			h.off[i + 1] = h.off[i] + t.n;
+			h.dflt[i] = t.default_value;
+			if (t.n > 0) { h.lo = std::min<int64_t>(h.lo, t.start[0]); h.hi = std::max<int64_t>(h.hi, t.end[t.n - 1]); }
+		}
+		h.I = h.off[N];
+		if (h.lo > h.hi) h.lo = h.hi;
+		h.cap = std::max<int64_t>(1, std::min<int64_t>(2 * h.I + 1, h.hi - h.lo + 1));
+		est += h.I + h.I / 2 + 1024;
+	}
+	CK(ctx->h_arena.ensure((size_t) est * 16));     // first guess S ~ 1.5 I; grown below if needed
+
+	auto stage = [&](int c) -> int {
+		Shard &h = sh[c];
+		const int b = c & 1;
+		CK(ctx->bin_start[b].ensure(std::max<int64_t>(1, h.I) * sizeof(int32_t)));
+		CK(ctx->bin_end[b].ensure(std::max<int64_t>(1, h.I) * sizeof(int32_t)));
+		CK(ctx->bin_value[b].ensure(std::max<int64_t>(1, h.I) * sizeof(double)));
+		if (c >= 2) CK(cudaStreamWaitEvent(ctx->s_h2d, ev_comp[c - 2], 0));   // input set b is free again
+		for (int i = 0; i < N; i++) {
+			const wb200_track &t = tracks[(size_t) c * N + i];
+			if (!t.n) continue;
+			CK(cudaMemcpyAsync(ctx->bin_start[b].as<int32_t>() + h.off[i], t.start, t.n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_h2d));
+			CK(cudaMemcpyAsync(ctx->bin_end[b].as<int32_t>() + h.off[i], t.end, t.n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_h2d));
+			CK(cudaMemcpyAsync(ctx->bin_value[b].as<double>() + h.off[i], t.value, t.n * sizeof(double), cudaMemcpyHostToDevice, ctx->s_h2d));
+		}
+		CK(cudaEventRecord(ev_h2d[c], ctx->s_h2d));
+		return WB200_OK;
+	};
+
+	// DevBuf::ensure may reallocate: size both buffer sets for the largest shard up front
+	int64_t maxI = 1, maxcap = 1;
+	for (auto &h : sh) { maxI = std::max(maxI, h.I); maxcap = std::max(maxcap, h.cap); }
+	for (int b = 0; b < 2; b++) {
+		CK(ctx->bin_start[b].ensure(maxI * sizeof(int32_t))); CK(ctx->bin_end[b].ensure(maxI * sizeof(int32_t)));
+		CK(ctx->bin_value[b].ensure(maxI * sizeof(double)));
+		CK(ctx->bout_start[b].ensure(maxcap * sizeof(int32_t))); CK(ctx->bout_end[b].ensure(maxcap * sizeof(int32_t)));
+		CK(ctx->bout_value[b].ensure(maxcap * sizeof(double)));
+	}
+
+	int64_t arena_used = 0, h2d = 0, d2h = 0;
+	wb200_stats total{};
+	if (nshards > 0) { int rc = stage(0); if (rc) return rc; }
+	for (int c = 0; c < nshards; c++) {
+		Shard &h = sh[c];
+		const int b = c & 1;
+		if (c + 1 < nshards) { int rc = stage(c + 1); if (rc) return rc; }
+		CK(cudaStreamWaitEvent(s, ev_h2d[c], 0));
+		if (c >= 2) CK(cudaStreamWaitEvent(s, ev_d2h[c - 2], 0));              // output set b has been drained
+		int rc = run_device(ctx, op, N, nset1, strict, ctx->bin_start[b].as<int32_t>(), ctx->bin_end[b].as<int32_t>(),
+		                    ctx->bin_value[b].as<double>(), h.off.data(), h.dflt.data(), (int32_t) h.lo, (int32_t) h.hi,
+		                    ctx->bout_start[b].as<int32_t>(), ctx->bout_end[b].as<int32_t>(), ctx->bout_value[b].as<double>(),
+		                    h.cap, &h.S, &h.dv, &h.auc);
+		if (rc != WB200_OK) return rc;
+		CK(cudaEventRecord(ev_comp[c], s));
+		// accumulate stats
+		total.intervals += ctx->stats.intervals; total.segments += ctx->stats.segments; total.windows += ctx->stats.windows;
+		total.slow_segments += ctx->stats.slow_segments; total.kernels += ctx->stats.kernels; total.fast_path = ctx->stats.fast_path;
+		total.ms_count += ctx->stats.ms_count; total.ms_emit += ctx->stats.ms_emit; total.ms_total += ctx->stats.ms_total;
+		// host space for this shard's segments
+		const int64_t need = (h.S + 2) * 16;
+		if ((size_t) (arena_used + need) > ctx->h_arena.cap) {
+			CK(cudaStreamSynchronize(ctx->s_d2h));
+			HostBuf bigger;
+			CK(bigger.ensure((size_t) ((arena_used + need) * 2)));
+			memcpy(bigger.p, ctx->h_arena.p, (size_t) arena_used);
+			ctx->h_arena.release();
+			ctx->h_arena = bigger;
+		}
+		h.arena_off = arena_used;
+		arena_used += need;
+		char *base = (char *) ctx->h_arena.p + h.arena_off;
+		CK(cudaStreamWaitEvent(ctx->s_d2h, ev_comp[c], 0));
+		if (h.S > 0) {
+			CK(cudaMemcpyAsync(base, ctx->bout_value[b].p, h.S * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_d2h));
+			CK(cudaMemcpyAsync(base + (h.S + 1) * 8, ctx->bout_start[b].p, h.S * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_d2h));
+			CK(cudaMemcpyAsync(base + (h.S + 1) * 12, ctx->bout_end[b].p, h.S * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_d2h));
+		}
+		CK(cudaEventRecord(ev_d2h[c], ctx->s_d2h));
+		h2d += h.I * 16; d2h += h.S * 16;
+	}
+	CK(cudaStreamSynchronize(ctx->s_d2h));
+	CK(cudaStreamSynchronize(ctx->s_h2d));
+	for (int c = 0; c < nshards; c++) {
+		Shard &h = sh[c];
+		char *base = (char *) ctx->h_arena.p + h.arena_off;
+		out[c].value = (double *) base;
+		out[c].start = (int32_t *) (base + (h.S + 1) * 8);
+		out[c].end = (int32_t *) (base + (h.S + 1) * 12);
+		out[c].n = h.S;
+		out[c].default_value = h.dv;
+		out[c].auc = h.auc;
+	}
+	ctx->stats = total;
+	ctx->stats.h2d_bytes = h2d;
+	ctx->stats.d2h_bytes = d2h;
+	return WB200_OK;
+}
 
 int wb200_pearson_host(wb200_ctx *ctx, const wb200_track *x, const wb200_track *y, double moments[6]) {
 	if (!ctx || !x || !y || !moments) return WB200_EINVAL;
