@@ -253,3 +253,50 @@ def test_dropin_cli_config1(tmp_path):
     # sum x x == scale 2 x (test/test.py:76), via the reference's own isZero/diff chain
     assert subprocess.run([exe, "do", "isZero", "diff", "sum", "fixedStep.wig", "fixedStep.wig", ":", "scale", "2", "fixedStep.wig"],
                           cwd=tmp_path).returncode == 0
+
+
+def test_fast_path_overflow_reruns_as_rows(engine, port):
+    """More unrepresentable segments than the fix-up list holds: the chromosome is
+    re-run on the row path; results still match the oracle exactly."""
+    tr = make_tracks(3, [2_000_000], seed=41, max_len=12, max_gap=6)
+    for t in tr:
+        t["value"][::2] = np.nan            # half of all intervals poison their segments
+    o, g = both(tr)
+    want = port.reduce("mean", o, ["chr1"])
+    got = engine.reduce("mean", g, ["chr1"])
+    assert_segments(got, want.chrom, want.start, want.end, want.value, exact=True, what="nan-heavy mean")
+    assert engine.last_stats[-1]["fast_path"] == 0 and engine.last_stats[-1]["slow_segments"] > 65536
+
+
+def test_long_intervals_and_sparse_windows(engine, port):
+    """Intervals spanning hundreds of windows, windows with no breakpoint at all,
+    and a track that is one single interval."""
+    L = 3_000_000
+    tr = make_tracks(5, [L], seed=52, max_len=50, max_gap=200000)      # very sparse
+    tr.append(dict(chrom=np.zeros(1, np.int32), start=np.array([7], np.int32), end=np.array([L - 3], np.int32), value=np.array([0.5])))
+    tr.append(dict(chrom=np.zeros(3, np.int32), start=np.array([1, 1_000_000, 2_999_000], np.int32),
+                   end=np.array([999_999, 2_998_000, L + 1], np.int32), value=np.array([1.0, 2.0, 4.0])))
+    o, g = both(tr)
+    for op in ("sum", "mean", "max", "stddev"):
+        for strict in (False, True):
+            want = port.reduce(op, o, ["chr1"], strict)
+            got = engine.reduce(op, g, ["chr1"], strict=strict)
+            assert_segments(got, want.chrom, want.start, want.end, want.value, exact=True, what="sparse %s" % op)
+
+
+def test_dense_every_base_a_breakpoint(engine, port):
+    """Unit-length abutting intervals on many tracks: every base pair is a breakpoint
+    (the regime of the 512-track configuration)."""
+    n, L = 40, 30000
+    rng = np.random.default_rng(3)
+    tr = []
+    for i in range(n):
+        s = np.arange(1 + i % 3, L, 1 + i % 2, dtype=np.int32)
+        tr.append(dict(chrom=np.zeros(len(s), np.int32), start=s, end=s + 1 + i % 2, value=rng.integers(0, 999, len(s)) / 8.0))
+    o, g = both(tr)
+    for op in ("mean", "min", "var"):
+        want = port.reduce(op, o, ["chr1"])
+        got = engine.reduce(op, g, ["chr1"])
+        assert_segments(got, want.chrom, want.start, want.end, want.value, exact=True, what="dense %s" % op)
+    st = engine.last_stats[-1]
+    assert st["segments"] >= L - 5
