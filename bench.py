@@ -33,6 +33,8 @@ from wiggletools_b200.shard import lpt_assign  # noqa: E402
 N_TRACKS = int(os.environ.get("WB200_BENCH_TRACKS", 64))
 SCALE = float(os.environ.get("WB200_BENCH_SCALE", 1.0))   # <1 shrinks every chromosome (development only)
 MAX_LEN, MAX_GAP, GAP_PROB, VMAX = 400, 200, 0.5, 100000
+BENCH_OP = os.environ.get("WB200_BENCH_OP", "mean")       # development: time another statistic of the path
+OP_CODE = {"sum": 0, "mult": 1, "mean": 2, "var": 3, "stddev": 4, "cv": 6, "min": 7, "max": 8, "median": 9}[BENCH_OP]
 
 
 def genome():
@@ -241,7 +243,7 @@ def main():
     def step(collect=None):
         total_auc = 0.0
         for sh in shards:
-            rc = lib.wb200_reduce_device(ctx, 2, N_TRACKS, N_TRACKS, 0,
+            rc = lib.wb200_reduce_device(ctx, OP_CODE, N_TRACKS, N_TRACKS, 0,
                                          sh["s"].data_ptr(), sh["e"].data_ptr(), sh["v"].data_ptr(),
                                          sh["off"].ctypes.data, dflt.ctypes.data, 1, sh["L"] + 1,
                                          sh["out"][0].data_ptr(), sh["out"][1].data_ptr(), sh["out"][2].data_ptr(),
@@ -329,7 +331,7 @@ def main():
         cpu = cpu_reference_sample(N_TRACKS, 12.0 * (64.0 / N_TRACKS) ** 2, cores)
 
     if rank == 0:
-        line = {"metric": "Mbp/s, mean over %d tracks" % N_TRACKS, "value": value, "unit": "Mbp/s", "n_gpus": world,
+        line = {"metric": "Mbp/s, %s over %d tracks" % (BENCH_OP, N_TRACKS), "value": value, "unit": "Mbp/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(lengths, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,

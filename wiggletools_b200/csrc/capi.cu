@@ -192,7 +192,7 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 			if (density > 0.6) wlog = 11;
 		}
 	}
-	wlog = std::min(12, std::max(10, wlog));
+	wlog = std::min(TLOG + 4, std::max(TLOG + 2, wlog));
 	const int64_t span = (int64_t) pos_hi - pos_lo;
 	const int nw = (int) (span >> wlog) + 1;
 
@@ -200,6 +200,7 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 	job.start = d_start; job.end = d_end; job.value = d_value;
 	job.N = N; job.n1 = n1; job.strict = strict ? 1 : 0; job.op = op;
 	job.p0 = pos_lo; job.wlog = wlog; job.nw = nw;
+	{ const char *e = getenv("WB200_LB_WARPS"); job.lb_warps = e ? std::max(1, std::min(WARPS, atoi(e))) : 1; }
 	job.out_start = d_out_start; job.out_end = d_out_end; job.out_value = d_out_value; job.out_cap = out_cap;
 
 	// small tables
@@ -214,7 +215,7 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 	memcpy(hm_dflt, h_dflt, N * sizeof(double));
 	CK(ctx->cursor.ensure((size_t) (nw + 1) * N * sizeof(int32_t)));
 	CK(ctx->state.ensure((size_t) nw * sizeof(unsigned long long)));
-	CK(ctx->aucp.ensure((size_t) nw * sizeof(double)));
+	CK(ctx->aucp.ensure((size_t) nw * WARPS * sizeof(double)));
 	CK(ctx->small.ensure(128));
 	CK(ctx->h_small.ensure(128));
 	if (moments_out) { CK(ctx->moments.ensure((size_t) nw * 6 * sizeof(double))); job.moments = ctx->moments.as<double>(); }

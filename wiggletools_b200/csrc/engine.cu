@@ -72,8 +72,10 @@ struct Misc {                        // scalars, warp totals
 	int wkeep[WARPS];                // warp totals (counts scan)
 	double wauc[WARPS];
 	double wmom[WARPS][6];           // Pearson moments per warp
+	unsigned long long lb_sum[WARPS]; // look-back: per-warp chunk sums
+	int lb_found[WARPS];             // look-back: chunk holds an inclusive prefix
 };
-constexpr int MISC_BYTES = 1024;
+constexpr int MISC_BYTES = 2048;
 static_assert(sizeof(Misc) <= MISC_BYTES, "Misc must fit its shared-memory slot");
 
 constexpr uint16_t BK_KEEP = 0x8000, BK_SLOW = 0x4000, BK_IDX = 0x3fff;
@@ -407,7 +409,6 @@ __device__ __forceinline__ void block_scan2(Misc *misc, int c, long long a, int 
 		tc += kc; ta += ka;
 	}
 	ec = bc + ic - c; ea = ba + ia - a;
-	__syncthreads();
 }
 
 __device__ __forceinline__ void block_scan1(Misc *misc, int c, int &ec, int &tc) {
@@ -420,7 +421,6 @@ __device__ __forceinline__ void block_scan1(Misc *misc, int c, int &ec, int &tc)
 #pragma unroll
 	for (int k = 0; k < WARPS; k++) { int kc = misc->wkeep[k]; if (k < warp) bc += kc; tc += kc; }
 	ec = bc + ic - c;
-	__syncthreads();
 }
 
 constexpr unsigned long long LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_VALUE = (1ull << 62) - 1;
@@ -680,23 +680,45 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	__syncthreads();
 
 	// ---- output offset: decoupled look-back over the preceding windows --------------------
-	// Windows are drawn from a global ticket counter, so every predecessor has been
-	// started by a resident CTA and will publish; lane l inspects window w-1-l.
+	// Windows are drawn in ascending order, so every predecessor has been started by
+	// a resident CTA and will publish.  Warp k inspects windows w-1-32k .. w-32-32k
+	// (lane l the l-th of them) and reduces its chunk up to the first inclusive
+	// prefix; the chunks are then chained in order.
+	const int lbw = job.lb_warps;        // warps taking part in the first look-back step
+	if (warp < lbw) {
+		const int idx = w - 1 - warp * 32 - lane;
+		unsigned long long st;
+		while (true) {
+			st = idx >= 0 ? ld_volatile(&job.state[idx]) : LB_PREFIX;      // before window 0: prefix 0
+			if (!__any_sync(FULL, (st >> 62) == 0)) break;
+			__nanosleep(40);
+		}
+		const unsigned pm = __ballot_sync(FULL, (st >> 62) == 2);
+		const int first = pm ? __ffs(pm) - 1 : 32;
+		unsigned long long v = (lane <= first) ? (st & LB_VALUE) : 0;
+		for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(FULL, v, d);
+		if (lane == 0) { misc->lb_sum[warp] = v; misc->lb_found[warp] = pm != 0; }
+	}
+	__syncthreads();
 	if (warp == 0) {
 		unsigned long long sum = 0;
-		int p = w - 1;
-		while (true) {
+		bool found = false;
+		for (int k = 0; k < lbw && !found; k++) { sum += misc->lb_sum[k]; found = misc->lb_found[k] != 0; }
+		int p = w - 1 - lbw * 32;
+		while (!found) {                                                     // rare: deeper than 32*WARPS windows
 			const int idx = p - lane;
 			unsigned long long st;
-			do {
-				st = idx >= 0 ? ld_volatile(&job.state[idx]) : LB_PREFIX;   // before window 0: prefix 0
-			} while (__any_sync(FULL, (st >> 62) == 0));
+			while (true) {
+				st = idx >= 0 ? ld_volatile(&job.state[idx]) : LB_PREFIX;
+				if (!__any_sync(FULL, (st >> 62) == 0)) break;
+				__nanosleep(40);
+			}
 			const unsigned pm = __ballot_sync(FULL, (st >> 62) == 2);
 			const int first = pm ? __ffs(pm) - 1 : 32;
 			unsigned long long v = (lane <= first) ? (st & LB_VALUE) : 0;
 			for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(FULL, v, d);
 			sum += __shfl_sync(FULL, v, 0);
-			if (pm) break;
+			found = pm != 0;
 			p -= 32;
 		}
 		if (lane == 0) {
@@ -816,25 +838,23 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 		}
 	}
 
-	// deterministic block reduction of the AUC partial / slow-path count / moments
+	// per-warp AUC partials go straight to global memory (fixed order, folded later)
 	for (int d = 16; d > 0; d >>= 1) {
 		auc += __shfl_down_sync(FULL, auc, d);
 		slow += __shfl_down_sync(FULL, slow, d);
 	}
-	if (lane == 0) { misc->wauc[warp] = auc; misc->wsum[warp] = (long long) slow; }
-	__syncthreads();
-	if (tid == 0) {
-		if (MODE == MODE_ROW && job.op == OP_PEARSON && job.moments) {
+	if (lane == 0) {
+		if (job.auc_partial) job.auc_partial[(size_t) w * WARPS + warp] = auc;
+		if (MODE == MODE_ROW && slow && job.slow_count) atomicAdd(job.slow_count, slow);
+	}
+	if (MODE == MODE_ROW && job.op == OP_PEARSON) {
+		__syncthreads();
+		if (tid == 0 && job.moments) {
 			double t[6] = {0, 0, 0, 0, 0, 0};
 			for (int k = 0; k < WARPS; k++) merge6(t, misc->wmom[k]);
 			for (int k = 0; k < 6; k++) job.moments[(size_t) w * 6 + k] = t[k];
 		}
-		double t = 0; long long sl = 0;
-		for (int k = 0; k < WARPS; k++) { t += misc->wauc[k]; sl += misc->wsum[k]; }
-		if (job.auc_partial) job.auc_partial[w] = t;
-		if (sl && job.slow_count) atomicAdd(job.slow_count, (unsigned long long) sl);
 	}
-	__syncthreads();
 }
 
 // cursor kernel: cursor[w][i] = first interval of track i whose end reaches the
@@ -855,7 +875,7 @@ __global__ void __launch_bounds__(256) cursor_kernel(const Job job) {
 }
 
 template <int MODE, int VLOG, int LIMBS>
-__global__ void __launch_bounds__(THREADS, MODE == MODE_FAST ? 3 : 1) emit_kernel(const Job job, int lw, double inv_scale, double lim, double scale, int rowbuf) {
+__global__ void __launch_bounds__(THREADS, MODE == MODE_FAST ? (THREADS == 512 ? 2 : 3) : 1) emit_kernel(const Job job, int lw, double inv_scale, double lim, double scale, int rowbuf) {
 	extern __shared__ __align__(16) unsigned char smem[];
 	const Layout L = make_layout(job.wlog, job.N, true, LIMBS, rowbuf);
 	int32_t *cur = (int32_t *) (smem + L.off_cur);
@@ -891,10 +911,9 @@ __global__ void __launch_bounds__(THREADS, MODE == MODE_FAST ? 3 : 1) emit_kerne
 		process_window<MODE, VLOG, LIMBS>(job, w, smem, L, ca, lw, inv_scale, lim, scale);
 		__pipeline_wait_prior(0);
 		if (threadIdx.x == 0) misc->ticket2 = (int) t2;
-		__syncthreads();
+		__syncthreads();      // dense list consumed, next cursor row landed, ticket visible
 		w = w1; w1 = misc->ticket2;
 		{ int32_t *t = ca; ca = cb; cb = t; }
-		__syncthreads();
 	}
 }
 
@@ -967,10 +986,10 @@ cudaError_t launch_emit(const Job &job, cudaStream_t s) {
 #define WB_EMIT(V) (!job.fast ? launch_emit_v<MODE_ROW, V, 2>(job, lw, inv_scale, lim, scale, rowbuf, s) \
                   : limbs == 2 ? launch_emit_v<MODE_FAST, V, 2>(job, lw, inv_scale, lim, scale, rowbuf, s) \
                                : launch_emit_v<MODE_FAST, V, 3>(job, lw, inv_scale, lim, scale, rowbuf, s))
-	switch (job.wlog) {
-	case 10: return WB_EMIT(2);
-	case 11: return WB_EMIT(3);
-	case 12: return WB_EMIT(4);
+	switch (job.wlog - TLOG) {       // positions per thread = 2^VLOG
+	case 2: return WB_EMIT(2);
+	case 3: return WB_EMIT(3);
+	case 4: return WB_EMIT(4);
 	}
 #undef WB_EMIT
 	return cudaErrorInvalidValue;
@@ -1030,7 +1049,7 @@ cudaError_t launch_reduce_moments(const double *moments, int nw, double *out6, c
 }
 
 cudaError_t launch_reduce_auc(const double *partial, int nw, double *out, cudaStream_t s) {
-	reduce_auc_kernel<<<1, 1024, 0, s>>>(partial, nw, out);
+	reduce_auc_kernel<<<1, 1024, 0, s>>>(partial, nw * WARPS, out);
 	return cudaGetLastError();
 }
 

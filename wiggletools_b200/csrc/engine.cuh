@@ -6,7 +6,12 @@
 
 namespace wb {
 
-constexpr int THREADS = 256;           // threads per CTA in the window kernels
+#ifndef WB_THREADS
+#define WB_THREADS 256
+#endif
+constexpr int THREADS = WB_THREADS;    // threads per CTA in the window kernels
+constexpr int TLOG = THREADS == 512 ? 9 : 8;
+static_assert(THREADS == 256 || THREADS == 512, "window kernels are written for 256 or 512 threads");
 constexpr int WARPS = THREADS / 32;
 constexpr int MAX_TRACKS = 1023;       // per set: 10-bit cover fields
 
@@ -47,12 +52,13 @@ struct Job {
 	unsigned long long *state; // [nw] look-back words: 2 flag bits | segments (aggregate or inclusive prefix)
 	unsigned int *ticket;   // window ticket counter
 	long long *total;       // S, written by the last window
+	int lb_warps;           // warps used by the first look-back step (1..WARPS)
 	// outputs
 	int32_t *out_start;
 	int32_t *out_end;
 	double *out_value;
 	int64_t out_cap;
-	double *auc_partial;    // [nw] per-window sum of (end-start)*value (NaN skipped), or null
+	double *auc_partial;    // [nw * WARPS] per-warp sums of (end-start)*value (NaN skipped), or null
 	unsigned long long *slow_count; // segments that took the row path
 	double *moments;        // [nw * 6] per-window Pearson moments (OP_PEARSON), or null
 	long long *slow_list;   // fast path: output indices of segments to recompute (fix-up kernel)
