@@ -156,6 +156,24 @@ int wb200_pearson_host(wb200_ctx *ctx, const wb200_track *x, const wb200_track *
 void wb200_pearson_merge(double a[6], const double b[6]);
 double wb200_pearson_result(const double moments[6]);
 
+/* -- host BigWig batch decoder ------------------------- */
+/* Stands where the reference goes through libBigWig one record at a time
+ * (src/bigWiggleReader.c:36-123): a whole chromosome is decoded at once (R-tree
+ * walk, parallel zlib inflate) into pinned SoA arrays.  Chromosomes are indexed
+ * in strcmp order of their names (the reference's visiting order, :97).
+ * Coordinates come out 1-based half-open; `stretch` (default 10000) reproduces
+ * the reference's chopping of intervals at 1+10000k (quirk Q9), 0 disables it. */
+typedef struct wb200_bigwig wb200_bigwig;
+wb200_bigwig *wb200_bw_open(const char *path);               /* NULL on error, see wb200_bw_last_error(NULL) */
+void wb200_bw_close(wb200_bigwig *bw);
+const char *wb200_bw_last_error(const wb200_bigwig *bw);
+int wb200_bw_nchrom(const wb200_bigwig *bw);
+const char *wb200_bw_chrom_name(const wb200_bigwig *bw, int i);
+int64_t wb200_bw_chrom_length(const wb200_bigwig *bw, int i);
+void wb200_bw_set_stretch(wb200_bigwig *bw, int stretch_bp);
+/* out->start/end/value are owned by the handle and valid until its next decode. */
+int wb200_bw_decode_chrom(wb200_bigwig *bw, int chrom_index, wb200_track *out);
+
 /* Student-t upper tail used by WB200_TTEST (stands where the reference calls
  * gsl_cdf_tdist_Q, src/setComparisons.c:117); exported for tests. */
 double wb200_tdist_Q(double t, double nu);

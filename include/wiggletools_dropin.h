@@ -115,6 +115,9 @@ WiggleIterator *MWUReduction(Multiset *);                   /* :269-390 */
 WiggleIterator *AUCIntegrator(WiggleIterator *);            /* :103-127 */
 WiggleIterator *PearsonIntegrator(Multiplexer *);           /* :414-465 */
 
+/* -- bigWiggleReader.c: BigWig source on the library's batch decoder ---------- */
+WiggleIterator *BigWiggleReader(char *filename, wt_bool holdFire);                         /* :147-151 */
+
 /* -- wiggleIterator.c / unaryOps.c: the few core entry points the path calls;
  * defined here too so the library is self-contained (a host program that
  * already defines them -- the reference CLI -- keeps its own). ---------------- */

@@ -250,6 +250,20 @@ def test_dropin_cli_config1(tmp_path):
     assert [float(l.split("\t")[3]) for l in bg] == [.25, .25, .5, 0, 2, .25, 4.5, 1, 8, 10.125]
     assert run("AUC", "mean", "fixedStep.wig", "variableStep.wig").strip() == "30.000000"
     assert run("pearson", "fixedStep.wig", "variableStep.wig").strip() == "-0.028968"   # test/expected/pearson.txt
+    # BASELINE.json configs[0], literally: the BigWig twins through the library's own
+    # decoder (BigWiggleReader of the drop-in), test/test.py:28,52,76 style identities
+    import shutil
+    for f in ("fixedStep.bw", "variableStep.bw"):
+        shutil.copy(os.path.join(os.path.dirname(__file__), "golden", f), tmp_path / f)
+    out = run("mean", "fixedStep.bw", "variableStep.bw").split("\n")
+    assert out[0] == "fixedStep chrom=chr1 start=1 step=1"
+    assert [float(x) for x in out[1:11]] == [.5, 1.5, 1, 3, 2, 4.5, 3, 6, 4, 4.5]
+    for args in (["do", "isZero", "diff", "fixedStep.bw", "fixedStep.wig"],
+                 ["do", "isZero", "diff", "variableStep.bw", "variableStep.wig"],
+                 ["do", "isZero", "diff", "sum", "fixedStep.bw", "fixedStep.bw", ":", "scale", "2", "fixedStep.bw"],
+                 ["do", "isZero", "seek", "chr1", "2", "6", "diff", "variableStep.bw", "variableStep.wig"]):
+        assert subprocess.run([exe] + args, cwd=tmp_path).returncode == 0, args
+    assert subprocess.run([exe, "do", "isZero", "diff", "fixedStep.bw", "variableStep.wig"], cwd=tmp_path).returncode == 1  # negative control, test/test.py:22
     # sum x x == scale 2 x (test/test.py:76), via the reference's own isZero/diff chain
     assert subprocess.run([exe, "do", "isZero", "diff", "sum", "fixedStep.wig", "fixedStep.wig", ":", "scale", "2", "fixedStep.wig"],
                           cwd=tmp_path).returncode == 0

@@ -63,6 +63,18 @@ def load():
     lib.wb200_pearson_merge.argtypes = [C.c_void_p, C.c_void_p]
     lib.wb200_pearson_result.restype = C.c_double
     lib.wb200_pearson_result.argtypes = [C.c_void_p]
+    lib.wb200_bw_open.restype = C.c_void_p
+    lib.wb200_bw_open.argtypes = [C.c_char_p]
+    lib.wb200_bw_close.argtypes = [C.c_void_p]
+    lib.wb200_bw_last_error.restype = C.c_char_p
+    lib.wb200_bw_last_error.argtypes = [C.c_void_p]
+    lib.wb200_bw_nchrom.argtypes = [C.c_void_p]
+    lib.wb200_bw_chrom_name.restype = C.c_char_p
+    lib.wb200_bw_chrom_name.argtypes = [C.c_void_p, C.c_int]
+    lib.wb200_bw_chrom_length.restype = C.c_int64
+    lib.wb200_bw_chrom_length.argtypes = [C.c_void_p, C.c_int]
+    lib.wb200_bw_set_stretch.argtypes = [C.c_void_p, C.c_int]
+    lib.wb200_bw_decode_chrom.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.wb200_tdist_Q.restype = C.c_double
     lib.wb200_tdist_Q.argtypes = [C.c_double, C.c_double]
     _lib = lib
@@ -74,5 +86,6 @@ EXPORTS = [
     "wb200_create", "wb200_destroy", "wb200_last_error", "wb200_last_stats", "wb200_set_stream",
     "wb200_set_window", "wb200_host_alloc", "wb200_host_free", "wb200_reduce_host", "wb200_reduce_host_batch",
     "wb200_reduce_device", "wb200_pearson_host", "wb200_pearson_merge", "wb200_pearson_result",
-    "wb200_tdist_Q",
+    "wb200_tdist_Q", "wb200_bw_open", "wb200_bw_close", "wb200_bw_last_error", "wb200_bw_nchrom", "wb200_bw_chrom_name",
+    "wb200_bw_chrom_length", "wb200_bw_set_stretch", "wb200_bw_decode_chrom",
 ]

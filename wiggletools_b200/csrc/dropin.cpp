@@ -15,6 +15,7 @@
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <set>
 #include <string>
@@ -67,6 +68,74 @@ void gpu_multiplexer_seek(Multiplexer *, const char *, int, int);
 bool is_gpu_multiplexer(const Multiplexer *m) { return m->pop == &gpu_multiplexer_pop; }
 
 // ---------------------------------------------------------------------------
+// BigWig source: the library's batch decoder behind the WiggleIterator protocol
+// (stands where src/bigWiggleReader.c goes through libBigWig)
+// ---------------------------------------------------------------------------
+struct BwSource {
+	wb200_bigwig *bw = nullptr;
+	int ci = -1;                 // chromosome being served (index in strcmp order)
+	wb200_track t{};             // decoded chromosome (arrays owned by the handle)
+	int64_t k = 0;               // next record to serve
+	char *chrom = nullptr;
+	bool hold = false;           // holdFire: nothing is read before the first seek (commandParser.c:615-624)
+	// region restriction after seek(): one boxed query, no 10 000-bp stretches (bigWiggleReader.c:52-71,125-145)
+	bool region = false;
+	std::vector<int32_t> rs, re;
+	std::vector<double> rv;
+
+	bool load_next_chrom() {
+		if (region) return false;
+		while (++ci < wb200_bw_nchrom(bw)) {
+			if (wb200_bw_decode_chrom(bw, ci, &t) != WB200_OK) die(wb200_bw_last_error(bw));
+			if (t.n > 0) { chrom = intern(wb200_bw_chrom_name(bw, ci)); k = 0; return true; }
+		}
+		t.n = 0; k = 0;
+		return false;
+	}
+};
+
+void bw_pop(WiggleIterator *wi) {
+	BwSource *b = (BwSource *) wi->data;
+	if (b->hold) { wi->done = true; return; }
+	while (b->k >= b->t.n)
+		if (!b->load_next_chrom()) { wi->done = true; return; }
+	wi->chrom = b->chrom;
+	wi->start = b->t.start[b->k];
+	wi->finish = b->t.end[b->k];
+	wi->value = b->t.value[b->k];
+	b->k++;
+}
+
+void bw_seek(WiggleIterator *wi, const char *chrom, int start, int finish) {
+	BwSource *b = (BwSource *) wi->data;
+	b->hold = false;
+	b->region = true;
+	b->rs.clear(); b->re.clear(); b->rv.clear();
+	b->t = wb200_track{nullptr, nullptr, nullptr, 0, 0};
+	b->k = 0;
+	if (start < 1) start = 1;
+	if (finish < 1) finish = 1;
+	for (int i = 0; i < wb200_bw_nchrom(b->bw); i++) {
+		if (strcmp(wb200_bw_chrom_name(b->bw, i), chrom) != 0) continue;
+		wb200_bw_set_stretch(b->bw, 0);
+		wb200_track full;
+		if (wb200_bw_decode_chrom(b->bw, i, &full) != WB200_OK) die(wb200_bw_last_error(b->bw));
+		wb200_bw_set_stretch(b->bw, 10000);
+		for (int64_t q = 0; q < full.n; q++) {
+			if (full.start[q] >= finish || full.end[q] <= start) continue;      // overlaps [start, finish)
+			b->rs.push_back(std::max(full.start[q], (int32_t) start));          // boxed into the query
+			b->re.push_back(std::min(full.end[q], (int32_t) finish));
+			b->rv.push_back(full.value[q]);
+		}
+		b->chrom = intern(chrom);
+		b->t = wb200_track{b->rs.data(), b->re.data(), b->rv.data(), (int64_t) b->rs.size(), 0};
+		b->ci = i;
+	}
+	wi->done = false;
+	bw_pop(wi);
+}
+
+// ---------------------------------------------------------------------------
 // batch reduction behind a WiggleIterator
 // ---------------------------------------------------------------------------
 struct Reducer {
@@ -97,9 +166,22 @@ struct Reducer {
 		chrom = intern(best);
 		s.resize(n); e.resize(n); v.resize(n);
 		std::vector<wb200_track> tracks(n);
+		std::vector<BwSource *> direct(n, nullptr);
 		for (size_t i = 0; i < n; i++) {
 			WiggleIterator *it = iters[i];
 			s[i].clear(); e[i].clear(); v[i].clear();
+			// A BigWig source positioned on its chromosome's first record hands over the
+			// decoded pinned arrays as they are: no per-record pop, no copy.
+			if (it->pop == &bw_pop && !it->done) {
+				BwSource *b = (BwSource *) it->data;
+				if (b->k == 1 && b->chrom == chrom) {
+					tracks[i].start = b->t.start; tracks[i].end = b->t.end; tracks[i].value = b->t.value;
+					tracks[i].n = b->t.n;
+					tracks[i].default_value = it->default_value;
+					direct[i] = b;
+					continue;
+				}
+			}
 			while (!it->done && strcmp(it->chrom, chrom) == 0) {
 				s[i].push_back(it->start);
 				e[i].push_back(it->finish);
@@ -115,6 +197,8 @@ struct Reducer {
 			double m[6];
 			if (wb200_pearson_host(engine(), &tracks[0], &tracks[1], m) != WB200_OK) die(wb200_last_error(engine()));
 			wb200_pearson_merge(moments, m);
+			for (size_t i = 0; i < n; i++)
+				if (direct[i]) { direct[i]->k = direct[i]->t.n; pop(iters[i]); }
 			return true;
 		}
 		wb200_segments out;
@@ -124,6 +208,9 @@ struct Reducer {
 		re.assign(out.end, out.end + out.n);
 		rv.assign(out.value, out.value + out.n);
 		auc += out.auc;
+		// the decoded arrays have been staged: move the direct sources to their next chromosome
+		for (size_t i = 0; i < n; i++)
+			if (direct[i]) { direct[i]->k = direct[i]->t.n; pop(iters[i]); }
 		return true;
 	}
 };
@@ -319,6 +406,18 @@ WiggleIterator *UnionWiggleIterator(WiggleIterator *i) {
 }
 
 WiggleIterator *NonOverlappingWiggleIterator(WiggleIterator *i) { return i->overlaps ? UnionWiggleIterator(i) : i; }
+
+// -- bigWiggleReader.c --------------------------------------------------------------
+WiggleIterator *BigWiggleReader(char *filename, wt_bool holdFire) {
+	BwSource *b = new BwSource();
+	b->bw = wb200_bw_open(filename);
+	if (!b->bw) {
+		printf("File %s is not in BigWig format\n", filename);   // bigWiggleReader.c:116-119
+		exit(1);
+	}
+	b->hold = holdFire != 0;
+	return newWiggleIterator(b, &bw_pop, &bw_seek, 0, 0);
+}
 
 // -- multiplexer.c --------------------------------------------------------------
 void popMultiplexer(Multiplexer *multi) { if (!multi->done) multi->pop(multi); }
