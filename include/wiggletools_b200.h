@@ -46,6 +46,8 @@ enum wb200_op {
 	WB200_MIN     = 7,  /* MinReduction      src/reducers.c:192-253 */
 	WB200_MAX     = 8,  /* MaxReduction      src/reducers.c:125-186 */
 	WB200_MEDIAN  = 9,  /* MedianReduction   src/reducers.c:780-834 */
+	WB200_FILLIN  = 10, /* FillInReduction(multi, false)  src/reducers.c:78-119 (exactly 2 tracks) */
+	WB200_TRIMFILL = 11,/* FillInReduction(multi, true)  (only where track 0 is in play) */
 	WB200_TTEST   = 16, /* TTestReduction    src/setComparisons.c:35-131 (over a Multiset of 2) */
 	WB200_MWU     = 17  /* MWUReduction      src/setComparisons.c:269-390 */
 };

@@ -113,6 +113,7 @@ static WiggleIterator *MemSourceIterator(const wt_track *t, char **names) {
 enum {
 	WT_SUM = 0, WT_PRODUCT = 1, WT_MEAN = 2, WT_VAR = 3, WT_STDDEV = 4,
 	WT_ENTROPY = 5, WT_CV = 6, WT_MIN = 7, WT_MAX = 8, WT_MEDIAN = 9,
+	WT_FILLIN = 10, WT_TRIMFILL = 11,
 	WT_TTEST = 16, WT_MWU = 17
 };
 
@@ -160,6 +161,8 @@ static WiggleIterator *build_reduction(int op, Multiplexer *multi) {
 	case WT_MIN: return MinReduction(multi);
 	case WT_MAX: return MaxReduction(multi);
 	case WT_MEDIAN: return MedianReduction(multi);
+	case WT_FILLIN: return FillInReduction(multi, false);
+	case WT_TRIMFILL: return FillInReduction(multi, true);
 	}
 	fprintf(stderr, "wtref: unknown op %d\n", op);
 	exit(1);

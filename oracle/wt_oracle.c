@@ -45,6 +45,7 @@ typedef struct {
 enum {
 	WT_SUM = 0, WT_PRODUCT = 1, WT_MEAN = 2, WT_VAR = 3, WT_STDDEV = 4,
 	WT_ENTROPY = 5, WT_CV = 6, WT_MIN = 7, WT_MAX = 8, WT_MEDIAN = 9,
+	WT_FILLIN = 10, WT_TRIMFILL = 11,
 	WT_TTEST = 16, WT_MWU = 17
 };
 
@@ -206,6 +207,8 @@ static double reduce_row(int op, int n, const double *x, const char *inplay, dou
 		for (i = 0; i < n; i++) { double d = mean - x[i]; acc += d * d; }
 		return sqrt(acc / n) / mean;
 	}
+	case WT_FILLIN: case WT_TRIMFILL: /* :78-107: track 1's value (or default) on the union segmentation */
+		return x[1];
 	case WT_MEDIAN: /* :780-813: upper median, no averaging */
 		for (i = 0; i < n; i++) { if (isnan(x[i])) return NAN; scratch[i] = x[i]; }
 		qsort(scratch, n, sizeof(double), cmp_double);
@@ -260,6 +263,8 @@ static double reduce_default(int op, int n, const double *d, double *scratch) {
 		}
 		return m;
 	}
+	case WT_FILLIN: case WT_TRIMFILL: /* :117 */
+		return d[1];
 	case WT_MEDIAN: { /* :815-834: through a float */
 		for (i = 0; i < n; i++) { if (isnan(d[i])) return NAN; scratch[i] = d[i]; }
 		qsort(scratch, n, sizeof(double), cmp_double);
@@ -290,6 +295,7 @@ int64_t wto_reduce(int op, int ntracks, const wt_track *tracks, int strict,
 	}
 	int64_t k = 0;
 	for (sweep_pop(&s, strict); !s.done; sweep_pop(&s, strict)) {
+		if (op == WT_TRIMFILL && !s.inplay[0]) continue;   /* trim: only where track 0 is in play (:88-96) */
 		put(out, k, s.chrom, s.start, s.finish, reduce_row(op, ntracks, s.x, s.inplay, scratch));
 		k++;
 	}

@@ -314,3 +314,23 @@ def test_dense_every_base_a_breakpoint(engine, port):
         assert_segments(got, want.chrom, want.start, want.end, want.value, exact=True, what="dense %s" % op)
     st = engine.last_stats[-1]
     assert st["segments"] >= L - 5
+
+
+def test_fillin(engine, port):
+    """fillIn / trimFill (FillInReduction, src/reducers.c:78-119) through the engine and the drop-in API."""
+    import os
+    from oracle.pyoracle import Oracle
+    tr = make_tracks(2, [30000, 8000], seed=77, max_len=40, max_gap=60, nan_prob=0.01)
+    o, g = both(tr, [0.0, 2.5])
+    for op in ("fillIn", "trimFill"):
+        want = port.reduce(op, o, NAMES)
+        got = engine.reduce(op, g, NAMES)
+        assert_segments(got, want.chrom, want.start, want.end, want.value, exact=True, what=op)
+        assert same_float(got.default, want.default)
+    if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "libwtdropin.so")):
+        drop = Oracle("dropin")
+        for op in ("fillIn", "trimFill"):
+            want, got = port.reduce(op, o, NAMES), drop.reduce(op, o, NAMES)
+            assert_segments(got, want.chrom, want.start, want.end, want.value, exact=True, what="dropin " + op)
+    with pytest.raises(api.WB200Error):
+        engine.reduce("fillIn", g + g, NAMES)

@@ -21,7 +21,7 @@ from . import _lib
 
 OPS = {
     "sum": 0, "mult": 1, "product": 1, "mean": 2, "var": 3, "stddev": 4, "entropy": 5,
-    "CV": 6, "cv": 6, "min": 7, "max": 8, "median": 9, "ttest": 16, "wilcoxon": 17, "mwu": 17,
+    "CV": 6, "cv": 6, "min": 7, "max": 8, "median": 9, "fillIn": 10, "trimFill": 11, "ttest": 16, "wilcoxon": 17, "mwu": 17,
 }
 
 

@@ -136,6 +136,8 @@ double derived_default(int op, int n, const double *d) {
 		}
 		return m;
 	}
+	case OP_FILLIN: case OP_TRIMFILL:
+		return d[1];                 // reducers.c:117
 	case OP_MEDIAN: {
 		std::vector<double> v(d, d + n);
 		for (int i = 0; i < n; i++) if (std::isnan(v[i])) return NAN;
@@ -148,7 +150,7 @@ double derived_default(int op, int n, const double *d) {
 }
 
 bool valid_op(int op) {
-	return (op >= OP_SUM && op <= OP_MEDIAN) || op == OP_TTEST || op == OP_MWU;
+	return (op >= OP_SUM && op <= OP_TRIMFILL) || op == OP_TTEST || op == OP_MWU;
 }
 
 int ceil_log2(long long v) { int l = 0; while ((1ll << l) < v) l++; return l; }
@@ -162,7 +164,10 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 	if (!valid_op(op) && !(op == OP_PEARSON && moments_out && N == 2)) return fail(ctx, WB200_EINVAL, "unknown op");
 	if (N < 1) return fail(ctx, WB200_EINVAL, "need at least one track");
 	const bool setop = (op == OP_TTEST || op == OP_MWU);
-	if (!setop) n1 = N;
+	const bool fill = (op == OP_FILLIN || op == OP_TRIMFILL);
+	if (fill && N != 2) return fail(ctx, WB200_EINVAL, "The fill in operator can only work on 2 iterators!");
+	if (fill) { n1 = 1; strict = 0; }      // cover counters: set A = track 0, set B = track 1
+	else if (!setop) n1 = N;
 	const int n2 = N - n1;
 	if (n1 > MAX_TRACKS || n2 > MAX_TRACKS) return fail(ctx, WB200_EUNSUPPORTED, "more than 1023 tracks in a set");
 	// the reference's arity checks (it prints and exit(1)s; here: an error code)

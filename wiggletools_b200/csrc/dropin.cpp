@@ -496,9 +496,7 @@ WiggleIterator *FillInReduction(Multiplexer *multi, wt_bool trim) {
 		printf("The fill in operator can only work on 2 iterators! Got %i\n", multi->count);
 		exit(1);
 	}
-	(void) trim;
-	die("fillIn needs multiplexer rows; not available on a batch (GPU) multiplexer yet");
-	return nullptr;
+	return make_reduction(trim ? WB200_TRIMFILL : WB200_FILLIN, multi);
 }
 
 // -- setComparisons.c -------------------------------------------------------------------

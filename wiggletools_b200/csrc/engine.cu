@@ -294,6 +294,9 @@ __device__ __noinline__ double row_eval(const Row &r) {
 		for (int i = 0; i < N; i++) { r.get(i, x); double d = mean - x; acc += d * d; }
 		return sqrt(acc / N) / mean;
 	}
+	case OP_FILLIN: case OP_TRIMFILL:    // :78-107: track 1's value, or its default where it is absent
+		r.get(1, x);
+		return x;
 	case OP_TTEST: {                     // src/setComparisons.c:56-117
 		const int n1 = job.n1, n2 = N - job.n1;
 		double sum1 = 0, sum2 = 0, sq1 = 0, sq2 = 0;
@@ -429,11 +432,14 @@ __device__ __forceinline__ void st_volatile(unsigned long long *p, unsigned long
 
 // A segment is emitted when enough tracks cover it: any track (gaps are skipped,
 // src/multiplexer.c:112-115), all N under `strict` (:123-128), or at least one of
-// each set for the set comparisons (src/setComparisons.c:48-54).  thr = 1, N, 0.
+// each set for the set comparisons (src/setComparisons.c:48-54).  thr = 1, N, 0;
+// thr = -1: at least one of either set (fillIn over two tracks, src/reducers.c:78-107).
 __device__ __forceinline__ bool keep_rule(int thr, int c) {
 	const int covA = c & COV_MASK;
-	if (thr) return covA >= thr;
-	return covA > 0 && ((c >> COV_B_SHIFT) & COV_MASK) > 0;
+	if (thr > 0) return covA >= thr;
+	const int covB = (c >> COV_B_SHIFT) & COV_MASK;
+	if (thr == 0) return covA > 0 && covB > 0;
+	return (covA | covB) != 0;                          // thr < 0: any track of either set (fillIn)
 }
 
 // ---------------------------------------------------------------------------
@@ -474,7 +480,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	const long long w0 = job.p0 + ((long long) w << job.wlog);
 	const long long w1 = w0 + W;
 	const bool setop = (job.op == OP_TTEST || job.op == OP_MWU);
-	const int thr = setop ? 0 : (job.strict ? N : 1);
+	const int thr = setop ? 0 : job.op == OP_FILLIN ? -1 : (job.strict ? N : 1);   // trimFill: set A is track 0 alone, thr 1
 	constexpr bool EMIT = true;
 	constexpr bool fast = MODE == MODE_FAST;      // fixed-point value path (sum / mean)
 

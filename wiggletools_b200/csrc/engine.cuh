@@ -27,7 +27,7 @@ constexpr int COV_MASK = 1023;
 
 enum Op : int {
 	OP_SUM = 0, OP_PRODUCT = 1, OP_MEAN = 2, OP_VAR = 3, OP_STDDEV = 4, OP_ENTROPY = 5,
-	OP_CV = 6, OP_MIN = 7, OP_MAX = 8, OP_MEDIAN = 9, OP_TTEST = 16, OP_MWU = 17,
+	OP_CV = 6, OP_MIN = 7, OP_MAX = 8, OP_MEDIAN = 9, OP_FILLIN = 10, OP_TRIMFILL = 11, OP_TTEST = 16, OP_MWU = 17,
 	OP_PEARSON = 32   // internal: 2-track moments (PearsonPop, src/statistics.c:414-458)
 };
 
