@@ -240,11 +240,14 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 	CK(cudaMemsetAsync(d_small, 0, 128, s));
 	st.kernels = 0;
 
-	// fixed-point fast path for sum / mean
+	// fixed-point fast paths: sum / mean (one exact accumulator) and var / stddev /
+	// CV (exact sum and sum of squares)
 	job.fast = 0;
-	if ((op == OP_SUM || op == OP_MEAN) && I > 0 && !force_row) {
+	const bool sum_like = (op == OP_SUM || op == OP_MEAN);
+	const bool moment_like = (op == OP_VAR || op == OP_STDDEV || op == OP_ENTROPY || op == OP_CV);
+	if ((sum_like || moment_like) && I > 0 && !force_row) {
 		bool ok = true;
-		for (int i = 0; i < N; i++) if (!std::isfinite(h_dflt[i])) ok = false;
+		for (int i = 0; i < N; i++) if (!std::isfinite(h_dflt[i]) || (moment_like && h_dflt[i] != 0)) ok = false;
 		if (ok) {
 			int64_t stride = std::max<int64_t>(1, I / (1 << 16));
 			CK(launch_sample_maxabs(d_value, I, stride, d_small, s));
@@ -252,32 +255,46 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 			CK(cudaMemcpyAsync(ctx->h_small.p, d_small, 16, cudaMemcpyDeviceToHost, s));
 			CK(cudaStreamSynchronize(s));
 			double maxabs = ctx->h_small.as<double>()[0];
+			const long long lsb_key = ctx->h_small.as<long long>()[1];
 			for (int i = 0; i < N; i++) maxabs = std::max(maxabs, std::fabs(h_dflt[i]));
 			int emax = 0;
 			if (maxabs > 0) { std::frexp(maxabs, &emax); }   // maxabs < 2^emax
-			// format: |m| < 2^mbits; two 32-bit limbs when that is enough for
-			// float32-grade inputs (24-bit mantissas), else three.
 			const int l2n = ceil_log2(2 * (int64_t) N);
 			const int lw = 32 - l2n;
-			const int cap2 = 29 - l2n + lw;
-			const int cap3 = std::min(29 - l2n + 2 * lw, 62 - ceil_log2(N + 1));
-			const char *env = getenv("WB200_LIMBS");
-			int limbs = (env && atoi(env) == 3) ? 3 : ((env && atoi(env) == 2) ? 2 : (cap2 >= 40 ? 2 : 3));
-			int mbits = limbs == 2 ? cap2 : cap3;
-			job.fx_mbits = mbits;
-			job.fx_q = emax + 2 - mbits;           // two bits of headroom above the sampled maximum
-			job.fx_q = std::max(-1000, std::min(1000, job.fx_q));
-			const double inv = std::ldexp(1.0, -job.fx_q), lim = std::ldexp(1.0, mbits);
-			long long base = 0;
-			for (int i = 0; i < N && ok; i++) {
-				double t = h_dflt[i] * inv;
-				if (!(std::fabs(t) < lim) || t != std::rint(t)) ok = false;
-				else { hm_fx[i] = (int64_t) t; base += hm_fx[i]; }
-			}
-			if (ok) {
-				job.fast = 1;
-				job.fx_base = base;
-				CK(cudaMemcpyAsync(ctx->dflt_fx.p, hm_fx, N * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+			if (sum_like) {
+				// format: |m| < 2^mbits; two 32-bit limbs when that is enough for
+				// float32-grade inputs (24-bit mantissas), else three.
+				const int cap2 = 29 - l2n + lw;
+				const int cap3 = std::min(29 - l2n + 2 * lw, 62 - ceil_log2(N + 1));
+				const char *env = getenv("WB200_LIMBS");
+				int limbs = (env && atoi(env) == 3) ? 3 : ((env && atoi(env) == 2) ? 2 : (cap2 >= 40 ? 2 : 3));
+				int mbits = limbs == 2 ? cap2 : cap3;
+				job.fx_mbits = mbits;
+				job.fx_q = emax + 2 - mbits;           // two bits of headroom above the sampled maximum
+				job.fx_q = std::max(-1000, std::min(1000, job.fx_q));
+				const double inv = std::ldexp(1.0, -job.fx_q), lim = std::ldexp(1.0, mbits);
+				long long base = 0;
+				for (int i = 0; i < N && ok; i++) {
+					double t = h_dflt[i] * inv;
+					if (!(std::fabs(t) < lim) || t != std::rint(t)) ok = false;
+					else { hm_fx[i] = (int64_t) t; base += hm_fx[i]; }
+				}
+				if (ok) {
+					job.fast = 1;
+					job.fx_base = base;
+					CK(cudaMemcpyAsync(ctx->dflt_fx.p, hm_fx, N * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+				}
+			} else {
+				// squares must stay exact in 64 bits: m = v 2^-q with q the finest bit seen in
+				// the sample, |m| < 2^mbits, N m^2 < 2^62.  Finer or larger values poison.
+				const int capm = std::min(30, (61 - ceil_log2(N + 1)) / 2);
+				const int q = lsb_key > 0 ? (int) (2048 - lsb_key) : 0;
+				if (emax - q <= capm && 2 * capm <= 29 - l2n + 2 * lw) {
+					job.fast = 2;
+					job.fx_q = std::max(-1000, std::min(1000, q));
+					job.fx_mbits = capm;
+					job.fx_base = 0;
+				}
 			}
 		}
 	}

@@ -68,6 +68,8 @@ struct Misc {                        // scalars, warp totals
 	int ticket, ticket1, ticket2;    // window indices drawn by this CTA (current, next, after next)
 	int pad0;
 	long long wsum[WARPS];           // warp totals (value scan / slow counter)
+	long long wsum2[WARPS];          // warp totals (sum-of-squares scan)
+	unsigned long long base_val2;    // carried-in sum of squares
 	int wcov[WARPS];                 // warp totals (cover scan)
 	int wkeep[WARPS];                // warp totals (counts scan)
 	double wauc[WARPS];
@@ -83,9 +85,10 @@ constexpr uint16_t BK_KEEP = 0x8000, BK_SLOW = 0x4000, BK_IDX = 0x3fff;
 struct Layout {
 	size_t off_cur, off_cur2, off_nxt, off_tn, off_toff, off_tmd, off_cov, off_limb, off_ev, off_rows, total;
 	// after the scan the position arrays are dead; the dense breakpoint list aliases them:
-	size_t off_bpos, off_bkid, off_bval;
+	size_t off_bpos, off_bkid, off_bval, off_bval2, off_bcnt;
 };
 
+// limbs = total number of 32-bit limb arrays (accumulators x limbs per accumulator)
 __host__ __device__ inline Layout make_layout(int wlog, int N, bool emit, int limbs, int rowbuf) {
 	Layout L;
 	const size_t W = (size_t) 1 << wlog;
@@ -97,13 +100,19 @@ __host__ __device__ inline Layout make_layout(int wlog, int N, bool emit, int li
 	L.off_tn = o;   o += nn;
 	L.off_toff = o; o += 2 * nn;
 	L.off_tmd = o;  o += emit ? 2 * nn : 0;
-	L.off_cov = o;  o += 4 * W;
-	L.off_limb = o; o += emit ? (size_t) limbs * 4 * W : 0;
-	L.off_ev = o;   o += W + 16;
-	// dense list: value[W] fp64 | pos[W+8] u16 | kid[W] u16  (12W+16 <= 4W + 8W + W+16)
+	L.off_cov = o;
+	L.off_limb = o + 4 * W;
+	L.off_ev = L.off_limb + (emit ? (size_t) limbs * 4 * W : 0);
+	const size_t pos_bytes = (L.off_ev + W + 16) - L.off_cov;
+	// dense list: sum[W] i64 | sum2[W] i64 (moments) | pos[W+8] u16 | kid[W] u16 | count[W] u16 (moments)
+	const bool two = limbs > 3;
 	L.off_bval = L.off_cov;
-	L.off_bpos = L.off_bval + 8 * W;
+	L.off_bval2 = L.off_bval + 8 * W;
+	L.off_bpos = L.off_bval2 + (two ? 8 * W : 0);
 	L.off_bkid = L.off_bpos + 2 * W + 16;
+	L.off_bcnt = L.off_bkid + 2 * W;
+	const size_t dense_bytes = (L.off_bcnt + (two ? 2 * W : 0)) - L.off_cov;
+	o += pos_bytes > dense_bytes ? pos_bytes : dense_bytes;
 	L.off_rows = (o + 15) / 16 * 16; o = L.off_rows + (size_t) rowbuf;
 	L.total = (o + 15) / 16 * 16;
 	return L;
@@ -414,6 +423,24 @@ __device__ __forceinline__ void block_scan2(Misc *misc, int c, long long a, int 
 	ec = bc + ic - c; ea = ba + ia - a;
 }
 
+// Same with a second 64-bit value (sum and sum of squares).
+__device__ __forceinline__ void block_scan3(Misc *misc, int c, long long a, long long b, int &ec, long long &ea, long long &eb) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int ic = c; long long ia = a, ib = b;
+	for (int d = 1; d < 32; d <<= 1) {
+		int vc = __shfl_up_sync(FULL, ic, d);
+		long long va = __shfl_up_sync(FULL, ia, d), vb = __shfl_up_sync(FULL, ib, d);
+		if (lane >= d) { ic += vc; ia += va; ib += vb; }
+	}
+	if (lane == 31) { misc->wcov[warp] = ic; misc->wsum[warp] = ia; misc->wsum2[warp] = ib; }
+	__syncthreads();
+	int bc = 0; long long ba = 0, bb = 0;
+#pragma unroll
+	for (int k = 0; k < WARPS; k++)
+		if (k < warp) { bc += misc->wcov[k]; ba += misc->wsum[k]; bb += misc->wsum2[k]; }
+	ec = bc + ic - c; ea = ba + ia - a; eb = bb + ib - b;
+}
+
 __device__ __forceinline__ void block_scan1(Misc *misc, int c, int &ec, int &tc) {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	int ic = c;
@@ -442,6 +469,79 @@ __device__ __forceinline__ bool keep_rule(int thr, int c) {
 	return (covA | covB) != 0;                          // thr < 0: any track of either set (fillIn)
 }
 
+// One fixed-point delta into the limb arrays of one accumulator (native 32-bit
+// shared atomics; the limbs are recombined after the scan).
+template <int VLOG, int LIMBS>
+__device__ __forceinline__ void add_limbs(uint32_t *limb, int ph, long long d, int lw) {
+	constexpr int W = THREADS << VLOG;
+	atomicAdd(&limb[ph], (uint32_t) (d & ((1ll << lw) - 1)));
+	if (LIMBS == 2) atomicAdd(&limb[W + ph], (uint32_t) (d >> lw));
+	else {
+		atomicAdd(&limb[W + ph], (uint32_t) ((d >> lw) & ((1ll << lw) - 1)));
+		atomicAdd(&limb[2 * W + ph], (uint32_t) (d >> (2 * lw)));
+	}
+}
+
+// This thread's V positions of one accumulator -> running prefix in registers.
+template <int VLOG, int LIMBS>
+__device__ __forceinline__ long long load_prefix(const uint32_t *limb, int tid, int lw, long long *run) {
+	constexpr int V = 1 << VLOG, W = THREADS << VLOG;
+	const int p0 = tid << VLOG;
+	uint32_t l0[V], l1[V], l2[V];
+	if (VLOG >= 2) {
+		constexpr int NV = V / 4, LV = VLOG - 2;
+		const int swz = (tid >> (3 - LV)) & (NV - 1);
+#pragma unroll
+		for (int q = 0; q < NV; q++) {
+			const int pq = p0 + ((q ^ swz) << 2);
+			const uint4 y = *(const uint4 *) (limb + pq);
+			l0[4 * q] = y.x; l0[4 * q + 1] = y.y; l0[4 * q + 2] = y.z; l0[4 * q + 3] = y.w;
+			const uint4 z = *(const uint4 *) (limb + W + pq);
+			l1[4 * q] = z.x; l1[4 * q + 1] = z.y; l1[4 * q + 2] = z.z; l1[4 * q + 3] = z.w;
+			if (LIMBS == 3) {
+				const uint4 u = *(const uint4 *) (limb + 2 * W + pq);
+				l2[4 * q] = u.x; l2[4 * q + 1] = u.y; l2[4 * q + 2] = u.z; l2[4 * q + 3] = u.w;
+			}
+		}
+	} else {
+#pragma unroll
+		for (int q = 0; q < V; q++) { l0[q] = limb[p0 + q]; l1[q] = limb[W + p0 + q]; if (LIMBS == 3) l2[q] = limb[2 * W + p0 + q]; }
+	}
+	long long a = 0;
+#pragma unroll
+	for (int q = 0; q < V; q++) {
+		if (LIMBS == 2) a += (long long) (unsigned long long) l0[q] + ((long long) (int32_t) l1[q] << lw);
+		else a += (long long) (unsigned long long) l0[q] + ((long long) (unsigned long long) l1[q] << lw)
+		        + ((long long) (int32_t) l2[q] << (2 * lw));
+		run[q] = a;
+	}
+	return a;
+}
+
+// var / stddev / CV of one segment from exact integer moments of the in-play
+// values: c tracks in play, Sx = sum m, Sxx = sum m^2 with value = m * 2^q.
+// Reference arithmetic being matched (src/reducers.c:428-479, :511-563, :672-725):
+//   mean = (sum over all N of float(x)) / N            -- absent tracks contribute 0 here
+//   var    = sum over in-play (mean - v)^2 / N
+//   stddev = sqrt(sum over all N (mean - x)^2 / N),  CV = stddev / mean
+// The sum of squared deviations is evaluated without cancellation:
+//   sum_C (mean - v)^2 = [ (c Sxx - Sx^2) 2^2q + (c mean - X)^2 ] / c ,  X = Sx 2^q
+// where c Sxx - Sx^2 >= 0 is exact in 128-bit integers.
+__device__ __forceinline__ double moments_stat(int op, int N, int c, long long Sx, long long Sxx, double scale) {
+	if (op == OP_VAR && N < 2) return NAN;
+	const double X = (double) Sx * scale;                  // exact: |Sx| < 2^53
+	const double mean = X / N;
+	if (op == OP_CV && mean == 0) return NAN;
+	const __int128 d1 = (__int128) c * (__int128) Sxx - (__int128) Sx * (__int128) Sx;
+	const double D1 = (double) d1 * scale * scale;
+	const double r = fma((double) c, mean, -X);
+	const double EC = (D1 + r * r) / c;
+	if (op == OP_VAR) return EC / N;
+	const double Eall = EC + (double) (N - c) * mean * mean;
+	const double sd = sqrt(Eall / N);
+	return op == OP_CV ? sd / mean : sd;
+}
+
 // ---------------------------------------------------------------------------
 // the window pipeline
 // ---------------------------------------------------------------------------
@@ -460,7 +560,7 @@ __device__ __forceinline__ bool keep_rule(int thr, int c) {
 //  3. compact: flagged positions (breakpoints) are written as a dense list over
 //              the now-dead position arrays; kept ones carry their output rank.
 //  4. emit   : one breakpoint per thread, coalesced 16 B/segment stores.
-enum { MODE_FAST = 1, MODE_ROW = 2 };
+enum { MODE_FAST = 1, MODE_ROW = 2, MODE_MOMENTS = 3 };
 
 template <int MODE, int VLOG, int LIMBS>
 __device__ void process_window(const Job &job, int w, unsigned char *smem, const Layout &L, int32_t *cur,
@@ -481,18 +581,18 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	const long long w1 = w0 + W;
 	const bool setop = (job.op == OP_TTEST || job.op == OP_MWU);
 	const int thr = setop ? 0 : job.op == OP_FILLIN ? -1 : (job.strict ? N : 1);   // trimFill: set A is track 0 alone, thr 1
-	constexpr bool EMIT = true;
-	constexpr bool fast = MODE == MODE_FAST;      // fixed-point value path (sum / mean)
+	constexpr bool fast = MODE == MODE_FAST || MODE == MODE_MOMENTS;   // fixed-point value path
+	constexpr int NACC = MODE == MODE_MOMENTS ? 2 : 1;                 // accumulators: sum (and sum of squares)
 
 	// ---- clear the position arrays -------------------------------------------
 	{
 		const uint4 z = make_uint4(0, 0, 0, 0);
 		uint4 *zc = (uint4 *) cov;
-		constexpr int n16 = (EMIT ? (1 + LIMBS) : 1) * W / 4;     // cov and limbs are contiguous
+		constexpr int n16 = (fast ? (1 + NACC * LIMBS) : 1) * W / 4;     // cov and limbs are contiguous
 		for (int t = tid; t < n16; t += THREADS) zc[t] = z;
 		uint4 *ze = (uint4 *) ev;
 		for (int t = tid; t < W / 16; t += THREADS) ze[t] = z;
-		if (tid == 0) { misc->next_bp = INT_MAX; misc->base_cov = 0; misc->base_val = 0; }
+		if (tid == 0) { misc->next_bp = INT_MAX; misc->base_cov = 0; misc->base_val = 0; misc->base_val2 = 0; }
 	}
 	__syncthreads();
 
@@ -500,7 +600,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	{
 		const int gid = tid >> 3, gl = tid & 7, gsh = (lane >> 3) << 3;
 		int in_cov = 0, my_next = INT_MAX;
-		long long in_val = 0;
+		long long in_val = 0, in_val2 = 0;
 		for (int rb = 0; rb < N; rb += THREADS / 8) {
 			const int i = rb + gid;
 			bool done = i >= N;
@@ -526,10 +626,13 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 				const bool inside = gl < Lst;                        // w0 <= e < w1
 				if (valid && (inside || (gl == Lst && (long long) s < w1))) {
 					int cd = f;
-					long long d = 0;
+					long long d = 0, d2 = 0;
 					if (fast) {
 						long long m;
-						if (to_fixed(val, inv_scale, lim, m)) d = m - md;
+						if (to_fixed(val, inv_scale, lim, m) && (NACC == 1 || (double) (float) val == val)) {
+							d = m - md;                        // moments: the reference rounds values through float
+							if (NACC == 2) d2 = m * m;
+						}
 						else cd += (1 << COV_P_SHIFT);
 					}
 					if ((long long) s >= w0) {
@@ -537,26 +640,17 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 						atomicAdd(&cov[ph], cd);
 						ev[x] = 1;
 						if (fast && d != 0) {
-							atomicAdd(&limb[ph], (uint32_t) (d & ((1ll << lw) - 1)));
-							if (LIMBS == 2) atomicAdd(&limb[W + ph], (uint32_t) (d >> lw));
-							else {
-								atomicAdd(&limb[W + ph], (uint32_t) ((d >> lw) & ((1ll << lw) - 1)));
-								atomicAdd(&limb[2 * W + ph], (uint32_t) (d >> (2 * lw)));
-							}
+							add_limbs<VLOG, LIMBS>(limb, ph, d, lw);
+							if (NACC == 2) add_limbs<VLOG, LIMBS>(limb + LIMBS * W, ph, d2, lw);
 						}
-					} else { in_cov += cd; in_val += d; }            // began before the window
+					} else { in_cov += cd; in_val += d; in_val2 += d2; }   // began before the window
 					if (inside) {
 						const int x = (int) (e - w0), ph = phys<VLOG>(x);
 						atomicAdd(&cov[ph], -cd);
 						ev[x] = 1;
 						if (fast && d != 0) {
-							const long long nd = -d;
-							atomicAdd(&limb[ph], (uint32_t) (nd & ((1ll << lw) - 1)));
-							if (LIMBS == 2) atomicAdd(&limb[W + ph], (uint32_t) (nd >> lw));
-							else {
-								atomicAdd(&limb[W + ph], (uint32_t) ((nd >> lw) & ((1ll << lw) - 1)));
-								atomicAdd(&limb[2 * W + ph], (uint32_t) (nd >> (2 * lw)));
-							}
+							add_limbs<VLOG, LIMBS>(limb, ph, -d, lw);
+							if (NACC == 2) add_limbs<VLOG, LIMBS>(limb + LIMBS * W, ph, -d2, lw);
 						}
 					}
 				}
@@ -574,46 +668,34 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 		my_next = __reduce_min_sync(FULL, my_next);
 		in_cov = __reduce_add_sync(FULL, in_cov);
 		for (int d = 16; d > 0; d >>= 1) in_val += __shfl_down_sync(FULL, in_val, d);
+		if (NACC == 2) for (int d = 16; d > 0; d >>= 1) in_val2 += __shfl_down_sync(FULL, in_val2, d);
 		if (lane == 0) {
 			if (my_next != INT_MAX) atomicMin(&misc->next_bp, my_next);
 			if (in_cov) atomicAdd(&misc->base_cov, in_cov);
 			if (fast && in_val) atomicAdd(&misc->base_val, (unsigned long long) in_val);
+			if (NACC == 2 && in_val2) atomicAdd(&misc->base_val2, (unsigned long long) in_val2);
 		}
 	}
 	__syncthreads();
 
 	// ---- 2. scan: this thread's V positions, in registers -------------------------
 	int c_run[V];
-	long long a_run[V];
+	long long a_run[V], b_run[NACC == 2 ? V : 1];
 	unsigned evbits = 0, keepbits = 0;
 	{
 		const int p0 = tid << VLOG;
-		int cv[V]; uint32_t l0[V], l1[V], l2[V];
+		int cv[V];
 		if (VLOG >= 2) {
 			constexpr int NV = V / 4, LV = VLOG - 2;
 			const int swz = (tid >> (3 - LV)) & (NV - 1);
 #pragma unroll
 			for (int q = 0; q < NV; q++) {
-				const int pq = p0 + ((q ^ swz) << 2);
-				const int4 x = *(const int4 *) (cov + pq);
+				const int4 x = *(const int4 *) (cov + p0 + ((q ^ swz) << 2));
 				cv[4 * q] = x.x; cv[4 * q + 1] = x.y; cv[4 * q + 2] = x.z; cv[4 * q + 3] = x.w;
-				if (fast) {
-					const uint4 y = *(const uint4 *) (limb + pq);
-					l0[4 * q] = y.x; l0[4 * q + 1] = y.y; l0[4 * q + 2] = y.z; l0[4 * q + 3] = y.w;
-					const uint4 z = *(const uint4 *) (limb + W + pq);
-					l1[4 * q] = z.x; l1[4 * q + 1] = z.y; l1[4 * q + 2] = z.z; l1[4 * q + 3] = z.w;
-					if (LIMBS == 3) {
-						const uint4 u = *(const uint4 *) (limb + 2 * W + pq);
-						l2[4 * q] = u.x; l2[4 * q + 1] = u.y; l2[4 * q + 2] = u.z; l2[4 * q + 3] = u.w;
-					}
-				}
 			}
 		} else {
 #pragma unroll
-			for (int q = 0; q < V; q++) {
-				cv[q] = cov[p0 + q];
-				if (fast) { l0[q] = limb[p0 + q]; l1[q] = limb[W + p0 + q]; if (LIMBS == 3) l2[q] = limb[2 * W + p0 + q]; }
-			}
+			for (int q = 0; q < V; q++) cv[q] = cov[p0 + q];
 		}
 		if (V >= 4) {
 			// flags are 0/1 bytes: gather one bit per byte, four positions per word
@@ -626,25 +708,26 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 #pragma unroll
 			for (int q = 0; q < V; q++) if (ev[p0 + q]) evbits |= 1u << q;
 		}
-		int c = 0; long long a = 0;
+		int c = 0;
 #pragma unroll
-		for (int q = 0; q < V; q++) {
-			c += cv[q];
-			c_run[q] = c;
-			if (fast) {
-				if (LIMBS == 2) a += (long long) (unsigned long long) l0[q] + ((long long) (int32_t) l1[q] << lw);
-				else a += (long long) (unsigned long long) l0[q] + ((long long) (unsigned long long) l1[q] << lw)
-				        + ((long long) (int32_t) l2[q] << (2 * lw));
-			}
-			a_run[q] = a;
+		for (int q = 0; q < V; q++) { c += cv[q]; c_run[q] = c; }
+		long long a = 0, b = 0;
+		if (fast) a = load_prefix<VLOG, LIMBS>(limb, tid, lw, a_run);
+		else {
+#pragma unroll
+			for (int q = 0; q < V; q++) a_run[q] = 0;
 		}
-		int ec, tc; long long ea, ta;
-		block_scan2(misc, c, a, ec, ea, tc, ta);          // its barriers also fence the loads above
+		if (NACC == 2) b = load_prefix<VLOG, LIMBS>(limb + LIMBS * W, tid, lw, b_run);
+		int ec; long long ea, eb = 0;
+		if (NACC == 2) block_scan3(misc, c, a, b, ec, ea, eb);
+		else { int tc; long long ta; block_scan2(misc, c, a, ec, ea, tc, ta); }   // the barrier also fences the loads above
 		ec += misc->base_cov;
 		ea += (long long) misc->base_val;
+		if (NACC == 2) eb += (long long) misc->base_val2;
 #pragma unroll
 		for (int q = 0; q < V; q++) {
 			c_run[q] += ec; a_run[q] += ea;
+			if (NACC == 2) b_run[q] += eb;
 			if (keep_rule(thr, c_run[q])) keepbits |= 1u << q;
 		}
 		keepbits &= evbits;
@@ -664,6 +747,8 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	long long *bval = (long long *) (smem + L.off_bval);   // exact fixed-point sum of the segment
 	uint16_t *bpos = (uint16_t *) (smem + L.off_bpos);
 	uint16_t *bkid = (uint16_t *) (smem + L.off_bkid);
+	long long *bval2 = (long long *) (smem + L.off_bval2);  // moments: exact sum of squares
+	uint16_t *bcnt = (uint16_t *) (smem + L.off_bcnt);      // moments: tracks in play
 	constexpr bool row_op = MODE == MODE_ROW;
 	{
 		int rank = epack & 0xffff, kidx = epack >> 16;
@@ -679,6 +764,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 				}
 				bkid[rank] = kd;
 				bval[rank] = a_run[q];
+				if (NACC == 2) { bval2[rank] = b_run[q]; bcnt[rank] = (uint16_t) (c_run[q] & COV_MASK); }
 				rank++;
 			}
 		}
@@ -741,7 +827,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	unsigned long long slow = 0;
 	double auc = 0;
 
-	if (MODE == MODE_FAST) {
+	if (MODE == MODE_FAST || MODE == MODE_MOMENTS) {
 		const bool npow2 = (N & (N - 1)) == 0;
 		const double inv_n = 1.0 / N;
 		for (int base = 0; base < nbp; base += THREADS) {
@@ -752,8 +838,12 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 			const long long oi = out_base + (kd & BK_IDX);
 			const int bs = (int) (w0 + bpos[r]);
 			const int be = (r + 1 < nbp) ? (int) (w0 + bpos[r + 1]) : next_bp;
-			double v = (double) (bval[r] + job.fx_base) * scale;   // correctly rounded exact sum
-			if (job.op == OP_MEAN) v = npow2 ? v * inv_n : v / N;  // 1/N is exact for a power of two
+			double v;
+			if (MODE == MODE_MOMENTS) v = moments_stat(job.op == OP_ENTROPY ? OP_STDDEV : job.op, N, bcnt[r], bval[r], bval2[r], scale);
+			else {
+				v = (double) (bval[r] + job.fx_base) * scale;      // correctly rounded exact sum
+				if (job.op == OP_MEAN) v = npow2 ? v * inv_n : v / N;  // 1/N is exact for a power of two
+			}
 			if (oi < job.out_cap) {
 				job.out_start[oi] = bs;
 				job.out_end[oi] = be;
@@ -881,9 +971,9 @@ __global__ void __launch_bounds__(256) cursor_kernel(const Job job) {
 }
 
 template <int MODE, int VLOG, int LIMBS>
-__global__ void __launch_bounds__(THREADS, MODE == MODE_FAST ? (THREADS == 512 ? 2 : 3) : 1) emit_kernel(const Job job, int lw, double inv_scale, double lim, double scale, int rowbuf) {
+__global__ void __launch_bounds__(THREADS, MODE == MODE_FAST ? (THREADS == 512 ? 2 : 3) : MODE == MODE_MOMENTS ? 2 : 1) emit_kernel(const Job job, int lw, double inv_scale, double lim, double scale, int rowbuf) {
 	extern __shared__ __align__(16) unsigned char smem[];
-	const Layout L = make_layout(job.wlog, job.N, true, LIMBS, rowbuf);
+	const Layout L = make_layout(job.wlog, job.N, true, (MODE == MODE_MOMENTS ? 2 : 1) * LIMBS, rowbuf);
 	int32_t *cur = (int32_t *) (smem + L.off_cur);
 	int32_t *tn = (int32_t *) (smem + L.off_tn);
 	long long *toff = (long long *) (smem + L.off_toff);
@@ -892,7 +982,7 @@ __global__ void __launch_bounds__(THREADS, MODE == MODE_FAST ? (THREADS == 512 ?
 		const long long o = job.off[i];
 		toff[i] = o;
 		tn[i] = (int) (job.off[i + 1] - o);
-		tmd[i] = MODE == MODE_FAST ? job.dflt_fx[i] : 0;
+		tmd[i] = MODE == MODE_FAST ? job.dflt_fx[i] : 0;   // moments path: all defaults are 0
 	}
 	Misc *misc = (Misc *) smem;
 	int32_t *ca = cur, *cb = (int32_t *) (smem + L.off_cur2);   // current / next cursor rows
@@ -923,17 +1013,30 @@ __global__ void __launch_bounds__(THREADS, MODE == MODE_FAST ? (THREADS == 512 ?
 	}
 }
 
-// max |v| over a strided sample of the values, and the largest exponent seen:
-// chooses the fixed-point scale.  out2[0] = max finite |v|.
+// max |v| over a strided sample of the values, and the finest significant bit seen:
+// they choose the fixed-point scale.  out2[0] = bits of the largest finite |v|;
+// out2[1] = 2048 - (exponent of the lowest set significand bit), 0 if no non-zero value.
 __global__ void sample_maxabs_kernel(const double *value, int64_t n, int64_t stride, double *out2) {
 	double m = 0;
+	long long key = 0;
 	for (int64_t i = (int64_t) (blockIdx.x * blockDim.x + threadIdx.x) * stride; i < n; i += (int64_t) gridDim.x * blockDim.x * stride) {
-		double v = fabs(value[i]);
+		const double v = fabs(value[i]);
 		if (v < DBL_MAX && v > m) m = v;   // skips NaN and Inf
+		if (v < DBL_MAX && v >= DBL_MIN) {
+			const long long bits = __double_as_longlong(v);
+			const long long mant = (bits & ((1ll << 52) - 1)) | (1ll << 52);
+			const int lsb = (int) (bits >> 52) - 1075 + (__ffsll(mant) - 1);
+			key = max(key, (long long) (2048 - lsb));
+		}
 	}
-	for (int d = 16; d > 0; d >>= 1) m = fmax(m, __shfl_down_sync(FULL, m, d));
-	if ((threadIdx.x & 31) == 0 && m > 0)
-		atomicMax((unsigned long long *) out2, (unsigned long long) __double_as_longlong(m)); // positive doubles order like integers
+	for (int d = 16; d > 0; d >>= 1) {
+		m = fmax(m, __shfl_down_sync(FULL, m, d));
+		key = max(key, __shfl_down_sync(FULL, key, d));
+	}
+	if ((threadIdx.x & 31) == 0) {
+		if (m > 0) atomicMax((unsigned long long *) out2, (unsigned long long) __double_as_longlong(m)); // positive doubles order like integers
+		if (key > 0) atomicMax((unsigned long long *) out2 + 1, (unsigned long long) key);
+	}
 }
 
 __global__ void __launch_bounds__(1024) reduce_auc_kernel(const double *partial, int nw, double *out) {
@@ -957,7 +1060,7 @@ static int row_buffer_bytes(int N, int op) {
 }
 
 size_t window_smem_bytes(int wlog, int N, bool emit, int op) {
-	return make_layout(wlog, N, emit, 3, emit ? row_buffer_bytes(N, op) : 0).total;
+	return make_layout(wlog, N, emit, 6, emit ? row_buffer_bytes(N, op) : 0).total;
 }
 
 cudaError_t launch_cursor(const Job &job, int64_t max_track_len, cudaStream_t s) {
@@ -968,7 +1071,7 @@ cudaError_t launch_cursor(const Job &job, int64_t max_track_len, cudaStream_t s)
 
 template <int MODE, int VLOG, int LIMBS>
 static cudaError_t launch_emit_v(const Job &job, int lw, double inv_scale, double lim, double scale, int rowbuf, cudaStream_t s) {
-	size_t smem = make_layout(job.wlog, job.N, true, LIMBS, rowbuf).total;
+	size_t smem = make_layout(job.wlog, job.N, true, (MODE == MODE_MOMENTS ? 2 : 1) * LIMBS, rowbuf).total;
 	int dev = 0, sms = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -986,10 +1089,14 @@ cudaError_t launch_emit(const Job &job, cudaStream_t s) {
 	int l2n = 1; while ((1 << l2n) < 2 * job.N) l2n++;
 	int lw = 32 - l2n;
 	int limbs = 2;
-	if (job.fast && job.fx_mbits > 29 - l2n + lw) limbs = 3;
+	// widest delta: |m| < 2^mbits (+1 for m - default), or m^2 < 2^(2 mbits) on the moments path
+	const int dbits = job.fast == 2 ? 2 * job.fx_mbits : job.fx_mbits + 1;
+	if (job.fast && dbits > 30 - l2n + lw) limbs = 3;
 	double inv_scale = ldexp(1.0, -job.fx_q), scale = ldexp(1.0, job.fx_q), lim = ldexp(1.0, job.fx_mbits);
 	int rowbuf = row_buffer_bytes(job.N, job.op);
 #define WB_EMIT(V) (!job.fast ? launch_emit_v<MODE_ROW, V, 2>(job, lw, inv_scale, lim, scale, rowbuf, s) \
+                  : job.fast == 2 ? (limbs == 2 ? launch_emit_v<MODE_MOMENTS, V, 2>(job, lw, inv_scale, lim, scale, rowbuf, s) \
+                                               : launch_emit_v<MODE_MOMENTS, V, 3>(job, lw, inv_scale, lim, scale, rowbuf, s)) \
                   : limbs == 2 ? launch_emit_v<MODE_FAST, V, 2>(job, lw, inv_scale, lim, scale, rowbuf, s) \
                                : launch_emit_v<MODE_FAST, V, 3>(job, lw, inv_scale, lim, scale, rowbuf, s))
 	switch (job.wlog - TLOG) {       // positions per thread = 2^VLOG
