@@ -80,6 +80,7 @@ struct Misc {                        // scalars, warp totals
 constexpr int MISC_BYTES = 2048;
 static_assert(sizeof(Misc) <= MISC_BYTES, "Misc must fit its shared-memory slot");
 
+constexpr int WALK_MAX_TRACKS = 512;    // order-statistic sweep: N keys per warp in shared memory
 constexpr uint16_t BK_KEEP = 0x8000, BK_SLOW = 0x4000, BK_IDX = 0x3fff;
 
 struct Layout {
@@ -467,6 +468,154 @@ __device__ __forceinline__ bool keep_rule(int thr, int c) {
 	const int covB = (c >> COV_B_SHIFT) & COV_MASK;
 	if (thr == 0) return covA > 0 && covB > 0;
 	return (covA | covB) != 0;                          // thr < 0: any track of either set (fillIn)
+}
+
+// ---------------------------------------------------------------------------
+// order statistics by an incremental sweep (min, max, median)
+// ---------------------------------------------------------------------------
+// The reference sorts (median: qsort, src/reducers.c:809) or scans (min/max,
+// :125-235) all N values again for every segment.  Consecutive segments differ
+// in the one or two tracks that start or end at the breakpoint between them, so
+// each warp keeps the N values of its current segment SORTED in shared memory
+// (key = value, track index: the stable order of the reference's merge sort)
+// and, walking its share of the window's breakpoints, replaces only the keys of
+// the tracks that change: O(N/32) per change instead of O(N log N) per segment.
+//   min = arr[0], max = arr[N-1], median = arr[N/2] (upper median, :810).
+// Per track the warp remembers the interval that covers / follows the current
+// position and the position of its next event; "which tracks change here" is
+// one compare per track and a ballot.
+struct TrackState { int j; int nextpos; };
+
+// Position a track at coordinate b: interval index j = first interval with
+// end > b inside the window's cursor range, value-or-default, next event.
+__device__ __forceinline__ void walk_locate(const Job &job, const int32_t *cur, const int32_t *nxt, int i, int b,
+                                            double dflt, TrackState &ts, double &x) {
+	const long long o = job.off[i];
+	const int n = (int) (job.off[i + 1] - o);
+	int lo = cur[i], hi = min(nxt[i], n - 1) + 1;         // search [lo, hi): ends ascending
+	while (lo < hi) {
+		const int mid = (lo + hi) >> 1;
+		if (job.end[o + mid] > b) hi = mid; else lo = mid + 1;
+	}
+	ts.j = lo;
+	if (lo < n) {
+		const int st = job.start[o + lo];
+		if (st <= b) { x = job.value[o + lo]; ts.nextpos = job.end[o + lo]; }
+		else { x = dflt; ts.nextpos = st; }
+	} else { x = dflt; ts.nextpos = INT_MAX; }
+}
+
+// One warp: segments [r0, r1) of the window's dense breakpoint list.
+__device__ void order_walk(const Job &job, const int32_t *cur, const int32_t *nxt, long long w0, int r0, int r1, int nbp,
+                           int next_bp, const uint16_t *bpos, const uint16_t *bkid, long long out_base,
+                           SortKey *arr, TrackState *tstate, int P, double &auc, unsigned long long &slow) {
+	const int N = job.N, lane = threadIdx.x & 31;
+	const bool minmax = (job.op == OP_MIN || job.op == OP_MAX);
+	const int sel = job.op == OP_MIN ? 0 : job.op == OP_MAX ? N - 1 : N / 2;
+	const int b0 = (int) (w0 + bpos[r0]);
+	int nan_cnt = 0;
+	for (int i = lane; i < P; i += 32) {
+		SortKey k;
+		k.pad = 0;
+		if (i < N) {
+			// min/max read a literal 0 for an absent track 0, not its default (reducers.c:142-145,209-212)
+			const double d = (minmax && i == 0) ? 0.0 : job.dflt[i];
+			TrackState ts; double x;
+			walk_locate(job, cur, nxt, i, b0, d, ts, x);
+			tstate[i] = ts;
+			if (isnan(x)) { nan_cnt++; x = INFINITY; }
+			k.v = x; k.ord = i;
+		} else { k.v = INFINITY; k.ord = INT_MAX; }
+		arr[i] = k;
+	}
+	nan_cnt = __reduce_add_sync(FULL, nan_cnt);
+	__syncwarp();
+	for (int k = 2; k <= P; k <<= 1)
+		for (int j = k >> 1; j > 0; j >>= 1) {
+			for (int t = lane; t < P / 2; t += 32) {
+				const int i = ((t / j) * 2 * j) + (t % j), l = i + j;
+				const bool up = ((i & k) == 0);
+				const SortKey a = arr[i], b = arr[l];
+				if (up ? key_less(b, a) : key_less(a, b)) { arr[i] = b; arr[l] = a; }
+			}
+			__syncwarp();
+		}
+	for (int r = r0; r < r1; r++) {
+		const int p = (int) (w0 + bpos[r]);
+		if (r > r0) {
+			// tracks with an event at p: replace their key in the sorted array
+			for (int base = 0; base < N; base += 32) {
+				const int i = base + lane;
+				unsigned bal = __ballot_sync(FULL, i < N && tstate[i].nextpos == p);
+				while (bal) {
+					const int src = __ffs(bal) - 1;
+					bal &= bal - 1;
+					double oldx = 0, newx = 0;
+					if (lane == src) {
+						const long long o = job.off[i];
+						const int n = (int) (job.off[i + 1] - o);
+						const double d = (minmax && i == 0) ? 0.0 : job.dflt[i];
+						TrackState ts = tstate[i];
+						const bool was_in = job.start[o + ts.j] < p;       // else its interval starts at p
+						oldx = was_in ? job.value[o + ts.j] : d;
+						if (was_in) ts.j++;
+						if (ts.j < n && job.start[o + ts.j] <= p) { newx = job.value[o + ts.j]; ts.nextpos = job.end[o + ts.j]; }
+						else { newx = d; ts.nextpos = ts.j < n ? job.start[o + ts.j] : INT_MAX; }
+						tstate[i] = ts;
+					}
+					oldx = __shfl_sync(FULL, oldx, src);
+					newx = __shfl_sync(FULL, newx, src);
+					const int t = base + src;
+					nan_cnt += (isnan(newx) ? 1 : 0) - (isnan(oldx) ? 1 : 0);
+					SortKey ko, kn;
+					ko.v = isnan(oldx) ? INFINITY : oldx; ko.ord = t; ko.pad = 0;
+					kn.v = isnan(newx) ? INFINITY : newx; kn.ord = t; kn.pad = 0;
+					// ranks of the old and the new key among the N keys
+					int lo = 0, ln = 0;
+					for (int q = lane; q < N; q += 32) {
+						const SortKey a = arr[q];
+						lo += key_less(a, ko) ? 1 : 0;
+						ln += key_less(a, kn) ? 1 : 0;
+					}
+					const int io = __reduce_add_sync(FULL, lo);
+					int in = __reduce_add_sync(FULL, ln);
+					if (key_less(ko, kn)) in--;                      // the old key itself was counted below the new one
+					if (in > io) {
+						for (int q = io; q < in; q += 32) {              // close the gap: shift (io, in] down
+							SortKey a; const bool act = q + lane < in;
+							if (act) a = arr[q + lane + 1];
+							__syncwarp();
+							if (act) arr[q + lane] = a;
+							__syncwarp();
+						}
+					} else if (in < io) {
+						for (int q = io; q > in; q -= 32) {              // open a gap: shift [in, io) up, from the top
+							SortKey a; const int idx = q - 1 - lane; const bool act = idx >= in;
+							if (act) a = arr[idx];
+							__syncwarp();
+							if (act) arr[idx + 1] = a;
+							__syncwarp();
+						}
+					}
+					if (lane == 0) arr[in] = kn;
+					__syncwarp();
+				}
+			}
+		}
+		const uint16_t kd = bkid[r];
+		if ((kd & BK_KEEP) && lane == 0) {
+			const int be = (r + 1 < nbp) ? (int) (w0 + bpos[r + 1]) : next_bp;
+			const double v = nan_cnt ? NAN : arr[sel].v;
+			const long long oi = out_base + (kd & BK_IDX);
+			if (oi < job.out_cap) {
+				job.out_start[oi] = p;
+				job.out_end[oi] = be;
+				job.out_value[oi] = v;
+			}
+			if (!isnan(v)) auc += (double) (be - p) * v;
+			slow++;
+		}
+	}
 }
 
 // One fixed-point delta into the limb arrays of one accumulator (native 32-bit
@@ -858,11 +1007,21 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 			if (!(kd & BK_SLOW) && !isnan(v)) auc += (double) (be - bs) * v;
 		}
 	} else {
+		const bool walk_op = (job.op == OP_MEDIAN || job.op == OP_MIN || job.op == OP_MAX) && N <= WALK_MAX_TRACKS;
 		const bool sorted_op = (job.op == OP_MEDIAN || job.op == OP_MWU);
 		const bool pearson = (job.op == OP_PEARSON);
 		Row row; row.job = &job; row.cur = cur; row.nxt = nxt; row.b = 0;
 		Mom mom = {0, 0, 0, 0, 0, 0};
-		for (int base = 0; base < nbp; base += THREADS) {
+		if (walk_op) {
+			// each warp sweeps a contiguous share of the window's breakpoints
+			int P = 1; while (P < N) P <<= 1;
+			SortKey *arr = (SortKey *) (smem + L.off_rows) + (size_t) warp * P;
+			TrackState *tstate = (TrackState *) (smem + L.off_rows + (size_t) WARPS * P * sizeof(SortKey)) + (size_t) warp * N;
+			const int chunk = (nbp + WARPS - 1) / WARPS;
+			const int r0 = warp * chunk, r1 = min(nbp, r0 + chunk);
+			if (r0 < r1) order_walk(job, cur, nxt, w0, r0, r1, nbp, next_bp, bpos, bkid, out_base, arr, tstate, P, auc, slow);
+		}
+		for (int base = 0; base < nbp && !walk_op; base += THREADS) {
 			const int r = base + tid;
 			uint16_t kd = 0;
 			if (r < nbp) kd = bkid[r];
@@ -1054,9 +1213,12 @@ __global__ void __launch_bounds__(1024) reduce_auc_kernel(const double *partial,
 // host-side launchers
 // ---------------------------------------------------------------------------
 static int row_buffer_bytes(int N, int op) {
-	if (op != OP_MEDIAN && op != OP_MWU) return 0;
+	if (op != OP_MEDIAN && op != OP_MWU && op != OP_MIN && op != OP_MAX) return 0;
+	if ((op == OP_MIN || op == OP_MAX) && N > WALK_MAX_TRACKS) return 0;      // plain row loop
 	int P = 1; while (P < N) P <<= 1;
-	return P * (int) sizeof(SortKey) * WARPS;
+	int bytes = P * (int) sizeof(SortKey) * WARPS;                             // sorted keys, one array per warp
+	if (op != OP_MWU && N <= WALK_MAX_TRACKS) bytes += N * (int) sizeof(TrackState) * WARPS;
+	return bytes;
 }
 
 size_t window_smem_bytes(int wlog, int N, bool emit, int op) {
