@@ -486,6 +486,21 @@ __device__ __forceinline__ bool keep_rule(int thr, int c) {
 // one compare per track and a ballot.
 struct TrackState { int j; int nextpos; };
 
+// The window's intervals, staged once in shared memory (start/end/value of
+// interval j of track i at tbase[i] + j - cur[i]); falls back to global memory
+// when a window holds more intervals than the staging area.
+constexpr int WALK_STAGE_CAP = 1536;
+struct IvAccess {
+	const Job *job;
+	const int32_t *cur;
+	const int32_t *tbase;      // null: not staged
+	const int32_t *ss, *se;
+	const double *sv;
+	__device__ __forceinline__ int start(int i, long long o, int j) const { return tbase ? ss[tbase[i] + j - cur[i]] : job->start[o + j]; }
+	__device__ __forceinline__ int end(int i, long long o, int j) const { return tbase ? se[tbase[i] + j - cur[i]] : job->end[o + j]; }
+	__device__ __forceinline__ double value(int i, long long o, int j) const { return tbase ? sv[tbase[i] + j - cur[i]] : job->value[o + j]; }
+};
+
 // Position a track at coordinate b: interval index j = first interval with
 // end > b inside the window's cursor range, value-or-default, next event.
 __device__ __forceinline__ void walk_locate(const Job &job, const int32_t *cur, const int32_t *nxt, int i, int b,
@@ -508,7 +523,7 @@ __device__ __forceinline__ void walk_locate(const Job &job, const int32_t *cur, 
 // One warp: segments [r0, r1) of the window's dense breakpoint list.
 __device__ void order_walk(const Job &job, const int32_t *cur, const int32_t *nxt, long long w0, int r0, int r1, int nbp,
                            int next_bp, const uint16_t *bpos, const uint16_t *bkid, long long out_base,
-                           SortKey *arr, TrackState *tstate, int P, double &auc, unsigned long long &slow) {
+                           SortKey *arr, TrackState *tstate, int P, const IvAccess &iv, double &auc, unsigned long long &slow) {
 	const int N = job.N, lane = threadIdx.x & 31;
 	const bool minmax = (job.op == OP_MIN || job.op == OP_MAX);
 	const int sel = job.op == OP_MIN ? 0 : job.op == OP_MAX ? N - 1 : N / 2;
@@ -556,11 +571,14 @@ __device__ void order_walk(const Job &job, const int32_t *cur, const int32_t *nx
 						const int n = (int) (job.off[i + 1] - o);
 						const double d = (minmax && i == 0) ? 0.0 : job.dflt[i];
 						TrackState ts = tstate[i];
-						const bool was_in = job.start[o + ts.j] < p;       // else its interval starts at p
-						oldx = was_in ? job.value[o + ts.j] : d;
+						// (intervals up to nxt[i] are staged; the sweep never moves past them inside the window)
+						const bool was_in = iv.start(i, o, ts.j) < p;      // else its interval starts at p
+						oldx = was_in ? iv.value(i, o, ts.j) : d;
 						if (was_in) ts.j++;
-						if (ts.j < n && job.start[o + ts.j] <= p) { newx = job.value[o + ts.j]; ts.nextpos = job.end[o + ts.j]; }
-						else { newx = d; ts.nextpos = ts.j < n ? job.start[o + ts.j] : INT_MAX; }
+						const bool have = ts.j < n && ts.j <= nxt[i];
+						const int ns = have ? iv.start(i, o, ts.j) : (ts.j < n ? job.start[o + ts.j] : INT_MAX);
+						if (have && ns <= p) { newx = iv.value(i, o, ts.j); ts.nextpos = iv.end(i, o, ts.j); }
+						else { newx = d; ts.nextpos = ns; }
 						tstate[i] = ts;
 					}
 					oldx = __shfl_sync(FULL, oldx, src);
@@ -709,7 +727,7 @@ __device__ __forceinline__ double moments_stat(int op, int N, int c, long long S
 //  3. compact: flagged positions (breakpoints) are written as a dense list over
 //              the now-dead position arrays; kept ones carry their output rank.
 //  4. emit   : one breakpoint per thread, coalesced 16 B/segment stores.
-enum { MODE_FAST = 1, MODE_ROW = 2, MODE_MOMENTS = 3 };
+enum { MODE_FAST = 1, MODE_ROW = 2, MODE_MOMENTS = 3, MODE_WALK = 4 };
 
 template <int MODE, int VLOG, int LIMBS>
 __device__ void process_window(const Job &job, int w, unsigned char *smem, const Layout &L, int32_t *cur,
@@ -1006,22 +1024,47 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 			}
 			if (!(kd & BK_SLOW) && !isnan(v)) auc += (double) (be - bs) * v;
 		}
-	} else {
-		const bool walk_op = (job.op == OP_MEDIAN || job.op == OP_MIN || job.op == OP_MAX) && N <= WALK_MAX_TRACKS;
-		const bool sorted_op = (job.op == OP_MEDIAN || job.op == OP_MWU);
-		const bool pearson = (job.op == OP_PEARSON);
-		Row row; row.job = &job; row.cur = cur; row.nxt = nxt; row.b = 0;
-		Mom mom = {0, 0, 0, 0, 0, 0};
-		if (walk_op) {
+	} else if (MODE == MODE_WALK) {
+		{
 			// each warp sweeps a contiguous share of the window's breakpoints
 			int P = 1; while (P < N) P <<= 1;
 			SortKey *arr = (SortKey *) (smem + L.off_rows) + (size_t) warp * P;
 			TrackState *tstate = (TrackState *) (smem + L.off_rows + (size_t) WARPS * P * sizeof(SortKey)) + (size_t) warp * N;
+			// stage the window's intervals: the sweep is a chain of dependent reads
+			unsigned char *stage = smem + L.off_rows + (size_t) WARPS * (P * sizeof(SortKey) + N * sizeof(TrackState));
+			double *sv = (double *) stage;
+			int32_t *ss = (int32_t *) (sv + WALK_STAGE_CAP), *se = ss + WALK_STAGE_CAP, *tbase = se + WALK_STAGE_CAP;
+			int run = 0;
+			for (int base = 0; base < N; base += THREADS) {
+				const int i = base + tid;
+				const int len = i < N ? max(0, min(nxt[i], tn[i] - 1) - cur[i] + 1) : 0;
+				int ec, tc;
+				block_scan1(misc, len, ec, tc);
+				if (i < N) tbase[i] = run + ec;
+				run += tc;
+				__syncthreads();
+			}
+			const bool staged = run <= WALK_STAGE_CAP;
+			if (staged) {
+				const int gid = tid >> 3, gl = tid & 7;
+				for (int i = gid; i < N; i += THREADS / 8) {
+					const long long o = toff[i];
+					const int jl = min(nxt[i], tn[i] - 1), b = tbase[i] - cur[i];
+					for (int j = cur[i] + gl; j <= jl; j += 8) { ss[b + j] = job.start[o + j]; se[b + j] = job.end[o + j]; sv[b + j] = job.value[o + j]; }
+				}
+			}
+			__syncthreads();
+			IvAccess iv; iv.job = &job; iv.cur = cur; iv.tbase = staged ? tbase : nullptr; iv.ss = ss; iv.se = se; iv.sv = sv;
 			const int chunk = (nbp + WARPS - 1) / WARPS;
 			const int r0 = warp * chunk, r1 = min(nbp, r0 + chunk);
-			if (r0 < r1) order_walk(job, cur, nxt, w0, r0, r1, nbp, next_bp, bpos, bkid, out_base, arr, tstate, P, auc, slow);
+			if (r0 < r1) order_walk(job, cur, nxt, w0, r0, r1, nbp, next_bp, bpos, bkid, out_base, arr, tstate, P, iv, auc, slow);
 		}
-		for (int base = 0; base < nbp && !walk_op; base += THREADS) {
+	} else {
+		const bool sorted_op = (job.op == OP_MEDIAN || job.op == OP_MWU);
+		const bool pearson = (job.op == OP_PEARSON);
+		Row row; row.job = &job; row.cur = cur; row.nxt = nxt; row.b = 0;
+		Mom mom = {0, 0, 0, 0, 0, 0};
+		for (int base = 0; base < nbp; base += THREADS) {
 			const int r = base + tid;
 			uint16_t kd = 0;
 			if (r < nbp) kd = bkid[r];
@@ -1100,7 +1143,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	}
 	if (lane == 0) {
 		if (job.auc_partial) job.auc_partial[(size_t) w * WARPS + warp] = auc;
-		if (MODE == MODE_ROW && slow && job.slow_count) atomicAdd(job.slow_count, slow);
+		if ((MODE == MODE_ROW || MODE == MODE_WALK) && slow && job.slow_count) atomicAdd(job.slow_count, slow);
 	}
 	if (MODE == MODE_ROW && job.op == OP_PEARSON) {
 		__syncthreads();
@@ -1130,7 +1173,7 @@ __global__ void __launch_bounds__(256) cursor_kernel(const Job job) {
 }
 
 template <int MODE, int VLOG, int LIMBS>
-__global__ void __launch_bounds__(THREADS, MODE == MODE_FAST ? (THREADS == 512 ? 2 : 3) : MODE == MODE_MOMENTS ? 2 : 1) emit_kernel(const Job job, int lw, double inv_scale, double lim, double scale, int rowbuf) {
+__global__ void __launch_bounds__(THREADS, MODE == MODE_FAST ? (THREADS == 512 ? 2 : 3) : MODE == MODE_MOMENTS ? 2 : MODE == MODE_WALK ? 3 : 1) emit_kernel(const Job job, int lw, double inv_scale, double lim, double scale, int rowbuf) {
 	extern __shared__ __align__(16) unsigned char smem[];
 	const Layout L = make_layout(job.wlog, job.N, true, (MODE == MODE_MOMENTS ? 2 : 1) * LIMBS, rowbuf);
 	int32_t *cur = (int32_t *) (smem + L.off_cur);
@@ -1217,7 +1260,8 @@ static int row_buffer_bytes(int N, int op) {
 	if ((op == OP_MIN || op == OP_MAX) && N > WALK_MAX_TRACKS) return 0;      // plain row loop
 	int P = 1; while (P < N) P <<= 1;
 	int bytes = P * (int) sizeof(SortKey) * WARPS;                             // sorted keys, one array per warp
-	if (op != OP_MWU && N <= WALK_MAX_TRACKS) bytes += N * (int) sizeof(TrackState) * WARPS;
+	if (op != OP_MWU && N <= WALK_MAX_TRACKS)
+		bytes += N * (int) sizeof(TrackState) * WARPS + WALK_STAGE_CAP * 16 + (N + 4) / 4 * 16;   // + staged intervals
 	return bytes;
 }
 
@@ -1256,7 +1300,9 @@ cudaError_t launch_emit(const Job &job, cudaStream_t s) {
 	if (job.fast && dbits > 30 - l2n + lw) limbs = 3;
 	double inv_scale = ldexp(1.0, -job.fx_q), scale = ldexp(1.0, job.fx_q), lim = ldexp(1.0, job.fx_mbits);
 	int rowbuf = row_buffer_bytes(job.N, job.op);
-#define WB_EMIT(V) (!job.fast ? launch_emit_v<MODE_ROW, V, 2>(job, lw, inv_scale, lim, scale, rowbuf, s) \
+	const bool walk = (job.op == OP_MEDIAN || job.op == OP_MIN || job.op == OP_MAX) && job.N <= WALK_MAX_TRACKS;
+#define WB_EMIT(V) (walk ? launch_emit_v<MODE_WALK, V, 2>(job, lw, inv_scale, lim, scale, rowbuf, s) \
+                  : !job.fast ? launch_emit_v<MODE_ROW, V, 2>(job, lw, inv_scale, lim, scale, rowbuf, s) \
                   : job.fast == 2 ? (limbs == 2 ? launch_emit_v<MODE_MOMENTS, V, 2>(job, lw, inv_scale, lim, scale, rowbuf, s) \
                                                : launch_emit_v<MODE_MOMENTS, V, 3>(job, lw, inv_scale, lim, scale, rowbuf, s)) \
                   : limbs == 2 ? launch_emit_v<MODE_FAST, V, 2>(job, lw, inv_scale, lim, scale, rowbuf, s) \
