@@ -1163,13 +1163,21 @@ __global__ void __launch_bounds__(256) cursor_kernel(const Job job) {
 	const int i = blockIdx.y;
 	const long long o = job.off[i];
 	const int n = (int) (job.off[i + 1] - o);
-	const long long j = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-	if (j > n) return;
-	const long long e_prev = j > 0 ? (long long) job.end[o + j - 1] : LLONG_MIN / 2;
-	const long long e = j < n ? (long long) job.end[o + j] : LLONG_MAX / 2;
-	long long wlo = e_prev < job.p0 ? 0 : ((e_prev - job.p0) >> job.wlog) + 1;
-	long long whi = e < job.p0 ? -1 : min((long long) job.nw, (e - job.p0) >> job.wlog);
-	for (long long w = wlo; w <= whi; w++) job.cursor[(size_t) w * job.N + i] = (int32_t) j;
+	// four consecutive intervals per thread: one pass over `end`, few threads
+	const long long j0 = ((long long) blockIdx.x * blockDim.x + threadIdx.x) * 4;
+	if (j0 > n) return;
+	long long e_prev = j0 > 0 ? (long long) job.end[o + j0 - 1] : LLONG_MIN / 2;
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		const long long j = j0 + k;
+		if (j > n) break;
+		const long long e = j < n ? (long long) job.end[o + j] : LLONG_MAX / 2;
+		// windows whose start lies in (e_prev, e]: usually none, sometimes one
+		const long long wlo = e_prev < job.p0 ? 0 : ((e_prev - job.p0) >> job.wlog) + 1;
+		const long long whi = e < job.p0 ? -1 : min((long long) job.nw, (e - job.p0) >> job.wlog);
+		for (long long w = wlo; w <= whi; w++) job.cursor[(size_t) w * job.N + i] = (int32_t) j;
+		e_prev = e;
+	}
 }
 
 template <int MODE, int VLOG, int LIMBS>
@@ -1270,7 +1278,7 @@ size_t window_smem_bytes(int wlog, int N, bool emit, int op) {
 }
 
 cudaError_t launch_cursor(const Job &job, int64_t max_track_len, cudaStream_t s) {
-	dim3 grid((unsigned) ((max_track_len + 1 + 255) / 256), (unsigned) job.N);
+	dim3 grid((unsigned) (((max_track_len + 4) / 4 + 255) / 256), (unsigned) job.N);
 	cursor_kernel<<<grid, 256, 0, s>>>(job);
 	return cudaGetLastError();
 }
