@@ -93,10 +93,10 @@ typedef struct wb200_stats {
 	int64_t intervals;       /* I: input intervals consumed */
 	int64_t segments;        /* S: segments emitted */
 	int64_t windows;
-	int64_t slow_segments;   /* segments evaluated by the row path inside the fast kernel */
+	int64_t slow_segments;   /* segments evaluated per segment (row / sweep paths, fix-ups of the exact paths) */
 	int32_t kernels;         /* kernel launches issued by the call */
-	int32_t fast_path;       /* 1 if the fixed-point scan path was used */
-	float ms_count;          /* device time of the count kernel(s) */
+	int32_t fast_path;       /* 0 row or sweep path, 1 exact sum path, 2 exact moments path */
+	float ms_count;          /* device time of the cursor kernel (historic name) */
 	float ms_emit;           /* device time of the emit kernel(s) */
 	float ms_total;          /* device time of the whole call (events on the call's stream) */
 	int64_t h2d_bytes, d2h_bytes;

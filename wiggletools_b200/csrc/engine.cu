@@ -3,33 +3,37 @@
 // What the reference does one segment at a time on one CPU thread
 // (popCoreMultiplexer2, /root/reference/src/multiplexer.c:98-121, followed by
 // an O(N) reducer loop such as MeanReductionPop, src/reducers.c:367-402), this
-// file does per genomic WINDOW of 2^wlog bp, one CTA per window:
+// file does per genomic WINDOW of 256*2^VLOG base pairs, one CTA per window:
 //
-//   1. mark   : every interval start/end that falls in the window sets a bit of
-//               a shared-memory bitmap  -> the window's union breakpoints
-//               (replaces the two Fibonacci heaps of multiplexer.c:37-96);
-//   2. rank   : popcount prefix over the bitmap words -> slot of each breakpoint;
-//   3. events : each interval adds +delta at slot(start) and -delta at
-//               slot(end): a packed cover counter (how many tracks of set A/B
-//               are in play) and, for sum/mean, the value as a fixed-point
-//               integer split in 32-bit limbs (native shared-memory atomics;
-//               integer adds commute, so the result is order-independent and
-//               exact -- no floating-point atomics anywhere);
-//   4. scan   : prefix sum over slots = state of the sweep after each
+//   1. events : every interval adds +delta at its start position and -delta at
+//               its end position of a position-indexed shared-memory array: a
+//               packed cover counter (how many tracks of set A/B are in play)
+//               and the value as a fixed-point integer split in 32-bit limbs
+//               (native shared-memory atomics; integer adds commute, so the
+//               result is order-independent and exact -- no floating-point
+//               atomics anywhere).  Replaces the two Fibonacci heaps of
+//               multiplexer.c:37-96;
+//   2. scan   : prefix sum over positions = state of the sweep after each
 //               breakpoint = cover set + exact sum of the segment that starts
 //               there (the reference recomputes this with an O(N) loop per
 //               segment; here it is O(1) per segment);
+//   3. compact: positions where an interval starts or ends are the breakpoints;
+//               they are packed into a dense list;
+//   4. look-back: the window's output offset comes from a decoupled look-back
+//               over the preceding windows (single pass, no counting kernel);
 //   5. emit   : segments with a non-empty cover (or a full one under `strict`,
-//               multiplexer.c:123-128) are compacted and written coalesced.
+//               multiplexer.c:123-128) are written coalesced.
 //
-// Statistics that are not sums (min/max/product/var/...) and segments whose
-// inputs do not fit the fixed-point format (NaN, Inf, huge dynamic range) are
-// evaluated by row_eval(): a per-segment loop over the N tracks in index order
-// that mirrors the reference's arithmetic operation for operation.
-//
-// Two kernels per chromosome: count_kernel (steps 1-4, segment counts and the
-// per-window cursor table) and emit_kernel (steps 1-5 with values), with a
-// scan of the per-window counts in between.
+// Kernel variants (emit_kernel<MODE,...>):
+//   MODE_FAST    sum / mean from one exact accumulator;
+//   MODE_MOMENTS var / stddev / CV from exact sum and sum of squares;
+//   MODE_WALK    min / max / median from an incrementally maintained sorted array;
+//   MODE_ROW     everything else: row_eval(), a per-segment loop over the N
+//                tracks in index order that mirrors the reference's arithmetic
+//                operation for operation (also the fix-up path for segments whose
+//                inputs do not fit the fixed-point formats: NaN, Inf, huge range).
+// cursor_kernel builds, per window and track, the first interval that can touch
+// the window, so that every window starts independently.
 #include "engine.cuh"
 #include <cuda_pipeline.h>
 #include <cfloat>
