@@ -358,3 +358,45 @@ def test_moments_fast_path_is_used_and_tight(engine, port):
     want = port.reduce("stddev", o, ["chr1"])
     got = engine.reduce("stddev", g, ["chr1"])
     assert_segments(got, want.chrom, want.start, want.end, want.value, exact=True, what="stddev doubles")
+
+
+def test_randomised_differential(port):
+    """Many small random configurations (track counts, densities, window sizes,
+    defaults, NaNs, strictness, every statistic) against the oracle."""
+    rng = np.random.default_rng(20260925)
+    engines = {w: api.Engine(0, window=w) for w in (1024, 2048, 4096)}
+    names = ["chr1", "chr10", "chr2"]
+    ops = REDUCE_OPS + ["fillIn", "trimFill"]
+    for case in range(120):
+        n = int(rng.integers(1, 41))
+        lengths = [int(rng.integers(50, 40000)) for _ in range(int(rng.integers(1, 4)))]
+        kw = dict(max_len=int(rng.integers(1, 400)), max_gap=int(rng.integers(1, 3000)),
+                  gap_prob=float(rng.choice([0.0, 0.3, 0.9])), vmax=int(rng.choice([2, 50, 100000])),
+                  align=int(rng.choice([1, 1, 7, 64])), nan_prob=float(rng.choice([0.0, 0.0, 0.05])),
+                  neg=bool(rng.integers(0, 2)))
+        tr = make_tracks(n, lengths, seed=int(rng.integers(0, 1 << 30)), **kw)
+        defaults = None if rng.random() < 0.6 else [float(rng.choice([0.0, 1.0, -2.5, 0.125])) for _ in range(n)]
+        o, g = both(tr, defaults)
+        eng = engines[int(rng.choice([1024, 2048, 4096]))]
+        for op in rng.choice(ops, size=3, replace=False):
+            op = str(op)
+            strict = bool(rng.integers(0, 2))
+            if op in ("fillIn", "trimFill"):
+                if n < 2:
+                    continue
+                oo, gg, strict = o[:2], g[:2], False
+            else:
+                oo, gg = o, g
+            want = port.reduce(op, oo, names[:len(lengths)], strict)
+            got = eng.reduce(op, gg, names[:len(lengths)], strict=strict)
+            assert_segments(got, want.chrom, want.start, want.end, want.value, exact=(op not in MOMENT_OPS),
+                            what="case %d %s n=%d strict=%d %s" % (case, op, n, strict, kw))
+            assert same_float(got.default, want.default)
+        if n >= 6 and case % 4 == 0:
+            k = int(rng.integers(3, n - 2))
+            for op in ("ttest", "wilcoxon"):
+                want = port.setcompare(op, o[:k], o[k:], names[:len(lengths)])
+                got = eng.setcompare(op, g[:k], g[k:], names[:len(lengths)])
+                assert_segments(got, want.chrom, want.start, want.end, want.value, what="case %d %s" % (case, op))
+    for e in engines.values():
+        e.close()
