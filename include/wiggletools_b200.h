@@ -154,6 +154,10 @@ int wb200_reduce_device(wb200_ctx *ctx, int op, int ntracks, int nset1, int stri
  * the reference's sequential update would (PearsonPop, src/statistics.c:414-458).
  * moments = {count, sum_X, sum_Y, T_XX, T_XY, T_YY}. */
 int wb200_pearson_host(wb200_ctx *ctx, const wb200_track *x, const wb200_track *y, double moments[6]);
+/* Same for tracks px and py of an ntracks-wide multiplexer: segments where only other
+ * tracks are in play still count, with the two tracks' default values (what
+ * NDPearsonPop sees through a Multiset, src/statistics.c:490-542). */
+int wb200_pearson_pair_host(wb200_ctx *ctx, int ntracks, const wb200_track *tracks, int px, int py, double moments[6]);
 /* Fold shard b into a (the sequential update applied to pre-reduced shards). */
 void wb200_pearson_merge(double a[6], const double b[6]);
 double wb200_pearson_result(const double moments[6]);

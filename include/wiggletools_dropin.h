@@ -114,6 +114,7 @@ WiggleIterator *MWUReduction(Multiset *);                   /* :269-390 */
 /* -- statistics.c (the two whole-genome scalars on the path) --------------- */
 WiggleIterator *AUCIntegrator(WiggleIterator *);            /* :103-127 */
 WiggleIterator *PearsonIntegrator(Multiplexer *);           /* :414-465 */
+WiggleIterator *NDPearsonIntegrator(Multiset *);            /* :490-556 (rank = 2 quirk of :551 kept) */
 
 /* -- bigWiggleReader.c: BigWig source on the library's batch decoder ---------- */
 WiggleIterator *BigWiggleReader(char *filename, wt_bool holdFire);                         /* :147-151 */

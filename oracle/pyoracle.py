@@ -97,6 +97,9 @@ class Oracle:
         f = self._f("pearson")
         f.restype = C.c_double
         f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        f = self._f("ndpearson")
+        f.restype = C.c_double
+        f.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         if kind != "dropin":
             f = self._f("rows")
             f.restype = C.c_int64
@@ -157,6 +160,10 @@ class Oracle:
     def pearson(self, x, y, names=("chr1",)):
         cx, cy, cn = x.c(), y.c(), self._names(names)
         return self._f("pearson")(C.addressof(cx), C.addressof(cy), len(names), C.addressof(cn))
+
+    def ndpearson(self, set1, set2, names=("chr1",)):
+        c1, c2, cn = self._tracks(set1), self._tracks(set2), self._names(names)
+        return self._f("ndpearson")(len(set1), C.addressof(c1), C.addressof(c2), len(names), C.addressof(cn))
 
     def rows(self, tracks, names=("chr1",), strict=False):
         cap = self._cap(tracks)

@@ -209,6 +209,17 @@ double wtref_pearson(const wt_track *x, const wt_track *y, int nnames, char **na
 	return *(double *) wi->data;
 }
 
+/* `ndpearson A1 A2 .. : B1 B2 ..` */
+double wtref_ndpearson(int n, const wt_track *a, const wt_track *b, int nnames, char **names) {
+	(void) nnames;
+	Multiplexer **multis = (Multiplexer **) calloc(2, sizeof(Multiplexer *));
+	multis[0] = build_multiplexer(n, a, names, 0);
+	multis[1] = build_multiplexer(n, b, names, 0);
+	WiggleIterator *wi = NDPearsonIntegrator(newMultiset(multis, 2));
+	runWiggleIterator(wi);
+	return *(double *) wi->data;
+}
+
 #ifndef WB200_DROPIN
 /* Raw multiplexer rows (what mWigWriter sees): values[count] + inplay[count]
  * per segment; row_values/row_inplay hold cap*count entries. */

@@ -462,6 +462,43 @@ double wto_pearson(const wt_track *x, const wt_track *y, int nnames, char **name
 	return NAN;
 }
 
+/* N-dimensional Pearson over two sets of equal size (src/statistics.c:490-556):
+ * rank = multi->count = 2 whatever the set size (:551); the sweep covers every
+ * segment where any track of either set is in play; an absent track reads its
+ * default. */
+double wto_ndpearson(int n, const wt_track *a, const wt_track *b, int nnames, char **names) {
+	(void) nnames;
+	wt_track *all = (wt_track *) calloc(2 * n, sizeof(wt_track));
+	memcpy(all, a, n * sizeof(wt_track));
+	memcpy(all + n, b, n * sizeof(wt_track));
+	Sweep s;
+	sweep_init(&s, 2 * n, all, names);
+	const int rank = 2;
+	int count = 0;
+	double sum_X[2] = {0, 0}, sum_Y[2] = {0, 0}, T_XX = 0, T_XY = 0, T_YY = 0;
+	for (sweep_pop(&s, 0); !s.done; sweep_pop(&s, 0)) {
+		int length = s.finish - s.start;
+		double ratio = (double) count / (count + length);
+		for (int dim = 0; dim < rank; dim++) {
+			double X = s.x[dim], Y = s.x[n + dim];
+			if (count) {
+				double omx = sum_X[dim] / count, nmx = sum_X[dim] / (count + length);
+				double omy = sum_Y[dim] / count, nmy = sum_Y[dim] / (count + length);
+				T_XY += (nmx * omy + ratio * X * Y - nmx * Y - nmy * X) * length;
+				T_XX += (nmx * (omx - 2 * X) + ratio * X * X) * length;
+				T_YY += (nmy * (omy - 2 * Y) + ratio * Y * Y) * length;
+			}
+			sum_X[dim] += X * length;
+			sum_Y[dim] += Y * length;
+		}
+		count += length;
+	}
+	sweep_free(&s);
+	free(all);
+	if (T_XX * T_YY != 0) return T_XY / sqrt(T_XX * T_YY);
+	return NAN;
+}
+
 /* Writer-side run-length compression (src/unaryOps.c:235-253) of a segment list. */
 int64_t wto_compress(int64_t n, const int32_t *chrom, const int32_t *start, const int32_t *end,
                      const double *value, wt_out *out) {

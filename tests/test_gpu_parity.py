@@ -367,7 +367,7 @@ def test_randomised_differential(port):
     engines = {w: api.Engine(0, window=w) for w in (1024, 2048, 4096)}
     names = ["chr1", "chr10", "chr2"]
     ops = REDUCE_OPS + ["fillIn", "trimFill"]
-    for case in range(120):
+    for case in range(300):
         n = int(rng.integers(1, 41))
         lengths = [int(rng.integers(50, 40000)) for _ in range(int(rng.integers(1, 4)))]
         kw = dict(max_len=int(rng.integers(1, 400)), max_gap=int(rng.integers(1, 3000)),
@@ -400,3 +400,17 @@ def test_randomised_differential(port):
                 assert_segments(got, want.chrom, want.start, want.end, want.value, what="case %d %s" % (case, op))
     for e in engines.values():
         e.close()
+
+
+def test_ndpearson(engine, port):
+    """NDPearsonIntegrator through the engine and through the drop-in API."""
+    import os
+    from oracle.pyoracle import Oracle
+    tr = make_tracks(8, [40000, 9000], seed=88, max_len=60, max_gap=400)
+    o, g = both(tr, [float(i % 2) for i in range(8)])
+    want = port.ndpearson(o[:4], o[4:], NAMES)
+    got = engine.ndpearson(g[:4], g[4:], NAMES)
+    assert math.isclose(got, want, rel_tol=1e-9), (got, want)
+    if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "libwtdropin.so")):
+        got = Oracle("dropin").ndpearson(o[:4], o[4:], NAMES)
+        assert math.isclose(got, want, rel_tol=1e-9), (got, want)

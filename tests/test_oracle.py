@@ -129,6 +129,12 @@ def test_port_equals_compiled_reference(port, reference, seed):
         if n >= 2:
             assert same_float(port.pearson(tracks[0], tracks[1], names), reference.pearson(tracks[0], tracks[1], names))
         assert port.auc("mean", tracks, names) == reference.auc("mean", tracks, names)
+        if n >= 6:
+            assert same_float(port.ndpearson(tracks[:3], tracks[3:6], names), reference.ndpearson(tracks[:3], tracks[3:6], names))
+        if n >= 2:
+            for op in ("fillIn", "trimFill"):
+                a, b = port.reduce(op, tracks[:2], names), reference.reduce(op, tracks[:2], names)
+                assert_segments(a, b.chrom, b.start, b.end, b.value, exact=True, what=op)
         ra, rb = port.rows(tracks, names), reference.rows(tracks, names)
         assert np.array_equal(ra[1], rb[1], equal_nan=True) and np.array_equal(ra[2], rb[2])
 

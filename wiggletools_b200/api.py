@@ -203,6 +203,27 @@ class Engine:
             self.lib.wb200_pearson_merge(C.addressof(total), C.addressof(m))
         return self.lib.wb200_pearson_result(C.addressof(total))
 
+    def ndpearson(self, set1, set2, names=("chr1",)):
+        """N-dimensional Pearson of two equally sized sets (NDPearsonIntegrator,
+        src/statistics.c:490-556; the reference reads rank = 2 dimensions, :551)."""
+        tracks = list(set1) + list(set2)
+        n, n1 = len(tracks), len(set1)
+        present = sorted({c for t in tracks for c in t.runs}, key=lambda c: names[c].encode())
+        total = [(C.c_double * 6)(0, 0, 0, 0, 0, 0) for _ in range(2)]
+        for c in present:
+            keep, arr = [], (_lib.CTrack * n)()
+            for i, t in enumerate(tracks):
+                lo, hi = t.runs.get(c, (0, 0))
+                s, e, v = t.start[lo:hi], t.end[lo:hi], t.value[lo:hi]
+                keep.append((s, e, v))
+                arr[i] = _lib.CTrack(s.ctypes.data, e.ctypes.data, v.ctypes.data, len(s), t.default)
+            for d in range(2):
+                m = (C.c_double * 6)()
+                self._check(self.lib.wb200_pearson_pair_host(self.ctx, n, C.addressof(arr), d, n1 + d, C.addressof(m)))
+                self.lib.wb200_pearson_merge(C.addressof(total[d]), C.addressof(m))
+        txx, txy, tyy = (sum(t[k] for t in total) for k in (3, 4, 5))
+        return txy / (txx * tyy) ** 0.5 if txx * tyy != 0 else float("nan")
+
     def auc(self, op, tracks, names=("chr1",), strict=False):
         return self.reduce(op, tracks, names, strict).auc
 

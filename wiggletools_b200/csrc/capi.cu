@@ -160,8 +160,9 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
                const int32_t *d_start, const int32_t *d_end, const double *d_value,
                const int64_t *h_off, const double *h_dflt, int32_t pos_lo, int32_t pos_hi,
                int32_t *d_out_start, int32_t *d_out_end, double *d_out_value, int64_t out_cap,
-               int64_t *n_out, double *default_out, double *auc_out, double *moments_out = nullptr, bool force_row = false) {
-	if (!valid_op(op) && !(op == OP_PEARSON && moments_out && N == 2)) return fail(ctx, WB200_EINVAL, "unknown op");
+               int64_t *n_out, double *default_out, double *auc_out, double *moments_out = nullptr, bool force_row = false,
+               int px = 0, int py = 1) {
+	if (!valid_op(op) && !(op == OP_PEARSON && moments_out && N >= 2)) return fail(ctx, WB200_EINVAL, "unknown op");
 	if (N < 1) return fail(ctx, WB200_EINVAL, "need at least one track");
 	const bool setop = (op == OP_TTEST || op == OP_MWU);
 	const bool fill = (op == OP_FILLIN || op == OP_TRIMFILL);
@@ -207,6 +208,7 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 	job.start = d_start; job.end = d_end; job.value = d_value;
 	job.N = N; job.n1 = n1; job.strict = strict ? 1 : 0; job.op = op;
 	job.p0 = pos_lo; job.wlog = wlog; job.nw = nw;
+	job.px = px; job.py = py;
 	{ const char *e = getenv("WB200_LB_WARPS"); job.lb_warps = e ? std::max(1, std::min(WARPS, atoi(e))) : 1; }
 	job.out_start = d_out_start; job.out_end = d_out_end; job.out_value = d_out_value; job.out_cap = out_cap;
 
@@ -336,7 +338,7 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 		// segments the fixed-point path could not represent exactly
 		if (h_small[3] > job.slow_cap || S > out_cap)
 			return run_device(ctx, op, N, n1, strict, d_start, d_end, d_value, h_off, h_dflt, pos_lo, pos_hi,
-			                  d_out_start, d_out_end, d_out_value, out_cap, n_out, default_out, auc_out, moments_out, true);
+			                  d_out_start, d_out_end, d_out_value, out_cap, n_out, default_out, auc_out, moments_out, true, px, py);
 		CK(launch_fixup(job, h_small[3], s));
 		st.kernels++;
 		CK(cudaMemcpyAsync(h_small + 10, d_small + 10, 8, cudaMemcpyDeviceToHost, s));
@@ -629,36 +631,51 @@ int wb200_reduce_host_batch(wb200_ctx *ctx, int op, int nshards, int ntracks, in
 	return WB200_OK;
 }
 
-int wb200_pearson_host(wb200_ctx *ctx, const wb200_track *x, const wb200_track *y, double moments[6]) {
-	if (!ctx || !x || !y || !moments) return WB200_EINVAL;
-	cudaSetDevice(ctx->device);
-	const wb200_track *tr[2] = {x, y};
-	int64_t off[3] = {0, x->n, x->n + y->n};
-	double dflt[2] = {x->default_value, y->default_value};
+// moments of tracks px and py over the union cover of all ntracks tracks
+static int pearson_shard(wb200_ctx *ctx, int ntracks, const wb200_track *tracks, int px, int py, double moments[6]) {
+	const int N = ntracks;
+	std::vector<int64_t> off(N + 1, 0);
+	std::vector<double> dflt(N);
 	int64_t lo = INT32_MAX, hi = 1;
-	for (int i = 0; i < 2; i++)
-		if (tr[i]->n > 0) {
-			lo = std::min<int64_t>(lo, tr[i]->start[0]);
-			hi = std::max<int64_t>(hi, tr[i]->end[tr[i]->n - 1]);
+	for (int i = 0; i < N; i++) {
+		off[i + 1] = off[i] + tracks[i].n;
+		dflt[i] = tracks[i].default_value;
+		if (tracks[i].n > 0) {
+			lo = std::min<int64_t>(lo, tracks[i].start[0]);
+			hi = std::max<int64_t>(hi, tracks[i].end[tracks[i].n - 1]);
 		}
+	}
 	if (lo > hi) lo = hi;
-	const int64_t I = off[2];
+	const int64_t I = off[N];
 	cudaStream_t s = ctx->stream;
 	CK(ctx->in_start.ensure(std::max<int64_t>(1, I) * sizeof(int32_t)));
 	CK(ctx->in_end.ensure(std::max<int64_t>(1, I) * sizeof(int32_t)));
 	CK(ctx->in_value.ensure(std::max<int64_t>(1, I) * sizeof(double)));
-	for (int i = 0; i < 2; i++) {
-		if (!tr[i]->n) continue;
-		CK(cudaMemcpyAsync(ctx->in_start.as<int32_t>() + off[i], tr[i]->start, tr[i]->n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-		CK(cudaMemcpyAsync(ctx->in_end.as<int32_t>() + off[i], tr[i]->end, tr[i]->n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-		CK(cudaMemcpyAsync(ctx->in_value.as<double>() + off[i], tr[i]->value, tr[i]->n * sizeof(double), cudaMemcpyHostToDevice, s));
+	for (int i = 0; i < N; i++) {
+		if (!tracks[i].n) continue;
+		CK(cudaMemcpyAsync(ctx->in_start.as<int32_t>() + off[i], tracks[i].start, tracks[i].n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+		CK(cudaMemcpyAsync(ctx->in_end.as<int32_t>() + off[i], tracks[i].end, tracks[i].n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+		CK(cudaMemcpyAsync(ctx->in_value.as<double>() + off[i], tracks[i].value, tracks[i].n * sizeof(double), cudaMemcpyHostToDevice, s));
 	}
-	int rc = run_device(ctx, OP_PEARSON, 2, 2, 0, ctx->in_start.as<int32_t>(), ctx->in_end.as<int32_t>(),
-	                    ctx->in_value.as<double>(), off, dflt, (int32_t) lo, (int32_t) hi,
-	                    nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, moments);
+	int rc = run_device(ctx, OP_PEARSON, N, N, 0, ctx->in_start.as<int32_t>(), ctx->in_end.as<int32_t>(),
+	                    ctx->in_value.as<double>(), off.data(), dflt.data(), (int32_t) lo, (int32_t) hi,
+	                    nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, moments, false, px, py);
 	ctx->stats.h2d_bytes = I * 16;
 	ctx->stats.d2h_bytes = 48;
 	return rc;
+}
+
+int wb200_pearson_host(wb200_ctx *ctx, const wb200_track *x, const wb200_track *y, double moments[6]) {
+	if (!ctx || !x || !y || !moments) return WB200_EINVAL;
+	cudaSetDevice(ctx->device);
+	const wb200_track two[2] = {*x, *y};
+	return pearson_shard(ctx, 2, two, 0, 1, moments);
+}
+
+int wb200_pearson_pair_host(wb200_ctx *ctx, int ntracks, const wb200_track *tracks, int px, int py, double moments[6]) {
+	if (!ctx || !tracks || !moments || ntracks < 2 || px < 0 || py < 0 || px >= ntracks || py >= ntracks) return WB200_EINVAL;
+	cudaSetDevice(ctx->device);
+	return pearson_shard(ctx, ntracks, tracks, px, py, moments);
 }
 
 // Shard merge for the Pearson moments {n, sum_X, sum_Y, T_XX, T_XY, T_YY}: the

@@ -143,6 +143,8 @@ struct Reducer {
 	int n1 = 0;
 	bool strict = false;
 	bool pearson = false;
+	int nd_rank = 0;           // > 0: N-dimensional Pearson over nd_rank track pairs (px = d, py = n1 + d)
+	double nd_moments[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
 	std::vector<WiggleIterator *> iters;
 	// staged inputs of the current chromosome
 	std::vector<std::vector<int32_t>> s, e;
@@ -193,6 +195,16 @@ struct Reducer {
 			tracks[i].default_value = it->default_value;
 		}
 		rs.clear(); re.clear(); rv.clear(); k = 0;
+		if (pearson && nd_rank > 0) {
+			for (int d = 0; d < nd_rank; d++) {
+				double m[6];
+				if (wb200_pearson_pair_host(engine(), (int) n, tracks.data(), d, n1 + d, m) != WB200_OK) die(wb200_last_error(engine()));
+				wb200_pearson_merge(nd_moments[d], m);
+			}
+			for (size_t i = 0; i < n; i++)
+				if (direct[i]) { direct[i]->k = direct[i]->t.n; pop(iters[i]); }
+			return true;
+		}
 		if (pearson) {
 			double m[6];
 			if (wb200_pearson_host(engine(), &tracks[0], &tracks[1], m) != WB200_OK) die(wb200_last_error(engine()));
@@ -368,10 +380,22 @@ void pearson_pop(WiggleIterator *wi) {
 	wi->done = true;
 }
 
+void ndpearson_pop(WiggleIterator *wi) {
+	// NDPearsonPop (statistics.c:490-542) as a batch.  rank = multi->count = 2 in the
+	// reference (:551), whatever the set sizes: only the first two track pairs count.
+	PearsonData *d = (PearsonData *) wi->data;
+	while (d->r->next_chromosome()) {}
+	double txx = 0, txy = 0, tyy = 0;
+	for (int k = 0; k < d->r->nd_rank; k++) { txx += d->r->nd_moments[k][3]; txy += d->r->nd_moments[k][4]; tyy += d->r->nd_moments[k][5]; }
+	d->res = (txx * tyy != 0) ? txy / std::sqrt(txx * tyy) : NAN;
+	wi->done = true;
+}
+
 void pearson_seek(WiggleIterator *wi, const char *chrom, int start, int finish) {
 	PearsonData *d = (PearsonData *) wi->data;
 	for (WiggleIterator *it : d->r->iters) seek(it, chrom, start, finish);
 	for (double &m : d->r->moments) m = 0;
+	for (auto &row : d->r->nd_moments) for (double &m : row) m = 0;
 	pop(wi);
 }
 
@@ -541,6 +565,27 @@ WiggleIterator *PearsonIntegrator(Multiplexer *multi) {
 	d->r->n1 = 2;
 	WiggleIterator *res = newWiggleIterator(d, &pearson_pop, &pearson_seek, multi->iters[1]->default_value, 0);
 	res->append = multi->iters[1];
+	return res;
+}
+
+WiggleIterator *NDPearsonIntegrator(Multiset *ms) {
+	if (ms->count != 2 || ms->multis[0]->count != ms->multis[1]->count) {
+		fprintf(stderr, "Incorrect number of input tracks to N-dimensional Pearson correlation!\n");
+		exit(1);
+	}
+	if (ms->multis[0]->count < 2) die("N-dimensional Pearson reads two dimensions (statistics.c:551); give at least two tracks per set");
+	PearsonData *d = (PearsonData *) calloc(1, sizeof(PearsonData));
+	d->res = NAN;
+	d->r = new Reducer();
+	d->r->pearson = true;
+	d->r->nd_rank = ms->count;     // = 2: the reference's quirk, kept
+	for (int m = 0; m < 2; m++) {
+		if (!is_gpu_multiplexer(ms->multis[m])) die("ndpearson needs multiplexers built by newMultiplexer()");
+		d->r->iters.insert(d->r->iters.end(), ms->multis[m]->iters, ms->multis[m]->iters + ms->multis[m]->count);
+	}
+	d->r->n1 = ms->multis[0]->count;
+	WiggleIterator *res = newWiggleIterator(d, &ndpearson_pop, &pearson_seek, 0, 0);
+	res->append = ms->multis[0]->iters[0];
 	return res;
 }
 

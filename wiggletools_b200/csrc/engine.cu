@@ -1079,7 +1079,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 					const int be = (r + 1 < nbp) ? (int) (w0 + bpos[r + 1]) : next_bp;
 					double X, Y;
 					row.b = bs;
-					row.get(0, X); row.get(1, Y);
+					row.get(job.px, X); row.get(job.py, Y);
 					const double len = (double) (be - bs);
 					Mom one = {len, X * len, Y * len, 0, 0, 0};
 					merge_mom(mom, one);

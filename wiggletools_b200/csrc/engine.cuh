@@ -61,6 +61,7 @@ struct Job {
 	double *auc_partial;    // [nw * WARPS] per-warp sums of (end-start)*value (NaN skipped), or null
 	unsigned long long *slow_count; // segments that took the row path
 	double *moments;        // [nw * 6] per-window Pearson moments (OP_PEARSON), or null
+	int px, py;             // OP_PEARSON: the two tracks correlated (the others only shape the cover)
 	long long *slow_list;   // fast path: output indices of segments to recompute (fix-up kernel)
 	long long slow_cap;
 	double *auc_fix;        // AUC contribution of the fixed-up segments
