@@ -599,6 +599,7 @@ __device__ void order_walk(const Job &job, const int32_t *cur, const int32_t *nx
 						lo += key_less(a, ko) ? 1 : 0;
 						ln += key_less(a, kn) ? 1 : 0;
 					}
+					__syncwarp();                                    // every lane has read its keys before any is moved
 					const int io = __reduce_add_sync(FULL, lo);
 					int in = __reduce_add_sync(FULL, ln);
 					if (key_less(ko, kn)) in--;                      // the old key itself was counted below the new one
