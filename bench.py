@@ -75,15 +75,42 @@ def gen_chrom_device(torch, dev, n_tracks, length, seed):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons during the timed region (NVML, every few ms;
+    falls back to polling nvidia-smi)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
 
     def run(self):
+        if self.nv is not None:
+            nv = self.nv
+            bits = [("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
+                    ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                    ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                    ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap)]
+            while not self.stop_flag:
+                try:
+                    sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    self.rows.append([str(sm), str(self.max_sm)] + ["Active" if r & b else "Not Active" for _, b in bits])
+                except Exception:
+                    pass
+                time.sleep(0.004)
+            return
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
@@ -93,7 +120,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append(parts)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def summary(self):
         if not self.rows:
@@ -103,7 +130,8 @@ class ClockSampler(threading.Thread):
         for j, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
             if any(r[2 + j].lower().startswith("active") for r in self.rows):
                 reasons.append(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(sm),
+                "source": "nvml" if self.nv is not None else "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------

@@ -197,7 +197,7 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 			double density = 2.0 * (double) I / ((double) pos_hi - pos_lo + 1.0);
 			if (density > 0.6) wlog = 11;
 			// the order-statistic sweep is a serial chain per warp: smaller windows, more CTAs per SM
-			if ((op == OP_MEDIAN || op == OP_MIN || op == OP_MAX) && N <= 512) wlog = 11;
+			if ((op == OP_MEDIAN || op == OP_MIN || op == OP_MAX) && N <= 512) wlog = N > 128 ? 10 : 11;
 		}
 	}
 	wlog = std::min(TLOG + 4, std::max(TLOG + 2, wlog));

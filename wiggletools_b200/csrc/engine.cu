@@ -490,10 +490,10 @@ __device__ __forceinline__ bool keep_rule(int thr, int c) {
 // one compare per track and a ballot.
 struct TrackState { int j; int nextpos; };
 
+
 // The window's intervals, staged once in shared memory (start/end/value of
 // interval j of track i at tbase[i] + j - cur[i]); falls back to global memory
 // when a window holds more intervals than the staging area.
-constexpr int WALK_STAGE_CAP = 1536;
 struct IvAccess {
 	const Job *job;
 	const int32_t *cur;
@@ -507,21 +507,23 @@ struct IvAccess {
 
 // Position a track at coordinate b: interval index j = first interval with
 // end > b inside the window's cursor range, value-or-default, next event.
-__device__ __forceinline__ void walk_locate(const Job &job, const int32_t *cur, const int32_t *nxt, int i, int b,
+__device__ __forceinline__ bool walk_locate(const Job &job, const IvAccess &iv, const int32_t *cur, const int32_t *nxt, int i, int b,
                                             double dflt, TrackState &ts, double &x) {
 	const long long o = job.off[i];
 	const int n = (int) (job.off[i + 1] - o);
 	int lo = cur[i], hi = min(nxt[i], n - 1) + 1;         // search [lo, hi): ends ascending
 	while (lo < hi) {
 		const int mid = (lo + hi) >> 1;
-		if (job.end[o + mid] > b) hi = mid; else lo = mid + 1;
+		if (iv.end(i, o, mid) > b) hi = mid; else lo = mid + 1;
 	}
 	ts.j = lo;
-	if (lo < n) {
-		const int st = job.start[o + lo];
-		if (st <= b) { x = job.value[o + lo]; ts.nextpos = job.end[o + lo]; }
-		else { x = dflt; ts.nextpos = st; }
-	} else { x = dflt; ts.nextpos = INT_MAX; }
+	if (lo < n && lo <= nxt[i]) {
+		const int st = iv.start(i, o, lo);
+		if (st <= b) { x = iv.value(i, o, lo); ts.nextpos = iv.end(i, o, lo); return true; }
+		x = dflt; ts.nextpos = st;
+	} else if (lo < n) { x = dflt; ts.nextpos = job.start[o + lo]; }
+	else { x = dflt; ts.nextpos = INT_MAX; }
+	return false;
 }
 
 // One warp: segments [r0, r1) of the window's dense breakpoint list.
@@ -540,7 +542,7 @@ __device__ void order_walk(const Job &job, const int32_t *cur, const int32_t *nx
 			// min/max read a literal 0 for an absent track 0, not its default (reducers.c:142-145,209-212)
 			const double d = (minmax && i == 0) ? 0.0 : job.dflt[i];
 			TrackState ts; double x;
-			walk_locate(job, cur, nxt, i, b0, d, ts, x);
+			walk_locate(job, iv, cur, nxt, i, b0, d, ts, x);
 			tstate[i] = ts;
 			if (isnan(x)) { nan_cnt++; x = INFINITY; }
 			k.v = x; k.ord = i;
@@ -637,6 +639,131 @@ __device__ void order_walk(const Job &job, const int32_t *cur, const int32_t *nx
 			}
 			if (!isnan(v)) auc += (double) (be - p) * v;
 			slow++;
+		}
+	}
+}
+
+// Shared-memory carve-up of the sweep kernels' row buffer (host and device agree).
+struct WalkLayout {
+	int P;            // pow2 >= N: keys per warp of the sorted-array sweep
+	int P2;           // universe capacity of the rank-bitset sweep (window intervals + N defaults)
+	int cap;          // staged intervals per window (P2 - N)
+	size_t off_tstate, off_keys, off_rank, off_stage, off_tbase, off_bits, total;
+};
+__host__ __device__ inline WalkLayout walk_layout(int N) {
+	WalkLayout w;
+	w.P = 1; while (w.P < N) w.P <<= 1;
+	w.P2 = N <= 64 ? 1024 : N <= 256 ? 2048 : 4096;
+	w.cap = w.P2 - N;
+	size_t o = 0;
+	w.off_tstate = o; o += (size_t) WARPS * N * sizeof(TrackState);
+	const size_t keys = (size_t) w.P2 * sizeof(SortKey), arrs = (size_t) WARPS * w.P * sizeof(SortKey);
+	w.off_keys = o;   o += keys > arrs ? keys : arrs;          // sorted universe | per-warp sorted arrays (fallback)
+	w.off_rank = o;   o += (size_t) w.P2 * 2;
+	w.off_stage = o;  o += (size_t) w.cap * 16 + 16;
+	w.off_tbase = o;  o += (size_t) (N + 4) / 4 * 16;
+	w.off_bits = o;   o += (size_t) WARPS * (w.P2 / 32) * 4;
+	w.total = (o + 15) / 16 * 16;
+	return w;
+}
+
+// Rank-bitset sweep (min / max / median).  The window's values -- every staged
+// interval plus one default per track -- are sorted ONCE per window by the whole
+// CTA; an interval's rank in that order is then a fixed number.  A warp keeps the
+// N values of its current segment as N set bits over the ranks: a track that
+// changes clears one bit and sets another (O(1)), and the k-th smallest value is
+// a popcount prefix over the words plus a find-n-th-set-bit.  Ties order by track
+// index, as in the reference's stable sort.
+__device__ void bitset_walk(const Job &job, const int32_t *cur, const int32_t *nxt, long long w0, int r0, int r1, int nbp,
+                            int next_bp, const uint16_t *bpos, const uint16_t *bkid, long long out_base,
+                            const SortKey *keys, const uint16_t *rank_of, uint32_t *bits, int nwords, int T,
+                            TrackState *tstate, const IvAccess &iv, double &auc, unsigned long long &slow) {
+	const int N = job.N, lane = threadIdx.x & 31;
+	const bool minmax = (job.op == OP_MIN || job.op == OP_MAX);
+	const int sel = job.op == OP_MIN ? 0 : job.op == OP_MAX ? N - 1 : N / 2;
+	const int nwl = (nwords + 31) / 32;                 // words owned by each lane, contiguous
+	const int b0 = (int) (w0 + bpos[r0]);
+	for (int q = lane; q < nwords; q += 32) bits[q] = 0;
+	__syncwarp();
+	int nan_cnt = 0;
+	for (int i = lane; i < N; i += 32) {
+		const double d = (minmax && i == 0) ? 0.0 : job.dflt[i];   // reducers.c:142-145,209-212
+		TrackState ts; double x;
+		const bool in = walk_locate(job, iv, cur, nxt, i, b0, d, ts, x);
+		tstate[i] = ts;
+		if (isnan(x)) nan_cnt++;
+		const int rk = rank_of[in ? iv.tbase[i] + ts.j - cur[i] : T + i];
+		atomicOr(&bits[rk >> 5], 1u << (rk & 31));
+	}
+	nan_cnt = __reduce_add_sync(FULL, nan_cnt);
+	__syncwarp();
+	for (int r = r0; r < r1; r++) {
+		const int p = (int) (w0 + bpos[r]);
+		if (r > r0) {
+			for (int base = 0; base < N; base += 32) {
+				const int i = base + lane;
+				unsigned bal = __ballot_sync(FULL, i < N && tstate[i].nextpos == p);
+				while (bal) {
+					const int src = __ffs(bal) - 1;
+					bal &= bal - 1;
+					int dn = 0;
+					if (lane == src) {
+						const long long o = job.off[i];
+						const int n = (int) (job.off[i + 1] - o);
+						const double d = (minmax && i == 0) ? 0.0 : job.dflt[i];
+						TrackState ts = tstate[i];
+						const bool was_in = iv.start(i, o, ts.j) < p;      // else its interval starts at p
+						const int uo = was_in ? iv.tbase[i] + ts.j - cur[i] : T + i;
+						const bool oldnan = isnan(was_in ? iv.value(i, o, ts.j) : d);
+						if (was_in) ts.j++;
+						const bool have = ts.j < n && ts.j <= nxt[i];
+						const int ns = have ? iv.start(i, o, ts.j) : (ts.j < n ? job.start[o + ts.j] : INT_MAX);
+						int un; bool newnan;
+						if (have && ns <= p) { un = iv.tbase[i] + ts.j - cur[i]; newnan = isnan(iv.value(i, o, ts.j)); ts.nextpos = iv.end(i, o, ts.j); }
+						else { un = T + i; newnan = isnan(d); ts.nextpos = ns; }
+						tstate[i] = ts;
+						const int ro = rank_of[uo], rn = rank_of[un];
+						bits[ro >> 5] &= ~(1u << (ro & 31));
+						bits[rn >> 5] |= 1u << (rn & 31);
+						dn = (newnan ? 1 : 0) - (oldnan ? 1 : 0);
+					}
+					nan_cnt += __shfl_sync(FULL, dn, src);
+					__syncwarp();
+				}
+			}
+		}
+		const uint16_t kd = bkid[r];
+		if (kd & BK_KEEP) {
+			// k-th set bit: popcount prefix over the lanes' words, then find-n-th inside one word
+			int cnt = 0;
+			for (int q = 0; q < nwl; q++) { const int wi = lane * nwl + q; if (wi < nwords) cnt += __popc(bits[wi]); }
+			int inc = cnt;
+			for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += v; }
+			const unsigned hit = __ballot_sync(FULL, inc > sel);
+			const int Lh = __ffs(hit) - 1;
+			double v = 0;
+			if (lane == Lh) {
+				int k = sel - (inc - cnt);
+				for (int q = 0; q < nwl && lane * nwl + q < nwords; q++) {
+					const uint32_t wd = bits[lane * nwl + q];
+					const int c = __popc(wd);
+					if (k < c) { v = keys[(lane * nwl + q) * 32 + __fns(wd, 0, k + 1)].v; break; }
+					k -= c;
+				}
+			}
+			v = __shfl_sync(FULL, v, Lh);
+			if (nan_cnt) v = NAN;
+			if (lane == 0) {
+				const int be = (r + 1 < nbp) ? (int) (w0 + bpos[r + 1]) : next_bp;
+				const long long oi = out_base + (kd & BK_IDX);
+				if (oi < job.out_cap) {
+					job.out_start[oi] = p;
+					job.out_end[oi] = be;
+					job.out_value[oi] = v;
+				}
+				if (!isnan(v)) auc += (double) (be - p) * v;
+				slow++;
+			}
 		}
 	}
 }
@@ -1031,14 +1158,15 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 		}
 	} else if (MODE == MODE_WALK) {
 		{
-			// each warp sweeps a contiguous share of the window's breakpoints
-			int P = 1; while (P < N) P <<= 1;
-			SortKey *arr = (SortKey *) (smem + L.off_rows) + (size_t) warp * P;
-			TrackState *tstate = (TrackState *) (smem + L.off_rows + (size_t) WARPS * P * sizeof(SortKey)) + (size_t) warp * N;
+			const WalkLayout wl = walk_layout(N);
+			unsigned char *rb = smem + L.off_rows;
+			TrackState *tstate = (TrackState *) (rb + wl.off_tstate) + (size_t) warp * N;
+			SortKey *keys = (SortKey *) (rb + wl.off_keys);
+			uint16_t *rank_of = (uint16_t *) (rb + wl.off_rank);
+			double *sv = (double *) (rb + wl.off_stage);
+			int32_t *ss = (int32_t *) (sv + wl.cap), *se = ss + wl.cap;
+			int32_t *tbase = (int32_t *) (rb + wl.off_tbase);
 			// stage the window's intervals: the sweep is a chain of dependent reads
-			unsigned char *stage = smem + L.off_rows + (size_t) WARPS * (P * sizeof(SortKey) + N * sizeof(TrackState));
-			double *sv = (double *) stage;
-			int32_t *ss = (int32_t *) (sv + WALK_STAGE_CAP), *se = ss + WALK_STAGE_CAP, *tbase = se + WALK_STAGE_CAP;
 			int run = 0;
 			for (int base = 0; base < N; base += THREADS) {
 				const int i = base + tid;
@@ -1049,20 +1177,62 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 				run += tc;
 				__syncthreads();
 			}
-			const bool staged = run <= WALK_STAGE_CAP;
+			const int T = run;
+			const bool staged = T <= wl.cap;
+			const int U = T + N;                              // universe: intervals + one default per track
+			int Ps = 64; while (Ps < U) Ps <<= 1;
+			const bool minmax = (job.op == OP_MIN || job.op == OP_MAX);
+			const bool bitset = staged && N > 128;
 			if (staged) {
 				const int gid = tid >> 3, gl = tid & 7;
 				for (int i = gid; i < N; i += THREADS / 8) {
 					const long long o = toff[i];
 					const int jl = min(nxt[i], tn[i] - 1), b = tbase[i] - cur[i];
-					for (int j = cur[i] + gl; j <= jl; j += 8) { ss[b + j] = job.start[o + j]; se[b + j] = job.end[o + j]; sv[b + j] = job.value[o + j]; }
+					for (int j = cur[i] + gl; j <= jl; j += 8) {
+						const double v = job.value[o + j];
+						ss[b + j] = job.start[o + j]; se[b + j] = job.end[o + j]; sv[b + j] = v;
+						if (bitset) { SortKey k; k.v = isnan(v) ? INFINITY : v; k.ord = i; k.pad = b + j; keys[b + j] = k; }
+					}
 				}
+				for (int u = T + tid; bitset && u < Ps; u += THREADS) {
+					SortKey k;
+					if (u < U) {
+						const int i = u - T;
+						const double d = (minmax && i == 0) ? 0.0 : job.dflt[i];
+						k.v = isnan(d) ? INFINITY : d; k.ord = i; k.pad = u;
+					} else { k.v = INFINITY; k.ord = INT_MAX; k.pad = INT_MAX; }
+					keys[u] = k;
+				}
+				__syncthreads();
+				for (int k = 2; bitset && k <= Ps; k <<= 1)
+					for (int j = k >> 1; j > 0; j >>= 1) {
+						for (int t = tid; t < Ps / 2; t += THREADS) {
+							const int i = ((t / j) * 2 * j) + (t % j), l = i + j;
+							const bool up = ((i & k) == 0);
+							const SortKey a = keys[i], b = keys[l];
+							if (up ? key_less(b, a) : key_less(a, b)) { keys[i] = b; keys[l] = a; }
+						}
+						__syncthreads();
+					}
+				for (int pos = tid; bitset && pos < Ps; pos += THREADS) { const int u = keys[pos].pad; if (u < U) rank_of[u] = (uint16_t) pos; }
 			}
 			__syncthreads();
 			IvAccess iv; iv.job = &job; iv.cur = cur; iv.tbase = staged ? tbase : nullptr; iv.ss = ss; iv.se = se; iv.sv = sv;
+			// each warp sweeps a contiguous share of the window's breakpoints
 			const int chunk = (nbp + WARPS - 1) / WARPS;
 			const int r0 = warp * chunk, r1 = min(nbp, r0 + chunk);
-			if (r0 < r1) order_walk(job, cur, nxt, w0, r0, r1, nbp, next_bp, bpos, bkid, out_base, arr, tstate, P, iv, auc, slow);
+			if (r0 < r1) {
+				if (bitset) {
+					uint32_t *bits = (uint32_t *) (rb + wl.off_bits) + (size_t) warp * (wl.P2 / 32);
+					bitset_walk(job, cur, nxt, w0, r0, r1, nbp, next_bp, bpos, bkid, out_base, keys, rank_of, bits, Ps / 32, T,
+					            tstate, iv, auc, slow);
+				} else {
+					// few tracks (a sorted array per warp is cheaper than sorting the window), or more
+					// intervals than the staging area holds: per-warp sorted arrays
+					SortKey *arr = keys + (size_t) warp * wl.P;
+					order_walk(job, cur, nxt, w0, r0, r1, nbp, next_bp, bpos, bkid, out_base, arr, tstate, wl.P, iv, auc, slow);
+				}
+			}
 		}
 	} else {
 		const bool sorted_op = (job.op == OP_MEDIAN || job.op == OP_MWU);
@@ -1269,13 +1439,11 @@ __global__ void __launch_bounds__(1024) reduce_auc_kernel(const double *partial,
 // host-side launchers
 // ---------------------------------------------------------------------------
 static int row_buffer_bytes(int N, int op) {
-	if (op != OP_MEDIAN && op != OP_MWU && op != OP_MIN && op != OP_MAX) return 0;
-	if ((op == OP_MIN || op == OP_MAX) && N > WALK_MAX_TRACKS) return 0;      // plain row loop
+	const bool order = (op == OP_MEDIAN || op == OP_MIN || op == OP_MAX);
+	if (order && N <= WALK_MAX_TRACKS) return (int) walk_layout(N).total;          // sweep kernels
+	if (op != OP_MEDIAN && op != OP_MWU) return 0;
 	int P = 1; while (P < N) P <<= 1;
-	int bytes = P * (int) sizeof(SortKey) * WARPS;                             // sorted keys, one array per warp
-	if (op != OP_MWU && N <= WALK_MAX_TRACKS)
-		bytes += N * (int) sizeof(TrackState) * WARPS + WALK_STAGE_CAP * 16 + (N + 4) / 4 * 16;   // + staged intervals
-	return bytes;
+	return P * (int) sizeof(SortKey) * WARPS;                                      // one sort buffer per warp
 }
 
 size_t window_smem_bytes(int wlog, int N, bool emit, int op) {
