@@ -345,6 +345,16 @@ def main():
     if world > 1:
         dist.all_reduce(tot)
     slow = sum(r[5] for r in per_launch)
+    checksum = None
+    if os.environ.get("WB200_BENCH_CHECKSUM"):      # development: order-sensitive digest of every output array
+        acc = torch.zeros((), dtype=torch.int64, device=dev)
+        for sh in shards:
+            S = sh["S"]
+            k = torch.arange(1, S + 1, device=dev, dtype=torch.int64)
+            acc += (sh["out"][0][:S].long() * k).sum() * 3 + (sh["out"][1][:S].long() * k).sum() * 5
+            acc += (sh["out"][2][:S].view(torch.int64) * k).sum()
+            del k
+        checksum = int(acc.item())
 
     # end to end through the host-buffer entry point: pinned host tracks ->
     # H2D -> kernels -> D2H of the segments, every step, timed with the wall
@@ -366,6 +376,13 @@ def main():
                 "gpu_launches": int(launches), "clocks": sampler.summary(),
                 "segments": int(tot[0].item()), "intervals": int(tot[1].item()), "slow_segments": int(slow),
                 "auc": float(auc_t.item())}
+        if checksum is not None:
+            line["checksum"] = checksum
+        ph = (C.c_uint64 * 16)()
+        lib.wb200_debug_phases(ctx, ph)
+        if any(ph):                                   # diagnostic builds only
+            names_ = ["clear", "events", "scan", "count", "compact", "lookback", "emit", "window_total", "windows"]
+            line["phase_cycles_per_window"] = {n: ph[k] / max(1, ph[8]) for k, n in enumerate(names_)}
         print(json.dumps(line))
     lib.wb200_destroy(ctx)
     if world > 1:

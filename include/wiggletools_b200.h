@@ -184,6 +184,10 @@ int wb200_bw_decode_chrom(wb200_bigwig *bw, int chrom_index, wb200_track *out);
  * gsl_cdf_tdist_Q, src/setComparisons.c:117); exported for tests. */
 double wb200_tdist_Q(double t, double nu);
 
+/* Diagnostic: per-phase cycle counters of the window kernel (thread 0 of every CTA, summed over
+ * windows) since the last call; zeros unless the library was built with -DWB_DIAG_PHASES. */
+void wb200_debug_phases(wb200_ctx *ctx, uint64_t out[16]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libwiggletools_b200.so")
+# WB200_LIB: development override (kernel experiments load alternative builds of the same library)
+LIB_PATH = os.environ.get("WB200_LIB") or os.path.join(HERE, "libwiggletools_b200.so")
 
 
 class CTrack(C.Structure):
@@ -76,6 +77,7 @@ def load():
     lib.wb200_bw_chrom_length.argtypes = [C.c_void_p, C.c_int]
     lib.wb200_bw_set_stretch.argtypes = [C.c_void_p, C.c_int]
     lib.wb200_bw_decode_chrom.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.wb200_debug_phases.argtypes = [C.c_void_p, C.c_void_p]
     lib.wb200_tdist_Q.restype = C.c_double
     lib.wb200_tdist_Q.argtypes = [C.c_double, C.c_double]
     _lib = lib
@@ -88,5 +90,5 @@ EXPORTS = [
     "wb200_set_window", "wb200_host_alloc", "wb200_host_free", "wb200_reduce_host", "wb200_reduce_host_batch",
     "wb200_reduce_device", "wb200_pearson_host", "wb200_pearson_pair_host", "wb200_pearson_merge", "wb200_pearson_result",
     "wb200_tdist_Q", "wb200_bw_open", "wb200_bw_close", "wb200_bw_last_error", "wb200_bw_nchrom", "wb200_bw_chrom_name",
-    "wb200_bw_chrom_length", "wb200_bw_set_stretch", "wb200_bw_decode_chrom",
+    "wb200_bw_chrom_length", "wb200_bw_set_stretch", "wb200_bw_decode_chrom", "wb200_debug_phases",
 ]

@@ -72,6 +72,7 @@ struct wb200_ctx {
 	DevBuf bin_start[2], bin_end[2], bin_value[2], bout_start[2], bout_end[2], bout_value[2];
 	HostBuf h_arena;
 	std::vector<cudaEvent_t> pipe_events;
+	unsigned long long diag[16] = {0};      // diagnostic builds: accumulated phase counters
 };
 
 namespace {
@@ -161,7 +162,7 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
                const int64_t *h_off, const double *h_dflt, int32_t pos_lo, int32_t pos_hi,
                int32_t *d_out_start, int32_t *d_out_end, double *d_out_value, int64_t out_cap,
                int64_t *n_out, double *default_out, double *auc_out, double *moments_out = nullptr, bool force_row = false,
-               int px = 0, int py = 1) {
+               int px = 0, int py = 1, int min_limbs = 1) {
 	if (!valid_op(op) && !(op == OP_PEARSON && moments_out && N >= 2)) return fail(ctx, WB200_EINVAL, "unknown op");
 	if (N < 1) return fail(ctx, WB200_EINVAL, "need at least one track");
 	const bool setop = (op == OP_TTEST || op == OP_MWU);
@@ -206,6 +207,12 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 
 	Job job{};
 	job.start = d_start; job.end = d_end; job.value = d_value;
+	job.I = I;
+	{
+		const char *e = getenv("WB200_VEC");
+		const bool aligned = (((uintptr_t) d_start | (uintptr_t) d_end | (uintptr_t) d_value) & 15) == 0;
+		job.vec = aligned && !(e && atoi(e) == 0);
+	}
 	job.N = N; job.n1 = n1; job.strict = strict ? 1 : 0; job.op = op;
 	job.p0 = pos_lo; job.wlog = wlog; job.nw = nw;
 	job.px = px; job.py = py;
@@ -225,8 +232,8 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 	CK(ctx->cursor.ensure((size_t) (nw + 1) * N * sizeof(int32_t)));
 	CK(ctx->state.ensure((size_t) nw * sizeof(unsigned long long)));
 	CK(ctx->aucp.ensure((size_t) nw * WARPS * sizeof(double)));
-	CK(ctx->small.ensure(128));
-	CK(ctx->h_small.ensure(128));
+	CK(ctx->small.ensure(256));
+	CK(ctx->h_small.ensure(256));
 	if (moments_out) { CK(ctx->moments.ensure((size_t) nw * 6 * sizeof(double))); job.moments = ctx->moments.as<double>(); }
 	job.off = ctx->off.as<int64_t>(); job.dflt = ctx->dflt.as<double>(); job.dflt_fx = ctx->dflt_fx.as<int64_t>();
 	job.cursor = ctx->cursor.as<int32_t>(); job.state = ctx->state.as<unsigned long long>();
@@ -237,11 +244,12 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 	job.auc_fix = d_small + 10;
 	job.total = (long long *) (d_small + 11);
 	job.ticket = (unsigned int *) (d_small + 12);
+	job.diag = (unsigned long long *) (d_small + 16);
 
 	CK(cudaEventRecord(ctx->ev[0], s));
 	CK(cudaMemcpyAsync(ctx->off.p, hm_off, (N + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
 	CK(cudaMemcpyAsync(ctx->dflt.p, hm_dflt, N * sizeof(double), cudaMemcpyHostToDevice, s));
-	CK(cudaMemsetAsync(d_small, 0, 128, s));
+	CK(cudaMemsetAsync(d_small, 0, 256, s));
 	st.kernels = 0;
 
 	// fixed-point fast paths: sum / mean (one exact accumulator) and var / stddev /
@@ -266,27 +274,42 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 			const int l2n = ceil_log2(2 * (int64_t) N);
 			const int lw = 32 - l2n;
 			if (sum_like) {
-				// format: |m| < 2^mbits; two 32-bit limbs when that is enough for
-				// float32-grade inputs (24-bit mantissas), else three.
+				// format: |m| < 2^mbits in one, two or three 32-bit limbs per position.
+				//  one  : the sampled values have no bit below 2^q1, q1 = emax + 2 - (29 - l2n): a single
+				//         32-bit accumulator holds every per-position delta sum (integer-like and
+				//         coarse fixed-point data, e.g. read counts);
+				//  two  : float32-grade inputs (24-bit mantissas) over a moderate exponent range;
+				//  three: anything wider.
+				// A value finer than the chosen 2^q poisons its interval; those segments are recomputed
+				// by the fix-up kernel, and a run with too many of them is repeated one format wider.
+				const int cap1 = 29 - l2n;
 				const int cap2 = 29 - l2n + lw;
 				const int cap3 = std::min(29 - l2n + 2 * lw, 62 - ceil_log2(N + 1));
 				const char *env = getenv("WB200_LIMBS");
-				int limbs = (env && atoi(env) == 3) ? 3 : ((env && atoi(env) == 2) ? 2 : (cap2 >= 40 ? 2 : 3));
-				int mbits = limbs == 2 ? cap2 : cap3;
-				job.fx_mbits = mbits;
-				job.fx_q = emax + 2 - mbits;           // two bits of headroom above the sampled maximum
-				job.fx_q = std::max(-1000, std::min(1000, job.fx_q));
-				const double inv = std::ldexp(1.0, -job.fx_q), lim = std::ldexp(1.0, mbits);
-				long long base = 0;
-				for (int i = 0; i < N && ok; i++) {
-					double t = h_dflt[i] * inv;
-					if (!(std::fabs(t) < lim) || t != std::rint(t)) ok = false;
-					else { hm_fx[i] = (int64_t) t; base += hm_fx[i]; }
-				}
-				if (ok) {
-					job.fast = 1;
-					job.fx_base = base;
-					CK(cudaMemcpyAsync(ctx->dflt_fx.p, hm_fx, N * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+				const int forced = env ? atoi(env) : 0;
+				const int lsb_q = lsb_key > 0 ? (int) (2048 - lsb_key) : 4096;          // finest significant bit seen
+				int first = std::max(min_limbs, (forced >= 1 && forced <= 3) ? forced : (cap1 >= 8 && lsb_q >= emax + 2 - cap1 ? 1 : (cap2 >= 40 ? 2 : 3)));
+				ok = false;
+				for (int limbs = first; limbs <= 3 && !ok; limbs++) {
+					const int mbits = limbs == 1 ? cap1 : limbs == 2 ? cap2 : cap3;
+					if (mbits < 4) continue;
+					job.fx_mbits = mbits;
+					job.fx_limbs = limbs;
+					job.fx_q = emax + 2 - mbits;           // two bits of headroom above the sampled maximum
+					job.fx_q = std::max(-1000, std::min(1000, job.fx_q));
+					const double inv = std::ldexp(1.0, -job.fx_q), lim = std::ldexp(1.0, mbits);
+					long long base = 0;
+					ok = true;
+					for (int i = 0; i < N && ok; i++) {
+						double t = h_dflt[i] * inv;
+						if (!(std::fabs(t) < lim) || t != std::rint(t)) ok = false;
+						else { hm_fx[i] = (int64_t) t; base += hm_fx[i]; }
+					}
+					if (ok) {
+						job.fast = 1;
+						job.fx_base = base;
+						CK(cudaMemcpyAsync(ctx->dflt_fx.p, hm_fx, N * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+					}
 				}
 			} else {
 				// squares must stay exact in 64 bits: m = v 2^-q with q the finest bit seen in
@@ -332,10 +355,23 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 	int64_t *h_small = ctx->h_small.as<int64_t>();
 	CK(cudaMemcpyAsync(h_small, d_small + 11, 8, cudaMemcpyDeviceToHost, s));
 	CK(cudaMemcpyAsync(h_small + 2, d_small + 2, 64, cudaMemcpyDeviceToHost, s));
+#ifdef WB_DIAG_PHASES
+	CK(cudaMemcpyAsync(h_small + 16, d_small + 16, 128, cudaMemcpyDeviceToHost, s));
+#endif
 	CK(cudaStreamSynchronize(s));
 	const int64_t S = h_small[0];
+#ifdef WB_DIAG_PHASES
+	for (int k = 0; k < 16; k++) ctx->diag[k] += (unsigned long long) h_small[16 + k];
+#endif
 	if (job.fast && h_small[3] > 0) {
 		// segments the fixed-point path could not represent exactly
+		// too many for the fix-up kernel: repeat one accumulator format wider (the sample missed
+		// values with finer bits), and on the row path when the widest format is not enough
+		const bool narrow = job.fast == 1 && job.fx_limbs < 3;
+		if (narrow && S <= out_cap && h_small[3] > std::max<int64_t>(1 << 12, S >> 8))
+			return run_device(ctx, op, N, n1, strict, d_start, d_end, d_value, h_off, h_dflt, pos_lo, pos_hi,
+			                  d_out_start, d_out_end, d_out_value, out_cap, n_out, default_out, auc_out, moments_out, false, px, py,
+			                  job.fx_limbs + 1);
 		if (h_small[3] > job.slow_cap || S > out_cap)
 			return run_device(ctx, op, N, n1, strict, d_start, d_end, d_value, h_off, h_dflt, pos_lo, pos_hi,
 			                  d_out_start, d_out_end, d_out_value, out_cap, n_out, default_out, auc_out, moments_out, true, px, py);
@@ -419,6 +455,12 @@ int wb200_set_stream(wb200_ctx *ctx, void *cuda_stream) {
 	ctx->stream = (cudaStream_t) cuda_stream;
 	ctx->own_stream = false;
 	return WB200_OK;
+}
+
+// Diagnostic builds (-DWB_DIAG_PHASES): cycles per pipeline phase summed over windows since the
+// last call; all zero in the shipped build.
+void wb200_debug_phases(wb200_ctx *ctx, uint64_t out[16]) {
+	for (int k = 0; k < 16; k++) { out[k] = ctx->diag[k]; ctx->diag[k] = 0; }
 }
 
 int wb200_set_window(wb200_ctx *ctx, int window_bp) {

@@ -43,6 +43,19 @@
 namespace wb {
 
 #define FULL 0xffffffffu
+// Diagnostic builds (profiles/): per-phase cycle counters of the window pipeline,
+// accumulated by thread 0 of every CTA into job.diag[phase].
+#ifdef WB_DIAG_PHASES
+#define WB_PHASE(k) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&job.diag[k], (unsigned long long) (t_ - diag_t)); diag_t = t_; } } while (0)
+#else
+#define WB_PHASE(k) do { } while (0)
+#endif
+#ifndef WB_PREF
+#define WB_PREF 0               // events phase: 0 plain loads, 1 register double buffering, 2 L1 prefetch, 3 L2 prefetch
+#endif
+#ifndef WB_FAST_MINB
+#define WB_FAST_MINB 3          // resident CTAs per SM the sum/mean kernel is compiled for
+#endif
 
 // ---------------------------------------------------------------------------
 // shared-memory layout
@@ -773,6 +786,7 @@ __device__ void bitset_walk(const Job &job, const int32_t *cur, const int32_t *n
 template <int VLOG, int LIMBS>
 __device__ __forceinline__ void add_limbs(uint32_t *limb, int ph, long long d, int lw) {
 	constexpr int W = THREADS << VLOG;
+	if (LIMBS == 1) { atomicAdd(&limb[ph], (uint32_t) d); return; }     // the delta sums fit 32 bits
 	atomicAdd(&limb[ph], (uint32_t) (d & ((1ll << lw) - 1)));
 	if (LIMBS == 2) atomicAdd(&limb[W + ph], (uint32_t) (d >> lw));
 	else {
@@ -795,8 +809,10 @@ __device__ __forceinline__ long long load_prefix(const uint32_t *limb, int tid, 
 			const int pq = p0 + ((q ^ swz) << 2);
 			const uint4 y = *(const uint4 *) (limb + pq);
 			l0[4 * q] = y.x; l0[4 * q + 1] = y.y; l0[4 * q + 2] = y.z; l0[4 * q + 3] = y.w;
-			const uint4 z = *(const uint4 *) (limb + W + pq);
-			l1[4 * q] = z.x; l1[4 * q + 1] = z.y; l1[4 * q + 2] = z.z; l1[4 * q + 3] = z.w;
+			if (LIMBS >= 2) {
+				const uint4 z = *(const uint4 *) (limb + W + pq);
+				l1[4 * q] = z.x; l1[4 * q + 1] = z.y; l1[4 * q + 2] = z.z; l1[4 * q + 3] = z.w;
+			}
 			if (LIMBS == 3) {
 				const uint4 u = *(const uint4 *) (limb + 2 * W + pq);
 				l2[4 * q] = u.x; l2[4 * q + 1] = u.y; l2[4 * q + 2] = u.z; l2[4 * q + 3] = u.w;
@@ -804,12 +820,13 @@ __device__ __forceinline__ long long load_prefix(const uint32_t *limb, int tid, 
 		}
 	} else {
 #pragma unroll
-		for (int q = 0; q < V; q++) { l0[q] = limb[p0 + q]; l1[q] = limb[W + p0 + q]; if (LIMBS == 3) l2[q] = limb[2 * W + p0 + q]; }
+		for (int q = 0; q < V; q++) { l0[q] = limb[p0 + q]; if (LIMBS >= 2) l1[q] = limb[W + p0 + q]; if (LIMBS == 3) l2[q] = limb[2 * W + p0 + q]; }
 	}
 	long long a = 0;
 #pragma unroll
 	for (int q = 0; q < V; q++) {
-		if (LIMBS == 2) a += (long long) (unsigned long long) l0[q] + ((long long) (int32_t) l1[q] << lw);
+		if (LIMBS == 1) a += (long long) (int32_t) l0[q];
+		else if (LIMBS == 2) a += (long long) (unsigned long long) l0[q] + ((long long) (int32_t) l1[q] << lw);
 		else a += (long long) (unsigned long long) l0[q] + ((long long) (unsigned long long) l1[q] << lw)
 		        + ((long long) (int32_t) l2[q] << (2 * lw));
 		run[q] = a;
@@ -841,6 +858,168 @@ __device__ __forceinline__ double moments_stat(int op, int N, int c, long long S
 	return op == OP_CV ? sd / mean : sd;
 }
 
+enum { MODE_FAST = 1, MODE_ROW = 2, MODE_MOMENTS = 3, MODE_WALK = 4 };
+
+// ---------------------------------------------------------------------------
+// events, vectorised (fixed-point modes)
+// ---------------------------------------------------------------------------
+// 8-lane groups walk one track each; a lane owns FOUR consecutive intervals per
+// step, fetched with 128-bit loads from a 16-byte aligned index grid, so one
+// step covers 32 intervals of the track -- normally its whole share of the
+// window.  The loads of the next round of tracks are issued before the current
+// round is consumed (register double buffering): one exposed memory latency per
+// window instead of one per 8 intervals.
+// Intervals of a track are sorted and disjoint, so no cross-lane bookkeeping is
+// needed: an interval adds +delta at its start if that lies in the window (or
+// feeds the carried-in state if it began before it), -delta at its end if that
+// lies in the window, and otherwise offers its first coordinate at or beyond the
+// window end as the window's closing breakpoint.
+// Ask for the first chunk of every track of the window ahead of the events phase
+// (one request per 16 bytes a lane will load): the lines travel while the
+// position arrays are cleared.
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+__device__ __forceinline__ void prefetch_window(const Job &job, const int32_t *cur, const long long *toff, const int32_t *tn) {
+	const int gid = threadIdx.x >> 3, gl = threadIdx.x & 7;
+	for (int i = gid; i < job.N; i += THREADS / 8) {
+		const long long o = toff[i], first = o + cur[i];
+		const long long g = (first & ~3ll) + 4 * gl;
+		if (g < o + tn[i] && g + 4 <= job.I) {
+#if WB_PREF == 2
+			prefetch_l1(job.start + g); prefetch_l1(job.end + g); prefetch_l1(job.value + g); prefetch_l1(job.value + g + 2);
+#else
+			prefetch_l2(job.start + g); prefetch_l2(job.end + g); prefetch_l2(job.value + g); prefetch_l2(job.value + g + 2);
+#endif
+		}
+	}
+}
+
+struct Chunk {
+	int4 s, e;
+	double v0, v1, v2, v3;
+	int lo, hi;          // slots lo <= x < hi hold intervals of this track at or after its cursor
+};
+
+template <int MODE, int VLOG, int LIMBS>
+__device__ __forceinline__ void events_vec(const Job &job, unsigned char *smem, const Layout &L, const int32_t *cur,
+                                           long long w0, int lw, double inv_scale, double lim) {
+	constexpr int W = THREADS << VLOG;
+	constexpr int NACC = MODE == MODE_MOMENTS ? 2 : 1;
+	constexpr int G = THREADS / 8;
+	Misc *misc = (Misc *) smem;
+	const int32_t *tn = (const int32_t *) (smem + L.off_tn);
+	const long long *toff = (const long long *) (smem + L.off_toff);
+	const long long *tmd = (const long long *) (smem + L.off_tmd);
+	int32_t *cov = (int32_t *) (smem + L.off_cov);
+	uint32_t *limb = (uint32_t *) (smem + L.off_limb);
+	unsigned char *ev = smem + L.off_ev;
+	const int tid = threadIdx.x, lane = tid & 31, gid = tid >> 3, gl = tid & 7, gsh = lane & 24;
+	const int N = job.N;
+	const int w0i = (int) w0;
+	int in_cov = 0, my_next = INT_MAX;
+	long long in_val = 0, in_val2 = 0;
+
+	auto load = [&](int i, int k, Chunk &c) {
+		c.lo = c.hi = 0;
+		if (i >= N) return;
+		const long long o = toff[i], first = o + cur[i];
+		const long long g = (first & ~3ll) + 32 * k + 4 * gl;      // 16-byte aligned index grid
+		c.lo = (int) max(first - g, 0ll);
+		c.hi = (int) min(o + tn[i] - g, 4ll);
+		if (c.hi <= c.lo) { c.lo = c.hi = 0; return; }
+		if (g + 4 <= job.I) {
+			c.s = *(const int4 *) (job.start + g);
+			c.e = *(const int4 *) (job.end + g);
+			const double2 a = *(const double2 *) (job.value + g), b = *(const double2 *) (job.value + g + 2);
+			c.v0 = a.x; c.v1 = a.y; c.v2 = b.x; c.v3 = b.y;
+		} else {                                                   // the last few intervals of the whole array
+			c.s = make_int4(0, 0, 0, 0); c.e = c.s; c.v0 = c.v1 = c.v2 = c.v3 = 0;
+			if (c.lo <= 0 && 0 < c.hi) { c.s.x = job.start[g]; c.e.x = job.end[g]; c.v0 = job.value[g]; }
+			if (c.lo <= 1 && 1 < c.hi) { c.s.y = job.start[g + 1]; c.e.y = job.end[g + 1]; c.v1 = job.value[g + 1]; }
+			if (c.lo <= 2 && 2 < c.hi) { c.s.z = job.start[g + 2]; c.e.z = job.end[g + 2]; c.v2 = job.value[g + 2]; }
+		}
+	};
+	auto one = [&](bool valid, int s, int e, double val, long long md) {
+		if (!valid) return;
+		const unsigned xs = (unsigned) (s - w0i), xe = (unsigned) (e - w0i);
+		const bool start_in = xs < (unsigned) W, end_in = xe < (unsigned) W;
+		if (!start_in && s >= w0i) { my_next = min(my_next, s); return; }   // begins at or beyond the window end
+		int cd = 1;
+		long long d = 0, d2 = 0, m;
+		if (to_fixed(val, inv_scale, lim, m) && (NACC == 1 || (double) (float) val == val)) {
+			d = m - md;                                // moments: the reference rounds values through float
+			if (NACC == 2) d2 = m * m;
+		} else cd += (1 << COV_P_SHIFT);
+		if (start_in) {
+			const int ph = phys<VLOG>((int) xs);
+			atomicAdd(&cov[ph], cd);
+			ev[xs] = 1;
+			if (d != 0) {
+				add_limbs<VLOG, LIMBS>(limb, ph, d, lw);
+				if (NACC == 2) add_limbs<VLOG, LIMBS>(limb + LIMBS * W, ph, d2, lw);
+			}
+		} else { in_cov += cd; in_val += d; in_val2 += d2; }              // began before the window
+		if (end_in) {
+			const int ph = phys<VLOG>((int) xe);
+			atomicAdd(&cov[ph], -cd);
+			ev[xe] = 1;
+			if (d != 0) {
+				add_limbs<VLOG, LIMBS>(limb, ph, -d, lw);
+				if (NACC == 2) add_limbs<VLOG, LIMBS>(limb + LIMBS * W, ph, -d2, lw);
+			}
+		} else my_next = min(my_next, e);
+	};
+	// returns true when the track may have further intervals in the window
+	auto apply = [&](const Chunk &c, long long md) -> bool {
+		one(c.lo <= 0 && 0 < c.hi, c.s.x, c.e.x, c.v0, md);
+		one(c.lo <= 1 && 1 < c.hi, c.s.y, c.e.y, c.v1, md);
+		one(c.lo <= 2 && 2 < c.hi, c.s.z, c.e.z, c.v2, md);
+		one(c.lo <= 3 && 3 < c.hi, c.s.w, c.e.w, c.v3, md);
+		const bool last_in = c.hi == 4 && (unsigned) (c.e.w - w0i) < (unsigned) W;
+		return __shfl_sync(FULL, last_in, gsh + 7);
+	};
+
+#if WB_PREF == 1
+	// register double buffering: the next round's loads fly while this round is consumed
+	Chunk c;
+	load(gid, 0, c);
+	for (int rb = 0; rb < N; rb += G) {
+		const int i = rb + gid;
+		Chunk nx;
+		load(i + G, 0, nx);
+		const long long md = (MODE == MODE_FAST && i < N) ? tmd[i] : 0;
+		bool more = apply(c, md);
+		for (int k = 1; __any_sync(FULL, more); k++) {   // rare: more than ~30 intervals of one track in the window
+			load(more ? i : N, k, c);
+			more = apply(c, md) && more;
+		}
+		c = nx;
+	}
+#else
+	for (int rb = 0; rb < N; rb += G) {
+		const int i = rb + gid;
+		const long long md = (MODE == MODE_FAST && i < N) ? tmd[i] : 0;
+		bool more = true;
+		for (int k = 0; k == 0 || __any_sync(FULL, more); k++) {   // k > 0 is rare: more than ~30 intervals of one track in the window
+			Chunk c;
+			load(more ? i : N, k, c);
+			more = apply(c, md) && more;
+		}
+	}
+#endif
+	// carried-in state and the look-ahead breakpoint: one shared atomic per warp
+	my_next = __reduce_min_sync(FULL, my_next);
+	in_cov = __reduce_add_sync(FULL, in_cov);
+	for (int d = 16; d > 0; d >>= 1) in_val += __shfl_down_sync(FULL, in_val, d);
+	if (NACC == 2) for (int d = 16; d > 0; d >>= 1) in_val2 += __shfl_down_sync(FULL, in_val2, d);
+	if (lane == 0) {
+		if (my_next != INT_MAX) atomicMin(&misc->next_bp, my_next);
+		if (in_cov) atomicAdd(&misc->base_cov, in_cov);
+		if (in_val) atomicAdd(&misc->base_val, (unsigned long long) in_val);
+		if (NACC == 2 && in_val2) atomicAdd(&misc->base_val2, (unsigned long long) in_val2);
+	}
+}
+
 // ---------------------------------------------------------------------------
 // the window pipeline
 // ---------------------------------------------------------------------------
@@ -859,7 +1038,6 @@ __device__ __forceinline__ double moments_stat(int op, int N, int c, long long S
 //  3. compact: flagged positions (breakpoints) are written as a dense list over
 //              the now-dead position arrays; kept ones carry their output rank.
 //  4. emit   : one breakpoint per thread, coalesced 16 B/segment stores.
-enum { MODE_FAST = 1, MODE_ROW = 2, MODE_MOMENTS = 3, MODE_WALK = 4 };
 
 template <int MODE, int VLOG, int LIMBS>
 __device__ void process_window(const Job &job, int w, unsigned char *smem, const Layout &L, int32_t *cur,
@@ -883,6 +1061,10 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	constexpr bool fast = MODE == MODE_FAST || MODE == MODE_MOMENTS;   // fixed-point value path
 	constexpr int NACC = MODE == MODE_MOMENTS ? 2 : 1;                 // accumulators: sum (and sum of squares)
 
+#ifdef WB_DIAG_PHASES
+	long long diag_t = clock64();
+#endif
+	if constexpr (fast && WB_PREF >= 2) { if (job.vec) prefetch_window(job, cur, toff, tn); }
 	// ---- clear the position arrays -------------------------------------------
 	{
 		const uint4 z = make_uint4(0, 0, 0, 0);
@@ -894,9 +1076,18 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 		if (tid == 0) { misc->next_bp = INT_MAX; misc->base_cov = 0; misc->base_val = 0; misc->base_val2 = 0; }
 	}
 	__syncthreads();
+	WB_PHASE(0);
 
 	// ---- 1. events --------------------------------------------------------------
-	{
+	bool vec_done = false;
+	if constexpr (fast) {
+#ifdef WB_DIAG_SKIP_EVENTS                  // diagnostic builds only (profiles/): time the window skeleton alone
+		vec_done = true;
+#else
+		if (job.vec) { events_vec<MODE, VLOG, LIMBS>(job, smem, L, cur, w0, lw, inv_scale, lim); vec_done = true; }
+#endif
+	}
+	if (!vec_done) {
 		const int gid = tid >> 3, gl = tid & 7, gsh = (lane >> 3) << 3;
 		int in_cov = 0, my_next = INT_MAX;
 		long long in_val = 0, in_val2 = 0;
@@ -976,6 +1167,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 		}
 	}
 	__syncthreads();
+	WB_PHASE(1);
 
 	// ---- 2. scan: this thread's V positions, in registers -------------------------
 	int c_run[V];
@@ -1031,12 +1223,14 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 		}
 		keepbits &= evbits;
 	}
+	WB_PHASE(2);
 
 	// breakpoints and kept segments of this thread; one packed block scan for both
 	const int nbp_l = __popc(evbits), kept_l = __popc(keepbits);
 	int epack, tpack;
 	block_scan1(misc, nbp_l | (kept_l << 16), epack, tpack);
 	const int nbp = tpack & 0xffff, kept_total = tpack >> 16;
+	WB_PHASE(3);
 
 	// publish this window's segment count so that later windows can start their
 	// look-back while we compact (single-pass chained scan over windows)
@@ -1069,6 +1263,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 		}
 	}
 	__syncthreads();
+	WB_PHASE(4);
 
 	// ---- output offset: decoupled look-back over the preceding windows --------------------
 	// Windows are drawn in ascending order, so every predecessor has been started by
@@ -1119,6 +1314,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 		}
 	}
 	__syncthreads();
+	WB_PHASE(5);
 
 	// ---- 4. emit, one breakpoint per thread (coalesced stores) ---------------------------
 	const long long out_base = misc->out_base;
@@ -1311,6 +1507,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 		}
 	}
 
+	WB_PHASE(6);
 	// per-warp AUC partials go straight to global memory (fixed order, folded later)
 	for (int d = 16; d > 0; d >>= 1) {
 		auc += __shfl_down_sync(FULL, auc, d);
@@ -1356,7 +1553,7 @@ __global__ void __launch_bounds__(256) cursor_kernel(const Job job) {
 }
 
 template <int MODE, int VLOG, int LIMBS>
-__global__ void __launch_bounds__(THREADS, MODE == MODE_FAST ? (THREADS == 512 ? 2 : 3) : MODE == MODE_MOMENTS ? 2 : MODE == MODE_WALK ? 3 : 1) emit_kernel(const Job job, int lw, double inv_scale, double lim, double scale, int rowbuf) {
+__global__ void __launch_bounds__(THREADS, MODE == MODE_FAST ? (THREADS == 512 ? 2 : WB_FAST_MINB) : MODE == MODE_MOMENTS ? 2 : MODE == MODE_WALK ? 3 : 1) emit_kernel(const Job job, int lw, double inv_scale, double lim, double scale, int rowbuf) {
 	extern __shared__ __align__(16) unsigned char smem[];
 	const Layout L = make_layout(job.wlog, job.N, true, (MODE == MODE_MOMENTS ? 2 : 1) * LIMBS, rowbuf);
 	int32_t *cur = (int32_t *) (smem + L.off_cur);
@@ -1383,6 +1580,9 @@ __global__ void __launch_bounds__(THREADS, MODE == MODE_FAST ? (THREADS == 512 ?
 		for (int i = threadIdx.x; i < job.N; i += THREADS) ca[i] = job.cursor[(size_t) w * job.N + i];
 	__syncthreads();
 	while (w < job.nw) {
+#ifdef WB_DIAG_PHASES
+		const long long diag_t0 = clock64();
+#endif
 		unsigned t2 = 0;
 		if (threadIdx.x == 0) t2 = atomicAdd(job.ticket, 1u) + 2u * gridDim.x;   // consumed two windows from now
 		if (w1 < job.nw)
@@ -1393,6 +1593,9 @@ __global__ void __launch_bounds__(THREADS, MODE == MODE_FAST ? (THREADS == 512 ?
 		__pipeline_wait_prior(0);
 		if (threadIdx.x == 0) misc->ticket2 = (int) t2;
 		__syncthreads();      // dense list consumed, next cursor row landed, ticket visible
+#ifdef WB_DIAG_PHASES
+		if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&job.diag[7], (unsigned long long) (t_ - diag_t0)); atomicAdd(&job.diag[8], 1ull); }
+#endif
 		w = w1; w1 = misc->ticket2;
 		{ int32_t *t = ca; ca = cb; cb = t; }
 	}
@@ -1479,6 +1682,7 @@ cudaError_t launch_emit(const Job &job, cudaStream_t s) {
 	// widest delta: |m| < 2^mbits (+1 for m - default), or m^2 < 2^(2 mbits) on the moments path
 	const int dbits = job.fast == 2 ? 2 * job.fx_mbits : job.fx_mbits + 1;
 	if (job.fast && dbits > 30 - l2n + lw) limbs = 3;
+	if (job.fast == 1) limbs = job.fx_limbs;      // sum / mean: chosen by the host from the sampled value range
 	double inv_scale = ldexp(1.0, -job.fx_q), scale = ldexp(1.0, job.fx_q), lim = ldexp(1.0, job.fx_mbits);
 	int rowbuf = row_buffer_bytes(job.N, job.op);
 	const bool walk = (job.op == OP_MEDIAN || job.op == OP_MIN || job.op == OP_MAX) && job.N <= WALK_MAX_TRACKS;
@@ -1486,6 +1690,7 @@ cudaError_t launch_emit(const Job &job, cudaStream_t s) {
                   : !job.fast ? launch_emit_v<MODE_ROW, V, 2>(job, lw, inv_scale, lim, scale, rowbuf, s) \
                   : job.fast == 2 ? (limbs == 2 ? launch_emit_v<MODE_MOMENTS, V, 2>(job, lw, inv_scale, lim, scale, rowbuf, s) \
                                                : launch_emit_v<MODE_MOMENTS, V, 3>(job, lw, inv_scale, lim, scale, rowbuf, s)) \
+                  : limbs == 1 ? launch_emit_v<MODE_FAST, V, 1>(job, lw, inv_scale, lim, scale, rowbuf, s) \
                   : limbs == 2 ? launch_emit_v<MODE_FAST, V, 2>(job, lw, inv_scale, lim, scale, rowbuf, s) \
                                : launch_emit_v<MODE_FAST, V, 3>(job, lw, inv_scale, lim, scale, rowbuf, s))
 	switch (job.wlog - TLOG) {       // positions per thread = 2^VLOG

@@ -40,6 +40,8 @@ struct Job {
 	const double *dflt;     // [N] device: default_value per track
 	const int64_t *dflt_fx; // [N] device: fixed-point defaults (fast path)
 	int N;                  // tracks
+	int64_t I;              // total intervals (length of start/end/value)
+	int vec;                // inputs are 16-byte aligned: 128-bit interval loads
 	int n1;                 // tracks in set A (== N for a plain multiplexer)
 	int strict;
 	int op;
@@ -69,7 +71,9 @@ struct Job {
 	int fast;               // 1: scan path enabled for this op
 	int fx_q;               // value = m * 2^fx_q
 	int fx_mbits;           // |m| < 2^fx_mbits
+	int fx_limbs;           // sum / mean: 32-bit limbs per position (1..3)
 	int64_t fx_base;        // sum of fixed-point defaults (all tracks absent)
+	unsigned long long *diag; // [16] diagnostic builds: per-phase cycle counters
 	double mwu_mu, mwu_sigma; // MWU normal approximation moments (host-computed, integer division quirk)
 };
 
