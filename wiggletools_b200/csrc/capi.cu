@@ -345,8 +345,9 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 	CK(cudaMemsetAsync(ctx->state.p, 0, (size_t) nw * sizeof(unsigned long long), s));
 	CK(launch_cursor(job, max_len, s));
 	CK(cudaEventRecord(ctx->ev[2], s));
-	CK(launch_emit(job, s));
-	CK(launch_reduce_auc(job.auc_partial, nw, d_small + 2, s));
+	int auc_per_window = WARPS;
+	CK(launch_emit(job, s, &auc_per_window));
+	CK(launch_reduce_auc(job.auc_partial, nw * auc_per_window, d_small + 2, s));
 	if (moments_out) { CK(launch_reduce_moments(job.moments, nw, d_small + 4, s)); st.kernels++; }
 	CK(cudaEventRecord(ctx->ev[3], s));
 	st.kernels += 3;

@@ -1,0 +1,43 @@
+// wiggletools_b200 -- small device helpers shared by the window kernels
+// (engine.cu, fastsum.cu).
+#pragma once
+#include <cstdint>
+#include <cmath>
+
+namespace wb {
+
+#define FULL 0xffffffffu
+
+// Diagnostic builds (profiles/): per-phase cycle counters of the window pipeline,
+// accumulated by thread 0 of every CTA into job.diag[phase].
+#ifdef WB_DIAG_PHASES
+#define WB_PHASE(k) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&job.diag[k], (unsigned long long) (t_ - diag_t)); diag_t = t_; } } while (0)
+#else
+#define WB_PHASE(k) do { } while (0)
+#endif
+
+// value -> fixed point: m = v * 2^-q exactly, |m| < lim; false for NaN, Inf, values out of
+// range or with bits below 2^q (those intervals take the row path)
+__device__ __forceinline__ bool to_fixed(double v, double inv_scale, double lim, long long &m) {
+	double t = v * inv_scale;
+	if (!(fabs(t) < lim)) return false;          // NaN, Inf, too large
+	if (t != rint(t)) return false;              // bits below 2^q
+	if (t == 0.0 && v != 0.0) return false;      // underflow
+	m = (long long) t;
+	return true;
+}
+
+// look-back words of the single-pass chained scan over windows: 2 flag bits | segment count
+constexpr unsigned long long LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_VALUE = (1ull << 62) - 1;
+__device__ __forceinline__ unsigned long long ld_volatile(const unsigned long long *p) { return *(const volatile unsigned long long *) p; }
+__device__ __forceinline__ void st_volatile(unsigned long long *p, unsigned long long v) { *(volatile unsigned long long *) p = v; }
+
+// one fixed-point delta into one or two 32-bit limb arrays (native 32-bit shared atomics)
+template <int LIMBS, int W>
+__device__ __forceinline__ void add_limbs_fs(uint32_t *limb, int ph, long long d, int lw) {
+	if (LIMBS == 1) { atomicAdd(&limb[ph], (uint32_t) d); return; }
+	atomicAdd(&limb[ph], (uint32_t) (d & ((1ll << lw) - 1)));
+	atomicAdd(&limb[W + ph], (uint32_t) (d >> lw));
+}
+
+} // namespace wb

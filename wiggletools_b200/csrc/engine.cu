@@ -35,21 +35,15 @@
 // cursor_kernel builds, per window and track, the first interval that can touch
 // the window, so that every window starts independently.
 #include "engine.cuh"
+#include "device_util.cuh"
 #include <cuda_pipeline.h>
 #include <cfloat>
+#include <cstdlib>
 #include <climits>
 #include <cmath>
 
 namespace wb {
 
-#define FULL 0xffffffffu
-// Diagnostic builds (profiles/): per-phase cycle counters of the window pipeline,
-// accumulated by thread 0 of every CTA into job.diag[phase].
-#ifdef WB_DIAG_PHASES
-#define WB_PHASE(k) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&job.diag[k], (unsigned long long) (t_ - diag_t)); diag_t = t_; } } while (0)
-#else
-#define WB_PHASE(k) do { } while (0)
-#endif
 #ifndef WB_PREF
 #define WB_PREF 0               // events phase: 0 plain loads, 1 register double buffering, 2 L1 prefetch, 3 L2 prefetch
 #endif
@@ -150,14 +144,6 @@ __device__ __forceinline__ int lower_bound_ge(const int32_t *a, int n, long long
 	return lo;
 }
 
-__device__ __forceinline__ bool to_fixed(double v, double inv_scale, double lim, long long &m) {
-	double t = v * inv_scale;
-	if (!(fabs(t) < lim)) return false;          // NaN, Inf, too large
-	if (t != rint(t)) return false;              // bits below 2^q
-	if (t == 0.0 && v != 0.0) return false;      // underflow
-	m = (long long) t;
-	return true;
-}
 
 // Student-t upper tail, Q(t; nu) = 1/2 I_{nu/(nu+t^2)}(nu/2, 1/2): stands where the
 // reference calls gsl_cdf_tdist_Q (src/setComparisons.c:117).  Continued
@@ -471,9 +457,6 @@ __device__ __forceinline__ void block_scan1(Misc *misc, int c, int &ec, int &tc)
 	ec = bc + ic - c;
 }
 
-constexpr unsigned long long LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_VALUE = (1ull << 62) - 1;
-__device__ __forceinline__ unsigned long long ld_volatile(const unsigned long long *p) { return *(const volatile unsigned long long *) p; }
-__device__ __forceinline__ void st_volatile(unsigned long long *p, unsigned long long v) { *(volatile unsigned long long *) p = v; }
 
 // A segment is emitted when enough tracks cover it: any track (gaps are skipped,
 // src/multiplexer.c:112-115), all N under `strict` (:123-128), or at least one of
@@ -1674,7 +1657,8 @@ static cudaError_t launch_emit_v(const Job &job, int lw, double inv_scale, doubl
 	return cudaGetLastError();
 }
 
-cudaError_t launch_emit(const Job &job, cudaStream_t s) {
+cudaError_t launch_emit(const Job &job, cudaStream_t s, int *auc_per_window) {
+	*auc_per_window = WARPS;
 	// fixed-point format: |m| < 2^mbits, limbs of lw bits
 	int l2n = 1; while ((1 << l2n) < 2 * job.N) l2n++;
 	int lw = 32 - l2n;
@@ -1684,6 +1668,13 @@ cudaError_t launch_emit(const Job &job, cudaStream_t s) {
 	if (job.fast && dbits > 30 - l2n + lw) limbs = 3;
 	if (job.fast == 1) limbs = job.fx_limbs;      // sum / mean: chosen by the host from the sampled value range
 	double inv_scale = ldexp(1.0, -job.fx_q), scale = ldexp(1.0, job.fx_q), lim = ldexp(1.0, job.fx_mbits);
+	{
+		const char *e = getenv("WB200_FASTSUM");       // development: 0 keeps sum / mean on emit_kernel<MODE_FAST>
+		if (!(e && atoi(e) == 0) && fastsum_supported(job)) {
+			*auc_per_window = 1;
+			return launch_fastsum(job, lw, inv_scale, lim, scale, s);
+		}
+	}
 	int rowbuf = row_buffer_bytes(job.N, job.op);
 	const bool walk = (job.op == OP_MEDIAN || job.op == OP_MIN || job.op == OP_MAX) && job.N <= WALK_MAX_TRACKS;
 #define WB_EMIT(V) (walk ? launch_emit_v<MODE_WALK, V, 2>(job, lw, inv_scale, lim, scale, rowbuf, s) \
@@ -1755,8 +1746,8 @@ cudaError_t launch_reduce_moments(const double *moments, int nw, double *out6, c
 	return cudaGetLastError();
 }
 
-cudaError_t launch_reduce_auc(const double *partial, int nw, double *out, cudaStream_t s) {
-	reduce_auc_kernel<<<1, 1024, 0, s>>>(partial, nw * WARPS, out);
+cudaError_t launch_reduce_auc(const double *partial, int count, double *out, cudaStream_t s) {
+	reduce_auc_kernel<<<1, 1024, 0, s>>>(partial, count, out);
 	return cudaGetLastError();
 }
 

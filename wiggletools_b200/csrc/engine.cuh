@@ -108,10 +108,14 @@ __host__ __device__ inline void merge_mom(Mom &a, const Mom &b) {
 // launch helpers implemented in engine.cu
 size_t window_smem_bytes(int wlog, int N, bool emit, int op);
 cudaError_t launch_cursor(const Job &job, int64_t max_track_len, cudaStream_t s);
-cudaError_t launch_emit(const Job &job, cudaStream_t s);
+// auc_per_window: how many AUC partials per window the chosen kernel writes to job.auc_partial
+cudaError_t launch_emit(const Job &job, cudaStream_t s, int *auc_per_window);
+// sum / mean sweep kernel (fastsum.cu)
+bool fastsum_supported(const Job &job);
+cudaError_t launch_fastsum(const Job &job, int lw, double inv_scale, double lim, double scale, cudaStream_t s);
 cudaError_t launch_fixup(const Job &job, long long count, cudaStream_t s);
 cudaError_t launch_sample_maxabs(const double *value, int64_t n, int64_t stride, double *out2, cudaStream_t s);
-cudaError_t launch_reduce_auc(const double *partial, int nw, double *out, cudaStream_t s);
+cudaError_t launch_reduce_auc(const double *partial, int count, double *out, cudaStream_t s);
 cudaError_t launch_reduce_moments(const double *moments, int nw, double *out6, cudaStream_t s);
 
 } // namespace wb
