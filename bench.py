@@ -34,6 +34,8 @@ N_TRACKS = int(os.environ.get("WB200_BENCH_TRACKS", 64))
 SCALE = float(os.environ.get("WB200_BENCH_SCALE", 1.0))   # <1 shrinks every chromosome (development only)
 MAX_LEN, MAX_GAP, GAP_PROB, VMAX = 400, 200, 0.5, 100000
 BENCH_OP = os.environ.get("WB200_BENCH_OP", "mean")       # development: time another statistic of the path
+# the kernel the roofline line is about: sum / mean run on fastsum_kernel (csrc/fastsum.cu), the rest on emit_kernel
+DOMINANT_KERNEL = "fastsum_kernel" if BENCH_OP in ("sum", "mean") and os.environ.get("WB200_FASTSUM") != "0" else "emit_kernel"
 OP_CODE = {"sum": 0, "mult": 1, "mean": 2, "var": 3, "stddev": 4, "cv": 6, "min": 7, "max": 8, "median": 9}[BENCH_OP]
 
 
@@ -332,7 +334,7 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu capture
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("emit_kernel_dram_bytes_per_algorithmic_byte")
-    roofline = {"bound": "hbm", "kernel": "emit_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": DOMINANT_KERNEL, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": (traffic * by / len(per_launch)) if traffic else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_step": by / args.steps,
                 "algorithmic_bytes_per_launch": by / max(1, len(per_launch)),

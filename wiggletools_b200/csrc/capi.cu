@@ -196,7 +196,9 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 		if (env && atoi(env) > 0) wlog = ceil_log2(atoi(env));
 		else {
 			double density = 2.0 * (double) I / ((double) pos_hi - pos_lo + 1.0);
-			if (density > 0.6) wlog = 11;
+			// dense data: smaller windows for the kernels that keep a window in registers; the sum / mean
+			// sweep (fastsum.cu) is fastest with the largest window at any density
+			if (density > 0.6 && !(op == OP_SUM || op == OP_MEAN)) wlog = 11;
 			// the order-statistic sweep is a serial chain per warp: smaller windows, more CTAs per SM
 			if ((op == OP_MEDIAN || op == OP_MIN || op == OP_MAX) && N <= 512) wlog = N > 128 ? 10 : 11;
 		}

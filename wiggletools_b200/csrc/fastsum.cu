@@ -28,12 +28,15 @@
 #include "device_util.cuh"
 #include <cuda_pipeline.h>
 #include <climits>
+#include <cstdlib>
 
 namespace wb {
 namespace fs {
 
-constexpr int TH = 128;                  // threads per CTA (one window per CTA at a time)
-constexpr int NWARP = TH / 32;
+constexpr int MAXWARP = 8;               // CTAs of 128 or 256 threads (one window per CTA at a time)
+#ifndef WB_FS_MINB
+#define WB_FS_MINB 4                  // resident CTAs per SM the 256-thread variant is compiled for
+#endif
 constexpr int END_SHIFT = 11;            // cover word: starts | ends << 11 (each <= 1023 per position)
 constexpr uint32_t FIELD = (1u << END_SHIFT) - 1;
 #ifndef WB_FS_LBK
@@ -58,10 +61,10 @@ struct Misc {
 	long long out_base;              // output offset of the window
 	int ticket2;
 	int pad;
-	long long wsum[NWARP];
-	int wcov[NWARP];
-	int wpack[NWARP];
-	double wauc[NWARP];
+	long long wsum[MAXWARP];
+	int wcov[MAXWARP];
+	int wpack[MAXWARP];
+	double wauc[MAXWARP];
 	PoisEv pois[POIS_CAP];
 };
 constexpr int MISC_BYTES = 1024;
@@ -104,7 +107,7 @@ struct Chunk {
 };
 
 // ---- events: +1 start / +1 end per interval in the cover word, +-value in the limbs ----
-template <int VLOG, int LIMBS>
+template <int TH, int VLOG, int LIMBS>
 __device__ __forceinline__ void events(const Job &job, unsigned char *smem, const Layout &L, const int32_t *cur,
                                        long long w0, int lw, double inv_scale, double lim) {
 	constexpr int W = TH << VLOG, G = TH / 8;
@@ -198,10 +201,10 @@ __device__ __forceinline__ void events(const Job &job, unsigned char *smem, cons
 }
 
 // ---- one window ------------------------------------------------------------------------
-template <int VLOG, int LIMBS>
+template <int TH, int VLOG, int LIMBS>
 __device__ void process_window(const Job &job, int w, unsigned char *smem, const Layout &L, const int32_t *cur,
                                const int32_t *nxt_cur, int lw, double inv_scale, double lim, double scale) {
-	constexpr int V = 1 << VLOG, W = TH << VLOG, NV = V / 4;
+	constexpr int V = 1 << VLOG, W = TH << VLOG, NV = V / 4, NWARP = TH / 32;
 	static_assert(V <= 32, "one 32-bit mask per thread");
 	Misc *misc = (Misc *) smem;
 	uint32_t *cov = (uint32_t *) (smem + L.off_cov);
@@ -228,7 +231,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 
 	// ---- 1. events ---------------------------------------------------------------------
 #ifndef WB_DIAG_SKIP_EVENTS
-	events<VLOG, LIMBS>(job, smem, L, cur, w0, lw, inv_scale, lim);
+	events<TH, VLOG, LIMBS>(job, smem, L, cur, w0, lw, inv_scale, lim);
 #endif
 	__syncthreads();
 	WB_PHASE(1);
@@ -423,42 +426,50 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	// ---- 4. emit, one breakpoint per thread (coalesced stores) -------------------------------
 	const long long out_base = misc->out_base;
 	const int next_bp = misc->next_bp;
+	const int w0i = (int) w0;
+	int32_t *const os = job.out_start + out_base, *const oe = job.out_end + out_base;
+	double *const ov = job.out_value + out_base;
+	const long long room = job.out_cap - out_base;             // output ranks below this are in range
 	const bool npow2 = (N & (N - 1)) == 0;
-	const double inv_n = 1.0 / N;
+	const bool mean = job.op == OP_MEAN;
+	// sum: x 2^q; mean over a power-of-two N: x 2^q / N is one exact power of two as well
+	const double mul = (mean && npow2) ? scale * (1.0 / N) : scale;
+	const bool div = mean && !npow2;
+	constexpr uint32_t PMASK = (1u << D_KID_SHIFT) - 1;
 	double auc = 0;
+#pragma unroll 2
 	for (int r = tid; r < nbp; r += TH) {
 		const uint32_t d = dense[r];
 		if (!(d & D_KEEP)) continue;
-		const int pos = (int) (d & ((1u << D_KID_SHIFT) - 1));
-		const long long oi = out_base + ((d >> D_KID_SHIFT) & ((1u << D_KID_SHIFT) - 1));
-		const int bs = (int) (w0 + pos);
-		const int be = (r + 1 < nbp) ? (int) (w0 + (dense[r + 1] & ((1u << D_KID_SHIFT) - 1))) : next_bp;
+		const int pos = (int) (d & PMASK), kid = (int) ((d >> D_KID_SHIFT) & PMASK);
+		const int bs = w0i + pos;
+		const int be = (r + 1 < nbp) ? w0i + (int) (dense[r + 1] & PMASK) : next_bp;
 		const int ph = phys<VLOG>(pos);
 		long long a;
 		if (LIMBS == 1) a = (long long) (int32_t) limb[ph];
 		else a = (long long) (((unsigned long long) limb[W + ph] << 32) | limb[ph]);
-		double v = (double) (a + job.fx_base) * scale;           // correctly rounded exact sum
-		if (job.op == OP_MEAN) v = npow2 ? v * inv_n : v / N;    // 1/N is exact for a power of two
-		if (oi < job.out_cap) {
-			job.out_start[oi] = bs;
-			job.out_end[oi] = be;
-			job.out_value[oi] = v;
+		double v = (double) (a + job.fx_base) * mul;             // correctly rounded exact sum
+		if (div) v = v / N;
+		if (kid < room) {
+			os[kid] = bs;
+			oe[kid] = be;
+			ov[kid] = v;
 			if (d & D_SLOW) {
 				// an input was not representable: the fix-up kernel recomputes this
 				// segment with the reference's own operation order
 				const unsigned long long k = atomicAdd(job.slow_count, 1ull);
-				if (k < (unsigned long long) job.slow_cap) job.slow_list[k] = oi;
+				if (k < (unsigned long long) job.slow_cap) job.slow_list[k] = out_base + kid;
 			}
 		}
-		if (!(d & D_SLOW) && !isnan(v)) auc += (double) (be - bs) * v;
+		if (!(d & D_SLOW)) auc += (double) (be - bs) * v;        // v is finite here
 	}
 	for (int d = 16; d > 0; d >>= 1) auc += __shfl_down_sync(FULL, auc, d);
 	if (lane == 0) misc->wauc[warp] = auc;
 	WB_PHASE(6);
 }
 
-template <int VLOG, int LIMBS>
-__global__ void __launch_bounds__(TH, 6) fastsum_kernel(const Job job, int lw, double inv_scale, double lim, double scale) {
+template <int TH, int VLOG, int LIMBS>
+__global__ void __launch_bounds__(TH, TH == 128 ? 6 : WB_FS_MINB) fastsum_kernel(const Job job, int lw, double inv_scale, double lim, double scale) {
 	extern __shared__ __align__(16) unsigned char smem[];
 	const Layout L = make_layout(job.wlog, job.N, LIMBS);
 	int32_t *tn = (int32_t *) (smem + L.off_tn);
@@ -488,12 +499,12 @@ __global__ void __launch_bounds__(TH, 6) fastsum_kernel(const Job job, int lw, d
 			for (int i = threadIdx.x; i < job.N; i += TH)
 				__pipeline_memcpy_async(&cb[i], &job.cursor[(size_t) w1 * job.N + i], 4);
 		__pipeline_commit();
-		process_window<VLOG, LIMBS>(job, w, smem, L, ca, w1 < job.nw ? cb : nullptr, lw, inv_scale, lim, scale);
+		process_window<TH, VLOG, LIMBS>(job, w, smem, L, ca, w1 < job.nw ? cb : nullptr, lw, inv_scale, lim, scale);
 		if (threadIdx.x == 0) misc->ticket2 = (int) t2;
 		__syncthreads();      // dense list consumed, next cursor row landed, ticket and AUC partials visible
 		if (threadIdx.x == 0 && job.auc_partial) {
 			double t = 0;
-			for (int k = 0; k < NWARP; k++) t += misc->wauc[k];
+			for (int k = 0; k < TH / 32; k++) t += misc->wauc[k];
 			job.auc_partial[w] = t;
 		}
 #ifdef WB_DIAG_PHASES
@@ -504,34 +515,48 @@ __global__ void __launch_bounds__(TH, 6) fastsum_kernel(const Job job, int lw, d
 	}
 }
 
-template <int VLOG, int LIMBS>
+template <int TH, int VLOG, int LIMBS>
 static cudaError_t launch_v(const Job &job, int lw, double inv_scale, double lim, double scale, cudaStream_t s) {
-	const size_t smem = make_layout(job.wlog, job.N, LIMBS).total;
+	size_t smem = make_layout(job.wlog, job.N, LIMBS).total;
+	{ const char *e = getenv("WB200_FS_PAD"); if (e) smem += (size_t) atoi(e) * 1024; }   // development: cap the CTAs per SM
 	int dev = 0, sms = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-	cudaError_t e = cudaFuncSetAttribute(fastsum_kernel<VLOG, LIMBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+	cudaError_t e = cudaFuncSetAttribute(fastsum_kernel<TH, VLOG, LIMBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 	if (e != cudaSuccess) return e;
 	int per = 1;
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fastsum_kernel<VLOG, LIMBS>, TH, smem);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fastsum_kernel<TH, VLOG, LIMBS>, TH, smem);
 	const int grid = min(job.nw, sms * max(per, 1));
-	fastsum_kernel<VLOG, LIMBS><<<grid, TH, smem, s>>>(job, lw, inv_scale, lim, scale);
+	fastsum_kernel<TH, VLOG, LIMBS><<<grid, TH, smem, s>>>(job, lw, inv_scale, lim, scale);
 	return cudaGetLastError();
 }
 
 } // namespace fs
 
+// threads per window (development override: WB200_FS_THREADS)
+static int fastsum_threads(const Job &job) {
+	const char *e = getenv("WB200_FS_THREADS");
+	const int th = e ? atoi(e) : 0;
+	return (th == 128 || th == 256) ? th : 128;
+}
+
 // Whether the sum / mean sweep kernel covers this job (else: emit_kernel<MODE_FAST>).
 bool fastsum_supported(const Job &job) {
 	if (job.fast != 1 || !job.vec || job.fx_limbs > 2 || job.N > MAX_TRACKS) return false;
-	if (job.wlog != 11 && job.wlog != 12) return false;
+	const int vlog = job.wlog - (fastsum_threads(job) == 256 ? 8 : 7);
+	if (vlog != 4 && vlog != 5) return false;
 	return fs::make_layout(job.wlog, job.N, job.fx_limbs).total <= 200 * 1024;
 }
 
 cudaError_t launch_fastsum(const Job &job, int lw, double inv_scale, double lim, double scale, cudaStream_t s) {
-	const int vlog = job.wlog - 7;
-	if (vlog == 5) return job.fx_limbs == 1 ? fs::launch_v<5, 1>(job, lw, inv_scale, lim, scale, s) : fs::launch_v<5, 2>(job, lw, inv_scale, lim, scale, s);
-	if (vlog == 4) return job.fx_limbs == 1 ? fs::launch_v<4, 1>(job, lw, inv_scale, lim, scale, s) : fs::launch_v<4, 2>(job, lw, inv_scale, lim, scale, s);
+	const bool big = fastsum_threads(job) == 256;
+	const int vlog = job.wlog - (big ? 8 : 7);
+	const bool one = job.fx_limbs == 1;
+#define WB_FS(TH, V) (one ? fs::launch_v<TH, V, 1>(job, lw, inv_scale, lim, scale, s) : fs::launch_v<TH, V, 2>(job, lw, inv_scale, lim, scale, s))
+	if (big && vlog == 4) return WB_FS(256, 4);
+	if (!big && vlog == 4) return WB_FS(128, 4);
+	if (!big && vlog == 5) return WB_FS(128, 5);
+#undef WB_FS
 	return cudaErrorInvalidValue;
 }
 
