@@ -100,6 +100,8 @@ typedef struct wb200_stats {
 	float ms_emit;           /* device time of the emit kernel(s) */
 	float ms_total;          /* device time of the whole call (events on the call's stream) */
 	int64_t h2d_bytes, d2h_bytes;
+	int32_t limbs;           /* exact sum path: 32-bit accumulator limbs per position (1..3), else 0 */
+	int32_t sweep_kernel;    /* 1: the call ran on the sum / mean sweep kernel (csrc/fastsum.cu), 0: emit_kernel */
 } wb200_stats;
 
 /* -- lifetime ------------------------------------------------------------ */

@@ -26,7 +26,8 @@ class CStats(C.Structure):
     _fields_ = [("intervals", C.c_int64), ("segments", C.c_int64), ("windows", C.c_int64),
                 ("slow_segments", C.c_int64), ("kernels", C.c_int32), ("fast_path", C.c_int32),
                 ("ms_count", C.c_float), ("ms_emit", C.c_float), ("ms_total", C.c_float),
-                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("limbs", C.c_int32), ("sweep_kernel", C.c_int32)]
 
 
 _lib = None

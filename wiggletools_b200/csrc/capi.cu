@@ -63,7 +63,7 @@ struct wb200_ctx {
 	int window_bp = 0;
 	std::string err;
 	wb200_stats stats{};
-	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+	cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 	DevBuf in_start, in_end, in_value, off, dflt, dflt_fx, cursor, state, aucp, small, moments, slow_list;
 	DevBuf out_start, out_end, out_value;
 	HostBuf h_small, h_meta, h_start, h_end, h_value;
@@ -254,6 +254,17 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 	CK(cudaMemsetAsync(d_small, 0, 256, s));
 	st.kernels = 0;
 
+	// the cursor table does not depend on the accumulator format: it is built while the host
+	// waits for the value sample below
+	{
+		CK(cudaEventRecord(ctx->ev[1], s));
+		int64_t max_len = 0;
+		for (int i = 0; i < N; i++) max_len = std::max<int64_t>(max_len, h_off[i + 1] - h_off[i]);
+		CK(cudaMemsetAsync(ctx->state.p, 0, (size_t) nw * sizeof(unsigned long long), s));
+		CK(launch_cursor(job, max_len, s));
+		CK(cudaEventRecord(ctx->ev[2], s));
+	}
+
 	// fixed-point fast paths: sum / mean (one exact accumulator) and var / stddev /
 	// CV (exact sum and sum of squares)
 	job.fast = 0;
@@ -341,12 +352,7 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 	size_t need = window_smem_bytes(wlog, N, true, op);
 	if (need > 227 * 1024) return fail(ctx, WB200_EUNSUPPORTED, "window does not fit shared memory; lower WB200_WINDOW");
 
-	CK(cudaEventRecord(ctx->ev[1], s));
-	int64_t max_len = 0;
-	for (int i = 0; i < N; i++) max_len = std::max<int64_t>(max_len, h_off[i + 1] - h_off[i]);
-	CK(cudaMemsetAsync(ctx->state.p, 0, (size_t) nw * sizeof(unsigned long long), s));
-	CK(launch_cursor(job, max_len, s));
-	CK(cudaEventRecord(ctx->ev[2], s));
+	CK(cudaEventRecord(ctx->ev[4], s));
 	int auc_per_window = WARPS;
 	CK(launch_emit(job, s, &auc_per_window));
 	CK(launch_reduce_auc(job.auc_partial, nw * auc_per_window, d_small + 2, s));
@@ -390,9 +396,11 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 	st.segments = S;
 	st.windows = nw;
 	st.fast_path = job.fast;
+	st.limbs = job.fast == 1 ? job.fx_limbs : 0;
+	st.sweep_kernel = auc_per_window == 1 ? 1 : 0;
 	st.slow_segments = h_small[3];
 	cudaEventElapsedTime(&st.ms_count, ctx->ev[1], ctx->ev[2]);
-	cudaEventElapsedTime(&st.ms_emit, ctx->ev[2], ctx->ev[3]);
+	cudaEventElapsedTime(&st.ms_emit, ctx->ev[4], ctx->ev[3]);
 	cudaEventElapsedTime(&st.ms_total, ctx->ev[0], ctx->ev[3]);
 	if (n_out) *n_out = S;
 	if (auc_out) memcpy(auc_out, h_small + 2, 8);
@@ -635,6 +643,7 @@ int wb200_reduce_host_batch(wb200_ctx *ctx, int op, int nshards, int ntracks, in
 		// accumulate stats
 		total.intervals += ctx->stats.intervals; total.segments += ctx->stats.segments; total.windows += ctx->stats.windows;
 		total.slow_segments += ctx->stats.slow_segments; total.kernels += ctx->stats.kernels; total.fast_path = ctx->stats.fast_path;
+		total.limbs = std::max(total.limbs, ctx->stats.limbs); total.sweep_kernel = ctx->stats.sweep_kernel;
 		total.ms_count += ctx->stats.ms_count; total.ms_emit += ctx->stats.ms_emit; total.ms_total += ctx->stats.ms_total;
 		// host space for this shard's segments
 		const int64_t need = (h.S + 2) * 16;

@@ -1516,22 +1516,31 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 // end coordinates once (4 B/interval); row nw closes the table.
 __global__ void __launch_bounds__(256) cursor_kernel(const Job job) {
 	const int i = blockIdx.y;
-	const long long o = job.off[i];
-	const int n = (int) (job.off[i + 1] - o);
-	// four consecutive intervals per thread: one pass over `end`, few threads
-	const long long j0 = ((long long) blockIdx.x * blockDim.x + threadIdx.x) * 4;
-	if (j0 > n) return;
-	long long e_prev = j0 > 0 ? (long long) job.end[o + j0 - 1] : LLONG_MIN / 2;
+	const long long o = job.off[i], oe = job.off[i + 1];
+	// four consecutive intervals per thread on a 16-byte aligned grid: one 128-bit load
+	const long long g = (o & ~3ll) + ((long long) blockIdx.x * blockDim.x + threadIdx.x) * 4;
+	if (g > oe) return;
+	// cnt(e) = number of windows that start at or before e; interval j is the cursor of the
+	// windows cnt(end[j-1]) .. cnt(end[j]) - 1, and j = n (one past the last) closes the table
+	const int p0 = (int) job.p0, wlog = job.wlog, rows = job.nw + 1;
+	auto cnt = [&](int e) { return e < p0 ? 0 : (int) (((unsigned) e - (unsigned) p0) >> wlog) + 1; };
+	int ev[4];
+	if (job.vec && g >= o && g + 4 <= oe) {
+		const int4 v = *(const int4 *) (job.end + g);
+		ev[0] = v.x; ev[1] = v.y; ev[2] = v.z; ev[3] = v.w;
+	} else {
+#pragma unroll
+		for (int k = 0; k < 4; k++) ev[k] = (g + k >= o && g + k < oe) ? job.end[g + k] : 0;
+	}
+	int c_prev = g > o ? cnt(job.end[g - 1]) : 0;
 #pragma unroll
 	for (int k = 0; k < 4; k++) {
-		const long long j = j0 + k;
-		if (j > n) break;
-		const long long e = j < n ? (long long) job.end[o + j] : LLONG_MAX / 2;
-		// windows whose start lies in (e_prev, e]: usually none, sometimes one
-		const long long wlo = e_prev < job.p0 ? 0 : ((e_prev - job.p0) >> job.wlog) + 1;
-		const long long whi = e < job.p0 ? -1 : min((long long) job.nw, (e - job.p0) >> job.wlog);
-		for (long long w = wlo; w <= whi; w++) job.cursor[(size_t) w * job.N + i] = (int32_t) j;
-		e_prev = e;
+		const long long j = g + k - o;
+		if (j < 0) continue;
+		if (j > oe - o) break;
+		const int c = j < oe - o ? min(cnt(ev[k]), rows) : rows;
+		for (int w = c_prev; w < c; w++) job.cursor[(size_t) w * job.N + i] = (int32_t) j;
+		c_prev = c;
 	}
 }
 
@@ -1637,7 +1646,8 @@ size_t window_smem_bytes(int wlog, int N, bool emit, int op) {
 }
 
 cudaError_t launch_cursor(const Job &job, int64_t max_track_len, cudaStream_t s) {
-	dim3 grid((unsigned) (((max_track_len + 4) / 4 + 255) / 256), (unsigned) job.N);
+	// max_track_len + 1 intervals (the closing one) + up to 3 slots of alignment, 4 per thread
+	dim3 grid((unsigned) (((max_track_len + 8) / 4 + 255) / 256), (unsigned) job.N);
 	cursor_kernel<<<grid, 256, 0, s>>>(job);
 	return cudaGetLastError();
 }
