@@ -436,6 +436,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	const double mul = (mean && npow2) ? scale * (1.0 / N) : scale;
 	const bool div = mean && !npow2;
 	constexpr uint32_t PMASK = (1u << D_KID_SHIFT) - 1;
+	const int32_t fx_base32 = (int32_t) job.fx_base;
 	double auc = 0;
 #pragma unroll 2
 	for (int r = tid; r < nbp; r += TH) {
@@ -445,10 +446,9 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 		const int bs = w0i + pos;
 		const int be = (r + 1 < nbp) ? w0i + (int) (dense[r + 1] & PMASK) : next_bp;
 		const int ph = phys<VLOG>(pos);
-		long long a;
-		if (LIMBS == 1) a = (long long) (int32_t) limb[ph];
-		else a = (long long) (((unsigned long long) limb[W + ph] << 32) | limb[ph]);
-		double v = (double) (a + job.fx_base) * mul;             // correctly rounded exact sum
+		double v;                                                // correctly rounded exact sum
+		if (LIMBS == 1) v = (double) ((int32_t) limb[ph] + fx_base32) * mul;     // |sum + defaults| < 2^30: one 32-bit conversion
+		else v = (double) ((long long) (((unsigned long long) limb[W + ph] << 32) | limb[ph]) + job.fx_base) * mul;
 		if (div) v = v / N;
 		if (kid < room) {
 			os[kid] = bs;
