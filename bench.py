@@ -383,7 +383,7 @@ def main():
         ph = (C.c_uint64 * 16)()
         lib.wb200_debug_phases(ctx, ph)
         if any(ph):                                   # diagnostic builds only
-            names_ = ["clear", "events", "scan", "count", "compact", "lookback", "emit", "window_total", "windows"]
+            names_ = ["clear", "events", "scan", "count", "compact", "lookback", "emit", "window_total", "windows", "lookback_polls", "lookback_steps"]
             line["phase_cycles_per_window"] = {n: ph[k] / max(1, ph[8]) for k, n in enumerate(names_)}
         print(json.dumps(line))
     lib.wb200_destroy(ctx)

@@ -597,21 +597,46 @@ int wb200_reduce_host_batch(wb200_ctx *ctx, int op, int nshards, int ntracks, in
 	}
 	CK(ctx->h_arena.ensure((size_t) est * 16));     // first guess S ~ 1.5 I; grown below if needed
 
-	auto stage = [&](int c) -> int {
+	// Pipeline order: the first H2D and the last D2H are the only transfers nothing overlaps, so
+	// the small shards go to the two ends and the large ones to the middle.  Results are
+	// returned per shard, in the caller's order.
+	std::vector<int> order(nshards);
+	{
+		std::vector<int> by_size(nshards);
+		for (int c = 0; c < nshards; c++) by_size[c] = c;
+		std::stable_sort(by_size.begin(), by_size.end(), [&](int x, int y) { return sh[x].I < sh[y].I; });
+		int lo = 0, hi = nshards - 1;
+		for (int r = 0; r < nshards; r++) { if (r & 1) order[hi--] = by_size[r]; else order[lo++] = by_size[r]; }
+	}
+	auto stage = [&](int k) -> int {
+		const int c = order[k];
 		Shard &h = sh[c];
-		const int b = c & 1;
+		const int b = k & 1;
 		CK(ctx->bin_start[b].ensure(std::max<int64_t>(1, h.I) * sizeof(int32_t)));
 		CK(ctx->bin_end[b].ensure(std::max<int64_t>(1, h.I) * sizeof(int32_t)));
 		CK(ctx->bin_value[b].ensure(std::max<int64_t>(1, h.I) * sizeof(double)));
-		if (c >= 2) CK(cudaStreamWaitEvent(ctx->s_h2d, ev_comp[c - 2], 0));   // input set b is free again
-		for (int i = 0; i < N; i++) {
+		if (k >= 2) CK(cudaStreamWaitEvent(ctx->s_h2d, ev_comp[k - 2], 0));   // input set b is free again
+		// Tracks that lie back to back in host memory (the layout the BigWig batch decoder and any
+		// SoA producer hand over) travel as one copy per array: measured on this box, 1 MiB
+		// transfers reach 46 GB/s and 63 GB/s with both directions busy, 64 MiB ones 55 and 97
+		// (profiles/pcie_probe.py).
+		for (int i = 0; i < N; ) {
 			const wb200_track &t = tracks[(size_t) c * N + i];
-			if (!t.n) continue;
-			CK(cudaMemcpyAsync(ctx->bin_start[b].as<int32_t>() + h.off[i], t.start, t.n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_h2d));
-			CK(cudaMemcpyAsync(ctx->bin_end[b].as<int32_t>() + h.off[i], t.end, t.n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_h2d));
-			CK(cudaMemcpyAsync(ctx->bin_value[b].as<double>() + h.off[i], t.value, t.n * sizeof(double), cudaMemcpyHostToDevice, ctx->s_h2d));
+			if (!t.n) { i++; continue; }
+			int64_t n = t.n;
+			int j = i + 1;
+			for (; j < N; j++) {
+				const wb200_track &u = tracks[(size_t) c * N + j];
+				if (!u.n) continue;
+				if (u.start != t.start + n || u.end != t.end + n || u.value != t.value + n) break;
+				n += u.n;
+			}
+			CK(cudaMemcpyAsync(ctx->bin_start[b].as<int32_t>() + h.off[i], t.start, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_h2d));
+			CK(cudaMemcpyAsync(ctx->bin_end[b].as<int32_t>() + h.off[i], t.end, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_h2d));
+			CK(cudaMemcpyAsync(ctx->bin_value[b].as<double>() + h.off[i], t.value, n * sizeof(double), cudaMemcpyHostToDevice, ctx->s_h2d));
+			i = j;
 		}
-		CK(cudaEventRecord(ev_h2d[c], ctx->s_h2d));
+		CK(cudaEventRecord(ev_h2d[k], ctx->s_h2d));
 		return WB200_OK;
 	};
 
@@ -628,18 +653,19 @@ int wb200_reduce_host_batch(wb200_ctx *ctx, int op, int nshards, int ntracks, in
 	int64_t arena_used = 0, h2d = 0, d2h = 0;
 	wb200_stats total{};
 	if (nshards > 0) { int rc = stage(0); if (rc) return rc; }
-	for (int c = 0; c < nshards; c++) {
+	for (int k = 0; k < nshards; k++) {
+		const int c = order[k];
 		Shard &h = sh[c];
-		const int b = c & 1;
-		if (c + 1 < nshards) { int rc = stage(c + 1); if (rc) return rc; }
-		CK(cudaStreamWaitEvent(s, ev_h2d[c], 0));
-		if (c >= 2) CK(cudaStreamWaitEvent(s, ev_d2h[c - 2], 0));              // output set b has been drained
+		const int b = k & 1;
+		if (k + 1 < nshards) { int rc = stage(k + 1); if (rc) return rc; }
+		CK(cudaStreamWaitEvent(s, ev_h2d[k], 0));
+		if (k >= 2) CK(cudaStreamWaitEvent(s, ev_d2h[k - 2], 0));              // output set b has been drained
 		int rc = run_device(ctx, op, N, nset1, strict, ctx->bin_start[b].as<int32_t>(), ctx->bin_end[b].as<int32_t>(),
 		                    ctx->bin_value[b].as<double>(), h.off.data(), h.dflt.data(), (int32_t) h.lo, (int32_t) h.hi,
 		                    ctx->bout_start[b].as<int32_t>(), ctx->bout_end[b].as<int32_t>(), ctx->bout_value[b].as<double>(),
 		                    h.cap, &h.S, &h.dv, &h.auc);
 		if (rc != WB200_OK) return rc;
-		CK(cudaEventRecord(ev_comp[c], s));
+		CK(cudaEventRecord(ev_comp[k], s));
 		// accumulate stats
 		total.intervals += ctx->stats.intervals; total.segments += ctx->stats.segments; total.windows += ctx->stats.windows;
 		total.slow_segments += ctx->stats.slow_segments; total.kernels += ctx->stats.kernels; total.fast_path = ctx->stats.fast_path;
@@ -658,13 +684,13 @@ int wb200_reduce_host_batch(wb200_ctx *ctx, int op, int nshards, int ntracks, in
 		h.arena_off = arena_used;
 		arena_used += need;
 		char *base = (char *) ctx->h_arena.p + h.arena_off;
-		CK(cudaStreamWaitEvent(ctx->s_d2h, ev_comp[c], 0));
+		CK(cudaStreamWaitEvent(ctx->s_d2h, ev_comp[k], 0));
 		if (h.S > 0) {
 			CK(cudaMemcpyAsync(base, ctx->bout_value[b].p, h.S * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_d2h));
 			CK(cudaMemcpyAsync(base + (h.S + 1) * 8, ctx->bout_start[b].p, h.S * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_d2h));
 			CK(cudaMemcpyAsync(base + (h.S + 1) * 12, ctx->bout_end[b].p, h.S * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_d2h));
 		}
-		CK(cudaEventRecord(ev_d2h[c], ctx->s_d2h));
+		CK(cudaEventRecord(ev_d2h[k], ctx->s_d2h));
 		h2d += h.I * 16; d2h += h.S * 16;
 	}
 	CK(cudaStreamSynchronize(ctx->s_d2h));

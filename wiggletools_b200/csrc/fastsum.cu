@@ -28,6 +28,7 @@
 #include "device_util.cuh"
 #include <cuda_pipeline.h>
 #include <climits>
+#include <type_traits>
 #include <cstdlib>
 
 namespace wb {
@@ -41,6 +42,18 @@ constexpr int END_SHIFT = 11;            // cover word: starts | ends << 11 (eac
 constexpr uint32_t FIELD = (1u << END_SHIFT) - 1;
 #ifndef WB_FS_LBK
 #define WB_FS_LBK 1
+#endif
+#ifndef WB_FS_LBRELAX
+#define WB_FS_LBRELAX 1               // look-back waits only for the predecessors it sums
+#endif
+#ifndef WB_FS_LATETICKET
+#define WB_FS_LATETICKET 2            // next window drawn: 0 two windows ahead, 1 after the events phase, 2 when the emit phase starts
+#endif
+#ifndef WB_FS_EVPIPE
+#define WB_FS_EVPIPE 1                // events: software-pipelined interval loads
+#endif
+#ifndef WB_FS_LBSLEEP
+#define WB_FS_LBSLEEP 40
 #endif
 #ifndef WB_FS_PREF
 #define WB_FS_PREF 3                  // next window's intervals: 0 no prefetch, 2 prefetch.L1, 3 prefetch.L2
@@ -120,8 +133,9 @@ __device__ __forceinline__ void events(const Job &job, unsigned char *smem, cons
 	const int tid = threadIdx.x, lane = tid & 31, gid = tid >> 3, gl = tid & 7, gsh = lane & 24;
 	const int N = job.N;
 	const int w0i = (int) w0;
+	using acc_t = typename std::conditional<LIMBS == 1, int, long long>::type;
 	int in_cov = 0, in_pois = 0, my_next = INT_MAX;
-	long long in_val = 0;
+	acc_t in_val = 0;
 
 	auto load = [&](int i, int k, Chunk &c) {
 		c.lo = c.hi = 0;
@@ -152,9 +166,20 @@ __device__ __forceinline__ void events(const Job &job, unsigned char *smem, cons
 		const unsigned xs = (unsigned) (s - w0i), xe = (unsigned) (e - w0i);
 		const bool start_in = xs < (unsigned) W, end_in = xe < (unsigned) W;
 		if (!start_in && s >= w0i) { my_next = min(my_next, s); return; }   // begins at or beyond the window end
-		long long d = 0, m;
-		const bool bad = !to_fixed(val, inv_scale, lim, m);
-		if (!bad) d = m - md;
+		acc_t d = 0;
+		bool bad;
+		if (LIMBS == 1) {
+			// one limb: |m| and the defaults are below 2^29 / 2N (capi.cu), so the whole
+			// delta arithmetic is 32-bit; same acceptance rule as to_fixed()
+			const double t = val * inv_scale;
+			const int mi = __double2int_rn(t);
+			bad = !((double) mi == t && fabs(t) < lim && (mi != 0 || val == 0.0));
+			if (!bad) d = (acc_t) (mi - (int) md);
+		} else {
+			long long m;
+			bad = !to_fixed(val, inv_scale, lim, m);
+			if (!bad) d = (acc_t) (m - md);
+		}
 		if (start_in) {
 			const int ph = phys<VLOG>((int) xs);
 			atomicAdd(&cov[ph], 1u);
@@ -177,6 +202,24 @@ __device__ __forceinline__ void events(const Job &job, unsigned char *smem, cons
 		const bool last_in = c.hi == 4 && (unsigned) (c.e.w - w0i) < (unsigned) W;
 		return __shfl_sync(FULL, last_in, gsh + 7);
 	};
+#if WB_FS_EVPIPE
+	// the first chunk of the next round of tracks is requested before this round's events are
+	// applied: one exposed load latency per window instead of one per round
+	Chunk nx;
+	load(gid, 0, nx);
+	for (int rb = 0; rb < N; rb += G) {
+		const int i = rb + gid;
+		const long long md = i < N ? tmd[i] : 0;
+		const Chunk c0 = nx;
+		load(i + G, 0, nx);
+		bool more = apply(c0, md);
+		for (int k = 1; __any_sync(FULL, more); k++) {             // rare: more than ~30 intervals of one track in the window
+			Chunk c;
+			load(more ? i : N, k, c);
+			more = apply(c, md) && more;
+		}
+	}
+#else
 	for (int rb = 0; rb < N; rb += G) {
 		const int i = rb + gid;
 		const long long md = i < N ? tmd[i] : 0;
@@ -187,23 +230,25 @@ __device__ __forceinline__ void events(const Job &job, unsigned char *smem, cons
 			more = apply(c, md) && more;
 		}
 	}
+#endif
 	// carried-in state and the look-ahead breakpoint: one shared atomic per warp
 	my_next = __reduce_min_sync(FULL, my_next);
 	in_cov = __reduce_add_sync(FULL, in_cov);
 	in_pois = __reduce_add_sync(FULL, in_pois);
-	for (int d = 16; d > 0; d >>= 1) in_val += __shfl_down_sync(FULL, in_val, d);
+	if (LIMBS == 1) in_val = (acc_t) __reduce_add_sync(FULL, (int) in_val);
+	else for (int d = 16; d > 0; d >>= 1) in_val += __shfl_down_sync(FULL, in_val, d);
 	if (lane == 0) {
 		if (my_next != INT_MAX) atomicMin(&misc->next_bp, my_next);
 		if (in_cov) atomicAdd(&misc->base_cov, in_cov);
 		if (in_pois) atomicAdd(&misc->base_pois, in_pois);
-		if (in_val) atomicAdd(&misc->base_val, (unsigned long long) in_val);
+		if (in_val) atomicAdd(&misc->base_val, (unsigned long long) (long long) in_val);
 	}
 }
 
 // ---- one window ------------------------------------------------------------------------
 template <int TH, int VLOG, int LIMBS>
 __device__ void process_window(const Job &job, int w, unsigned char *smem, const Layout &L, const int32_t *cur,
-                               const int32_t *nxt_cur, int lw, double inv_scale, double lim, double scale) {
+                               int32_t *nxt_buf, int w1_early, int lw, double inv_scale, double lim, double scale) {
 	constexpr int V = 1 << VLOG, W = TH << VLOG, NV = V / 4, NWARP = TH / 32;
 	static_assert(V <= 32, "one 32-bit mask per thread");
 	Misc *misc = (Misc *) smem;
@@ -226,6 +271,9 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 		for (int t = tid; t < n16; t += TH) zc[t] = z;
 		if (tid == 0) { misc->next_bp = INT_MAX; misc->base_cov = 0; misc->base_pois = 0; misc->npois = 0; misc->base_val = 0; }
 	}
+#if WB_FS_LATETICKET == 2
+	__pipeline_wait_prior(0);                                  // this window's cursor row, requested before the clear
+#endif
 	__syncthreads();
 	WB_PHASE(0);
 
@@ -235,12 +283,20 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 #endif
 	__syncthreads();
 	WB_PHASE(1);
+	// The look-back of window w waits for every window below w, so the less time passes between
+	// drawing a window and starting it, the less the windows in flight run out of order.
+#if WB_FS_LATETICKET == 1
+	// as late as the draw's own cursor row and interval prefetch allow
+	unsigned next_ticket = 0;
+	if (tid == 0) next_ticket = atomicAdd(job.ticket, 1u) + gridDim.x;
+#endif
 
 	// ---- 2. scan, pass 1: totals of this thread's V positions -------------------------------
 	const int p0 = tid << VLOG, sw = swz<VLOG>(tid);
+	using acc_t = typename std::conditional<LIMBS == 1, int, long long>::type;   // one limb: every prefix fits 32 bits
 	unsigned evbits = 0;
 	int ctot = 0;
-	long long atot = 0;
+	acc_t atot = 0;
 #pragma unroll
 	for (int k = 0; k < NV; k++) {
 		const int pv = p0 + ((k ^ sw) << 2);
@@ -252,37 +308,37 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 			if (cw[j]) evbits |= 1u << (4 * k + j);
 		}
 		const uint4 l = *(const uint4 *) (limb + pv);
-		if (LIMBS == 1) atot += (long long) (int32_t) l.x + (int32_t) l.y + (int32_t) l.z + (int32_t) l.w;
+		if (LIMBS == 1) atot += (acc_t) (l.x + l.y + l.z + l.w);
 		else {
 			const uint4 h = *(const uint4 *) (limb + W + pv);
-			atot += (long long) ((unsigned long long) l.x + l.y + l.z + l.w)
-			      + (((long long) (int32_t) h.x + (int32_t) h.y + (int32_t) h.z + (int32_t) h.w) << lw);
+			atot += (acc_t) ((long long) ((unsigned long long) l.x + l.y + l.z + l.w)
+			      + (((long long) (int32_t) h.x + (int32_t) h.y + (int32_t) h.z + (int32_t) h.w) << lw));
 		}
 	}
 	// exclusive block scan of (cover, value)
-	int ec; long long ea;
+	int ec; acc_t ea;
 	{
-		int ic = ctot; long long ia = atot;
+		int ic = ctot; acc_t ia = atot;
 #pragma unroll
 		for (int d = 1; d < 32; d <<= 1) {
 			const int vc = __shfl_up_sync(FULL, ic, d);
-			const long long va = __shfl_up_sync(FULL, ia, d);
+			const acc_t va = __shfl_up_sync(FULL, ia, d);
 			if (lane >= d) { ic += vc; ia += va; }
 		}
-		if (lane == 31) { misc->wcov[warp] = ic; misc->wsum[warp] = ia; }
+		if (lane == 31) { misc->wcov[warp] = ic; misc->wsum[warp] = (long long) ia; }
 		__syncthreads();
-		int bc = 0; long long ba = 0;
+		int bc = 0; acc_t ba = 0;
 #pragma unroll
-		for (int k = 0; k < NWARP; k++) if (k < warp) { bc += misc->wcov[k]; ba += misc->wsum[k]; }
+		for (int k = 0; k < NWARP; k++) if (k < warp) { bc += misc->wcov[k]; ba += (acc_t) misc->wsum[k]; }
 		ec = bc + ic - ctot + misc->base_cov;
-		ea = ba + ia - atot + (long long) misc->base_val;
+		ea = ba + ia - atot + (acc_t) (long long) misc->base_val;
 	}
 	WB_PHASE(2);
 
 	// ---- pass 2: running state after every position; the exact prefix goes back in place -----
 	unsigned keepbits = 0;
 	{
-		int c = ec; long long a = ea;
+		int c = ec; acc_t a = ea;
 #pragma unroll
 		for (int k = 0; k < NV; k++) {
 			const int pv = p0 + ((k ^ sw) << 2);
@@ -294,8 +350,8 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 #pragma unroll
 			for (int j = 0; j < 4; j++) {
 				c += (int) (cw[j] & FIELD) - (int) (cw[j] >> END_SHIFT);
-				if (LIMBS == 1) a += (long long) (int32_t) lo[j];
-				else a += (long long) (unsigned long long) lo[j] + ((long long) (int32_t) hi[j] << lw);
+				if (LIMBS == 1) a += (acc_t) lo[j];
+				else a += (acc_t) ((long long) (unsigned long long) lo[j] + ((long long) (int32_t) hi[j] << lw));
 				if (c >= thr) keepbits |= 1u << (4 * k + j);
 				lo[j] = (uint32_t) a;                                  // LIMBS == 1: the sum itself fits 32 bits
 				if (LIMBS == 2) hi[j] = (uint32_t) ((unsigned long long) a >> 32);
@@ -330,6 +386,9 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 #pragma unroll
 		for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(FULL, ip, d); if (lane >= d) ip += v; }
 		if (lane == 31) misc->wpack[warp] = ip;
+#if WB_FS_LATETICKET == 1
+		if (tid == 0) misc->ticket2 = (int) next_ticket;
+#endif
 		__syncthreads();                                       // every thread is past its reads of cov
 		int bp = 0, tp = 0;
 #pragma unroll
@@ -340,6 +399,18 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	}
 	// publish this window's segment count so that later windows can start their look-back
 	if (tid == 0) st_volatile(&job.state[w], LB_AGG | (unsigned long long) kept_total);
+#if WB_FS_LATETICKET
+	// mode 2: the draw happens after the look-back, too late to prefetch for; windows are handed
+	// out in order, so window w + grid starts about one window time after this one did -- its
+	// intervals are pulled into L2 for whichever CTA draws it
+	const int w1 = WB_FS_LATETICKET == 2 ? w + (int) gridDim.x : misc->ticket2;
+	if (w1 < job.nw)
+		for (int i = tid; i < N; i += TH) __pipeline_memcpy_async(&nxt_buf[i], &job.cursor[(size_t) w1 * N + i], 4);
+	__pipeline_commit();
+#else
+	const int w1 = w1_early;
+#endif
+	const int32_t *nxt_cur = w1 < job.nw ? nxt_buf : nullptr;
 	WB_PHASE(3);
 
 	// ---- 3. dense breakpoint list over the dead cover array ---------------------------------
@@ -389,22 +460,46 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 		unsigned long long sum = 0;
 		int p = w - 1;
 		bool found = false;
+#ifdef WB_DIAG_PHASES
+		unsigned long long diag_polls = 0, diag_steps = 0;
+#endif
 		while (!found) {
 			unsigned long long st[LBK];
+			int use = LBK;                                         // groups of 32 states summed in this step
 			while (true) {
-				bool ready = true;
 #pragma unroll
 				for (int j = 0; j < LBK; j++) {
 					const int idx = p - 32 * j - lane;
 					st[j] = idx >= 0 ? ld_volatile(&job.state[idx]) : LB_PREFIX;      // before window 0: prefix 0
-					ready = ready && (st[j] >> 62) != 0;
 				}
-				if (__all_sync(FULL, ready)) break;
-				__nanosleep(40);
+#ifdef WB_DIAG_PHASES
+				diag_polls++;
+#endif
+				// only the states between this window and the nearest known prefix are summed: the
+				// ones behind that prefix need not have been published yet
+				bool wait = false;
+				use = LBK;
+#pragma unroll
+				for (int j = 0; j < LBK; j++) {
+					if (j >= use || wait) break;
+					const unsigned nr = __ballot_sync(FULL, (st[j] >> 62) == 0), pm = __ballot_sync(FULL, (st[j] >> 62) == 2);
+#if WB_FS_LBRELAX
+					if (pm != 0 && (nr == 0 || (pm & -pm) < (nr & -nr))) use = j + 1;
+					else if (nr != 0) wait = true;
+#else
+					if (nr != 0) wait = true;
+					else if (pm != 0) use = j + 1;
+#endif
+				}
+				if (!wait) break;
+				__nanosleep(WB_FS_LBSLEEP);
 			}
+#ifdef WB_DIAG_PHASES
+			diag_steps++;
+#endif
 #pragma unroll
 			for (int j = 0; j < LBK; j++) {
-				if (found) break;
+				if (j >= use) break;
 				const unsigned pm = __ballot_sync(FULL, (st[j] >> 62) == 2);
 				const int first = pm ? __ffs(pm) - 1 : 32;
 				unsigned long long v = (lane <= first) ? (st[j] & LB_VALUE) : 0;
@@ -414,6 +509,9 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 			}
 			p -= 32 * LBK;
 		}
+#ifdef WB_DIAG_PHASES
+		if (lane == 0) { atomicAdd(&job.diag[9], diag_polls); atomicAdd(&job.diag[10], diag_steps); }
+#endif
 		if (lane == 0) {
 			misc->out_base = (long long) sum;
 			st_volatile(&job.state[w], LB_PREFIX | (sum + (unsigned long long) kept_total));
@@ -422,13 +520,17 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	}
 	__syncthreads();
 	WB_PHASE(5);
+#if WB_FS_LATETICKET == 2
+	unsigned next_ticket = 0;
+	if (tid == 0) next_ticket = atomicAdd(job.ticket, 1u) + gridDim.x;      // lands while this window is emitted
+#endif
 
 	// ---- 4. emit, one breakpoint per thread (coalesced stores) -------------------------------
 	const long long out_base = misc->out_base;
 	const int next_bp = misc->next_bp;
 	const int w0i = (int) w0;
-	int32_t *const os = job.out_start + out_base, *const oe = job.out_end + out_base;
-	double *const ov = job.out_value + out_base;
+	int32_t *os = job.out_start + out_base, *oe = job.out_end + out_base;
+	double *ov = job.out_value + out_base;
 	const long long room = job.out_cap - out_base;             // output ranks below this are in range
 	const bool npow2 = (N & (N - 1)) == 0;
 	const bool mean = job.op == OP_MEAN;
@@ -438,33 +540,44 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	constexpr uint32_t PMASK = (1u << D_KID_SHIFT) - 1;
 	const int32_t fx_base32 = (int32_t) job.fx_base;
 	double auc = 0;
+	// the three output pointers of this window, opaque to the optimiser: one 32-bit
+	// index per store instead of a re-derived 64-bit (out_base + rank) chain
+	asm volatile("" : "+l"(os), "+l"(oe), "+l"(ov));
+	const int room32 = (int) min(room, (long long) INT_MAX);
+	auto emit_loop = [&](auto div_tag) {
+		constexpr bool DIV = decltype(div_tag)::value;      // mean over a non-power-of-two N: one fp64 division per segment
 #pragma unroll 2
-	for (int r = tid; r < nbp; r += TH) {
-		const uint32_t d = dense[r];
-		if (!(d & D_KEEP)) continue;
-		const int pos = (int) (d & PMASK), kid = (int) ((d >> D_KID_SHIFT) & PMASK);
-		const int bs = w0i + pos;
-		const int be = (r + 1 < nbp) ? w0i + (int) (dense[r + 1] & PMASK) : next_bp;
-		const int ph = phys<VLOG>(pos);
-		double v;                                                // correctly rounded exact sum
-		if (LIMBS == 1) v = (double) ((int32_t) limb[ph] + fx_base32) * mul;     // |sum + defaults| < 2^30: one 32-bit conversion
-		else v = (double) ((long long) (((unsigned long long) limb[W + ph] << 32) | limb[ph]) + job.fx_base) * mul;
-		if (div) v = v / N;
-		if (kid < room) {
-			os[kid] = bs;
-			oe[kid] = be;
-			ov[kid] = v;
-			if (d & D_SLOW) {
-				// an input was not representable: the fix-up kernel recomputes this
-				// segment with the reference's own operation order
-				const unsigned long long k = atomicAdd(job.slow_count, 1ull);
-				if (k < (unsigned long long) job.slow_cap) job.slow_list[k] = out_base + kid;
+		for (int r = tid; r < nbp; r += TH) {
+			const uint32_t d = dense[r];
+			if (!(d & D_KEEP)) continue;
+			const int pos = (int) (d & PMASK), kid = (int) ((d >> D_KID_SHIFT) & PMASK);
+			const int bs = w0i + pos;
+			const int be = (r + 1 < nbp) ? w0i + (int) (dense[r + 1] & PMASK) : next_bp;
+			const int ph = phys<VLOG>(pos);
+			double v;                                                // correctly rounded exact sum
+			if (LIMBS == 1) v = (double) ((int32_t) limb[ph] + fx_base32) * mul;     // |sum + defaults| < 2^30: one 32-bit conversion
+			else v = (double) ((long long) (((unsigned long long) limb[W + ph] << 32) | limb[ph]) + job.fx_base) * mul;
+			if (DIV) v = v / N;
+			if (kid < room32) {
+				os[kid] = bs;
+				oe[kid] = be;
+				ov[kid] = v;
+				if (d & D_SLOW) {
+					// an input was not representable: the fix-up kernel recomputes this
+					// segment with the reference's own operation order
+					const unsigned long long k = atomicAdd(job.slow_count, 1ull);
+					if (k < (unsigned long long) job.slow_cap) job.slow_list[k] = out_base + kid;
+				}
 			}
+			if (!(d & D_SLOW)) auc += (double) (be - bs) * v;        // v is finite here
 		}
-		if (!(d & D_SLOW)) auc += (double) (be - bs) * v;        // v is finite here
-	}
+	};
+	if (div) emit_loop(std::true_type{}); else emit_loop(std::false_type{});
 	for (int d = 16; d > 0; d >>= 1) auc += __shfl_down_sync(FULL, auc, d);
 	if (lane == 0) misc->wauc[warp] = auc;
+#if WB_FS_LATETICKET == 2
+	if (tid == 0) misc->ticket2 = (int) next_ticket;
+#endif
 	WB_PHASE(6);
 }
 
@@ -485,6 +598,37 @@ __global__ void __launch_bounds__(TH, TH == 128 ? 6 : WB_FS_MINB) fastsum_kernel
 	int32_t *ca = (int32_t *) (smem + L.off_cur), *cb = (int32_t *) (smem + L.off_cur2);   // current / next cursor rows
 	// Windows are handed out in ascending order (the first two per CTA statically, then a
 	// ticket counter): the look-back only ever waits on windows a resident CTA has drawn.
+#if WB_FS_LATETICKET
+	int w = blockIdx.x;
+	if (w < job.nw)
+		for (int i = threadIdx.x; i < job.N; i += TH) ca[i] = job.cursor[(size_t) w * job.N + i];
+	__syncthreads();
+	while (w < job.nw) {
+#ifdef WB_DIAG_PHASES
+		const long long diag_t0 = clock64();
+#endif
+		process_window<TH, VLOG, LIMBS>(job, w, smem, L, ca, cb, 0, lw, inv_scale, lim, scale);
+		__syncthreads();      // dense list consumed, next cursor row landed, AUC partials visible
+		if (threadIdx.x == 0 && job.auc_partial) {
+			double t = 0;
+			for (int k = 0; k < TH / 32; k++) t += misc->wauc[k];
+			job.auc_partial[w] = t;
+		}
+#ifdef WB_DIAG_PHASES
+		if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&job.diag[7], (unsigned long long) (t_ - diag_t0)); atomicAdd(&job.diag[8], 1ull); }
+#endif
+		w = misc->ticket2;
+#if WB_FS_LATETICKET == 2
+		// cb only ever holds the row of the window being prefetched for; the row of the window
+		// just drawn travels into ca while the window arrays are cleared
+		if (w < job.nw)
+			for (int i = threadIdx.x; i < job.N; i += TH) __pipeline_memcpy_async(&ca[i], &job.cursor[(size_t) w * job.N + i], 4);
+		__pipeline_commit();
+#else
+		{ int32_t *t = ca; ca = cb; cb = t; }
+#endif
+	}
+#else
 	int w = blockIdx.x, w1 = blockIdx.x + gridDim.x;
 	if (w < job.nw)
 		for (int i = threadIdx.x; i < job.N; i += TH) ca[i] = job.cursor[(size_t) w * job.N + i];
@@ -499,7 +643,7 @@ __global__ void __launch_bounds__(TH, TH == 128 ? 6 : WB_FS_MINB) fastsum_kernel
 			for (int i = threadIdx.x; i < job.N; i += TH)
 				__pipeline_memcpy_async(&cb[i], &job.cursor[(size_t) w1 * job.N + i], 4);
 		__pipeline_commit();
-		process_window<TH, VLOG, LIMBS>(job, w, smem, L, ca, w1 < job.nw ? cb : nullptr, lw, inv_scale, lim, scale);
+		process_window<TH, VLOG, LIMBS>(job, w, smem, L, ca, cb, w1, lw, inv_scale, lim, scale);
 		if (threadIdx.x == 0) misc->ticket2 = (int) t2;
 		__syncthreads();      // dense list consumed, next cursor row landed, ticket and AUC partials visible
 		if (threadIdx.x == 0 && job.auc_partial) {
@@ -513,6 +657,7 @@ __global__ void __launch_bounds__(TH, TH == 128 ? 6 : WB_FS_MINB) fastsum_kernel
 		w = w1; w1 = misc->ticket2;
 		{ int32_t *t = ca; ca = cb; cb = t; }
 	}
+#endif
 }
 
 template <int TH, int VLOG, int LIMBS>
