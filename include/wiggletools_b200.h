@@ -182,6 +182,39 @@ void wb200_bw_set_stretch(wb200_bigwig *bw, int stretch_bp);
 /* out->start/end/value are owned by the handle and valid until its next decode. */
 int wb200_bw_decode_chrom(wb200_bigwig *bw, int chrom_index, wb200_track *out);
 
+/* -- text sink on the device --------------------------- */
+/* Stands where the reference's default sink works on one host thread: the
+ * writer-side CompressionWiggleIterator (src/unaryOps.c:235-263; `write` only),
+ * the 10000-record block hand-over of TeeWiggleIteratorPop (src/wigWriter.c:159-200)
+ * and printBlock (src/wigWriter.c:55-119): "fixedStep chrom=.. start=.. step=1"
+ * runs for records shorter than 2 bp (left again above 5 bp), bedGraph lines
+ * otherwise, values as "%lf".  The bytes returned are exactly what
+ * toFile()/toStdout() (src/wigWriter.c:278-290) print for the same records.
+ *
+ * One call per chromosome, in the order the records reach the sink; `state`
+ * (zero-initialised before the first call) carries what the reference's writer
+ * carries from one record to the next: the number of records so far (its
+ * per-block reset) and the point-by-point flag.  *text points to pinned host
+ * memory owned by the context, valid until the next call on it.
+ * WB200_EUNSUPPORTED for |value| >= 2^63 (the device formatter prints up to 19
+ * integer digits). */
+enum wb200_sink_mode {
+	WB200_SINK_WIG = 0,       /* `write`:    toFile(wi, f, false, ..)  src/wigWriter.c:278 */
+	WB200_SINK_BEDGRAPH = 1   /* `write_bg`: toFile(wi, f, true, ..)   no compression, bedGraph lines only */
+};
+typedef struct wb200_sink_state {
+	int64_t records;          /* records handed to the sink so far */
+	int32_t point_by_point;   /* printBlock's pointByPoint after the last record */
+	int32_t reserved;
+} wb200_sink_state;
+int wb200_format_device(wb200_ctx *ctx, int mode, const char *chrom,
+                        const int32_t *d_start, const int32_t *d_end, const double *d_value, int64_t n,
+                        wb200_sink_state *state, const char **text, int64_t *nbytes);
+/* Same with the segments in host memory (staged to HBM inside the call). */
+int wb200_format_host(wb200_ctx *ctx, int mode, const char *chrom,
+                      const int32_t *start, const int32_t *end, const double *value, int64_t n,
+                      wb200_sink_state *state, const char **text, int64_t *nbytes);
+
 /* Student-t upper tail used by WB200_TTEST (stands where the reference calls
  * gsl_cdf_tdist_Q, src/setComparisons.c:117); exported for tests. */
 double wb200_tdist_Q(double t, double nu);

@@ -107,6 +107,9 @@ class Oracle:
             f = self._f("tdist_Q")
             f.restype = C.c_double
             f.argtypes = [C.c_double, C.c_double]
+            f = self._f("write")
+            f.restype = C.c_int64
+            f.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_char_p]
 
     def _f(self, name):
         return getattr(self.lib, self.p + name)
@@ -179,3 +182,16 @@ class Oracle:
 
     def tdist_Q(self, t, nu):
         return self._f("tdist_Q")(t, nu)
+
+    def write(self, chrom, start, end, value, names=("chr1",), bedgraph=False):
+        """Bytes the default sink prints for the segment list (`write` / `write_bg`)."""
+        import tempfile
+        chrom = np.ascontiguousarray(chrom, np.int32); start = np.ascontiguousarray(start, np.int32)
+        end = np.ascontiguousarray(end, np.int32); value = np.ascontiguousarray(value, np.float64)
+        cn = self._names(names)
+        with tempfile.NamedTemporaryFile(suffix=".wig") as tmp:
+            rc = self._f("write")(len(start), chrom.ctypes.data, start.ctypes.data, end.ctypes.data, value.ctypes.data,
+                                  len(names), C.addressof(cn), int(bedgraph), tmp.name.encode())
+            assert rc >= 0
+            with open(tmp.name, "rb") as f:
+                return f.read()

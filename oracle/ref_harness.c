@@ -252,6 +252,21 @@ int64_t wtref_reduce_compressed(int op, int ntracks, const wt_track *tracks, int
 	return drain(wi, names, nnames, out);
 }
 
+/* The reference's own sink on an in-memory segment list: TeeWiggleIterator +
+ * runWiggleIterator, i.e. what toFile() does (src/wigWriter.c:261-284). */
+WiggleIterator *TeeWiggleIterator(WiggleIterator *, FILE *, bool, bool);
+int64_t wtref_write(int64_t n, const int32_t *chrom, const int32_t *start, const int32_t *end,
+                    const double *value, int nnames, char **names, int bedgraph, const char *path) {
+	(void) nnames;
+	FILE *f = fopen(path, "w");
+	if (!f) return -1;
+	wt_track t = { chrom, start, end, value, n, 0.0 };
+	WiggleIterator *src = MemSourceIterator(&t, names);
+	runWiggleIterator(TeeWiggleIterator(src, f, bedgraph ? true : false, false));
+	fclose(f);
+	return n;
+}
+
 #endif /* !WB200_DROPIN */
 
 #ifndef WB200_DROPIN

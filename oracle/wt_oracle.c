@@ -24,6 +24,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <stdio.h>
 
 double gsl_cdf_tdist_Q(double x, double nu); /* oracle/wt_special.c */
 
@@ -516,6 +517,50 @@ int64_t wto_compress(int64_t n, const int32_t *chrom, const int32_t *start, cons
 		k++;
 	}
 	return k;
+}
+
+/* The default text sink (src/wigWriter.c) restated for a segment list that is already
+ * in memory: `bedgraph` = write_bg (no compression, bedGraph lines only), else `write`
+ * (compress first, src/wigWriter.c:261-266).  Records are handed over in blocks of
+ * 10000 (BLOCK_LENGTH, :29, :174-186) and every block is printed with fresh state
+ * (printBlock, :55-119): point-by-point mode is entered by a record shorter than 2 bp
+ * and left by one longer than 5 bp; in that mode a "fixedStep" header is printed when
+ * the mode was just entered, the chromosome changed or the record does not abut the
+ * previous one, then one "%lf" line per position; otherwise a 0-based bedGraph line.
+ * Returns the number of records printed. */
+int64_t wto_write(int64_t n, const int32_t *chrom, const int32_t *start, const int32_t *end,
+                  const double *value, int nnames, char **names, int bedgraph, const char *path) {
+	FILE *f = fopen(path, "w");
+	if (!f) return -1;
+	(void) nnames;
+	int64_t records = 0, i = 0;
+	int pbp = 0, last_chrom = -1, last_finish = -1;
+	while (i < n) {
+		int32_t c = chrom[i], s = start[i], e = end[i];
+		double v = value[i];
+		i++;
+		if (!bedgraph)
+			while (i < n && chrom[i] == c && start[i] == e &&
+			       ((isnan(value[i]) && isnan(v)) || fabs(value[i] - v) < 0.000001)) {
+				e = end[i];
+				i++;
+			}
+		if (records % 10000 == 0) { pbp = 0; last_chrom = -1; last_finish = -1; }
+		int make_header = 0;
+		if (!bedgraph && e - s < 2 && !pbp) { pbp = 1; make_header = 1; }
+		else if (e - s > 5 && pbp) pbp = 0;
+		if (pbp) {
+			if (make_header || last_chrom != c || s > last_finish)
+				fprintf(f, "fixedStep chrom=%s start=%i step=1\n", names[c], s);
+			for (int j = 0; j < e - s; j++) fprintf(f, "%lf\n", v);
+		} else
+			fprintf(f, "%s\t%i\t%i\t%lf\n", names[c], s - 1, e - 1, v);
+		last_chrom = c;
+		last_finish = e;
+		records++;
+	}
+	fclose(f);
+	return records;
 }
 
 double wto_tdist_Q(double t, double nu) { return gsl_cdf_tdist_Q(t, nu); }

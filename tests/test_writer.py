@@ -1,0 +1,165 @@
+"""Text sink: the device formatter must print the bytes the
+reference's own sink prints (CompressionWiggleIterator + TeeWiggleIterator +
+printBlock, src/unaryOps.c:235-263, src/wigWriter.c:55-200) -- compared byte for byte.
+
+CPU: the C restatement (oracle/wt_oracle.c: wto_write) against the unmodified reference
+sink compiled into oracle/_ref and against the committed golden texts.
+GPU: wb200_format_host against the restatement (and the reference sink when present)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from util import HERE
+
+NAMES = ("chr1", "chr10", "chrX")
+VALUE_POOL = np.array([0.5, 0.5, 0.5000004, 0.5000009, 0.4999991, 1.25, np.nan, -3.0000005, 1e-7, -1e-7, 0.0, -0.0,
+                       123456.7890125, 0.0000005, 0.0000015, 0.0000025, 2.5e-7, 1e15 + 0.5, -1e18, np.inf, -np.inf,
+                       1 / 3, 2 / 3, 1e-300, 5e-324, 9007199254740993.0, 0.9999995, 0.99999949999, 1234.5678905])
+
+
+def make_segments(n, seed, nchrom=3, pool=VALUE_POOL, runs=True):
+    rng = np.random.default_rng(seed)
+    lens = rng.choice([1, 1, 1, 2, 3, 5, 6, 7, 30], n)
+    gaps = rng.integers(0, 3, n) * rng.integers(0, 2, n)
+    chrom = np.sort(rng.integers(0, nchrom, n)).astype(np.int32)
+    start = np.empty(n, np.int64)
+    pos, prev = 1, -1
+    for i in range(n):
+        if chrom[i] != prev:
+            pos, prev = 1, chrom[i]
+        pos += gaps[i]
+        start[i] = pos
+        pos += lens[i]
+    value = pool[rng.integers(0, len(pool), n)]
+    if runs:   # long runs of near-equal values: chains of the compress rule
+        k = 0
+        while k < n:
+            m = int(rng.integers(1, 80))
+            if rng.random() < 0.3:
+                value[k:k + m] = 7.0 + rng.integers(-9, 10, min(m, n - k)) * 1e-7
+            k += m
+    return chrom, start.astype(np.int32), (start + lens).astype(np.int32), value
+
+
+CASES = [(300, 1), (25000, 2), (25000, 3), (61000, 4)]
+
+
+def golden_digest():
+    with open(os.path.join(HERE, "golden", "writer_digests.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("n,seed", CASES)
+@pytest.mark.parametrize("bedgraph", [False, True])
+def test_port_matches_golden(port, n, seed, bedgraph):
+    c, s, e, v = make_segments(n, seed)
+    text = port.write(c, s, e, v, NAMES, bedgraph)
+    want = golden_digest()["%d/%d/%d" % (n, seed, int(bedgraph))]
+    assert hashlib.sha256(text).hexdigest() == want["sha256"] and len(text) == want["bytes"]
+
+
+@pytest.mark.parametrize("n,seed", CASES + [(12000, 11), (12000, 12)])
+@pytest.mark.parametrize("bedgraph", [False, True])
+def test_port_matches_reference_sink(port, reference, n, seed, bedgraph):
+    c, s, e, v = make_segments(n, seed)
+    assert port.write(c, s, e, v, NAMES, bedgraph) == reference.write(c, s, e, v, NAMES, bedgraph)
+
+
+def test_reference_fixture_text(port):
+    """`mean fixedStep.wig variableStep.wig` through the default sink: the text SURVEY 8(d)
+    config 1 quotes from the reference CLI."""
+    start = np.arange(1, 11, dtype=np.int32)
+    value = np.array([.5, 1.5, 1, 3, 2, 4.5, 3, 6, 4, 4.5])
+    text = port.write(np.zeros(10, np.int32), start, start + 1, value, ("chr1",), False)
+    assert text == b"fixedStep chrom=chr1 start=1 step=1\n" + b"".join(b"%.6f\n" % x for x in value)
+
+
+# ---- GPU --------------------------------------------------------------------------------------
+class _Seg:
+    def __init__(self, c, s, e, v):
+        self.chrom, self.start, self.end, self.value = c, s, e, v
+
+
+def first_diff(a, b):
+    m = min(len(a), len(b))
+    k = next((i for i in range(m) if a[i] != b[i]), m)
+    return "lengths %d / %d, first difference at byte %d: %r vs %r" % (len(a), len(b), k, a[max(0, k - 60):k + 40], b[max(0, k - 60):k + 40])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,seed", CASES + [(12000, 11), (200000, 13)])
+@pytest.mark.parametrize("bedgraph", [False, True])
+def test_device_sink_matches_oracle(engine, port, n, seed, bedgraph):
+    c, s, e, v = make_segments(n, seed)
+    finite = np.where(np.abs(v) >= 2.0 ** 63, 1.0, v)      # infinities stay; the formatter's documented limit is 2^63
+    finite = np.where(np.isinf(v), v, finite)
+    got = engine.format_segments(_Seg(c, s, e, finite), NAMES, bedgraph)
+    want = port.write(c, s, e, finite, NAMES, bedgraph)
+    assert got == want, first_diff(got, want)
+
+
+@pytest.mark.gpu
+def test_device_sink_decimal_rounding(engine, port):
+    """"%lf": round-half-even on the exact binary value, carries into the integer part, signs."""
+    rng = np.random.default_rng(5)
+    v = np.concatenate([
+        (rng.integers(0, 1 << 20, 4000) + 0.5) / (1 << rng.integers(1, 30, 4000)).astype(np.float64),     # exact ties and near-ties
+        rng.integers(0, 1 << 30, 2000) * 2.0 ** -rng.integers(0, 80, 2000),
+        np.ldexp(rng.random(2000), rng.integers(-80, 62, 2000)) * rng.choice([-1, 1], 2000),
+        np.array([0.9999995, 0.9999994999999999, 1.9999995, 999999.9999995, 0.0000005, 0.00000049999999, 0.0000015,
+                  -0.0000005, 4503599627370496.5, 9223372036854774784.0, -9223372036854774784.0, 2.0 ** -1074, 2.0 ** -64,
+                  2.0 ** -65 * 3, 0.5 ** 20]),
+    ])
+    n = len(v)
+    start = np.arange(1, 1 + 10 * n, 10, dtype=np.int32)
+    for bedgraph in (True, False):
+        got = engine.format_segments(_Seg(np.zeros(n, np.int32), start, start + 7, v), ("chr7",), bedgraph)
+        want = port.write(np.zeros(n, np.int32), start, start + 7, v, ("chr7",), bedgraph)
+        assert got == want, first_diff(got, want)
+
+
+@pytest.mark.gpu
+def test_device_sink_long_chain_and_blocks(engine, port):
+    """One chain of near-equal neighbours longer than a resolve tile, drifting past the
+    tolerance several times (heads must be chosen against the run's first value), and
+    record counts straddling the 10000-record block reset."""
+    n = 50000
+    start = np.arange(1, n + 1, dtype=np.int32)
+    v = 3.0 + np.arange(n) * 4e-8                      # neighbours 4e-8 apart: a new head every 25 steps
+    v[30000:30040] = np.nan
+    c = np.zeros(n, np.int32)
+    for bedgraph in (False, True):
+        got = engine.format_segments(_Seg(c, start, start + 1, v), ("chrQ",), bedgraph)
+        want = port.write(c, start, start + 1, v, ("chrQ",), bedgraph)
+        assert got == want, first_diff(got, want)
+
+
+@pytest.mark.gpu
+def test_device_sink_rejects_huge_values(engine):
+    from wiggletools_b200.api import WB200Error
+    s = np.array([1], np.int32)
+    with pytest.raises(WB200Error):
+        engine.format_segments(_Seg(np.zeros(1, np.int32), s, s + 1, np.array([1e19])), ("chr1",), True)
+
+
+@pytest.mark.gpu
+def test_device_sink_after_reduction(engine, port):
+    """mean over random tracks, then the sink: the CLI's `write - mean ...` end to end."""
+    from oracle.pyoracle import Track as OTrack
+    from wiggletools_b200.api import Track
+    rng = np.random.default_rng(9)
+    tracks, otracks = [], []
+    for _ in range(5):
+        st = np.cumsum(rng.integers(1, 9, 4000)).astype(np.int32)
+        en = np.minimum(st + rng.integers(1, 6, 4000), np.r_[st[1:], st[-1] + 9]).astype(np.int32)
+        val = rng.integers(0, 4, 4000) / 2.0
+        tracks.append(Track(np.zeros(4000, np.int32), st, en, val))
+        otracks.append(OTrack(np.zeros(4000, np.int32), st, en, val))
+    seg = engine.reduce("mean", tracks, ("chr1",))
+    ref = port.reduce("mean", otracks, ("chr1",))
+    for bedgraph in (False, True):
+        got = engine.format_segments(seg, ("chr1",), bedgraph)
+        assert got == port.write(ref.chrom, ref.start, ref.end, ref.value, ("chr1",), bedgraph)

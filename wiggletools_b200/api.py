@@ -227,6 +227,30 @@ class Engine:
     def auc(self, op, tracks, names=("chr1",), strict=False):
         return self.reduce(op, tracks, names, strict).auc
 
+    # -- text sink (wigWriter.c: toFile / toStdout) ------------------------------
+    def format_segments(self, seg, names=("chr1",), bedgraph=False):
+        """Bytes the reference's default sink prints for a Segments list: `write`
+        (compress + fixedStep / bedGraph lines) or `write_bg`.  One
+        wb200_format_host call per chromosome, sink state carried across them."""
+        state = _lib.CSinkState(0, 0, 0)
+        chrom = np.asarray(seg.chrom)
+        out = []
+        # chromosomes in the order the records arrive
+        bounds = np.flatnonzero(np.diff(chrom)) + 1 if len(chrom) else np.empty(0, np.int64)
+        lo = 0
+        for hi in list(bounds) + [len(chrom)]:
+            if hi == lo:
+                continue
+            s = np.ascontiguousarray(seg.start[lo:hi], np.int32); e = np.ascontiguousarray(seg.end[lo:hi], np.int32)
+            v = np.ascontiguousarray(seg.value[lo:hi], np.float64)
+            text, nbytes = C.c_char_p(), C.c_int64(0)
+            self._check(self.lib.wb200_format_host(self.ctx, 1 if bedgraph else 0, names[int(chrom[lo])].encode(),
+                                                   s.ctypes.data, e.ctypes.data, v.ctypes.data, hi - lo,
+                                                   C.addressof(state), C.addressof(text), C.addressof(nbytes)))
+            out.append(C.string_at(text, nbytes.value))
+            lo = hi
+        return b"".join(out)
+
 
 _default_engine = None
 

@@ -73,6 +73,10 @@ struct wb200_ctx {
 	HostBuf h_arena;
 	std::vector<cudaEvent_t> pipe_events;
 	unsigned long long diag[16] = {0};      // diagnostic builds: accumulated phase counters
+	// text sink (wb200_format_*)
+	DevBuf w_certain, w_heads, w_hp, w_tile_count, w_tile_base, w_small, w_bbytes, w_boff, w_text;
+	DevBuf w_in_start, w_in_end, w_in_value;
+	HostBuf hw_text, hw_blocks, hw_small;
 };
 
 namespace {
@@ -444,6 +448,10 @@ void wb200_destroy(wb200_ctx *ctx) {
 	DevBuf *d[] = {&ctx->in_start, &ctx->in_end, &ctx->in_value, &ctx->off, &ctx->dflt, &ctx->dflt_fx, &ctx->cursor,
 	               &ctx->state, &ctx->aucp, &ctx->small, &ctx->moments, &ctx->slow_list, &ctx->out_start, &ctx->out_end, &ctx->out_value};
 	for (auto *b : d) b->release();
+	DevBuf *wd[] = {&ctx->w_certain, &ctx->w_heads, &ctx->w_hp, &ctx->w_tile_count, &ctx->w_tile_base, &ctx->w_small, &ctx->w_bbytes,
+	                &ctx->w_boff, &ctx->w_text, &ctx->w_in_start, &ctx->w_in_end, &ctx->w_in_value};
+	for (auto *b : wd) b->release();
+	ctx->hw_text.release(); ctx->hw_blocks.release(); ctx->hw_small.release();
 	for (int k = 0; k < 2; k++) {
 		ctx->bin_start[k].release(); ctx->bin_end[k].release(); ctx->bin_value[k].release();
 		ctx->bout_start[k].release(); ctx->bout_end[k].release(); ctx->bout_value[k].release();
@@ -466,6 +474,94 @@ int wb200_set_stream(wb200_ctx *ctx, void *cuda_stream) {
 	ctx->stream = (cudaStream_t) cuda_stream;
 	ctx->own_stream = false;
 	return WB200_OK;
+}
+
+// -- text sink ------------------------------------------------------------
+// Replaces, for one chromosome of segments: CompressionWiggleIterator (src/unaryOps.c:235-263,
+// `write` only) + the Tee block hand-over (src/wigWriter.c:159-200) + printBlock (:55-119).
+int wb200_format_device(wb200_ctx *ctx, int mode, const char *chrom,
+                        const int32_t *d_start, const int32_t *d_end, const double *d_value, int64_t n,
+                        wb200_sink_state *state, const char **text, int64_t *nbytes) {
+	if (!ctx || !chrom || !state || !text || !nbytes || n < 0 || n > INT32_MAX - 1) return WB200_EINVAL;
+	if (mode != WB200_SINK_WIG && mode != WB200_SINK_BEDGRAPH) return fail(ctx, WB200_EINVAL, "unknown sink mode");
+	if (strlen(chrom) > 63) return fail(ctx, WB200_EUNSUPPORTED, "chromosome name longer than 63 bytes");
+	cudaSetDevice(ctx->device);
+	cudaStream_t s = ctx->stream;
+	*text = "";
+	*nbytes = 0;
+	if (n == 0) return WB200_OK;
+	const int wig = mode == WB200_SINK_WIG;
+	const int BR = sink_block_records();
+	CK(ctx->w_small.ensure(64));
+	CK(ctx->hw_small.ensure(64));
+	int *d_flags = ctx->w_small.as<int>();                       // [0] unsupported value, [1] state after the last record
+	long long *d_R = (long long *) (ctx->w_small.as<char>() + 16);
+	CK(cudaMemsetAsync(ctx->w_small.p, 0, 64, s));
+	// 1. records: every segment (write_bg) or the heads of the compress rule (write)
+	int64_t R = n;
+	const int32_t *hp = nullptr;
+	if (wig) {
+		const int ntiles = sink_tiles(n);
+		CK(ctx->w_certain.ensure((size_t) n)); CK(ctx->w_heads.ensure((size_t) n));
+		CK(ctx->w_hp.ensure((size_t) (n + 1) * sizeof(int32_t)));
+		CK(ctx->w_tile_count.ensure((size_t) ntiles * sizeof(int))); CK(ctx->w_tile_base.ensure((size_t) ntiles * sizeof(long long)));
+		CK(sink_heads(d_start, d_end, d_value, n, ctx->w_certain.as<unsigned char>(), ctx->w_heads.as<unsigned char>(),
+		              ctx->w_tile_count.as<int>(), ctx->w_tile_base.as<long long>(), d_R, ctx->w_hp.as<int32_t>(), s));
+		CK(cudaMemcpyAsync(ctx->hw_small.p, d_R, 8, cudaMemcpyDeviceToHost, s));
+		CK(cudaStreamSynchronize(s));
+		R = ctx->hw_small.as<long long>()[0];
+		hp = ctx->w_hp.as<int32_t>();
+	}
+	// 2. measuring pass: bytes per writer block of 10000 records (blocks are counted over the whole sink)
+	const int64_t base = state->records;
+	const int nblocks = (int) ((base % BR + R + BR - 1) / BR);
+	CK(ctx->w_bbytes.ensure((size_t) nblocks * sizeof(int))); CK(ctx->w_boff.ensure((size_t) nblocks * sizeof(long long)));
+	CK(ctx->hw_blocks.ensure((size_t) nblocks * (sizeof(int) + sizeof(long long))));
+	CK(sink_format(false, d_start, d_end, d_value, hp, R, base, wig, state->point_by_point, chrom,
+	               ctx->w_bbytes.as<int>(), nullptr, nullptr, d_flags, nblocks, s));
+	long long *h_off = ctx->hw_blocks.as<long long>();
+	int *h_bytes = (int *) (h_off + nblocks);
+	CK(cudaMemcpyAsync(h_bytes, ctx->w_bbytes.p, (size_t) nblocks * sizeof(int), cudaMemcpyDeviceToHost, s));
+	CK(cudaMemcpyAsync(ctx->hw_small.as<char>() + 8, d_flags, 8, cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+	const int *h_flags = (const int *) (ctx->hw_small.as<char>() + 8);
+	if (h_flags[0])
+		return fail(ctx, WB200_EUNSUPPORTED, "a value of 2^63 or more in magnitude: outside the device formatter's range");
+	long long total = 0;
+	for (int b = 0; b < nblocks; b++) { h_off[b] = total; total += h_bytes[b]; }
+	// 3. writing pass
+	CK(ctx->w_text.ensure((size_t) total + 32));
+	CK(ctx->hw_text.ensure((size_t) total + 32));
+	CK(cudaMemcpyAsync(ctx->w_boff.p, h_off, (size_t) nblocks * sizeof(long long), cudaMemcpyHostToDevice, s));
+	CK(sink_format(true, d_start, d_end, d_value, hp, R, base, wig, state->point_by_point, chrom,
+	               nullptr, ctx->w_boff.as<long long>(), ctx->w_text.as<char>(), d_flags, nblocks, s));
+	CK(cudaMemcpyAsync(ctx->hw_text.p, ctx->w_text.p, (size_t) total, cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+	ctx->hw_text.as<char>()[total] = 0;
+	state->records = base + R;
+	state->point_by_point = h_flags[1];
+	*text = ctx->hw_text.as<char>();
+	*nbytes = total;
+	ctx->stats.d2h_bytes = total;
+	ctx->stats.kernels = wig ? 7 : 2;
+	return WB200_OK;
+}
+
+int wb200_format_host(wb200_ctx *ctx, int mode, const char *chrom,
+                      const int32_t *start, const int32_t *end, const double *value, int64_t n,
+                      wb200_sink_state *state, const char **text, int64_t *nbytes) {
+	if (!ctx || n < 0 || (n > 0 && (!start || !end || !value))) return WB200_EINVAL;
+	cudaSetDevice(ctx->device);
+	cudaStream_t s = ctx->stream;
+	const size_t m = (size_t) std::max<int64_t>(1, n);
+	CK(ctx->w_in_start.ensure(m * sizeof(int32_t))); CK(ctx->w_in_end.ensure(m * sizeof(int32_t))); CK(ctx->w_in_value.ensure(m * sizeof(double)));
+	if (n > 0) {
+		CK(cudaMemcpyAsync(ctx->w_in_start.p, start, (size_t) n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+		CK(cudaMemcpyAsync(ctx->w_in_end.p, end, (size_t) n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+		CK(cudaMemcpyAsync(ctx->w_in_value.p, value, (size_t) n * sizeof(double), cudaMemcpyHostToDevice, s));
+	}
+	return wb200_format_device(ctx, mode, chrom, ctx->w_in_start.as<int32_t>(), ctx->w_in_end.as<int32_t>(),
+	                           ctx->w_in_value.as<double>(), n, state, text, nbytes);
 }
 
 // Diagnostic builds (-DWB_DIAG_PHASES): cycles per pipeline phase summed over windows since the

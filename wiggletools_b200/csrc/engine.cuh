@@ -117,5 +117,13 @@ cudaError_t launch_fixup(const Job &job, long long count, cudaStream_t s);
 cudaError_t launch_sample_maxabs(const double *value, int64_t n, int64_t stride, double *out2, cudaStream_t s);
 cudaError_t launch_reduce_auc(const double *partial, int count, double *out, cudaStream_t s);
 cudaError_t launch_reduce_moments(const double *moments, int nw, double *out6, cudaStream_t s);
+// text sink (writer.cu): record heads of the compress rule, then the two formatting passes
+cudaError_t sink_heads(const int32_t *start, const int32_t *end, const double *value, int64_t n, unsigned char *D, unsigned char *H,
+                       int *tile_count, long long *tile_base, long long *R, int32_t *hp, cudaStream_t s);
+int sink_tiles(int64_t n);
+int sink_block_records();
+cudaError_t sink_format(bool write, const int32_t *start, const int32_t *end, const double *value, const int32_t *hp,
+                        long long R, long long rec_base, int wig, int pbp_in, const char *chrom,
+                        int *block_bytes, const long long *block_off, char *text, int *flags, int nblocks, cudaStream_t s);
 
 } // namespace wb
