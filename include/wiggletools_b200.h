@@ -210,6 +210,12 @@ typedef struct wb200_sink_state {
 int wb200_format_device(wb200_ctx *ctx, int mode, const char *chrom,
                         const int32_t *d_start, const int32_t *d_end, const double *d_value, int64_t n,
                         wb200_sink_state *state, const char **text, int64_t *nbytes);
+/* Reduction and sink in one call (what `write out.wig mean a b c` runs per
+ * chromosome): wb200_reduce_host without the read-back of the segments, then
+ * wb200_format_device on them.  n_segments / auc may be NULL. */
+int wb200_reduce_format_host(wb200_ctx *ctx, int op, int ntracks, int nset1, int strict, const wb200_track *tracks,
+                             int mode, const char *chrom, wb200_sink_state *state,
+                             const char **text, int64_t *nbytes, int64_t *n_segments, double *auc);
 /* Same with the segments in host memory (staged to HBM inside the call). */
 int wb200_format_host(wb200_ctx *ctx, int mode, const char *chrom,
                       const int32_t *start, const int32_t *end, const double *value, int64_t n,

@@ -132,6 +132,17 @@ void destroyWiggleIterator(WiggleIterator *);                                   
 WiggleIterator *UnionWiggleIterator(WiggleIterator *);                                     /* unaryOps.c:60-91 */
 WiggleIterator *NonOverlappingWiggleIterator(WiggleIterator *);                            /* unaryOps.c:98-103 */
 
+/* -- wigWriter.c: the default text sink on the device -------------------------------
+ * What toFile() / toStdout() (src/wigWriter.c:278-290) do for an iterator returned by
+ * one of the reductions above: compress (write only), 10000-record writer blocks,
+ * fixedStep / bedGraph lines with "%lf" values -- computed per chromosome on the
+ * device right after the reduction, so that segments never cross PCIe and the host
+ * only fwrites text.  wb200_sink_accepts() says whether `wi` is such an iterator in
+ * its freshly constructed state; anything else stays with the reference's writer. */
+#include <stdio.h>
+int wb200_sink_accepts(WiggleIterator *wi);
+void wb200_sink_run(WiggleIterator *wi, FILE *out, wt_bool bedGraph);
+
 #ifdef __cplusplus
 }
 #endif

@@ -163,3 +163,46 @@ def test_device_sink_after_reduction(engine, port):
     for bedgraph in (False, True):
         got = engine.format_segments(seg, ("chr1",), bedgraph)
         assert got == port.write(ref.chrom, ref.start, ref.end, ref.value, ("chr1",), bedgraph)
+
+
+@pytest.mark.gpu
+def test_cli_write_through_device_sink(tmp_path):
+    """`write f mean ...`, `write_bg f mean ...`, plain `mean ...` (stdout) and a Tee in the middle of
+    a pipeline: the reference CLI linked against the library (device sink routed in by
+    oracle/dropin_binding.c) must print the bytes of the unmodified reference CLI."""
+    import subprocess
+    ref = os.path.join(HERE, "..", "oracle", "_ref", "wiggletools")
+    exe = os.path.join(HERE, "..", "oracle", "_ref", "wiggletools_b200")
+    if not (os.path.exists(ref) and os.path.exists(exe)):
+        pytest.skip("oracle/_ref CLIs not built (needs /root/reference at build time)")
+    rng = np.random.default_rng(21)
+    files = []
+    for t in range(4):
+        path = tmp_path / ("t%d.bg" % t)
+        with open(path, "w") as f:
+            for chrom in ("chr1", "chr10", "chr2"):
+                pos = 1
+                for _ in range(6000):
+                    pos += int(rng.integers(0, 4)) * int(rng.integers(0, 2))
+                    ln = int(rng.choice([1, 1, 2, 3, 6, 9]))
+                    f.write("%s\t%d\t%d\t%g\n" % (chrom, pos - 1, pos - 1 + ln, rng.integers(0, 5) / 4.0))
+                    pos += ln
+        files.append(path.name)
+
+    def run(binary, args, out=None):
+        r = subprocess.run([binary] + args, capture_output=True, cwd=tmp_path, check=True)
+        return open(tmp_path / out, "rb").read() if out else r.stdout
+
+    for verb in ("write", "write_bg"):
+        want = run(ref, [verb, "ref_%s.out" % verb, "mean"] + files, "ref_%s.out" % verb)      # the CLI refuses to overwrite
+        got = run(exe, [verb, "gpu_%s.out" % verb, "mean"] + files, "gpu_%s.out" % verb)
+        assert len(want) > 100000 and got == want, verb + ": " + first_diff(got, want)
+    want = run(ref, ["sum"] + files)
+    got = run(exe, ["sum"] + files)
+    assert got == want, "stdout: " + first_diff(got, want)
+    # a Tee whose records are consumed downstream stays the reference's Tee
+    want = run(ref, ["AUC", "write", "ref2.out", "mean"] + files) + run(ref, ["do", "unit", "write_bg", "ref3.out", "mean"] + files)
+    got = run(exe, ["AUC", "write", "gpu2.out", "mean"] + files) + run(exe, ["do", "unit", "write_bg", "gpu3.out", "mean"] + files)
+    assert got == want
+    assert open(tmp_path / "gpu2.out", "rb").read() == open(tmp_path / "ref2.out", "rb").read()
+    assert open(tmp_path / "gpu3.out", "rb").read() == open(tmp_path / "ref3.out", "rb").read()

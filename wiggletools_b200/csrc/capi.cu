@@ -564,6 +564,29 @@ int wb200_format_host(wb200_ctx *ctx, int mode, const char *chrom,
 	                           ctx->w_in_value.as<double>(), n, state, text, nbytes);
 }
 
+namespace {
+int reduce_host_to_device(wb200_ctx *ctx, int op, int ntracks, int nset1, int strict, const wb200_track *tracks,
+                          int64_t *S_out, double *dv_out, double *auc_out);
+}
+
+// Reduction and sink in one call: the segments of the chromosome never leave HBM.
+int wb200_reduce_format_host(wb200_ctx *ctx, int op, int ntracks, int nset1, int strict, const wb200_track *tracks,
+                             int mode, const char *chrom, wb200_sink_state *state,
+                             const char **text, int64_t *nbytes, int64_t *n_segments, double *auc_out) {
+	if (!ctx || !tracks || !state || !text || !nbytes) return WB200_EINVAL;
+	int64_t S = 0;
+	double dv = NAN, auc = 0;
+	int rc = reduce_host_to_device(ctx, op, ntracks, nset1, strict, tracks, &S, &dv, &auc);
+	if (rc != WB200_OK) return rc;
+	const int64_t h2d = ctx->stats.h2d_bytes;
+	rc = wb200_format_device(ctx, mode, chrom, ctx->out_start.as<int32_t>(), ctx->out_end.as<int32_t>(),
+	                         ctx->out_value.as<double>(), S, state, text, nbytes);
+	ctx->stats.h2d_bytes = h2d;
+	if (n_segments) *n_segments = S;
+	if (auc_out) *auc_out = auc;
+	return rc;
+}
+
 // Diagnostic builds (-DWB_DIAG_PHASES): cycles per pipeline phase summed over windows since the
 // last call; all zero in the shipped build.
 void wb200_debug_phases(wb200_ctx *ctx, uint64_t out[16]) {
@@ -595,9 +618,10 @@ int wb200_reduce_device(wb200_ctx *ctx, int op, int ntracks, int nset1, int stri
 	                  d_out_start, d_out_end, d_out_value, out_cap, n_out, default_out, auc_out);
 }
 
-int wb200_reduce_host(wb200_ctx *ctx, int op, int ntracks, int nset1, int strict,
-                      const wb200_track *tracks, wb200_segments *out) {
-	if (!ctx || !tracks || !out) return WB200_EINVAL;
+namespace {
+// host tracks of one chromosome -> HBM -> kernels; the segments stay in ctx->out_*
+int reduce_host_to_device(wb200_ctx *ctx, int op, int ntracks, int nset1, int strict, const wb200_track *tracks,
+                          int64_t *S_out, double *dv_out, double *auc_out) {
 	cudaSetDevice(ctx->device);
 	const int N = ntracks;
 	if (N < 1) return fail(ctx, WB200_EINVAL, "need at least one track");
@@ -628,13 +652,23 @@ int wb200_reduce_host(wb200_ctx *ctx, int op, int ntracks, int nset1, int strict
 	CK(ctx->out_start.ensure(cap * sizeof(int32_t)));
 	CK(ctx->out_end.ensure(cap * sizeof(int32_t)));
 	CK(ctx->out_value.ensure(cap * sizeof(double)));
-	int64_t S = 0;
-	double dv = NAN, auc = 0;
 	int rc = run_device(ctx, op, N, nset1, strict, ctx->in_start.as<int32_t>(), ctx->in_end.as<int32_t>(),
 	                    ctx->in_value.as<double>(), off.data(), dflt.data(), (int32_t) lo, (int32_t) hi,
 	                    ctx->out_start.as<int32_t>(), ctx->out_end.as<int32_t>(), ctx->out_value.as<double>(),
-	                    cap, &S, &dv, &auc);
+	                    cap, S_out, dv_out, auc_out);
+	if (rc == WB200_OK) ctx->stats.h2d_bytes = I * 16;
+	return rc;
+}
+} // namespace
+
+int wb200_reduce_host(wb200_ctx *ctx, int op, int ntracks, int nset1, int strict,
+                      const wb200_track *tracks, wb200_segments *out) {
+	if (!ctx || !tracks || !out) return WB200_EINVAL;
+	int64_t S = 0;
+	double dv = NAN, auc = 0;
+	int rc = reduce_host_to_device(ctx, op, ntracks, nset1, strict, tracks, &S, &dv, &auc);
 	if (rc != WB200_OK) return rc;
+	cudaStream_t s = ctx->stream;
 	CK(ctx->h_start.ensure(std::max<int64_t>(1, S) * sizeof(int32_t)));
 	CK(ctx->h_end.ensure(std::max<int64_t>(1, S) * sizeof(int32_t)));
 	CK(ctx->h_value.ensure(std::max<int64_t>(1, S) * sizeof(double)));
@@ -644,7 +678,6 @@ int wb200_reduce_host(wb200_ctx *ctx, int op, int ntracks, int nset1, int strict
 		CK(cudaMemcpyAsync(ctx->h_value.p, ctx->out_value.p, S * sizeof(double), cudaMemcpyDeviceToHost, s));
 	}
 	CK(cudaStreamSynchronize(s));
-	ctx->stats.h2d_bytes = I * 16;
 	ctx->stats.d2h_bytes = S * 16;
 	out->start = ctx->h_start.as<int32_t>();
 	out->end = ctx->h_end.as<int32_t>();

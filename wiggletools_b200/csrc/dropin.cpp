@@ -158,8 +158,8 @@ struct Reducer {
 	double moments[6] = {0, 0, 0, 0, 0, 0};
 
 	// Drain every input positioned on the strcmp-smallest chromosome
-	// (multiplexer.c:50-74) and run the engine on it.  false = inputs exhausted.
-	bool next_chromosome() {
+	// (multiplexer.c:50-74) into SoA arrays.  false = inputs exhausted.
+	bool drain(std::vector<wb200_track> &tracks, std::vector<BwSource *> &direct) {
 		const size_t n = iters.size();
 		const char *best = nullptr;
 		for (WiggleIterator *it : iters)
@@ -167,8 +167,8 @@ struct Reducer {
 		if (!best) return false;
 		chrom = intern(best);
 		s.resize(n); e.resize(n); v.resize(n);
-		std::vector<wb200_track> tracks(n);
-		std::vector<BwSource *> direct(n, nullptr);
+		tracks.assign(n, wb200_track{});
+		direct.assign(n, nullptr);
 		for (size_t i = 0; i < n; i++) {
 			WiggleIterator *it = iters[i];
 			s[i].clear(); e[i].clear(); v[i].clear();
@@ -194,6 +194,39 @@ struct Reducer {
 			tracks[i].n = (int64_t) s[i].size();
 			tracks[i].default_value = it->default_value;
 		}
+		return true;
+	}
+
+	// the decoded arrays have been staged: move the direct sources to their next chromosome
+	void release(std::vector<BwSource *> &direct) {
+		for (size_t i = 0; i < direct.size(); i++)
+			if (direct[i]) { direct[i]->k = direct[i]->t.n; pop(iters[i]); }
+	}
+
+	// Next chromosome straight into the text sink: reduction and formatting on the device,
+	// only the text comes back (wb200_reduce_format_host).  false = inputs exhausted.
+	bool next_chromosome_to_sink(FILE *out, int mode, wb200_sink_state *state) {
+		std::vector<wb200_track> tracks;
+		std::vector<BwSource *> direct;
+		if (!drain(tracks, direct)) return false;
+		const char *text = nullptr;
+		int64_t nbytes = 0, nseg = 0;
+		double a = 0;
+		if (wb200_reduce_format_host(engine(), op, (int) tracks.size(), n1, strict ? 1 : 0, tracks.data(), mode, chrom, state,
+		                             &text, &nbytes, &nseg, &a) != WB200_OK)
+			die(wb200_last_error(engine()));
+		if (nbytes > 0 && fwrite(text, 1, (size_t) nbytes, out) != (size_t) nbytes) die("short write to the output file");
+		auc += a;
+		release(direct);
+		return true;
+	}
+
+	// Same as drain(), then run the engine on the chromosome.
+	bool next_chromosome() {
+		std::vector<wb200_track> tracks;
+		std::vector<BwSource *> direct;
+		if (!drain(tracks, direct)) return false;
+		const size_t n = iters.size();
 		rs.clear(); re.clear(); rv.clear(); k = 0;
 		if (pearson && nd_rank > 0) {
 			for (int d = 0; d < nd_rank; d++) {
@@ -201,16 +234,14 @@ struct Reducer {
 				if (wb200_pearson_pair_host(engine(), (int) n, tracks.data(), d, n1 + d, m) != WB200_OK) die(wb200_last_error(engine()));
 				wb200_pearson_merge(nd_moments[d], m);
 			}
-			for (size_t i = 0; i < n; i++)
-				if (direct[i]) { direct[i]->k = direct[i]->t.n; pop(iters[i]); }
+			release(direct);
 			return true;
 		}
 		if (pearson) {
 			double m[6];
 			if (wb200_pearson_host(engine(), &tracks[0], &tracks[1], m) != WB200_OK) die(wb200_last_error(engine()));
 			wb200_pearson_merge(moments, m);
-			for (size_t i = 0; i < n; i++)
-				if (direct[i]) { direct[i]->k = direct[i]->t.n; pop(iters[i]); }
+			release(direct);
 			return true;
 		}
 		wb200_segments out;
@@ -220,9 +251,7 @@ struct Reducer {
 		re.assign(out.end, out.end + out.n);
 		rv.assign(out.value, out.value + out.n);
 		auc += out.auc;
-		// the decoded arrays have been staged: move the direct sources to their next chromosome
-		for (size_t i = 0; i < n; i++)
-			if (direct[i]) { direct[i]->k = direct[i]->t.n; pop(iters[i]); }
+		release(direct);
 		return true;
 	}
 };
@@ -587,6 +616,35 @@ WiggleIterator *NDPearsonIntegrator(Multiset *ms) {
 	WiggleIterator *res = newWiggleIterator(d, &ndpearson_pop, &pearson_seek, 0, 0);
 	res->append = ms->multis[0]->iters[0];
 	return res;
+}
+
+// -- wigWriter.c -------------------------------------------------------------------------------
+// toFile() / toStdout() (src/wigWriter.c:278-290) for an iterator this library produced: each
+// chromosome is reduced AND turned into text on the device, the host only fwrites.  The
+// reference keeps its own writer for everything else; the binding that routes between the
+// two is shown in INTEGRATION.md (oracle/ref_stubs.c holds it for the CLI built here).
+int wb200_sink_accepts(WiggleIterator *wi) {
+	if (!wi || wi->done || wi->overlaps || wi->pop != &reducer_pop) return 0;
+	Reducer *r = (Reducer *) wi->data;
+	return !r->pearson && r->k == 1;                       // freshly constructed: positioned on its first record
+}
+
+void wb200_sink_run(WiggleIterator *wi, FILE *out, wt_bool bedGraph) {
+	if (!wb200_sink_accepts(wi)) die("wb200_sink_run: not a fresh reduction of this library");
+	Reducer *r = (Reducer *) wi->data;
+	const int mode = bedGraph ? WB200_SINK_BEDGRAPH : WB200_SINK_WIG;
+	wb200_sink_state state{0, 0, 0};
+	// the constructor's first pop already computed the first chromosome: its segments are on the host
+	const char *text = nullptr;
+	int64_t nbytes = 0;
+	if (wb200_format_host(engine(), mode, r->chrom, r->rs.data(), r->re.data(), r->rv.data(), (int64_t) r->rs.size(), &state,
+	                      &text, &nbytes) != WB200_OK)
+		die(wb200_last_error(engine()));
+	if (nbytes > 0 && fwrite(text, 1, (size_t) nbytes, out) != (size_t) nbytes) die("short write to the output file");
+	r->k = r->rs.size();
+	while (r->next_chromosome_to_sink(out, mode, &state)) { }
+	fflush(out);
+	wi->done = true;
 }
 
 } // extern "C"
