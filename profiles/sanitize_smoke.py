@@ -12,3 +12,17 @@ for op in ("mean", "var", "median", "max", "mult", "wilcoxon", "ttest"):
         r = eng.reduce(op, g, ["chr1", "chr2"])
     print(op, len(r), float(np.nansum(r.value)))
 print("pearson", eng.pearson(g[0], g[1], ["chr1", "chr2"]))
+# the sum / mean sweep kernel on a larger chromosome (many windows per CTA: tickets, look-back), one and two limbs
+tr2 = make_tracks(6, [900000], seed=5)
+g2 = [api.Track(t["chrom"], t["start"], t["end"], t["value"]) for t in tr2]
+r = eng.reduce("mean", g2, ["chr1"]); print("mean (sweep kernel)", len(r), float(np.nansum(r.value)), eng.last_stats[-1]["sweep_kernel"], eng.last_stats[-1]["limbs"])
+for t in g2: t.value[:] = t.value * 1.0000001
+r = eng.reduce("sum", g2, ["chr1"]); print("sum (two limbs)", len(r), float(np.nansum(r.value)), eng.last_stats[-1]["sweep_kernel"], eng.last_stats[-1]["limbs"])
+# the text sink: compress chains, writer blocks, both modes
+rng = np.random.default_rng(1)
+n = 30000
+start = np.cumsum(rng.integers(1, 4, n)).astype(np.int32)
+seg = api.Segments(np.zeros(n, np.int32), start, (start + rng.integers(1, 3, n)).astype(np.int32).clip(max=np.r_[start[1:], start[-1] + 2]),
+                   np.round(rng.random(n), 1) + rng.integers(-3, 4, n) * 2e-7)
+for bg in (False, True):
+    print("sink", bg, len(eng.format_segments(seg, ["chr1"], bg)))
