@@ -47,6 +47,9 @@ namespace wb {
 #ifndef WB_PREF
 #define WB_PREF 0               // events phase: 0 plain loads, 1 register double buffering, 2 L1 prefetch, 3 L2 prefetch
 #endif
+#ifndef WB_LATETICKET
+#define WB_LATETICKET 1         // next window drawn when the emit phase starts (0: two windows ahead); see fastsum.cu
+#endif
 #ifndef WB_FAST_MINB
 #define WB_FAST_MINB 3          // resident CTAs per SM the sum/mean kernel is compiled for
 #endif
@@ -1058,6 +1061,9 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 		for (int t = tid; t < W / 16; t += THREADS) ze[t] = z;
 		if (tid == 0) { misc->next_bp = INT_MAX; misc->base_cov = 0; misc->base_val = 0; misc->base_val2 = 0; }
 	}
+#if WB_LATETICKET
+	__pipeline_wait_prior(0);              // this window's cursor row, requested before the clear
+#endif
 	__syncthreads();
 	WB_PHASE(0);
 
@@ -1259,7 +1265,9 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 		unsigned long long st;
 		while (true) {
 			st = idx >= 0 ? ld_volatile(&job.state[idx]) : LB_PREFIX;      // before window 0: prefix 0
-			if (!__any_sync(FULL, (st >> 62) == 0)) break;
+			// only the states up to the nearest published prefix are summed
+			const unsigned nr = __ballot_sync(FULL, (st >> 62) == 0), pq = __ballot_sync(FULL, (st >> 62) == 2);
+			if (nr == 0 || (pq != 0 && (pq & -pq) < (nr & -nr))) break;
 			__nanosleep(40);
 		}
 		const unsigned pm = __ballot_sync(FULL, (st >> 62) == 2);
@@ -1279,7 +1287,8 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 			unsigned long long st;
 			while (true) {
 				st = idx >= 0 ? ld_volatile(&job.state[idx]) : LB_PREFIX;
-				if (!__any_sync(FULL, (st >> 62) == 0)) break;
+				const unsigned nr = __ballot_sync(FULL, (st >> 62) == 0), pq = __ballot_sync(FULL, (st >> 62) == 2);
+				if (nr == 0 || (pq != 0 && (pq & -pq) < (nr & -nr))) break;
 				__nanosleep(40);
 			}
 			const unsigned pm = __ballot_sync(FULL, (st >> 62) == 2);
@@ -1298,6 +1307,13 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	}
 	__syncthreads();
 	WB_PHASE(5);
+#if WB_LATETICKET
+	// The look-back of a window waits for every window below it, so windows should start in
+	// the order they were drawn: the next one is drawn only now (the atomic lands during the
+	// emit phase), not two windows ahead (measured in fastsum.cu: look-back waits 8.5k -> 5k cycles).
+	unsigned next_ticket = 0;
+	if (tid == 0) next_ticket = atomicAdd(job.ticket, 1u) + gridDim.x;
+#endif
 
 	// ---- 4. emit, one breakpoint per thread (coalesced stores) ---------------------------
 	const long long out_base = misc->out_base;
@@ -1491,6 +1507,9 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	}
 
 	WB_PHASE(6);
+#if WB_LATETICKET
+	if (tid == 0) misc->ticket2 = (int) next_ticket;
+#endif
 	// per-warp AUC partials go straight to global memory (fixed order, folded later)
 	for (int d = 16; d > 0; d >>= 1) {
 		auc += __shfl_down_sync(FULL, auc, d);
@@ -1567,6 +1586,29 @@ __global__ void __launch_bounds__(THREADS, MODE == MODE_FAST ? (THREADS == 512 ?
 	// The first two windows of every CTA are assigned statically (the whole grid is
 	// resident: it is sized by occupancy), interleaved across CTAs so that no window
 	// waits behind a CTA's second window at start-up; later ones come from the counter.
+#if WB_LATETICKET
+	int w = blockIdx.x;
+	if (w < job.nw)
+		for (int i = threadIdx.x; i < job.N; i += THREADS) ca[i] = job.cursor[(size_t) w * job.N + i];
+	__syncthreads();
+	while (w < job.nw) {
+#ifdef WB_DIAG_PHASES
+		const long long diag_t0 = clock64();
+#endif
+		process_window<MODE, VLOG, LIMBS>(job, w, smem, L, ca, lw, inv_scale, lim, scale);
+		__syncthreads();      // dense list consumed, ticket visible
+#ifdef WB_DIAG_PHASES
+		if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&job.diag[7], (unsigned long long) (t_ - diag_t0)); atomicAdd(&job.diag[8], 1ull); }
+#endif
+		w = misc->ticket2;
+		// the drawn window's cursor row travels while the window arrays are cleared
+		if (w < job.nw)
+			for (int i = threadIdx.x; i < job.N; i += THREADS) __pipeline_memcpy_async(&ca[i], &job.cursor[(size_t) w * job.N + i], 4);
+		__pipeline_commit();
+	}
+	(void) cb;
+}
+#else
 	int w = blockIdx.x, w1 = blockIdx.x + gridDim.x;
 	if (w < job.nw)
 		for (int i = threadIdx.x; i < job.N; i += THREADS) ca[i] = job.cursor[(size_t) w * job.N + i];
@@ -1592,6 +1634,7 @@ __global__ void __launch_bounds__(THREADS, MODE == MODE_FAST ? (THREADS == 512 ?
 		{ int32_t *t = ca; ca = cb; cb = t; }
 	}
 }
+#endif
 
 // max |v| over a strided sample of the values, and the finest significant bit seen:
 // they choose the fixed-point scale.  out2[0] = bits of the largest finite |v|;
