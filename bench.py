@@ -249,6 +249,9 @@ def main():
         raise SystemExit(lib.wb200_last_error(None).decode())
     stream = torch.cuda.current_stream()
     lib.wb200_set_stream(ctx, C.c_void_p(stream.cuda_stream))
+    # one process per GPU: keep this rank's host thread (and the pinned buffers it allocates from
+    # here on) on the NUMA node of its GPU
+    local_cpus = 0 if os.environ.get("WB200_NO_BIND") else lib.wb200_bind_host_thread(ctx)
 
     names, lengths = genome()
     owner = lpt_assign(lengths, world)
@@ -364,6 +367,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(torch, dist, lib, ctx, shards, dev, world, genome_bp, max(1, min(args.steps, 3)))
+        e2e["host_thread_cpus"] = int(local_cpus)     # CPUs local to this rank's GPU the host thread was pinned to (0: not pinned)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -116,6 +116,12 @@ int wb200_set_stream(wb200_ctx *ctx, void *cuda_stream);
 /* Tuning knobs: window size in bp (power of two, 0 = automatic). */
 int wb200_set_window(wb200_ctx *ctx, int window_bp);
 
+/* Pin the calling host thread to the CPUs local to the context's GPU (its PCIe root's NUMA
+ * node), so that staging buffers allocated afterwards live in that node's memory: matters
+ * on multi-socket boxes with one process per GPU.  Returns the number of CPUs in the mask,
+ * 0 if the topology is not exposed (nothing changed). */
+int wb200_bind_host_thread(wb200_ctx *ctx);
+
 /* Pinned host memory for staging (cudaHostAlloc). */
 void *wb200_host_alloc(int64_t bytes);
 void wb200_host_free(void *p);

@@ -7,6 +7,8 @@
 #include "engine.cuh"
 
 #include <algorithm>
+#include <cctype>
+#include <sched.h>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -591,6 +593,38 @@ int wb200_reduce_format_host(wb200_ctx *ctx, int op, int ntracks, int nset1, int
 // last call; all zero in the shipped build.
 void wb200_debug_phases(wb200_ctx *ctx, uint64_t out[16]) {
 	for (int k = 0; k < 16; k++) { out[k] = ctx->diag[k]; ctx->diag[k] = 0; }
+}
+
+// Pin the calling host thread to the CPUs that are local to the context's GPU (the NUMA node
+// its PCIe root hangs off, /sys/bus/pci/devices/<id>/local_cpulist): pinned staging buffers
+// allocated and touched afterwards land in that node's memory.  Returns the number of CPUs in
+// the mask, 0 when the topology is not exposed (nothing changed), < 0 on error.
+int wb200_bind_host_thread(wb200_ctx *ctx) {
+	if (!ctx) return WB200_EINVAL;
+	char bus[32] = {0};
+	if (cudaDeviceGetPCIBusId(bus, sizeof(bus), ctx->device) != cudaSuccess) return 0;
+	for (char *c = bus; *c; c++) *c = (char) tolower(*c);
+	char path[128];
+	snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bus);
+	FILE *f = fopen(path, "r");
+	if (!f) return 0;
+	char line[4096] = {0};
+	const bool got = fgets(line, sizeof(line), f) != nullptr;
+	fclose(f);
+	if (!got) return 0;
+	cpu_set_t set;
+	CPU_ZERO(&set);
+	int count = 0;
+	for (char *tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+		int a = 0, b = 0;
+		const int k = sscanf(tok, "%d-%d", &a, &b);
+		if (k < 1) continue;
+		if (k == 1) b = a;
+		for (int c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET(c, &set); count++; }
+	}
+	if (count == 0) return 0;
+	if (sched_setaffinity(0, sizeof(set), &set) != 0) return fail(ctx, WB200_EINVAL, "sched_setaffinity failed");
+	return count;
 }
 
 int wb200_set_window(wb200_ctx *ctx, int window_bp) {
