@@ -1580,12 +1580,12 @@ __global__ void __launch_bounds__(THREADS, MODE == MODE_FAST ? (THREADS == 512 ?
 	Misc *misc = (Misc *) smem;
 	int32_t *ca = cur, *cb = (int32_t *) (smem + L.off_cur2);   // current / next cursor rows
 	// Windows are handed out in order by a ticket counter: the look-back only ever
-	// waits on windows that a resident CTA has already drawn.  Each CTA runs two
-	// tickets ahead so that the next window's cursor row is already in shared
-	// memory (cp.async) when the current one finishes.
-	// The first two windows of every CTA are assigned statically (the whole grid is
-	// resident: it is sized by occupancy), interleaved across CTAs so that no window
-	// waits behind a CTA's second window at start-up; later ones come from the counter.
+	// waits on windows that a resident CTA has already drawn.  The first window of
+	// every CTA is assigned statically (the whole grid is resident: it is sized by
+	// occupancy); each later one is drawn when the previous window's emit phase starts,
+	// so that windows start in (nearly) the order they were drawn, and its cursor row
+	// travels by cp.async while the window arrays are cleared.  (WB_LATETICKET=0: the
+	// earlier scheme, two tickets ahead with the next cursor row prefetched.)
 #if WB_LATETICKET
 	int w = blockIdx.x;
 	if (w < job.nw)
