@@ -188,6 +188,30 @@ void wb200_bw_set_stretch(wb200_bigwig *bw, int stretch_bp);
 /* out->start/end/value are owned by the handle and valid until its next decode. */
 int wb200_bw_decode_chrom(wb200_bigwig *bw, int chrom_index, wb200_track *out);
 
+/* -- element-wise maps on the inputs --------------------- */
+/* `mean map ln a b c`, `sum scale 2 x : ...`: the reference wraps each source in a
+ * unary iterator that rewrites one record at a time (src/unaryOps.c:650-960,
+ * built by src/commandParser.c:115-211).  Here a chain of up to 8 maps per track
+ * is applied to the staged values in HBM before the sweep:
+ *   SCALE  s   NaN -> NaN, else s*v                         ScaleWiggleIteratorPop  :650-665
+ *   OFFSET s   s+v                                          ShiftWiggleIteratorPop  :722-734
+ *   LOG    l   records with v <= 0 are dropped, NaN stays,
+ *              else log(v)/l  (l = 1 for `ln`, log(base) for `log base`)   LogWiggleIteratorPop :760-779
+ *   EXP    l   exp(v*l)       (l = 1 for `exp`)             ExpWiggleIteratorPop    :823-835
+ *   POW    s   (s<0 and v<=0) or NaN -> NaN, else pow(v,s)  PowerWiggleIteratorPop  :873-889
+ *   ABS        NaN -> NaN, else |v|                         AbsWiggleIteratorPop    :934-949
+ * wb200_set_input_maps() arms the chains for the NEXT wb200_reduce_host /
+ * wb200_reduce_format_host call on the context (one chromosome; call it again for
+ * the next one).  wb200_track.default_value must already be the mapped default:
+ * wb200_map_default() applies one map's constructor rule (some round through
+ * float, as the reference does). */
+enum wb200_map_op {
+	WB200_MAP_SCALE = 1, WB200_MAP_OFFSET = 2, WB200_MAP_LOG = 3, WB200_MAP_EXP = 4, WB200_MAP_POW = 5, WB200_MAP_ABS = 6
+};
+typedef struct wb200_map { int32_t op; int32_t reserved; double arg; } wb200_map;
+int wb200_set_input_maps(wb200_ctx *ctx, int ntracks, const wb200_map *const *maps, const int *nmaps);
+double wb200_map_default(int op, double arg, double default_value);
+
 /* -- text sink on the device --------------------------- */
 /* Stands where the reference's default sink works on one host thread: the
  * writer-side CompressionWiggleIterator (src/unaryOps.c:235-263; `write` only),

@@ -107,6 +107,12 @@ class Oracle:
             f = self._f("tdist_Q")
             f.restype = C.c_double
             f.argtypes = [C.c_double, C.c_double]
+            f = self._f("map")
+            f.restype = C.c_int64
+            if kind == "port":
+                f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+            else:
+                f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
             f = self._f("write")
             f.restype = C.c_int64
             f.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_char_p]
@@ -182,6 +188,25 @@ class Oracle:
 
     def tdist_Q(self, t, nu):
         return self._f("tdist_Q")(t, nu)
+
+    MAP_CODES = {"scale": 1, "offset": 2, "log": 3, "ln": 3, "exp": 4, "pow": 5, "abs": 6, "default": 7}
+
+    def map(self, track, chain, names=("chr1",)):
+        """A chain of unary operators over one track, innermost first:
+        [("scale", 2.0), ("ln",), ("log", 10.0), ("pow", 0.5), ("abs",), ("offset", 1), ("exp",), ("default", 3)]."""
+        codes = np.array([self.MAP_CODES[c[0]] for c in chain], np.int32)
+        args = np.array([0.0 if c[0] in ("ln", "exp", "abs") else float(c[1]) for c in chain], np.float64)
+        cap = len(track) + 1
+        o, arrs = self._out(cap)
+        ct = track.c()
+        dflt = C.c_double(0)
+        if self.kind == "port":
+            n = self._f("map")(C.addressof(ct), len(chain), codes.ctypes.data, args.ctypes.data, C.addressof(o), C.addressof(dflt))
+        else:
+            cn = self._names(names)
+            n = self._f("map")(C.addressof(ct), len(chain), codes.ctypes.data, args.ctypes.data, len(names), C.addressof(cn),
+                               C.addressof(o), C.addressof(dflt))
+        return Track(arrs[0][:n].copy(), arrs[1][:n].copy(), arrs[2][:n].copy(), arrs[3][:n].copy(), default=dflt.value)
 
     def write(self, chrom, start, end, value, names=("chr1",), bedgraph=False):
         """Bytes the default sink prints for the segment list (`write` / `write_bg`)."""

@@ -267,6 +267,34 @@ int64_t wtref_write(int64_t n, const int32_t *chrom, const int32_t *start, const
 	return n;
 }
 
+/* The reference's own unary operators chained over an in-memory track (codes as in
+ * wto_map of wt_oracle.c), built the way src/commandParser.c:115-211 builds them. */
+WiggleIterator *ScaleWiggleIterator(WiggleIterator *, double);
+WiggleIterator *ShiftWiggleIterator(WiggleIterator *, double);
+WiggleIterator *NaturalLogWiggleIterator(WiggleIterator *);
+WiggleIterator *LogWiggleIterator(WiggleIterator *, double);
+WiggleIterator *NaturalExpWiggleIterator(WiggleIterator *);
+WiggleIterator *PowerWiggleIterator(WiggleIterator *, double);
+WiggleIterator *AbsWiggleIterator(WiggleIterator *);
+WiggleIterator *DefaultValueWiggleIterator(WiggleIterator *, double);
+int64_t wtref_map(const wt_track *t, int nmaps, const int *codes, const double *args, int nnames, char **names,
+                  wt_out *out, double *default_out) {
+	WiggleIterator *wi = MemSourceIterator(t, names);
+	for (int c = 0; c < nmaps; c++) {
+		switch (codes[c]) {
+		case 1: wi = ScaleWiggleIterator(wi, args[c]); break;
+		case 2: wi = ShiftWiggleIterator(wi, args[c]); break;
+		case 3: wi = args[c] > 0 ? LogWiggleIterator(wi, args[c]) : NaturalLogWiggleIterator(wi); break;
+		case 4: wi = NaturalExpWiggleIterator(wi); break;
+		case 5: wi = PowerWiggleIterator(wi, args[c]); break;
+		case 6: wi = AbsWiggleIterator(wi); break;
+		case 7: wi = DefaultValueWiggleIterator(wi, args[c]); break;
+		}
+	}
+	if (default_out) *default_out = wi->default_value;
+	return drain(wi, names, nnames, out);
+}
+
 #endif /* !WB200_DROPIN */
 
 #ifndef WB200_DROPIN

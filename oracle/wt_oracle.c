@@ -563,4 +563,59 @@ int64_t wto_write(int64_t n, const int32_t *chrom, const int32_t *start, const i
 	return records;
 }
 
+/* Element-wise unary operators of `map` / the unary_operator grammar (src/commandParser.c:115-211),
+ * restated from their pop functions and constructors in src/unaryOps.c: a chain applied to one
+ * track, innermost first.  codes: 1 scale s (:650-682), 2 offset s (:722-745), 3 log base, base <= 0
+ * meaning `ln` (:760-811; records with value <= 0 are dropped), 4 exp (:823-866, natural), 5 pow s
+ * (:873-901), 6 abs (:934-960), 7 default d (:210-229).  Returns the number of records kept;
+ * *default_out receives the chain's derived default_value (some constructors round it to float). */
+int64_t wto_map(const wt_track *t, int nmaps, const int *codes, const double *args, wt_out *out, double *default_out) {
+	double dflt = t->default_value;
+	double *v = (double *) malloc(sizeof(double) * (size_t) (t->n > 0 ? t->n : 1));
+	char *keep = (char *) malloc((size_t) (t->n > 0 ? t->n : 1));
+	for (int64_t j = 0; j < t->n; j++) { v[j] = t->value[j]; keep[j] = 1; }
+	for (int c = 0; c < nmaps; c++) {
+		const double a = args[c];
+		double l = 1;
+		switch (codes[c]) {
+		case 1:
+			for (int64_t j = 0; j < t->n; j++) if (keep[j]) v[j] = isnan(v[j]) ? NAN : a * v[j];
+			dflt = isnan(dflt) ? NAN : (double) (float) (dflt * a);
+			break;
+		case 2:
+			for (int64_t j = 0; j < t->n; j++) if (keep[j]) v[j] = a + v[j];
+			dflt = isnan(dflt) ? NAN : (double) (float) (dflt + a);
+			break;
+		case 3:
+			if (a > 0) l = log(a);
+			for (int64_t j = 0; j < t->n; j++) if (keep[j]) {
+				if (v[j] <= 0) keep[j] = 0;
+				else v[j] = (isnan(v[j]) || v[j] < 0) ? NAN : log(v[j]) / l;
+			}
+			dflt = (!isnan(dflt) && dflt > 0) ? log(dflt) / l : NAN;
+			break;
+		case 4:
+			for (int64_t j = 0; j < t->n; j++) if (keep[j]) v[j] = exp(v[j] * 1);
+			dflt = isnan(dflt) ? NAN : (double) (float) exp(dflt * 1);
+			break;
+		case 5:
+			for (int64_t j = 0; j < t->n; j++) if (keep[j]) v[j] = ((a < 0 && v[j] <= 0) || isnan(v[j])) ? NAN : pow(v[j], a);
+			dflt = (!isnan(dflt) && (dflt > 0 || a > 0)) ? pow(dflt, a) : NAN;
+			break;
+		case 6:
+			for (int64_t j = 0; j < t->n; j++) if (keep[j]) v[j] = isnan(v[j]) ? NAN : fabs(v[j]);
+			dflt = isnan(dflt) ? NAN : fabs(dflt);
+			break;
+		case 7:
+			dflt = a;
+			break;
+		}
+	}
+	int64_t k = 0;
+	for (int64_t j = 0; j < t->n; j++) if (keep[j]) { put(out, k, t->chrom[j], t->start[j], t->end[j], v[j]); k++; }
+	free(v); free(keep);
+	if (default_out) *default_out = dflt;
+	return k;
+}
+
 double wto_tdist_Q(double t, double nu) { return gsl_cdf_tdist_Q(t, nu); }

@@ -30,6 +30,10 @@ class CStats(C.Structure):
                 ("limbs", C.c_int32), ("sweep_kernel", C.c_int32)]
 
 
+class CMap(C.Structure):
+    _fields_ = [("op", C.c_int32), ("reserved", C.c_int32), ("arg", C.c_double)]
+
+
 class CSinkState(C.Structure):
     _fields_ = [("records", C.c_int64), ("point_by_point", C.c_int32), ("reserved", C.c_int32)]
 
@@ -84,6 +88,9 @@ def load():
     lib.wb200_bw_set_stretch.argtypes = [C.c_void_p, C.c_int]
     lib.wb200_bw_decode_chrom.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.wb200_debug_phases.argtypes = [C.c_void_p, C.c_void_p]
+    lib.wb200_set_input_maps.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.wb200_map_default.restype = C.c_double
+    lib.wb200_map_default.argtypes = [C.c_int, C.c_double, C.c_double]
     lib.wb200_format_device.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                         C.c_void_p, C.c_void_p, C.c_void_p]
     lib.wb200_format_host.argtypes = lib.wb200_format_device.argtypes
@@ -102,5 +109,5 @@ EXPORTS = [
     "wb200_reduce_device", "wb200_pearson_host", "wb200_pearson_pair_host", "wb200_pearson_merge", "wb200_pearson_result",
     "wb200_tdist_Q", "wb200_bw_open", "wb200_bw_close", "wb200_bw_last_error", "wb200_bw_nchrom", "wb200_bw_chrom_name",
     "wb200_bw_chrom_length", "wb200_bw_set_stretch", "wb200_bw_decode_chrom", "wb200_debug_phases",
-    "wb200_format_device", "wb200_format_host", "wb200_reduce_format_host",
+    "wb200_format_device", "wb200_format_host", "wb200_reduce_format_host", "wb200_set_input_maps", "wb200_map_default",
 ]

@@ -100,17 +100,43 @@ class Engine:
         s = self.lib.wb200_last_stats(self.ctx).contents
         return {k: getattr(s, k) for k, _ in s._fields_}
 
+    # -- element-wise maps (unaryOps.c; `map` in the CLI grammar) ---------------
+    MAP_CODES = {"scale": 1, "offset": 2, "log": 3, "ln": 3, "exp": 4, "pow": 5, "abs": 6}
+
+    def _lower_chain(self, chain, default):
+        """CLI-level chain [("scale", 2), ("ln",), ("log", 10), ("default", 1) ...] -> (C maps,
+        mapped default): arguments become what the reference's constructors store
+        (log base -> log(base), ln / exp -> 1) and the default follows their rules."""
+        import math
+        maps = []
+        for c in chain:
+            if c[0] == "default":                      # DefaultValueWiggleIterator: records untouched
+                default = float(c[1])
+                continue
+            code = self.MAP_CODES[c[0]]
+            arg = 1.0 if c[0] in ("ln", "exp") else 0.0 if c[0] == "abs" else math.log(float(c[1])) if c[0] == "log" else float(c[1])
+            default = self.lib.wb200_map_default(code, arg, default)
+            maps.append(_lib.CMap(code, 0, arg))
+        return maps, default
+
     # -- one chromosome, host arrays ---------------------------------------
-    def reduce_chrom(self, op, tracks, nset1=None, strict=False):
-        """tracks: list of (start, end, value, default) numpy arrays of ONE chromosome."""
+    def reduce_chrom(self, op, tracks, nset1=None, strict=False, maps=None):
+        """tracks: list of (start, end, value, default) numpy arrays of ONE chromosome;
+        maps: optional list (one per track) of unary-operator chains applied on the device."""
         n = len(tracks)
         arr = (_lib.CTrack * n)()
         keep = []
+        lowered = [self._lower_chain(maps[i], float(tracks[i][3])) for i in range(n)] if maps else None
         for i, (s, e, v, d) in enumerate(tracks):
             s = np.ascontiguousarray(s, np.int32); e = np.ascontiguousarray(e, np.int32)
             v = np.ascontiguousarray(v, np.float64)
             keep.append((s, e, v))
-            arr[i] = _lib.CTrack(s.ctypes.data, e.ctypes.data, v.ctypes.data, len(s), float(d))
+            arr[i] = _lib.CTrack(s.ctypes.data, e.ctypes.data, v.ctypes.data, len(s), float(lowered[i][1] if lowered else d))
+        if lowered:
+            chains = [(_lib.CMap * max(1, len(m)))(*m) for m, _ in lowered]
+            ptrs = (C.c_void_p * n)(*[C.addressof(c) for c in chains])
+            counts = (C.c_int * n)(*[len(m) for m, _ in lowered])
+            self._check(self.lib.wb200_set_input_maps(self.ctx, n, C.addressof(ptrs), C.addressof(counts)))
         out = _lib.CSegments()
         code = OPS[op] if isinstance(op, str) else int(op)
         self._check(self.lib.wb200_reduce_host(self.ctx, code, n, n if nset1 is None else nset1,
@@ -157,11 +183,23 @@ class Engine:
         return res
 
     # -- whole genome -------------------------------------------------------
-    def reduce(self, op, tracks, names=("chr1",), strict=False, nset1=None):
+    def reduce(self, op, tracks, names=("chr1",), strict=False, nset1=None, maps=None):
         """<op> over N genome tracks: segments of every chromosome, in the
-        reference's visiting order (ascending strcmp of the names)."""
+        reference's visiting order (ascending strcmp of the names).  maps: optional
+        unary-operator chain per track (`<op> map ln a b c`), applied on the device."""
         self.last_stats = []
         present = sorted({c for t in tracks for c in t.runs}, key=lambda c: names[c].encode())
+        if maps is not None:
+            parts, auc, dflt = [], 0.0, float("nan")
+            for c in present or [None]:
+                per = []
+                for t in tracks:
+                    lo, hi = t.runs.get(c, (0, 0)) if c is not None else (0, 0)
+                    per.append((t.start[lo:hi], t.end[lo:hi], t.value[lo:hi], t.default))
+                s_, e_, v_, dflt, a_ = self.reduce_chrom(op, per, nset1=nset1, strict=strict, maps=maps)
+                parts.append((np.full(len(s_), 0 if c is None else c, np.int32), s_, e_, v_))
+                auc += a_
+            return Segments(*[np.concatenate([p[k] for p in parts]) for k in range(4)], dflt, auc)
         if not present:
             # defaults only: constructor semantics still apply
             per = [(np.empty(0, np.int32), np.empty(0, np.int32), np.empty(0), t.default) for t in tracks]

@@ -79,6 +79,11 @@ struct wb200_ctx {
 	DevBuf w_certain, w_heads, w_hp, w_tile_count, w_tile_base, w_small, w_bbytes, w_boff, w_text;
 	DevBuf w_in_start, w_in_end, w_in_value;
 	HostBuf hw_text, hw_blocks, hw_small;
+	// element-wise input maps (wb200_set_input_maps): chains consumed by the next staging call
+	std::vector<MapOp> map_chains;
+	std::vector<int> map_nchain;
+	DevBuf m_chains, m_nchain, m_keep, m_hp, m_tile_count, m_tile_base, m_small, m_newoff, m_off, in2_start, in2_end, in2_value;
+	HostBuf hm_small;
 };
 
 namespace {
@@ -453,7 +458,10 @@ void wb200_destroy(wb200_ctx *ctx) {
 	DevBuf *wd[] = {&ctx->w_certain, &ctx->w_heads, &ctx->w_hp, &ctx->w_tile_count, &ctx->w_tile_base, &ctx->w_small, &ctx->w_bbytes,
 	                &ctx->w_boff, &ctx->w_text, &ctx->w_in_start, &ctx->w_in_end, &ctx->w_in_value};
 	for (auto *b : wd) b->release();
-	ctx->hw_text.release(); ctx->hw_blocks.release(); ctx->hw_small.release();
+	ctx->hw_text.release(); ctx->hw_blocks.release(); ctx->hw_small.release(); ctx->hm_small.release();
+	DevBuf *md[] = {&ctx->m_chains, &ctx->m_nchain, &ctx->m_keep, &ctx->m_hp, &ctx->m_tile_count, &ctx->m_tile_base, &ctx->m_small,
+	                &ctx->m_newoff, &ctx->m_off, &ctx->in2_start, &ctx->in2_end, &ctx->in2_value};
+	for (auto *b : md) b->release();
 	for (int k = 0; k < 2; k++) {
 		ctx->bin_start[k].release(); ctx->bin_end[k].release(); ctx->bin_value[k].release();
 		ctx->bout_start[k].release(); ctx->bout_end[k].release(); ctx->bout_value[k].release();
@@ -589,6 +597,42 @@ int wb200_reduce_format_host(wb200_ctx *ctx, int op, int ntracks, int nset1, int
 	return rc;
 }
 
+// -- element-wise maps on the inputs ---------------------------------------
+int wb200_set_input_maps(wb200_ctx *ctx, int ntracks, const wb200_map *const *maps, const int *nmaps) {
+	if (!ctx || ntracks < 0) return WB200_EINVAL;
+	ctx->map_chains.clear(); ctx->map_nchain.clear();
+	if (ntracks == 0 || !maps || !nmaps) return WB200_OK;
+	bool any = false;
+	ctx->map_chains.assign((size_t) ntracks * MAX_MAP_CHAIN, MapOp{0, 0, 0.0});
+	ctx->map_nchain.assign(ntracks, 0);
+	for (int i = 0; i < ntracks; i++) {
+		if (nmaps[i] < 0 || nmaps[i] > MAX_MAP_CHAIN) { ctx->map_chains.clear(); ctx->map_nchain.clear(); return fail(ctx, WB200_EUNSUPPORTED, "more than 8 maps on one track"); }
+		for (int c = 0; c < nmaps[i]; c++) {
+			const wb200_map &m = maps[i][c];
+			if (m.op < WB200_MAP_SCALE || m.op > WB200_MAP_ABS) { ctx->map_chains.clear(); ctx->map_nchain.clear(); return fail(ctx, WB200_EINVAL, "unknown map"); }
+			ctx->map_chains[(size_t) i * MAX_MAP_CHAIN + c] = MapOp{m.op, 0, m.arg};
+			any = true;
+		}
+		ctx->map_nchain[i] = nmaps[i];
+	}
+	if (!any) { ctx->map_chains.clear(); ctx->map_nchain.clear(); }
+	return WB200_OK;
+}
+
+double wb200_map_default(int op, double arg, double default_value) {
+	// the constructors' derived default_value (src/unaryOps.c:673-682, 736-745, 787-811, 843-866, 891-901, 951-960)
+	const double d = default_value;
+	switch (op) {
+	case WB200_MAP_SCALE: return std::isnan(d) ? NAN : (double) (float) (d * arg);
+	case WB200_MAP_OFFSET: return std::isnan(d) ? NAN : (double) (float) (d + arg);
+	case WB200_MAP_LOG: return (!std::isnan(d) && d > 0) ? std::log(d) / arg : NAN;
+	case WB200_MAP_EXP: return std::isnan(d) ? NAN : (double) (float) std::exp(d * arg);
+	case WB200_MAP_POW: return (!std::isnan(d) && (d > 0 || arg > 0)) ? std::pow(d, arg) : NAN;
+	case WB200_MAP_ABS: return std::isnan(d) ? NAN : std::fabs(d);
+	}
+	return NAN;
+}
+
 // Diagnostic builds (-DWB_DIAG_PHASES): cycles per pipeline phase summed over windows since the
 // last call; all zero in the shipped build.
 void wb200_debug_phases(wb200_ctx *ctx, uint64_t out[16]) {
@@ -653,6 +697,52 @@ int wb200_reduce_device(wb200_ctx *ctx, int op, int ntracks, int nset1, int stri
 }
 
 namespace {
+// The chains set by wb200_set_input_maps, applied to the staged tracks in ctx->in_*: values are
+// rewritten in place; if a log dropped records the survivors are compacted into ctx->in2_* and
+// `off` is rebuilt.  On return *s / *e / *v point at the arrays to reduce.
+int apply_input_maps(wb200_ctx *ctx, int N, std::vector<int64_t> &off, const int32_t **s_io, const int32_t **e_io, const double **v_io) {
+	if ((int) ctx->map_nchain.size() != N) return fail(ctx, WB200_EINVAL, "wb200_set_input_maps was called for a different number of tracks");
+	const int64_t I = off[N];
+	if (I == 0) return WB200_OK;
+	cudaStream_t st = ctx->stream;
+	int64_t max_len = 0;
+	for (int i = 0; i < N; i++) max_len = std::max(max_len, off[i + 1] - off[i]);
+	CK(ctx->m_chains.ensure((size_t) N * MAX_MAP_CHAIN * sizeof(MapOp))); CK(ctx->m_nchain.ensure((size_t) N * sizeof(int)));
+	CK(ctx->m_off.ensure((size_t) (N + 1) * sizeof(int64_t))); CK(ctx->m_newoff.ensure((size_t) (N + 1) * sizeof(int64_t)));
+	CK(ctx->m_keep.ensure((size_t) I)); CK(ctx->m_small.ensure(64)); CK(ctx->hm_small.ensure(64 + (size_t) (N + 1) * sizeof(int64_t)));
+	CK(cudaMemcpyAsync(ctx->m_chains.p, ctx->map_chains.data(), (size_t) N * MAX_MAP_CHAIN * sizeof(MapOp), cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(ctx->m_nchain.p, ctx->map_nchain.data(), (size_t) N * sizeof(int), cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(ctx->m_off.p, off.data(), (size_t) (N + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+	CK(cudaMemsetAsync(ctx->m_small.p, 0, 64, st));
+	int *d_any = ctx->m_small.as<int>();
+	long long *d_R = (long long *) (ctx->m_small.as<char>() + 16);
+	CK(launch_map(const_cast<double *>(*v_io), ctx->m_off.as<int64_t>(), ctx->m_chains.as<MapOp>(), ctx->m_nchain.as<int>(), N, max_len,
+	              ctx->m_keep.as<unsigned char>(), d_any, st));
+	CK(cudaMemcpyAsync(ctx->hm_small.p, d_any, 4, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));      // pageable sources of the chains / offsets are free again, and: anything dropped?
+	if (ctx->hm_small.as<int>()[0] == 0) return WB200_OK;
+	// compaction of the surviving records
+	const int ntiles = sink_tiles(I);
+	CK(ctx->m_hp.ensure((size_t) (I + 1) * sizeof(int32_t)));
+	CK(ctx->m_tile_count.ensure((size_t) ntiles * sizeof(int))); CK(ctx->m_tile_base.ensure((size_t) ntiles * sizeof(long long)));
+	CK(sink_compact(ctx->m_keep.as<unsigned char>(), I, ctx->m_tile_count.as<int>(), ctx->m_tile_base.as<long long>(), d_R, ctx->m_hp.as<int32_t>(), st));
+	CK(cudaMemcpyAsync(ctx->hm_small.as<char>() + 8, d_R, 8, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	const long long R = *(const long long *) (ctx->hm_small.as<char>() + 8);
+	const size_t m = (size_t) std::max<long long>(1, R);
+	CK(ctx->in2_start.ensure(m * sizeof(int32_t))); CK(ctx->in2_end.ensure(m * sizeof(int32_t))); CK(ctx->in2_value.ensure(m * sizeof(double)));
+	CK(launch_map_gather(ctx->m_hp.as<int32_t>(), d_R, R, *s_io, *e_io, *v_io, ctx->in2_start.as<int32_t>(), ctx->in2_end.as<int32_t>(),
+	                     ctx->in2_value.as<double>(), ctx->m_off.as<int64_t>(), N, ctx->m_newoff.as<int64_t>(), st));
+	int64_t *h_new = (int64_t *) (ctx->hm_small.as<char>() + 64);
+	CK(cudaMemcpyAsync(h_new, ctx->m_newoff.p, (size_t) (N + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	for (int i = 0; i <= N; i++) off[i] = h_new[i];
+	*s_io = ctx->in2_start.as<int32_t>(); *e_io = ctx->in2_end.as<int32_t>(); *v_io = ctx->in2_value.as<double>();
+	return WB200_OK;
+}
+} // namespace
+
+namespace {
 // host tracks of one chromosome -> HBM -> kernels; the segments stay in ctx->out_*
 int reduce_host_to_device(wb200_ctx *ctx, int op, int ntracks, int nset1, int strict, const wb200_track *tracks,
                           int64_t *S_out, double *dv_out, double *auc_out) {
@@ -686,8 +776,15 @@ int reduce_host_to_device(wb200_ctx *ctx, int op, int ntracks, int nset1, int st
 	CK(ctx->out_start.ensure(cap * sizeof(int32_t)));
 	CK(ctx->out_end.ensure(cap * sizeof(int32_t)));
 	CK(ctx->out_value.ensure(cap * sizeof(double)));
-	int rc = run_device(ctx, op, N, nset1, strict, ctx->in_start.as<int32_t>(), ctx->in_end.as<int32_t>(),
-	                    ctx->in_value.as<double>(), off.data(), dflt.data(), (int32_t) lo, (int32_t) hi,
+	const int32_t *in_s = ctx->in_start.as<int32_t>(), *in_e = ctx->in_end.as<int32_t>();
+	const double *in_v = ctx->in_value.as<double>();
+	if (!ctx->map_nchain.empty()) {
+		int rc = apply_input_maps(ctx, N, off, &in_s, &in_e, &in_v);
+		ctx->map_chains.clear(); ctx->map_nchain.clear();
+		if (rc != WB200_OK) return rc;
+	}
+	int rc = run_device(ctx, op, N, nset1, strict, in_s, in_e,
+	                    in_v, off.data(), dflt.data(), (int32_t) lo, (int32_t) hi,
 	                    ctx->out_start.as<int32_t>(), ctx->out_end.as<int32_t>(), ctx->out_value.as<double>(),
 	                    cap, S_out, dv_out, auc_out);
 	if (rc == WB200_OK) ctx->stats.h2d_bytes = I * 16;

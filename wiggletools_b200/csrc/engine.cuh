@@ -117,6 +117,17 @@ cudaError_t launch_fixup(const Job &job, long long count, cudaStream_t s);
 cudaError_t launch_sample_maxabs(const double *value, int64_t n, int64_t stride, double *out2, cudaStream_t s);
 cudaError_t launch_reduce_auc(const double *partial, int count, double *out, cudaStream_t s);
 cudaError_t launch_reduce_moments(const double *moments, int nw, double *out6, cudaStream_t s);
+// element-wise maps on staged inputs (maps.cu)
+constexpr int MAX_MAP_CHAIN = 8;
+enum MapCode : int { MAP_SCALE = 1, MAP_OFFSET = 2, MAP_LOG = 3, MAP_EXP = 4, MAP_POW = 5, MAP_ABS = 6 };
+struct MapOp { int op; int pad; double arg; };
+cudaError_t launch_map(double *value, const int64_t *d_off, const MapOp *d_chains, const int *d_nchain, int N, int64_t max_len,
+                       unsigned char *keep, int *any_dropped, cudaStream_t s);
+cudaError_t launch_map_gather(const int32_t *hp, const long long *d_R, long long R, const int32_t *s_in, const int32_t *e_in,
+                              const double *v_in, int32_t *s_out, int32_t *e_out, double *v_out,
+                              const int64_t *d_off, int N, int64_t *d_new_off, cudaStream_t s);
+// positions of the set bytes of H[0..n): hp[0..R), hp[R] = n (count / scan / scatter of writer.cu)
+cudaError_t sink_compact(const unsigned char *H, int64_t n, int *tile_count, long long *tile_base, long long *R, int32_t *hp, cudaStream_t s);
 // text sink (writer.cu): record heads of the compress rule, then the two formatting passes
 cudaError_t sink_heads(const int32_t *start, const int32_t *end, const double *value, int64_t n, unsigned char *D, unsigned char *H,
                        int *tile_count, long long *tile_base, long long *R, int32_t *hp, cudaStream_t s);

@@ -380,6 +380,11 @@ cudaError_t sink_heads(const int32_t *start, const int32_t *end, const double *v
 	sink::heads_kernel<<<grid, 256, 0, s>>>(start, end, value, n, D, H);
 	const int64_t warps = (n + 1023) / 1024;
 	sink::resolve_kernel<<<(unsigned) ((warps + 3) / 4), 128, 0, s>>>(value, n, D, H);
+	return sink_compact(H, n, tile_count, tile_base, R, hp, s);
+}
+
+cudaError_t sink_compact(const unsigned char *H, int64_t n, int *tile_count, long long *tile_base, long long *R, int32_t *hp, cudaStream_t s) {
+	if (n <= 0) return cudaSuccess;
 	const int ntiles = (int) ((n + sink::TILE - 1) / sink::TILE);
 	sink::count_kernel<<<ntiles, sink::TH, 0, s>>>(H, n, tile_count);
 	sink::scan_kernel<<<1, 1024, 0, s>>>(tile_count, ntiles, tile_base, R);
