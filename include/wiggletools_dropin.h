@@ -140,6 +140,13 @@ WiggleIterator *NonOverlappingWiggleIterator(WiggleIterator *);                 
  * only fwrites text.  wb200_sink_accepts() says whether `wi` is such an iterator in
  * its freshly constructed state; anything else stays with the reference's writer. */
 #include <stdio.h>
+/* -- unaryOps.c: the element-wise operators (scale, offset, ln / log, exp, pow, abs, default;
+ * src/unaryOps.c:210-229,650-960) as one constructor.  Popped on the host the iterator
+ * behaves as the reference's; as input of one of the reductions above its maps run on
+ * the device (wb200_set_input_maps).  op: WB200_MAP_* of wiggletools_b200.h, 0 for
+ * `default`; arg: the CLI-level argument (log base <= 0 means ln). */
+WiggleIterator *wb200_mapped_iterator(WiggleIterator *i, int op, double arg);
+
 int wb200_sink_accepts(WiggleIterator *wi);
 void wb200_sink_run(WiggleIterator *wi, FILE *out, wt_bool bedGraph);
 

@@ -111,3 +111,19 @@ void __wrap_toStdout(WiggleIterator *wi, bool bedGraph, bool holdFire) {
 	}
 	wb200_sink_run(wi, stdout, bedGraph);
 }
+
+/* ---- element-wise unary operators -------------------------------------------------
+ * In src/unaryOps.c the edit would be one line at the top of each constructor, e.g.
+ *     WiggleIterator * ScaleWiggleIterator(WiggleIterator * i, double s) {
+ *         return wb200_mapped_iterator(i, WB200_MAP_SCALE, s);
+ * Popped on the host the returned iterator does what the reference's does; as the input
+ * of a GPU reduction its maps run on the device (`mean map ln a.bw b.bw c.bw`). */
+WiggleIterator *wb200_mapped_iterator(WiggleIterator *i, int op, double arg);
+WiggleIterator *__wrap_ScaleWiggleIterator(WiggleIterator *i, double s) { return wb200_mapped_iterator(i, 1, s); }
+WiggleIterator *__wrap_ShiftWiggleIterator(WiggleIterator *i, double s) { return wb200_mapped_iterator(i, 2, s); }
+WiggleIterator *__wrap_NaturalLogWiggleIterator(WiggleIterator *i) { return wb200_mapped_iterator(i, 3, 0); }
+WiggleIterator *__wrap_LogWiggleIterator(WiggleIterator *i, double s) { return wb200_mapped_iterator(i, 3, s); }
+WiggleIterator *__wrap_NaturalExpWiggleIterator(WiggleIterator *i) { return wb200_mapped_iterator(i, 4, 0); }
+WiggleIterator *__wrap_PowerWiggleIterator(WiggleIterator *i, double s) { return wb200_mapped_iterator(i, 5, s); }
+WiggleIterator *__wrap_AbsWiggleIterator(WiggleIterator *i) { return wb200_mapped_iterator(i, 6, 0); }
+WiggleIterator *__wrap_DefaultValueWiggleIterator(WiggleIterator *i, double v) { return wb200_mapped_iterator(i, 0, v); }

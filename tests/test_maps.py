@@ -103,3 +103,47 @@ def test_device_maps_everything_dropped_and_errors(engine):
     assert len(got) == 0
     with pytest.raises(api.WB200Error):
         engine.reduce("mean", [t], ["chr1"], maps=[[("scale", 1.0)] * 9])             # more than 8 maps on a track
+
+
+@pytest.mark.gpu
+def test_cli_maps_on_the_device(tmp_path):
+    """`mean map ln ...`, `sum map scale ...`, nested maps, a map feeding a host-side operator: the
+    reference CLI linked against the library (unary constructors routed to wb200_mapped_iterator
+    by oracle/dropin_binding.c) prints what the unmodified reference CLI prints."""
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    ref = os.path.join(here, "..", "oracle", "_ref", "wiggletools")
+    exe = os.path.join(here, "..", "oracle", "_ref", "wiggletools_b200")
+    if not (os.path.exists(ref) and os.path.exists(exe)):
+        pytest.skip("oracle/_ref CLIs not built (needs /root/reference at build time)")
+    rng = np.random.default_rng(31)
+    files = []
+    for t in range(4):
+        path = tmp_path / ("t%d.bg" % t)
+        with open(path, "w") as f:
+            for chrom in ("chr1", "chr10", "chr2"):
+                pos = 1
+                for _ in range(3000):
+                    pos += int(rng.integers(0, 4)) * int(rng.integers(0, 2))
+                    ln = int(rng.choice([1, 2, 3, 6, 9]))
+                    f.write("%s\t%d\t%d\t%g\n" % (chrom, pos - 1, pos - 1 + ln, rng.integers(-1, 6) / 4.0))
+                    pos += ln
+        files.append(path.name)
+    programs = [
+        ["mean", "map", "ln"] + files,
+        ["write_bg", "-", "sum", "map", "scale", "0.5"] + files,
+        ["mean", "map", "offset", "-0.5", "map", "abs"] + files,
+        ["max", "map", "pow", "2"] + files,
+        ["AUC", "mean", "map", "log", "2", "map", "offset", "1.5"] + files,
+        ["write_bg", "-", "sum", "scale", "3", files[0], "ln", files[1], "default", "2", files[2], files[3]],
+        ["write_bg", "-", "unit", "sum", "map", "exp"] + files[:2],
+        ["write_bg", "-", "gt", "0.3", "scale", "2", files[0]],                    # a map consumed by a host-side operator
+    ]
+    env = dict(os.environ, WB200_VERBOSE="1")
+    for k, prog in enumerate(programs):
+        want = subprocess.run([ref] + prog, capture_output=True, cwd=tmp_path, check=True).stdout
+        run = subprocess.run([exe] + prog, capture_output=True, cwd=tmp_path, check=True, env=env)
+        assert len(want) > 0 and run.stdout == want, " ".join(prog)
+        if k < 7:     # every program but the last feeds its maps to a GPU reduction: they must have run there
+            assert b"inputs run on the device" in run.stderr, " ".join(prog)

@@ -136,6 +136,73 @@ void bw_seek(WiggleIterator *wi, const char *chrom, int start, int finish) {
 }
 
 // ---------------------------------------------------------------------------
+// element-wise unary operators (unaryOps.c: scale, offset, ln, log, exp, pow, abs,
+// default) behind the WiggleIterator protocol.  Popped on the host they behave as the
+// reference's own iterators do; drained by a reduction of this library they are seen
+// through: the raw records of the source underneath go to the device with the chain of
+// maps (wb200_set_input_maps), so `mean map ln a.bw b.bw` maps on the GPU.
+// ---------------------------------------------------------------------------
+struct RawRecord { char *chrom; int start, finish; double value; bool valid; };
+
+struct MappedSource {
+	WiggleIterator *inner = nullptr;
+	int op = 0;                 // WB200_MAP_* or 0: records untouched (`default`)
+	double arg = 0;             // as the reference's constructor stores it (log base -> log(base), ln / exp -> 1)
+	RawRecord raw{nullptr, 0, 0, 0, false};   // the SOURCE's record behind the one currently presented
+};
+
+void mapped_pop(WiggleIterator *wi);
+void mapped_seek(WiggleIterator *wi, const char *chrom, int start, int finish);
+bool is_mapped(const WiggleIterator *wi) { return wi->pop == &mapped_pop; }
+
+RawRecord raw_of(WiggleIterator *it) {
+	if (is_mapped(it)) return ((MappedSource *) it->data)->raw;
+	return RawRecord{it->chrom, it->start, it->finish, it->value, !it->done};
+}
+
+void mapped_pop(WiggleIterator *wi) {
+	MappedSource *m = (MappedSource *) wi->data;
+	WiggleIterator *iter = m->inner;
+	if (m->op == WB200_MAP_LOG)
+		while (!iter->done && iter->value <= 0) pop(iter);        // LogWiggleIteratorPop, unaryOps.c:764-765
+	if (iter->done) { wi->done = true; m->raw.valid = false; return; }
+	wi->chrom = iter->chrom;
+	wi->start = iter->start;
+	wi->finish = iter->finish;
+	const double v = iter->value, a = m->arg;
+	switch (m->op) {
+	case WB200_MAP_SCALE: wi->value = std::isnan(v) ? NAN : a * v; break;                                  // :650-665
+	case WB200_MAP_OFFSET: wi->value = a + v; break;                                                       // :722-734
+	case WB200_MAP_LOG: wi->value = (std::isnan(v) || v < 0) ? NAN : std::log(v) / a; break;               // :760-779
+	case WB200_MAP_EXP: wi->value = std::exp(v * a); break;                                                // :823-835
+	case WB200_MAP_POW: wi->value = ((a < 0 && v <= 0) || std::isnan(v)) ? NAN : std::pow(v, a); break;    // :873-889
+	case WB200_MAP_ABS: wi->value = std::isnan(v) ? NAN : std::fabs(v); break;                             // :934-949
+	default: wi->value = v; break;                                                                         // :210-223
+	}
+	m->raw = raw_of(iter);
+	pop(iter);
+}
+
+void mapped_seek(WiggleIterator *wi, const char *chrom, int start, int finish) {
+	MappedSource *m = (MappedSource *) wi->data;
+	seek(m->inner, chrom, start, finish);
+	wi->done = false;
+	pop(wi);
+}
+
+// The chain under `it` down to the first iterator that is not a map (innermost map first), and
+// the source's records that the wrappers have already consumed, in stream order.
+WiggleIterator *see_through(WiggleIterator *it, std::vector<wb200_map> &chain, std::vector<RawRecord> &pending) {
+	std::vector<MappedSource *> levels;
+	while (is_mapped(it)) { levels.push_back((MappedSource *) it->data); it = ((MappedSource *) it->data)->inner; }
+	for (size_t k = levels.size(); k-- > 0; )                    // innermost first
+		if (levels[k]->op) chain.push_back(wb200_map{levels[k]->op, 0, levels[k]->arg});
+	for (MappedSource *m : levels)                               // outermost wrapper presents the earliest record
+		if (m->raw.valid) pending.push_back(m->raw);
+	return it;
+}
+
+// ---------------------------------------------------------------------------
 // batch reduction behind a WiggleIterator
 // ---------------------------------------------------------------------------
 struct Reducer {
@@ -149,6 +216,7 @@ struct Reducer {
 	// staged inputs of the current chromosome
 	std::vector<std::vector<int32_t>> s, e;
 	std::vector<std::vector<double>> v;
+	std::vector<std::vector<wb200_map>> chains;   // per input: the maps applied on the device (empty: none)
 	// results of the current chromosome
 	std::vector<int32_t> rs, re;
 	std::vector<double> rv;
@@ -169,9 +237,12 @@ struct Reducer {
 		s.resize(n); e.resize(n); v.resize(n);
 		tracks.assign(n, wb200_track{});
 		direct.assign(n, nullptr);
+		chains.assign(n, std::vector<wb200_map>());
 		for (size_t i = 0; i < n; i++) {
 			WiggleIterator *it = iters[i];
 			s[i].clear(); e[i].clear(); v[i].clear();
+			// (the Pearson entry points stage their tracks themselves: maps stay on the host there)
+			if (!pearson && is_mapped(it) && !it->done && strcmp(it->chrom, chrom) == 0 && drain_mapped(i, tracks[i])) continue;
 			// A BigWig source positioned on its chromosome's first record hands over the
 			// decoded pinned arrays as they are: no per-record pop, no copy.
 			if (it->pop == &bw_pop && !it->done) {
@@ -197,6 +268,47 @@ struct Reducer {
 		return true;
 	}
 
+	// Input i is a chain of element-wise maps: its source's raw records of this chromosome are
+	// staged and the chain goes to the device.  The wrappers are then re-primed on the source's
+	// next record (the first of the next chromosome), as if they had been popped all along.
+	bool drain_mapped(size_t i, wb200_track &track) {
+		std::vector<RawRecord> pending;
+		WiggleIterator *base = see_through(iters[i], chains[i], pending);
+		if (chains[i].size() > 8) { chains[i].clear(); return false; }
+		for (const RawRecord &r : pending)
+			if (r.chrom == chrom || strcmp(r.chrom, chrom) == 0) { s[i].push_back(r.start); e[i].push_back(r.finish); v[i].push_back(r.value); }
+			else { chains[i].clear(); s[i].clear(); e[i].clear(); v[i].clear(); return false; }   // wrappers straddle a chromosome boundary: host path
+		while (!base->done && strcmp(base->chrom, chrom) == 0) {
+			s[i].push_back(base->start);
+			e[i].push_back(base->finish);
+			v[i].push_back(base->value);
+			pop(base);
+		}
+		// re-prime innermost first: each wrapper presents the next record of its (now advanced) input
+		std::vector<WiggleIterator *> levels;
+		for (WiggleIterator *it = iters[i]; is_mapped(it); it = ((MappedSource *) it->data)->inner) levels.push_back(it);
+		for (size_t k = levels.size(); k-- > 0; ) { levels[k]->done = false; ((MappedSource *) levels[k]->data)->raw.valid = false; levels[k]->pop(levels[k]); }
+		track.start = s[i].data(); track.end = e[i].data(); track.value = v[i].data();
+		track.n = (int64_t) s[i].size();
+		track.default_value = iters[i]->default_value;
+		return true;
+	}
+
+	void arm_maps() {
+		bool any = false;
+		for (auto &c : chains) any = any || !c.empty();
+		if (!any) return;
+		std::vector<const wb200_map *> ptrs(chains.size());
+		std::vector<int> counts(chains.size());
+		for (size_t i = 0; i < chains.size(); i++) { ptrs[i] = chains[i].data(); counts[i] = (int) chains[i].size(); }
+		if (wb200_set_input_maps(engine(), (int) chains.size(), ptrs.data(), counts.data()) != WB200_OK) die(wb200_last_error(engine()));
+		if (getenv("WB200_VERBOSE")) {
+			int mapped = 0;
+			for (auto &c : chains) mapped += c.empty() ? 0 : 1;
+			fprintf(stderr, "wiggletools_b200: %s: maps of %d of %d inputs run on the device\n", chrom, mapped, (int) chains.size());
+		}
+	}
+
 	// the decoded arrays have been staged: move the direct sources to their next chromosome
 	void release(std::vector<BwSource *> &direct) {
 		for (size_t i = 0; i < direct.size(); i++)
@@ -212,6 +324,7 @@ struct Reducer {
 		const char *text = nullptr;
 		int64_t nbytes = 0, nseg = 0;
 		double a = 0;
+		arm_maps();
 		if (wb200_reduce_format_host(engine(), op, (int) tracks.size(), n1, strict ? 1 : 0, tracks.data(), mode, chrom, state,
 		                             &text, &nbytes, &nseg, &a) != WB200_OK)
 			die(wb200_last_error(engine()));
@@ -245,6 +358,7 @@ struct Reducer {
 			return true;
 		}
 		wb200_segments out;
+		arm_maps();
 		if (wb200_reduce_host(engine(), op, (int) n, n1, strict ? 1 : 0, tracks.data(), &out) != WB200_OK)
 			die(wb200_last_error(engine()));
 		rs.assign(out.start, out.start + out.n);
@@ -645,6 +759,28 @@ void wb200_sink_run(WiggleIterator *wi, FILE *out, wt_bool bedGraph) {
 	while (r->next_chromosome_to_sink(out, mode, &state)) { }
 	fflush(out);
 	wi->done = true;
+}
+
+// -- unaryOps.c: element-wise operators -----------------------------------------------------------
+// ScaleWiggleIterator, ShiftWiggleIterator, NaturalLogWiggleIterator, LogWiggleIterator,
+// NaturalExpWiggleIterator, PowerWiggleIterator, AbsWiggleIterator, DefaultValueWiggleIterator
+// (src/unaryOps.c:210-229, 650-960) in one constructor: op is a WB200_MAP_* code (0: `default`),
+// arg the CLI-level argument (scale factor, offset, log base with <= 0 meaning ln, exponent,
+// the new default).  oracle/dropin_binding.c routes the reference's constructors here.
+WiggleIterator *wb200_mapped_iterator(WiggleIterator *i, int op, double arg) {
+	MappedSource *m = new MappedSource();
+	double dflt;
+	// the reference wraps the input in NonOverlappingWiggleIterator for these (unaryOps.c:675,738,802,858,893,953)
+	const bool nonoverlap = op == WB200_MAP_SCALE || op == WB200_MAP_OFFSET || (op == WB200_MAP_LOG && arg > 0) ||
+	                        op == WB200_MAP_EXP || op == WB200_MAP_POW || op == WB200_MAP_ABS;
+	m->inner = nonoverlap ? NonOverlappingWiggleIterator(i) : i;
+	m->op = op;
+	if (op == 0) { m->arg = 0; dflt = arg; }
+	else {
+		m->arg = op == WB200_MAP_LOG ? (arg > 0 ? std::log(arg) : 1.0) : op == WB200_MAP_EXP ? 1.0 : arg;
+		dflt = wb200_map_default(op, m->arg, i->default_value);
+	}
+	return newWiggleIterator(m, &mapped_pop, &mapped_seek, dflt, i->overlaps);
 }
 
 } // extern "C"
