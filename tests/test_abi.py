@@ -49,10 +49,10 @@ def test_dropin_symbols_exported():
     text = open(os.path.join(ROOT, "include", "wiggletools_dropin.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     body = text[text.index("-- multiplexer.c") if "-- multiplexer.c" in text else 0:]
-    names = set(re.findall(r"\b([A-Za-z][A-Za-z0-9]*)\s*\(", text)) - {"void", "defined", "pop", "seek"}
-    names = {n for n in names if n[0].isupper() or n.startswith(("new", "pop", "seek", "run", "destroy"))}
+    names = set(re.findall(r"\b([A-Za-z][A-Za-z0-9_]*)\s*\(", text)) - {"void", "defined", "pop", "seek"}
+    names = {n for n in names if n[0].isupper() or n.startswith(("new", "pop", "seek", "run", "destroy", "wb200_"))}
     names |= {"pop", "seek"}
     lib = ctypes.CDLL(_lib.LIB_PATH)
-    assert len(names) >= 30
+    assert len(names) >= 30 and {"wb200_sink_accepts", "wb200_sink_run", "wb200_mapped_iterator"} <= names
     for n in sorted(names):
         assert hasattr(lib, n), "missing drop-in export " + n
