@@ -26,3 +26,6 @@ seg = api.Segments(np.zeros(n, np.int32), start, (start + rng.integers(1, 3, n))
                    np.round(rng.random(n), 1) + rng.integers(-3, 4, n) * 2e-7)
 for bg in (False, True):
     print("sink", bg, len(eng.format_segments(seg, ["chr1"], bg)))
+# element-wise maps: in-place map, a log that drops records (compaction + rebuilt offsets), nested chains
+r = eng.reduce("mean", g, ["chr1", "chr2"], maps=[[("abs",), ("offset", 0.5), ("ln",)] if i % 2 else [("scale", -1.0), ("log", 2.0)] for i in range(len(g))])
+print("maps", len(r), float(np.nansum(r.value)))

@@ -1535,30 +1535,42 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 // end coordinates once (4 B/interval); row nw closes the table.
 __global__ void __launch_bounds__(256) cursor_kernel(const Job job) {
 	const int i = blockIdx.y;
-	const long long o = job.off[i], oe = job.off[i + 1];
-	// four consecutive intervals per thread on a 16-byte aligned grid: one 128-bit load
-	const long long g = (o & ~3ll) + ((long long) blockIdx.x * blockDim.x + threadIdx.x) * 4;
-	if (g > oe) return;
+	const long long o = job.off[i];
+	const int n = (int) (job.off[i + 1] - o);
+	// four consecutive intervals per thread on a 16-byte aligned grid: one 128-bit load; j0 is the
+	// track-relative index of the first of them (negative in the track's first, partial group)
+	const int a = (int) (o & 3);
+	const int j0 = 4 * (int) (blockIdx.x * blockDim.x + threadIdx.x) - a;
+	const int32_t *end = job.end + o;
 	// cnt(e) = number of windows that start at or before e; interval j is the cursor of the
 	// windows cnt(end[j-1]) .. cnt(end[j]) - 1, and j = n (one past the last) closes the table
 	const int p0 = (int) job.p0, wlog = job.wlog, rows = job.nw + 1;
 	auto cnt = [&](int e) { return e < p0 ? 0 : (int) (((unsigned) e - (unsigned) p0) >> wlog) + 1; };
-	int ev[4];
-	if (job.vec && g >= o && g + 4 <= oe) {
-		const int4 v = *(const int4 *) (job.end + g);
-		ev[0] = v.x; ev[1] = v.y; ev[2] = v.z; ev[3] = v.w;
-	} else {
+	int ev[4] = {0, 0, 0, 0};
+	const bool live = j0 <= n;
+	if (live) {
+		if (job.vec && j0 >= 0 && j0 + 4 <= n) {
+			const int4 v = *(const int4 *) (end + j0);
+			ev[0] = v.x; ev[1] = v.y; ev[2] = v.z; ev[3] = v.w;
+		} else {
 #pragma unroll
-		for (int k = 0; k < 4; k++) ev[k] = (g + k >= o && g + k < oe) ? job.end[g + k] : 0;
+			for (int k = 0; k < 4; k++) if (j0 + k >= 0 && j0 + k < n) ev[k] = end[j0 + k];
+		}
 	}
-	int c_prev = g > o ? cnt(job.end[g - 1]) : 0;
+	// the end before this thread's group sits in the previous lane; only lane 0 loads it
+	int e_prev = __shfl_up_sync(FULL, ev[3], 1);
+	if (!live) return;
+	if ((threadIdx.x & 31) == 0 && j0 > 0) e_prev = end[j0 - 1];
+	int c_prev = j0 > 0 ? cnt(e_prev) : 0;
+	int32_t *col = job.cursor + i;
+	const size_t N = (size_t) job.N;
 #pragma unroll
 	for (int k = 0; k < 4; k++) {
-		const long long j = g + k - o;
+		const int j = j0 + k;
 		if (j < 0) continue;
-		if (j > oe - o) break;
-		const int c = j < oe - o ? min(cnt(ev[k]), rows) : rows;
-		for (int w = c_prev; w < c; w++) job.cursor[(size_t) w * job.N + i] = (int32_t) j;
+		if (j > n) break;
+		const int c = j < n ? min(cnt(ev[k]), rows) : rows;
+		for (int w = c_prev; w < c; w++) col[(size_t) w * N] = j;
 		c_prev = c;
 	}
 }
