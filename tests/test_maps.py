@@ -147,3 +147,19 @@ def test_cli_maps_on_the_device(tmp_path):
         assert len(want) > 0 and run.stdout == want, " ".join(prog)
         if k < 7:     # every program but the last feeds its maps to a GPU reduction: they must have run there
             assert b"inputs run on the device" in run.stderr, " ".join(prog)
+
+
+def test_map_default_matches_the_constructors(port):
+    """wb200_map_default (host code, no device needed) against the oracle's derived defaults, which are
+    pinned on the reference's constructors above: every operator, defaults that hit each branch."""
+    from wiggletools_b200 import _lib
+    import math
+    lib = _lib.load()
+    empty = lambda d: OTrack(np.empty(0, np.int32), np.empty(0, np.int32), np.empty(0, np.int32), np.empty(0), default=d)
+    cases = [("scale", 1, 0.3), ("offset", 2, -1.7), ("ln", 3, None), ("log", 3, 10.0), ("exp", 4, None), ("pow", 5, 2.0), ("pow", 5, -0.5), ("abs", 6, None)]
+    for d in (0.0, 2.5, -3.25, 1e-3, float("nan"), 1e30):
+        for name, code, arg in cases:
+            want = port.map(empty(d), [(name,) if arg is None else (name, arg)], NAMES).default
+            lowered = 1.0 if name in ("ln", "exp") else 0.0 if name == "abs" else math.log(arg) if name == "log" else arg
+            got = lib.wb200_map_default(code, lowered, d)
+            assert got == want or (math.isnan(got) and math.isnan(want)), (name, arg, d, got, want)
