@@ -255,6 +255,10 @@ int wb200_format_host(wb200_ctx *ctx, int mode, const char *chrom,
  * gsl_cdf_tdist_Q, src/setComparisons.c:117); exported for tests. */
 double wb200_tdist_Q(double t, double nu);
 
+/* Diagnostic: the device formatter's "%lf" compiled for the host (same source function as the
+ * kernel's): writes the text of v into out32 (>= 32 bytes), returns its length, -1 for |v| >= 2^63. */
+int wb200_debug_format_value(double v, char *out32);
+
 /* Diagnostic: per-phase cycle counters of the window kernel (thread 0 of every CTA, summed over
  * windows) since the last call; zeros unless the library was built with -DWB_DIAG_PHASES. */
 void wb200_debug_phases(wb200_ctx *ctx, uint64_t out[16]);

@@ -206,3 +206,36 @@ def test_cli_write_through_device_sink(tmp_path):
     assert got == want
     assert open(tmp_path / "gpu2.out", "rb").read() == open(tmp_path / "ref2.out", "rb").read()
     assert open(tmp_path / "gpu3.out", "rb").read() == open(tmp_path / "ref3.out", "rb").read()
+
+
+def test_formatter_host_build_against_printf():
+    """The device formatter's "%lf" is plain integer arithmetic; the same source function is also
+    compiled for the host (wb200_debug_format_value).  Fuzz it against the C library's printf:
+    random doubles of every magnitude, exact ties of the 6th decimal, subnormals, signs, NaN / Inf."""
+    import ctypes as C
+    from wiggletools_b200 import _lib
+    lib = _lib.load()
+    libc = C.CDLL(None)
+    libc.snprintf.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_double]
+    rng = np.random.default_rng(123)
+    parts = [
+        np.ldexp(rng.random(200000), rng.integers(-1080, 63, 200000)) * rng.choice([-1.0, 1.0], 200000),
+        (rng.integers(0, 1 << 40, 100000) * 2 + 1) / 2.0 ** rng.integers(1, 60, 100000),            # odd / 2^k: many exact ties
+        rng.integers(0, 10 ** 9, 100000) / 1e6 + rng.choice([0.0, 5e-7, -5e-7, 4.999999e-7], 100000),
+        rng.integers(-(1 << 62), 1 << 62, 50000).astype(np.float64),
+        np.frombuffer(rng.integers(0, 1 << 63, 100000, dtype=np.int64).tobytes(), dtype=np.float64),  # random bit patterns
+        np.array([0.0, -0.0, 5e-324, -5e-324, 2.0 ** -1074, 0.9999995, 0.99999949999999994, 1e-7, 4.5e-7, 5e-7, 1.5e-6, 2.5e-6,
+                  9223372036854774784.0, -9223372036854774784.0, 4503599627370495.5, np.inf, -np.inf, np.nan, -np.nan,
+                  123456789.1234565, 0.1234565, 0.1234575, 1e22, 999999.9999995]),
+    ]
+    buf, ref = C.create_string_buffer(64), C.create_string_buffer(512)
+    checked = 0
+    for v in np.concatenate(parts):
+        n = lib.wb200_debug_format_value(float(v), buf)
+        if abs(v) >= 2.0 ** 63 and np.isfinite(v):
+            assert n == -1
+            continue
+        libc.snprintf(ref, 512, b"%lf", float(v))
+        assert n == len(ref.value) and buf.value == ref.value, (float(v).hex(), buf.value, ref.value)
+        checked += 1
+    assert checked > 400000

@@ -88,6 +88,7 @@ def load():
     lib.wb200_bw_set_stretch.argtypes = [C.c_void_p, C.c_int]
     lib.wb200_bw_decode_chrom.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.wb200_debug_phases.argtypes = [C.c_void_p, C.c_void_p]
+    lib.wb200_debug_format_value.argtypes = [C.c_double, C.c_char_p]
     lib.wb200_set_input_maps.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.wb200_map_default.restype = C.c_double
     lib.wb200_map_default.argtypes = [C.c_int, C.c_double, C.c_double]
@@ -108,6 +109,6 @@ EXPORTS = [
     "wb200_set_window", "wb200_bind_host_thread", "wb200_host_alloc", "wb200_host_free", "wb200_reduce_host", "wb200_reduce_host_batch",
     "wb200_reduce_device", "wb200_pearson_host", "wb200_pearson_pair_host", "wb200_pearson_merge", "wb200_pearson_result",
     "wb200_tdist_Q", "wb200_bw_open", "wb200_bw_close", "wb200_bw_last_error", "wb200_bw_nchrom", "wb200_bw_chrom_name",
-    "wb200_bw_chrom_length", "wb200_bw_set_stretch", "wb200_bw_decode_chrom", "wb200_debug_phases",
+    "wb200_bw_chrom_length", "wb200_bw_set_stretch", "wb200_bw_decode_chrom", "wb200_debug_phases", "wb200_debug_format_value",
     "wb200_format_device", "wb200_format_host", "wb200_reduce_format_host", "wb200_set_input_maps", "wb200_map_default",
 ]

@@ -597,6 +597,9 @@ int wb200_reduce_format_host(wb200_ctx *ctx, int op, int ntracks, int nset1, int
 	return rc;
 }
 
+// Host build of the device formatter's "%lf" (same source function): for CPU-side fuzzing against printf.
+int wb200_debug_format_value(double v, char *out32) { return out32 ? sink_debug_format_value(v, out32) : WB200_EINVAL; }
+
 // -- element-wise maps on the inputs ---------------------------------------
 int wb200_set_input_maps(wb200_ctx *ctx, int ntracks, const wb200_map *const *maps, const int *nmaps) {
 	if (!ctx || ntracks < 0) return WB200_EINVAL;

@@ -132,6 +132,7 @@ cudaError_t sink_compact(const unsigned char *H, int64_t n, int *tile_count, lon
 cudaError_t sink_heads(const int32_t *start, const int32_t *end, const double *value, int64_t n, unsigned char *D, unsigned char *H,
                        int *tile_count, long long *tile_base, long long *R, int32_t *hp, cudaStream_t s);
 int sink_tiles(int64_t n);
+int sink_debug_format_value(double v, char *out);
 int sink_block_records();
 cudaError_t sink_format(bool write, const int32_t *start, const int32_t *end, const double *value, const int32_t *hp,
                         long long R, long long rec_base, int wig, int pbp_in, const char *chrom,

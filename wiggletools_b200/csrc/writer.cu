@@ -29,6 +29,7 @@
 #include "engine.cuh"
 #include "device_util.cuh"
 #include <climits>
+#include <cstring>
 
 namespace wb {
 namespace sink {
@@ -170,9 +171,25 @@ struct Dec { unsigned long long ip; unsigned frac; int neg, special; };   // spe
 
 // exact decimal of a double with 6 fractional digits, round-half-even on the binary value
 // (what glibc's "%lf" prints); *bad is set for |v| >= 2^63
-__device__ Dec to_dec(double v, int *bad) {
+__host__ __device__ inline unsigned long long mulhi_u64(unsigned long long a, unsigned long long b) {
+#ifdef __CUDA_ARCH__
+	return __umul64hi(a, b);
+#else
+	return (unsigned long long) (((unsigned __int128) a * b) >> 64);
+#endif
+}
+__host__ __device__ inline unsigned long long bits_of(double v) {
+#ifdef __CUDA_ARCH__
+	return (unsigned long long) __double_as_longlong(v);
+#else
+	unsigned long long b; memcpy(&b, &v, 8); return b;
+#endif
+}
+
+// (also compiled for the host: wb200_debug_format_value lets a CPU test fuzz this very code against printf)
+__host__ __device__ Dec to_dec(double v, int *bad) {
 	Dec d;
-	const unsigned long long bits = (unsigned long long) __double_as_longlong(v);
+	const unsigned long long bits = bits_of(v);
 	d.neg = (int) (bits >> 63);
 	const int ex = (int) ((bits >> 52) & 0x7ff);
 	const unsigned long long man = bits & ((1ull << 52) - 1);
@@ -188,7 +205,7 @@ __device__ Dec to_dec(double v, int *bad) {
 	const int k = -e;
 	unsigned long long fm = m;
 	if (k < 64) { d.ip = m >> k; fm = m & ((1ull << k) - 1); }
-	const unsigned long long lo = fm * 1000000ull, hi = __umul64hi(fm, 1000000ull);   // fm * 10^6 < 2^73
+	const unsigned long long lo = fm * 1000000ull, hi = mulhi_u64(fm, 1000000ull);   // fm * 10^6 < 2^73
 	if (k >= 128) return d;                                              // below half of the last digit
 	unsigned long long q, rem_hi, rem_lo, half_hi, half_lo;
 	if (k < 64) {
@@ -211,28 +228,28 @@ __device__ Dec to_dec(double v, int *bad) {
 	return d;
 }
 
-__device__ __forceinline__ int ndigits_u64(unsigned long long x) {
+__host__ __device__ __forceinline__ int ndigits_u64(unsigned long long x) {
 	int n = 1;
 	while (x >= 10) { x /= 10; n++; }
 	return n;
 }
-__device__ __forceinline__ int len_int(int x) {
+__host__ __device__ __forceinline__ int len_int(int x) {
 	const unsigned a = x < 0 ? 0u - (unsigned) x : (unsigned) x;
 	return (x < 0 ? 1 : 0) + ndigits_u64(a);
 }
-__device__ __forceinline__ int len_value(const Dec &d) {
+__host__ __device__ __forceinline__ int len_value(const Dec &d) {
 	return d.neg + (d.special ? 3 : ndigits_u64(d.ip) + 7);
 }
-__device__ __forceinline__ char *put_u64(char *p, unsigned long long x) {
+__host__ __device__ __forceinline__ char *put_u64(char *p, unsigned long long x) {
 	const int n = ndigits_u64(x);
 	for (int i = n - 1; i >= 0; i--) { p[i] = (char) ('0' + (int) (x % 10)); x /= 10; }
 	return p + n;
 }
-__device__ __forceinline__ char *put_int(char *p, int x) {
+__host__ __device__ __forceinline__ char *put_int(char *p, int x) {
 	if (x < 0) *p++ = '-';
 	return put_u64(p, x < 0 ? 0u - (unsigned) x : (unsigned) x);
 }
-__device__ __forceinline__ char *put_value(char *p, const Dec &d) {
+__host__ __device__ __forceinline__ char *put_value(char *p, const Dec &d) {
 	if (d.neg) *p++ = '-';
 	if (d.special == 1) { *p++ = 'n'; *p++ = 'a'; *p++ = 'n'; return p; }
 	if (d.special == 2) { *p++ = 'i'; *p++ = 'n'; *p++ = 'f'; return p; }
@@ -242,7 +259,7 @@ __device__ __forceinline__ char *put_value(char *p, const Dec &d) {
 	for (int i = 5; i >= 0; i--) { p[i] = (char) ('0' + (int) (f % 10)); f /= 10; }
 	return p + 6;
 }
-__device__ __forceinline__ char *put_str(char *p, const char *s, int n) {
+__host__ __device__ __forceinline__ char *put_str(char *p, const char *s, int n) {
 	for (int i = 0; i < n; i++) p[i] = s[i];
 	return p + n;
 }
@@ -390,6 +407,17 @@ cudaError_t sink_compact(const unsigned char *H, int64_t n, int *tile_count, lon
 	sink::scan_kernel<<<1, 1024, 0, s>>>(tile_count, ntiles, tile_base, R);
 	sink::scatter_kernel<<<ntiles, sink::TH, 0, s>>>(H, n, tile_base, R, hp);
 	return cudaGetLastError();
+}
+
+// host build of the device formatter's value path: "%lf" of one double into out (>= 32 bytes), returns
+// the length, -1 for a value outside the formatter's range (tests/test_writer.py fuzzes it against printf)
+int sink_debug_format_value(double v, char *out) {
+	int bad = 0;
+	const sink::Dec d = sink::to_dec(v, &bad);
+	if (bad) return -1;
+	char *p = sink::put_value(out, d);
+	*p = 0;
+	return (int) (p - out);
 }
 
 int sink_tiles(int64_t n) { return (int) ((n + sink::TILE - 1) / sink::TILE); }
