@@ -113,6 +113,8 @@ class Oracle:
                 f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
             else:
                 f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+            f = self._f("apply")
+            f.restype = C.c_int64
             f = self._f("write")
             f.restype = C.c_int64
             f.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_char_p]
@@ -207,6 +209,26 @@ class Oracle:
             n = self._f("map")(C.addressof(ct), len(chain), codes.ctypes.data, args.ctypes.data, len(names), C.addressof(cn),
                                C.addressof(o), C.addressof(dflt))
         return Track(arrs[0][:n].copy(), arrs[1][:n].copy(), arrs[2][:n].copy(), arrs[3][:n].copy(), default=dflt.value)
+
+    STAT_CODES = {"AUC": 1, "meanI": 2, "varI": 3, "stddevI": 4, "CVI": 5, "maxI": 6, "minI": 7, "spanI": 8}
+
+    def apply(self, dataset, regions, stats, names=("chr1",), strict=False):
+        """`apply` of a list of statistics over the regions of a sorted BED-like track:
+        array [len(regions), len(stats)]."""
+        codes = np.array([self.STAT_CODES[s] for s in stats], np.int32)
+        out = np.full((len(regions), len(stats)), np.nan)
+        if self.kind == "port":
+            n = self._f("apply")(C.c_int64(len(dataset)), C.c_void_p(dataset.chrom.ctypes.data), C.c_void_p(dataset.start.ctypes.data),
+                                 C.c_void_p(dataset.end.ctypes.data), C.c_void_p(dataset.value.ctypes.data), C.c_double(dataset.default),
+                                 C.c_int64(len(regions)), C.c_void_p(regions.chrom.ctypes.data), C.c_void_p(regions.start.ctypes.data),
+                                 C.c_void_p(regions.end.ctypes.data), C.c_int(len(stats)), C.c_void_p(codes.ctypes.data),
+                                 C.c_int(int(strict)), C.c_void_p(out.ctypes.data))
+        else:
+            cd, cr, cn = dataset.c(), regions.c(), self._names(names)
+            n = self._f("apply")(C.c_void_p(C.addressof(cd)), C.c_void_p(C.addressof(cr)), C.c_int(len(stats)), C.c_void_p(codes.ctypes.data),
+                                 C.c_int(int(strict)), C.c_int(len(names)), C.c_void_p(C.addressof(cn)), C.c_void_p(out.ctypes.data))
+        assert n == len(regions), (n, len(regions))
+        return out
 
     def write(self, chrom, start, end, value, names=("chr1",), bedgraph=False):
         """Bytes the default sink prints for the segment list (`write` / `write_bg`)."""

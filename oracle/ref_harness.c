@@ -295,6 +295,44 @@ int64_t wtref_map(const wt_track *t, int nmaps, const int *codes, const double *
 	return drain(wi, names, nnames, out);
 }
 
+/* The reference's own `apply`: ApplyMultiplexer(regions, statistics, count, dataset, strict)
+ * (src/apply.c:330-344) over an in-memory dataset and in-memory regions; one row of `count`
+ * statistics per region (codes as in wto_apply of wt_oracle.c). */
+WiggleIterator *MeanIntegrator(WiggleIterator *);
+WiggleIterator *SpanIntegrator(WiggleIterator *);
+WiggleIterator *MaxIntegrator(WiggleIterator *);
+WiggleIterator *MinIntegrator(WiggleIterator *);
+WiggleIterator *VarianceIntegrator(WiggleIterator *);
+WiggleIterator *StandardDeviationIntegrator(WiggleIterator *);
+WiggleIterator *CoefficientOfVariationIntegrator(WiggleIterator *);
+Multiplexer *ApplyMultiplexer(WiggleIterator *, WiggleIterator *(**)(WiggleIterator *), int, WiggleIterator *, bool);
+int64_t wtref_apply(const wt_track *dataset, const wt_track *regions, int nstats, const int *codes, int strict,
+                    int nnames, char **names, double *out) {
+	(void) nnames;
+	WiggleIterator *(**stats)(WiggleIterator *) = calloc(nstats, sizeof(*stats));
+	for (int k = 0; k < nstats; k++) {
+		switch (codes[k]) {
+		case 1: stats[k] = &AUCIntegrator; break;
+		case 2: stats[k] = &MeanIntegrator; break;
+		case 3: stats[k] = &VarianceIntegrator; break;
+		case 4: stats[k] = &StandardDeviationIntegrator; break;
+		case 5: stats[k] = &CoefficientOfVariationIntegrator; break;
+		case 6: stats[k] = &MaxIntegrator; break;
+		case 7: stats[k] = &MinIntegrator; break;
+		case 8: stats[k] = &SpanIntegrator; break;
+		}
+	}
+	Multiplexer *apply = ApplyMultiplexer(MemSourceIterator(regions, names), stats, nstats, MemSourceIterator(dataset, names),
+	                                      strict ? true : false);
+	int64_t r = 0;
+	while (!apply->done) {
+		for (int k = 0; k < nstats; k++) out[r * nstats + k] = apply->values[k];
+		r++;
+		popMultiplexer(apply);
+	}
+	return r;
+}
+
 #endif /* !WB200_DROPIN */
 
 #ifndef WB200_DROPIN

@@ -618,4 +618,84 @@ int64_t wto_map(const wt_track *t, int nmaps, const int *codes, const double *ar
 	return k;
 }
 
+/* `apply` (src/apply.c + the integrators of src/statistics.c:62-326), restated per
+ * region.  Every region is served from a per-base buffer (createBufferedWiggleIteratorData always
+ * allocates one, so the seek / fill-in branches of computeApplyValues, apply.c:266-273, are never taken):
+ * dataset records are written base by base into values[]/set[] (pushDataOnBuffer, :217-237) and read back
+ *   - strict: one 1-bp record per set base (StrictBufferedWiggleIteratorPop, :87-101);
+ *   - loose : one 1-bp record per set base, one record with the dataset's default value (rounded to
+ *             float by createBufferedWiggleIteratorData's parameter type, :41) per run of unset bases
+ *             (LooseBufferedWiggleIteratorPop, :66-85);
+ * in region-relative coordinates, and the chained integrators fold those records in order.
+ * codes: 1 AUC (:103-126), 2 meanI (:62-96), 3 varI, 4 stddevI, 5 CVI (:233-326; a NaN record would hang
+ * the reference, :238-239 -- not reproduced, NaN is skipped), 6 maxI (:162-186), 7 minI (:192-216),
+ * 8 spanI (:132-156).  out[r * nstats + k] = statistic k of region r.  Regions and the dataset's segments
+ * are sorted by (chrom, start); segments do not overlap. */
+int64_t wto_apply(int64_t nseg, const int32_t *chrom, const int32_t *start, const int32_t *end, const double *value,
+                  double default_value, int64_t nreg, const int32_t *rchrom, const int32_t *rstart, const int32_t *rend,
+                  int nstats, const int *codes, int strict, double *out) {
+	const double dflt = (double) (float) default_value;
+	int64_t first = 0;
+	for (int64_t r = 0; r < nreg; r++) {
+		const int len = rend[r] - rstart[r];
+		double *vals = (double *) calloc(len > 0 ? len : 1, sizeof(double));
+		char *set = (char *) calloc(len > 0 ? len : 1, 1);
+		/* first segment that can reach this region (regions are sorted, so the scan only moves forward) */
+		while (first < nseg && (chrom[first] < rchrom[r] || (chrom[first] == rchrom[r] && end[first] <= rstart[r]))) first++;
+		int64_t back = first;      /* an earlier, longer region may have pushed `first` too far: step back over overlaps */
+		while (back > 0 && chrom[back - 1] == rchrom[r] && end[back - 1] > rstart[r]) back--;
+		for (int64_t k = back; k < nseg && chrom[k] == rchrom[r] && start[k] < rend[r]; k++) {
+			int a = start[k] > rstart[r] ? start[k] - rstart[r] : 0;
+			int b = end[k] < rend[r] ? end[k] - rstart[r] : len;
+			for (int p = a; p < b; p++) { vals[p] = value[k]; set[p] = 1; }
+		}
+		/* integrator states */
+		double auc = 0, msum = 0, mspan = 0, span = 0, mx = NAN, mn = NAN;
+		double T = 0, vsum = 0; long vcount = 0;
+		int idx = 0;
+		while (idx < len) {
+			int rs = idx, rf;
+			double v;
+			if (set[idx]) { v = vals[idx]; idx++; rf = idx; }
+			else {
+				while (idx < len && !set[idx]) idx++;
+				rf = idx;
+				if (strict) continue;
+				v = dflt;
+			}
+			const int L = rf - rs;
+			if (isnan(v)) continue;
+			auc += L * v;
+			msum += L * v; mspan += L;
+			span += L;
+			if (isnan(mx) || v > mx) mx = v;
+			if (isnan(mn) || v < mn) mn = v;
+			if (vcount) {
+				double old_mean = vsum / vcount;
+				double new_mean = vsum / (vcount + L);
+				double delta_T = old_mean * new_mean - new_mean * 2 * v + ((double) vcount / (vcount + L)) * v * v;
+				T += delta_T * L;
+			}
+			vcount += L;
+			vsum += L * v;
+		}
+		for (int k = 0; k < nstats; k++) {
+			double res = NAN;
+			switch (codes[k]) {
+			case 1: res = auc; break;
+			case 2: res = mspan > 0 ? msum / mspan : NAN; break;
+			case 3: res = T / (vcount - 1); break;
+			case 4: res = sqrt(T / (vcount - 1)); break;
+			case 5: res = sqrt(T / (vcount - 1)) / (vsum / vcount); break;
+			case 6: res = mx; break;
+			case 7: res = mn; break;
+			case 8: res = span; break;
+			}
+			out[r * nstats + k] = res;
+		}
+		free(vals); free(set);
+	}
+	return nreg;
+}
+
 double wto_tdist_Q(double t, double nu) { return gsl_cdf_tdist_Q(t, nu); }
