@@ -61,6 +61,24 @@ def build(ref=None):
         subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
 
 
+def reference_read_bigwig(path, names, cap=4_000_000):
+    """Records of a BigWig file as the reference's OWN reader emits them: src/bigWiggleReader.c,
+    unmodified, compiled into oracle/_ref/libwtrefbw.so over a libBigWig-interface shim
+    (oracle/bigwig_shim.c).  Chromosome indices refer to `names`."""
+    path_so = os.path.join(HERE, "_ref", "libwtrefbw.so")
+    if not os.path.exists(path_so):
+        raise FileNotFoundError(path_so + " (run `make -C oracle refbw`)")
+    lib = C.CDLL(path_so)
+    lib.wtref_read_bigwig.restype = C.c_int64
+    lib.wtref_read_bigwig.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p]
+    chrom = np.empty(cap, np.int32); start = np.empty(cap, np.int32); end = np.empty(cap, np.int32); value = np.empty(cap, np.float64)
+    o = COut(chrom.ctypes.data, start.ctypes.data, end.ctypes.data, value.ctypes.data, cap)
+    arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    n = lib.wtref_read_bigwig(str(path).encode(), len(names), C.addressof(arr), C.addressof(o))
+    assert n <= cap
+    return Track(chrom[:n].copy(), start[:n].copy(), end[:n].copy(), value[:n].copy())
+
+
 class Segments:
     def __init__(self, chrom, start, end, value, default=None):
         self.chrom, self.start, self.end, self.value, self.default = chrom, start, end, value, default

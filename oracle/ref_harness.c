@@ -43,11 +43,15 @@ static void wtref_absent(const char *what) {
 	fprintf(stderr, "oracle/_ref: %s needs a library that is not in this image\n", what);
 	exit(1);
 }
+#ifndef WTREF_WITH_BIGWIG   /* oracle/_ref/libwtrefbw.so links the reference's own bigWiggleReader.c over oracle/bigwig_shim.c */
 WiggleIterator *BigWiggleReader(char *f, bool h) { (void)f; (void)h; wtref_absent("BigWiggleReader"); return NULL; }
+#endif
 WiggleIterator *BigBedReader(char *f, bool h) { (void)f; (void)h; wtref_absent("BigBedReader"); return NULL; }
 WiggleIterator *BamReader(char *f, bool h, bool r) { (void)f; (void)h; (void)r; wtref_absent("BamReader"); return NULL; }
 WiggleIterator *BcfReader(char *f, bool h) { (void)f; (void)h; wtref_absent("BcfReader"); return NULL; }
+#ifndef WTREF_WITH_BIGWIG
 void libBigWigInit(int n) { (void)n; }
+#endif
 #endif
 
 /* ---- 2. in-memory source ------------------------------------------------ */
@@ -334,6 +338,16 @@ int64_t wtref_apply(const wt_track *dataset, const wt_track *regions, int nstats
 }
 
 #endif /* !WB200_DROPIN */
+
+#ifdef WTREF_WITH_BIGWIG
+/* A BigWig file through the reference's own reader (src/bigWiggleReader.c: 10000-bp stretch
+ * queries, boxing, producer thread) -- records as the reference's consumers see them. */
+WiggleIterator *BigWiggleReader(char *, bool);
+int64_t wtref_read_bigwig(char *path, int nnames, char **names, wt_out *out) {
+	WiggleIterator *wi = BigWiggleReader(path, false);
+	return drain(wi, names, nnames, out);
+}
+#endif
 
 #ifndef WB200_DROPIN
 double wtref_tdist_Q(double t, double nu);

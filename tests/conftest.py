@@ -21,6 +21,9 @@ def _built():
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
     if os.path.isdir("/root/reference/src") and not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libwtref.so")):
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
+    if os.path.isdir("/root/reference/src") and not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libwtrefbw.so")) \
+            and os.path.exists(os.path.join(ROOT, "wiggletools_b200", "libwiggletools_b200.so")):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "refbw"])
 
 
 @pytest.fixture(scope="session")

@@ -47,11 +47,12 @@ def test_not_a_bigwig(tmp_path):
         BigWig(p)
 
 
-@pytest.mark.parametrize("compress", [True, False])
-def test_written_files_all_section_types(tmp_path, compress):
-    rng = np.random.default_rng(5)
-    chroms = [("chr2", 65000), ("chr10", 30001), ("chr1", 123457)]   # ids 0,1,2; strcmp order chr1 < chr10 < chr2
-    per = {0: [], 1: [], 2: []}
+def mixed_file(tmp_path, compress, seed=5, chroms=(("chr2", 65000), ("chr10", 30001), ("chr1", 123457))):
+    """A BigWig with all three section types, long intervals crossing stretch boundaries and several
+    chromosomes (ids in list order; strcmp order differs).  Returns (path, chroms, per-chromosome items)."""
+    rng = np.random.default_rng(seed)
+    chroms = list(chroms)
+    per = {k: [] for k in range(len(chroms))}
     sections = []
     for cid, (name, length) in enumerate(chroms):
         pos = 0
@@ -93,8 +94,14 @@ def test_written_files_all_section_types(tmp_path, compress):
                 per[cid] += [(s, s + span, v) for s, v in items]
                 pos += n * step + span
     sections.sort(key=lambda t: (t[0], t[2][0][0]))
-    path = tmp_path / "t.bw"
+    path = tmp_path / ("t%d.bw" % seed)
     write_bigwig(path, chroms, sections, compress=compress, rtree_block=5)
+    return path, chroms, per
+
+
+@pytest.mark.parametrize("compress", [True, False])
+def test_written_files_all_section_types(tmp_path, compress):
+    path, chroms, per = mixed_file(tmp_path, compress)
     names = sorted(n for n, _ in chroms)
     for stretch in (0, 10000):
         b = BigWig(path, stretch=stretch)
@@ -121,3 +128,38 @@ def test_last_base_quirk(tmp_path):
     s, e, v = BigWig(tmp_path / "q.bw").decode(0)
     want = reference_stretch_records(items, 10001)
     assert list(zip(s, e, v)) == want == [(1, 10000, 1.0), (10000, 10001, 2.0)]
+
+
+def reference_reader():
+    from oracle.pyoracle import reference_read_bigwig
+    if not os.path.exists(os.path.join(HERE, "..", "oracle", "_ref", "libwtrefbw.so")):
+        pytest.skip("oracle/_ref/libwtrefbw.so not built (`make -C oracle refbw`, needs /root/reference)")
+    return reference_read_bigwig
+
+
+@pytest.mark.parametrize("seed", [5, 6, 7])
+def test_decoder_matches_the_references_own_reader(tmp_path, seed):
+    """The decoder's emulation of the reference's reader (10000-bp stretch queries, boxing, visiting order,
+    last-base quirk: Q9) against that reader itself: src/bigWiggleReader.c, unmodified, compiled over a
+    libBigWig-interface shim that only hands out the stored records (oracle/bigwig_shim.c)."""
+    read = reference_reader()
+    chroms = (("chr2", 65000), ("chr10", 30001), ("chr1", 123457), ("chrM", 10001), ("chr21", 20001), ("chrX", 9999))
+    path, chroms, _ = mixed_file(tmp_path, True, seed=seed, chroms=chroms)
+    b = BigWig(path, stretch=10000)
+    names = [c[0] for c in b.chroms]                                   # strcmp order
+    want = read(path, names)
+    got_c, got_s, got_e, got_v = [], [], [], []
+    for i in range(len(names)):
+        s, e, v = b.decode(i)
+        got_c.append(np.full(len(s), i, np.int32)); got_s.append(s); got_e.append(e); got_v.append(v)
+    got_c, got_s, got_e, got_v = map(np.concatenate, (got_c, got_s, got_e, got_v))
+    assert len(want) == len(got_s) and len(got_s) > 1000
+    assert np.array_equal(want.chrom, got_c) and np.array_equal(want.start, got_s) and np.array_equal(want.end, got_e)
+    assert np.array_equal(want.value, got_v)
+
+
+def test_reference_reader_on_the_reference_fixtures():
+    read = reference_reader()
+    for name, values, starts in (("fixedStep.bw", np.arange(10.0), np.arange(1, 11)), ("variableStep.bw", np.arange(1.0, 6.0), [1, 2, 4, 6, 8])):
+        t = read(os.path.join(HERE, "golden", name), ["chr1"])
+        assert list(t.start) == list(starts) and list(t.value) == list(values)
