@@ -163,3 +163,22 @@ def test_reference_reader_on_the_reference_fixtures():
     for name, values, starts in (("fixedStep.bw", np.arange(10.0), np.arange(1, 11)), ("variableStep.bw", np.arange(1.0, 6.0), [1, 2, 4, 6, 8])):
         t = read(os.path.join(HERE, "golden", name), ["chr1"])
         assert list(t.start) == list(starts) and list(t.value) == list(values)
+
+
+def test_config0_with_the_reference_itself(tmp_path):
+    """BASELINE.json configs[0], literally, run by the REFERENCE (its own BigWig reader over the shim, its
+    own multiplexer, reducers and writer): `wiggletools mean test/fixedStep.bw test/variableStep.bw`, plus
+    the reference's goldens on the BigWig twins (test/expected/pearson.txt, test/test.py:95-98 style AUC)."""
+    import shutil
+    import subprocess
+    exe = os.path.join(HERE, "..", "oracle", "_ref", "wiggletools_bw")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/wiggletools_bw not built (`make -C oracle refbw`, needs /root/reference)")
+    for f in ("fixedStep.bw", "variableStep.bw"):
+        shutil.copy(os.path.join(HERE, "golden", f), tmp_path / f)
+    run = lambda *a: subprocess.run([exe] + list(a), capture_output=True, text=True, check=True, cwd=tmp_path).stdout
+    out = run("mean", "fixedStep.bw", "variableStep.bw").split("\n")
+    assert out[0] == "fixedStep chrom=chr1 start=1 step=1"
+    assert [float(x) for x in out[1:11]] == [.5, 1.5, 1, 3, 2, 4.5, 3, 6, 4, 4.5]
+    assert run("pearson", "fixedStep.bw", "variableStep.bw").strip() == "-0.028968"
+    assert run("AUC", "mean", "fixedStep.bw", "variableStep.bw").strip() == "30.000000"

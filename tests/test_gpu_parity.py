@@ -261,6 +261,14 @@ def test_dropin_cli_config1(tmp_path):
     out = run("mean", "fixedStep.bw", "variableStep.bw").split("\n")
     assert out[0] == "fixedStep chrom=chr1 start=1 step=1"
     assert [float(x) for x in out[1:11]] == [.5, 1.5, 1, 3, 2, 4.5, 3, 6, 4, 4.5]
+    # ... and byte for byte what the REFERENCE prints for the same command line (its own BigWig reader
+    # compiled over oracle/bigwig_shim.c, its own multiplexer, reducer and writer)
+    ref_bw = os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "wiggletools_bw")
+    if os.path.exists(ref_bw):
+        for prog in (["mean", "fixedStep.bw", "variableStep.bw"], ["write_bg", "-", "var", "fixedStep.bw", "variableStep.bw"],
+                     ["pearson", "fixedStep.bw", "variableStep.bw"]):
+            want = subprocess.run([ref_bw] + prog, capture_output=True, text=True, check=True, cwd=tmp_path).stdout
+            assert run(*prog) == want, prog
     for args in (["do", "isZero", "diff", "fixedStep.bw", "fixedStep.wig"],
                  ["do", "isZero", "diff", "variableStep.bw", "variableStep.wig"],
                  ["do", "isZero", "diff", "sum", "fixedStep.bw", "fixedStep.bw", ":", "scale", "2", "fixedStep.bw"],
