@@ -287,7 +287,7 @@ def main():
             total_auc += auc.value
             if collect is not None:
                 st = lib.wb200_last_stats(ctx).contents
-                collect.append((sh["I"], sh["S"], st.ms_count, st.ms_emit, st.kernels, st.slow_segments))
+                collect.append((sh["I"], sh["S"], st.ms_count, st.ms_emit, st.kernels, st.slow_segments, st.limbs))
         t = torch.tensor([total_auc], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t)   # whole-genome AUC scalar: the path's only exchange step
@@ -342,7 +342,10 @@ def main():
                 "peak_source": peak_src, "algorithmic_bytes_per_step": by / args.steps,
                 "algorithmic_bytes_per_launch": by / max(1, len(per_launch)),
                 "emit_ms_per_step": 1e3 * t_emit / args.steps, "cursor_ms_per_step": 1e3 * t_count / args.steps,
-                "path_frac": (by / (t_emit + t_count) / 1e9) / peak if t_emit + t_count > 0 else 0.0}
+                "path_frac": (by / (t_emit + t_count) / 1e9) / peak if t_emit + t_count > 0 else 0.0,
+                # exact-sum format the library chose from the value range: 32-bit limbs per position (1: values like
+                # this generator's; 2: full float32 mantissas; 3: wider), 0 for the statistics without it
+                "accumulator_limbs": max((r[6] for r in per_launch), default=0)}
     launches = sum(r[4] for r in per_launch)
     seg_local = sum(sh["S"] for sh in shards)
     int_local = sum(sh["I"] for sh in shards)
