@@ -1,24 +1,37 @@
 #!/usr/bin/env python
 """Benchmark of the merge+reduce hot path: Mbp/s for `mean` over N synthetic
 genome tracks (BASELINE.json), on 1..8 B200s, with the HBM roofline of the
-dominant kernel and the reference's CPU path timed beside it.
+dominant kernel, an in-bench parity gate against the compiled reference, and the
+reference's CPU path timed beside it.
 
   python bench.py --gpus 1 --steps 5 --warmup 3
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
   python bench.py --impl reference        # the reference's CPU path on host cores
 
 A step = one pass of the hot path over the whole synthetic genome (24 hg38-like
-chromosomes, 3.1 Gbp, 64 tracks of ~1.2e7 intervals): per chromosome one
-wb200_reduce_device call (cursor kernel, single-pass emit kernel) on inputs resident in
-HBM.  With N GPUs the chromosomes are sharded across ranks (no data-path
-collective); the whole-genome AUC scalar is all-reduced over NCCL.
+chromosomes, 3.09 Gbp): ONE wb200_reduce_device_batch call (per chromosome a
+cursor kernel and a sweep kernel, queued back to back) on inputs resident in HBM.
+With N GPUs the chromosomes are sharded across ranks (no data-path collective);
+the whole-genome AUC scalar is all-reduced over NCCL.
+
+The headline line is BASELINE configs[1] (`mean`, 64 tracks).  The same run also
+measures the other BASELINE configurations on track-prefix views of one resident
+512-track data set and reports them under "extra": mean over 8 and 512 tracks,
+var + stddev over 512, median over 256, and mean over 64 tracks whose values carry
+full float32 mantissas (the two-limb accumulator).  Every workload is parity-gated:
+after its timed region the segments it produced are compared with the unmodified
+reference (oracle/_ref, else the oracle port) on whole chromosomes / regions --
+segment count, bit-identical (start, end), values within 1e-10 relative -- and the
+process exits non-zero on a mismatch.
 """
 import argparse
 import ctypes as C
 import json
 import os
+import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -30,13 +43,35 @@ sys.path.insert(0, ROOT)
 from wiggletools_b200.synth import sorted_chroms  # noqa: E402
 from wiggletools_b200.shard import lpt_assign  # noqa: E402
 
-N_TRACKS = int(os.environ.get("WB200_BENCH_TRACKS", 64))
 SCALE = float(os.environ.get("WB200_BENCH_SCALE", 1.0))   # <1 shrinks every chromosome (development only)
 MAX_LEN, MAX_GAP, GAP_PROB, VMAX = 400, 200, 0.5, 100000
-BENCH_OP = os.environ.get("WB200_BENCH_OP", "mean")       # development: time another statistic of the path
-# the kernel the roofline line is about: sum / mean run on fastsum_kernel (csrc/fastsum.cu), the rest on emit_kernel
-DOMINANT_KERNEL = "fastsum_kernel" if BENCH_OP in ("sum", "mean") and os.environ.get("WB200_FASTSUM") != "0" else "emit_kernel"
-OP_CODE = {"sum": 0, "mult": 1, "mean": 2, "var": 3, "stddev": 4, "cv": 6, "min": 7, "max": 8, "median": 9}[BENCH_OP]
+MEAN_STEP = (MAX_LEN + 1) / 2 + GAP_PROB * (MAX_GAP + 1) / 2
+OP_CODE = {"sum": 0, "mult": 1, "mean": 2, "var": 3, "stddev": 4, "cv": 6, "min": 7, "max": 8, "median": 9}
+PAD = 1024          # parity regions: intervals are at most MAX_LEN long, so every segment that starts in a region ends within PAD of it
+REL_TOL = 1e-10     # north_star: fp64 reductions within 1e-10 relative of the reference
+
+
+def workloads(world):
+    """The headline (first) and the extra workloads of this run."""
+    dev_n, dev_op = os.environ.get("WB200_BENCH_TRACKS"), os.environ.get("WB200_BENCH_OP")
+    if dev_n or dev_op:     # development: one workload, no extras
+        return [dict(key="dev", op=dev_op or "mean", N=int(dev_n or 64), f32=False, e2e=True)]
+    wl = [dict(key="mean64", op="mean", N=64, f32=False, e2e=True, config="configs[1]")]
+    if os.environ.get("WB200_BENCH_EXTRAS", "1") == "0":
+        return wl
+    wl += [dict(key="mean8", op="mean", N=8, f32=False, e2e=world == 1, config="north_star N=8"),
+           dict(key="mean512", op="mean", N=512, f32=False, e2e=False, config="configs[4] / north_star N=512")]
+    if world == 1:
+        wl += [dict(key="var512", op="var", N=512, f32=False, e2e=False, config="configs[2]"),
+               dict(key="stddev512", op="stddev", N=512, f32=False, e2e=False, config="configs[2]"),
+               dict(key="median256", op="median", N=256, f32=False, e2e=False, config="configs[3]",
+                    chroms=os.environ.get("WB200_BENCH_MEDIAN_CHROMS", "chr19,chr20,chr21,chr22").split(",")),
+               dict(key="mean64_f32", op="mean", N=64, f32=True, e2e=False, config="configs[1] with float32-mantissa values (two-limb accumulator)")]
+    return wl
+
+
+def dominant_kernel(op):
+    return "fastsum_kernel" if op in ("sum", "mean") and os.environ.get("WB200_FASTSUM") != "0" else "emit_kernel"
 
 
 def genome():
@@ -48,14 +83,15 @@ def genome():
 # ---------------------------------------------------------------------------
 # synthetic data on the device (torch is plumbing: memory + RNG + NCCL)
 # ---------------------------------------------------------------------------
-def gen_chrom_device(torch, dev, n_tracks, length, seed):
-    """All tracks of one chromosome, concatenated track-major, on the GPU."""
+def gen_chrom_device(torch, dev, n_tracks, length, seed, n_f32=0):
+    """All tracks of one chromosome, concatenated track-major, on the GPU.  Values are
+    multiples of 1/64 below 1563; the first n_f32 tracks also get a second
+    value array with full float32 mantissas."""
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
-    mean_step = (MAX_LEN + 1) / 2 + GAP_PROB * (MAX_GAP + 1) / 2
-    n = int(length / mean_step * 1.06) + 64
+    n = int(length / MEAN_STEP * 1.06) + 64
     starts, ends, values, counts = [], [], [], []
-    chunk = max(1, min(n_tracks, int(2.5e8 // n)))
+    chunk = max(1, min(n_tracks, int(1.2e8 // n)))
     for t0 in range(0, n_tracks, chunk):
         k = min(chunk, n_tracks - t0)
         lens = torch.randint(1, MAX_LEN + 1, (k, n), device=dev, generator=g, dtype=torch.int64)
@@ -73,7 +109,11 @@ def gen_chrom_device(torch, dev, n_tracks, length, seed):
         del lens, gaps, step, s, e, keep, v
     counts = torch.cat(counts).cpu().numpy().astype(np.int64)
     off = np.concatenate(([0], np.cumsum(counts))).astype(np.int64)
-    return torch.cat(starts), torch.cat(ends), torch.cat(values), off
+    v32 = None
+    if n_f32:
+        m = int(off[min(n_f32, n_tracks)])
+        v32 = (torch.rand(m, device=dev, generator=g, dtype=torch.float32) * (VMAX / 64.0)).to(torch.float64)
+    return torch.cat(starts), torch.cat(ends), torch.cat(values), off, v32
 
 
 class ClockSampler(threading.Thread):
@@ -137,8 +177,37 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------
-# the reference's CPU path on a bounded sample (oracle/_ref or the oracle port)
+# the reference's CPU path: the parity checker of every workload, and the CPU baseline
 # ---------------------------------------------------------------------------
+def oracle_kind():
+    return "reference" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libwtref.so")) else "port"
+
+
+def _region_worker(args):
+    """One parity region [a, b) of an exported shard: the reference (oracle/_ref) reduces the
+    intervals that overlap [a, b + PAD); the segments that start inside [a, b) come back."""
+    kind, path, n_tracks, op, a, b = args
+    from oracle.pyoracle import Oracle, Track
+    s = np.load(os.path.join(path, "s.npy"), mmap_mode="r")
+    e = np.load(os.path.join(path, "e.npy"), mmap_mode="r")
+    v = np.load(os.path.join(path, "v.npy"), mmap_mode="r")
+    off = np.load(os.path.join(path, "off.npy"))
+    tracks = []
+    for i in range(n_tracks):
+        si, ei = s[off[i]:off[i + 1]], e[off[i]:off[i + 1]]
+        lo = int(np.searchsorted(ei, a, side="right"))           # first interval that ends after a
+        hi = int(np.searchsorted(si, b + PAD, side="left"))      # first interval that starts at or after b + PAD
+        hi = max(hi, lo)
+        tracks.append(Track(np.zeros(hi - lo, np.int32), np.array(si[lo:hi]), np.array(ei[lo:hi]),
+                            np.array(v[off[i] + lo:off[i] + hi])))
+    orc = Oracle(kind)
+    t0 = time.perf_counter()
+    seg = orc.reduce(op, tracks, ["chr1"])
+    dt = time.perf_counter() - t0
+    m = (seg.start >= a) & (seg.start < b)
+    return a, b, dt, seg.start[m], seg.end[m], seg.value[m]
+
+
 def _cpu_worker(args):
     kind, n_tracks, length, seed = args
     from oracle.pyoracle import Oracle, Track
@@ -160,15 +229,13 @@ def cpu_reference_sample(n_tracks, mbp_per_core, cores):
     mbp_per_core Mbp each (the reference's own scale-out model: one process per
     genome region, python/wiggletools/parallelWiggleTools.py:66-68)."""
     import multiprocessing as mp
-    kind = "reference" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libwtref.so")) else "port"
+    kind = oracle_kind()
     length = int(mbp_per_core * 1e6)
     jobs = [(kind, n_tracks, length, 1000 + i) for i in range(cores)]
-    t0 = time.perf_counter()
     if cores == 1:
         res = [_cpu_worker(jobs[0])]
     else:
         with mp.get_context("spawn").Pool(cores) as pool:
-            t0 = time.perf_counter()
             res = pool.map(_cpu_worker, jobs)
     wall = max(r[1] for r in res)     # slowest shard, generation excluded
     total_bp = sum(r[0] for r in res)
@@ -186,36 +253,151 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
+    n_tracks = int(os.environ.get("WB200_BENCH_TRACKS", 64))
     ncpu = os.cpu_count() or 1
-    mbp = 8.0 * (64.0 / N_TRACKS) ** 2          # ~1 s per step per core at N=64
+    mbp = 8.0 * (64.0 / n_tracks) ** 2          # ~1 s per step per core at N=64
     candidates = sorted({ncpu, max(1, ncpu // 2), max(1, ncpu // 4)}, reverse=True)
     best, tried = None, []
     for i in range(max(1, args.warmup)):
         c = candidates[min(i, len(candidates) - 1)]
-        r = cpu_reference_sample(N_TRACKS, mbp, c)
+        r = cpu_reference_sample(n_tracks, mbp, c)
         tried.append((c, r["value"]))
         if best is None or r["value"] > best[1]:
             best = (c, r["value"])
     cores = best[0]
-    times = [cpu_reference_sample(N_TRACKS, mbp, cores) for _ in range(args.steps)]
+    times = [cpu_reference_sample(n_tracks, mbp, cores) for _ in range(args.steps)]
     value = float(np.mean([t["value"] for t in times]))
     cb = dict(times[-1]); cb["value"] = value
     cb["sample"] += "; process counts tried in warm-up: " + ", ".join("%d -> %.0f Mbp/s" % t for t in tried)
     names, lengths = genome()
-    line = {"impl": "reference", "metric": "Mbp/s, mean over %d tracks" % N_TRACKS, "value": value, "unit": "Mbp/s",
+    line = {"impl": "reference", "metric": "Mbp/s, mean over %d tracks" % n_tracks, "value": value, "unit": "Mbp/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * (cores * mbp) / value, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(lengths, args.gpus), "cpu_baseline": cb,
+            "config": workload_config("mean", n_tracks, lengths, args.gpus, False), "cpu_baseline": cb,
             "e2e": {"value": value, "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def workload_config(lengths, gpus):
-    return {"workload": "mean over %d synthetic tracks, %d hg38-like chromosomes (%.2f Gbp), ~%.1e intervals/track"
-                        % (N_TRACKS, len(lengths), sum(lengths) / 1e9, sum(lengths) / 250.75),
-            "tracks": N_TRACKS, "genome_bp": int(sum(lengths)), "sharding": "chromosomes over %d GPU(s), LPT" % gpus,
-            "l2": "inputs (%.1f GB/step) larger than L2; no flush needed" % (N_TRACKS * sum(lengths) / 250.75 * 16 / 1e9)}
+def workload_config(op, n_tracks, lengths, gpus, f32):
+    return {"workload": "%s over %d synthetic tracks, %d hg38-like chromosomes (%.2f Gbp), ~%.1e intervals/track%s"
+                        % (op, n_tracks, len(lengths), sum(lengths) / 1e9, sum(lengths) / MEAN_STEP,
+                           ", float32-mantissa values" if f32 else ""),
+            "tracks": n_tracks, "genome_bp": int(sum(lengths)), "sharding": "chromosomes over %d GPU(s), LPT" % gpus,
+            "l2": "inputs (%.1f GB/step) larger than L2; no flush needed" % (n_tracks * sum(lengths) / MEAN_STEP * 16 / 1e9)}
+
+
+# ---------------------------------------------------------------------------
+# the parity gate
+# ---------------------------------------------------------------------------
+class ParityChecker:
+    """Compares segments left in HBM by a timed workload with the reference CPU path on the
+    same inputs, region by region, on a pool of host processes (which also yields the CPU
+    baseline of the workload: the reference timed on this box's cores)."""
+
+    def __init__(self, torch, procs):
+        import multiprocessing as mp
+        self.torch = torch
+        self.procs = max(1, procs)
+        self.pool = mp.get_context("spawn").Pool(self.procs)
+        self.dir = tempfile.mkdtemp(prefix="wb200_parity_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        self.exports = {}
+        self.kind = oracle_kind()
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+        shutil.rmtree(self.dir, ignore_errors=True)
+
+    def export(self, sh, a, b, f32):
+        """Intervals of every track of shard `sh` overlapping [a, b + PAD), as .npy files the workers map."""
+        key = (sh["ci"], a, b, bool(f32))
+        if key in self.exports:
+            return self.exports[key]
+        torch = self.torch
+        path = os.path.join(self.dir, "x%d" % len(self.exports))
+        os.makedirs(path)
+        off = sh["off"]
+        ntr = len(off) - 1 if not f32 else sh["n_f32"]
+        vals = sh["v32"] if f32 else sh["v"]
+        if a <= 1 and b >= sh["L"] + 1:
+            m = int(off[ntr])
+            s_h, e_h, v_h, off_h = sh["s"][:m].cpu().numpy(), sh["e"][:m].cpu().numpy(), vals[:m].cpu().numpy(), off[:ntr + 1].copy()
+        else:
+            ps, pe, pv, cnt = [], [], [], []
+            for i in range(ntr):
+                o0, o1 = int(off[i]), int(off[i + 1])
+                lo = int(torch.searchsorted(sh["e"][o0:o1], a, right=True))
+                hi = max(lo, int(torch.searchsorted(sh["s"][o0:o1], b + PAD)))
+                ps.append(sh["s"][o0 + lo:o0 + hi]); pe.append(sh["e"][o0 + lo:o0 + hi]); pv.append(vals[o0 + lo:o0 + hi])
+                cnt.append(hi - lo)
+            s_h, e_h, v_h = torch.cat(ps).cpu().numpy(), torch.cat(pe).cpu().numpy(), torch.cat(pv).cpu().numpy()
+            off_h = np.concatenate(([0], np.cumsum(cnt))).astype(np.int64)
+        for name, arr in (("s", s_h), ("e", e_h), ("v", v_h), ("off", off_h)):
+            np.save(os.path.join(path, name + ".npy"), arr)
+        self.exports[key] = path
+        return path
+
+    def check(self, wl, regions):
+        """regions: [(shard, a, b, out_start, out_end, out_value (device, S valid entries), S)].
+        Every region is cut into chunks for the process pool."""
+        torch = self.torch
+        jobs, meta = [], []
+        per_mbp = {"mean": 0.0016, "sum": 0.0016, "var": 0.005, "stddev": 0.005, "median": 0.025}.get(wl["op"], 0.01) * wl["N"]  # ~core-seconds per Mbp
+        for ri, (sh, a, b, os_, oe_, ov_, S) in enumerate(regions):
+            path = self.export(sh, a, b, wl["f32"])
+            # chunks of ~0.5 core-seconds, at least one per process
+            nchunk = int(max(self.procs if (b - a) > 2e5 else 1, min(4096, per_mbp * (b - a) / 1e6 / 0.5)))
+            edges = np.linspace(a, b, nchunk + 1).astype(np.int64)
+            for k in range(nchunk):
+                if edges[k + 1] > edges[k]:
+                    jobs.append((self.kind, path, wl["N"], wl["op"], int(edges[k]), int(edges[k + 1])))
+                    meta.append(ri)
+        t0 = time.perf_counter()
+        res = self.pool.map(_region_worker, jobs, chunksize=1)
+        wall = time.perf_counter() - t0
+        ok, nseg, bad_coord, max_rel, n_bits, cpu_s, bp = True, 0, 0, 0.0, 0, 0.0, 0
+        detail = []
+        host = {}
+        for ri, (a, b, dt, rs, re_, rv) in zip(meta, res):
+            sh, ra, rb, os_, oe_, ov_, S = regions[ri]
+            if ri not in host:
+                host[ri] = (os_[:S].cpu().numpy(), oe_[:S].cpu().numpy(), ov_[:S].cpu().numpy())
+            hs, he, hv = host[ri]
+            i0, i1 = int(np.searchsorted(hs, a, side="left")), int(np.searchsorted(hs, b, side="left"))
+            gs, ge, gv = hs[i0:i1], he[i0:i1], hv[i0:i1]
+            cpu_s += dt; bp += b - a
+            if len(gs) != len(rs):
+                ok = False
+                detail.append("region [%d,%d) of shard %d: %d segments, reference has %d" % (a, b, sh["ci"], len(gs), len(rs)))
+                continue
+            nseg += len(gs)
+            if not (np.array_equal(gs, rs) and np.array_equal(ge, re_)):
+                ok = False
+                bad_coord += int(np.count_nonzero((gs != rs) | (ge != re_)))
+                detail.append("region [%d,%d) of shard %d: coordinates differ" % (a, b, sh["ci"]))
+                continue
+            both_nan = np.isnan(gv) & np.isnan(rv)
+            with np.errstate(invalid="ignore", divide="ignore"):
+                rel = np.abs(gv - rv) / np.maximum(np.abs(gv), np.abs(rv))
+            rel[(gv == rv) | both_nan] = 0.0
+            rel[np.isnan(rel)] = np.inf                     # NaN on one side only
+            if len(rel):
+                max_rel = max(max_rel, float(rel.max()))
+            n_bits += int(np.count_nonzero((gv == rv) | both_nan))
+            if len(rel) and rel.max() > REL_TOL:
+                ok = False
+                detail.append("region [%d,%d) of shard %d: value error %.3g" % (a, b, sh["ci"], float(rel.max())))
+        out = {"ok": bool(ok), "oracle": "%s (%s)" % (self.kind, "oracle/_ref/libwtref.so: the unmodified reference" if self.kind == "reference" else "oracle/liboracle.so"),
+               "regions": ["shard %d [%d,%d)" % (r[0]["ci"], r[1], r[2]) for r in regions], "bp_checked": int(bp),
+               "segments_checked": int(nseg), "coords": "bit-identical" if bad_coord == 0 and ok or bad_coord == 0 and not detail else "%d differ" % bad_coord,
+               "values_max_rel_err": max_rel, "values_bit_identical": int(n_bits), "tolerance": REL_TOL}
+        if detail:
+            out["mismatch"] = detail[:8]
+        cpu = {"value": bp / 1e6 / wall if wall > 0 else 0.0, "unit": "Mbp/s", "cores": self.procs, "kind": self.kind,
+               "sample": "%s over %d tracks: the parity regions (%.1f Mbp in %d chunks on %d processes, %.1f core-seconds of reference time, %.1f s wall)"
+                         % (wl["op"], wl["N"], bp / 1e6, len(jobs), self.procs, cpu_s, wall)}
+        return out, cpu
 
 
 # ---------------------------------------------------------------------------
@@ -226,7 +408,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the parity gate / CPU baseline (development A/B runs only)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -234,6 +416,7 @@ def main():
     import torch
     import torch.distributed as dist
     from wiggletools_b200 import _lib
+    from wiggletools_b200._lib import CDeviceShard
 
     rank = int(os.environ.get("RANK", 0))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -256,190 +439,263 @@ def main():
     names, lengths = genome()
     owner = lpt_assign(lengths, world)
     mine = [i for i in range(len(lengths)) if owner[i] == rank]
+    wls = workloads(world)
+    n_max = max(w["N"] for w in wls)
+    n_f32 = max([w["N"] for w in wls if w["f32"]] + [0])
 
-    # resident inputs and outputs for this rank's chromosomes
+    # resident inputs for this rank's chromosomes: one data set of n_max tracks; every workload
+    # reads a track-prefix view of it (tracks are concatenated track-major per chromosome)
     shards = []
     for ci in mine:
-        s, e, v, off = gen_chrom_device(torch, dev, N_TRACKS, lengths[ci], seed=7919 * (ci + 1))
-        I = int(off[-1])
-        cap = min(2 * I + 1, lengths[ci] + 1)
-        out_s = torch.empty(cap, dtype=torch.int32, device=dev)
-        out_e = torch.empty(cap, dtype=torch.int32, device=dev)
-        out_v = torch.empty(cap, dtype=torch.float64, device=dev)
-        shards.append(dict(ci=ci, s=s, e=e, v=v, off=off, I=I, cap=cap, out=(out_s, out_e, out_v), L=lengths[ci]))
+        s, e, v, off, v32 = gen_chrom_device(torch, dev, n_max, lengths[ci], seed=7919 * (ci + 1), n_f32=n_f32)
+        shards.append(dict(ci=ci, s=s, e=e, v=v, v32=v32, n_f32=n_f32, off=off, L=lengths[ci]))
     torch.cuda.synchronize()
-    dflt = np.zeros(N_TRACKS, np.float64)
-    nout = C.c_int64(0)
-    auc = C.c_double(0)
-    dv = C.c_double(0)
 
-    def step(collect=None):
-        total_auc = 0.0
-        for sh in shards:
-            rc = lib.wb200_reduce_device(ctx, OP_CODE, N_TRACKS, N_TRACKS, 0,
-                                         sh["s"].data_ptr(), sh["e"].data_ptr(), sh["v"].data_ptr(),
-                                         sh["off"].ctypes.data, dflt.ctypes.data, 1, sh["L"] + 1,
-                                         sh["out"][0].data_ptr(), sh["out"][1].data_ptr(), sh["out"][2].data_ptr(),
-                                         sh["cap"], C.addressof(nout), C.addressof(dv), C.addressof(auc))
-            if rc != 0:
-                raise SystemExit("wb200_reduce_device: %s" % lib.wb200_last_error(ctx).decode())
-            sh["S"] = nout.value
-            total_auc += auc.value
-            if collect is not None:
-                st = lib.wb200_last_stats(ctx).contents
-                collect.append((sh["I"], sh["S"], st.ms_count, st.ms_emit, st.kernels, st.slow_segments, st.limbs))
-        t = torch.tensor([total_auc], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t)   # whole-genome AUC scalar: the path's only exchange step
-        return t
+    checker = None
+    if not args.no_cpu:
+        ncpu = os.cpu_count() or 1
+        checker = ParityChecker(torch, max(1, min(32, ncpu // (4 * world) if ncpu >= 8 * world else ncpu // world)))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
-    per_launch = []
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        auc_t = step(per_launch)
-    ev1.record()
-    barrier()
-    sampler.stop_flag = True
-    elapsed_ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    ms_per_step = elapsed_ms / args.steps
-    genome_bp = float(sum(lengths))
-    value = genome_bp / 1e6 / (ms_per_step / 1e3)
-
-    # roofline of the dominant kernel (emit_kernel): algorithmic bytes 16 B per
-    # input interval read + 16 B per segment written, per launch; duration from
-    # CUDA events recorded around the launches on the launching stream.
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    by = sum(16.0 * i + 16.0 * s for i, s, *_ in per_launch)
-    t_emit = sum(r[3] for r in per_launch) / 1e3
-    t_count = sum(r[2] for r in per_launch) / 1e3
-    achieved = by / t_emit / 1e9 if t_emit > 0 else 0.0
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu capture
+    traffic_ratio = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes / algorithmic bytes from the committed ncu --set full capture
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("emit_kernel_dram_bytes_per_algorithmic_byte")
-    roofline = {"bound": "hbm", "kernel": DOMINANT_KERNEL, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": (traffic * by / len(per_launch)) if traffic else None,
-                "peak_source": peak_src, "algorithmic_bytes_per_step": by / args.steps,
-                "algorithmic_bytes_per_launch": by / max(1, len(per_launch)),
-                "emit_ms_per_step": 1e3 * t_emit / args.steps, "cursor_ms_per_step": 1e3 * t_count / args.steps,
-                "path_frac": (by / (t_emit + t_count) / 1e9) / peak if t_emit + t_count > 0 else 0.0,
-                # exact-sum format the library chose from the value range: 32-bit limbs per position (1: values like
-                # this generator's; 2: full float32 mantissas; 3: wider), 0 for the statistics without it
-                "accumulator_limbs": max((r[6] for r in per_launch), default=0)}
-    launches = sum(r[4] for r in per_launch)
-    seg_local = sum(sh["S"] for sh in shards)
-    int_local = sum(sh["I"] for sh in shards)
-    tot = torch.tensor([seg_local, int_local], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tot)
-    slow = sum(r[5] for r in per_launch)
-    checksum = None
-    if os.environ.get("WB200_BENCH_CHECKSUM"):      # development: order-sensitive digest of every output array
-        acc = torch.zeros((), dtype=torch.int64, device=dev)
-        for sh in shards:
-            S = sh["S"]
-            k = torch.arange(1, S + 1, device=dev, dtype=torch.int64)
-            acc += (sh["out"][0][:S].long() * k).sum() * 3 + (sh["out"][1][:S].long() * k).sum() * 5
-            acc += (sh["out"][2][:S].view(torch.int64) * k).sum()
-            del k
-        checksum = int(acc.item())
+        traffic_ratio = json.load(open(tpath)).get("emit_kernel_dram_bytes_per_algorithmic_byte")
 
-    # end to end through the host-buffer entry point: pinned host tracks ->
-    # H2D -> kernels -> D2H of the segments, every step, timed with the wall
-    # clock around synchronous calls (max over ranks).
-    e2e = None
-    if not args.no_e2e:
-        e2e = run_e2e(torch, dist, lib, ctx, shards, dev, world, genome_bp, max(1, min(args.steps, 3)))
-        e2e["host_thread_cpus"] = int(local_cpus)     # CPUs local to this rank's GPU the host thread was pinned to (0: not pinned)
+    def run_workload(wl, headline):
+        N, op = wl["N"], wl["op"]
+        use = [sh for sh in shards if "chroms" not in wl or names[sh["ci"]] in wl["chroms"]]
+        if SCALE < 1.0 and "chroms" in wl:
+            use = shards
+        wl_lengths = [lengths[i] for i in range(len(lengths)) if "chroms" not in wl or SCALE < 1.0 or names[i] in wl["chroms"]]
+        genome_bp = float(sum(wl_lengths))
+        # outputs: one arena per workload
+        caps = [int(min(2 * int(sh["off"][N]) + 1, sh["L"] + 1)) for sh in use]
+        tot = sum(caps) + 16
+        arena_s = torch.empty(tot, dtype=torch.int32, device=dev)
+        arena_e = torch.empty(tot, dtype=torch.int32, device=dev)
+        arena_v = torch.empty(tot, dtype=torch.float64, device=dev)
+        arr = (CDeviceShard * max(1, len(use)))()
+        offs, outs, o = [], [], 0
+        for k, sh in enumerate(use):
+            off = np.ascontiguousarray(sh["off"][:N + 1])
+            offs.append(off)
+            o = (o + 3) & ~3                       # 16-byte aligned output slices
+            outs.append((arena_s[o:o + caps[k]], arena_e[o:o + caps[k]], arena_v[o:o + caps[k]]))
+            vals = sh["v32"] if wl["f32"] else sh["v"]
+            arr[k] = CDeviceShard(sh["s"].data_ptr(), sh["e"].data_ptr(), vals.data_ptr(), off.ctypes.data, 1, sh["L"] + 1,
+                                  outs[k][0].data_ptr(), outs[k][1].data_ptr(), outs[k][2].data_ptr(), caps[k])
+            o += caps[k]
+        dflt = np.zeros(N, np.float64)
+        dv = C.c_double(0)
+        per_launch = []
+        kernels = 0
 
-    # the device text sink on this rank's smallest shard, outside the timed region:
-    # `write_bg` of the HBM-resident segments, D2H of the text included
-    sink = None
-    if rank == 0 and shards and not args.no_e2e and BENCH_OP in ("sum", "mean"):
-        from wiggletools_b200._lib import CSinkState
-        sh = min(shards, key=lambda x: x["S"])
-        best = None
-        for rep in range(3):
-            state = CSinkState(0, 0, 0)
-            text, nbytes = C.c_char_p(), C.c_int64(0)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            rc = lib.wb200_format_device(ctx, 1, names[sh["ci"]].encode(), sh["out"][0].data_ptr(), sh["out"][1].data_ptr(),
-                                         sh["out"][2].data_ptr(), sh["S"], C.addressof(state), C.addressof(text), C.addressof(nbytes))
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-            if rc != 0:
-                raise SystemExit("wb200_format_device: %s" % lib.wb200_last_error(ctx).decode())
-            if rep and (best is None or dt < best):
-                best = dt
-        sink = {"mode": "write_bg", "shard": names[sh["ci"]], "records": int(state.records), "text_bytes": int(nbytes.value),
-                "ms": 1e3 * best, "records_per_s": state.records / best, "d2h_GBps": nbytes.value / best / 1e9,
-                "note": "wb200_format_device on HBM-resident segments, text copied to pinned host memory inside the call"}
+        def step(collect):
+            nonlocal kernels
+            total_auc = 0.0
+            if use:
+                rc = lib.wb200_reduce_device_batch(ctx, OP_CODE[op], N, N, 0, dflt.ctypes.data, len(use), C.addressof(arr), C.addressof(dv))
+                if rc != 0:
+                    raise SystemExit("wb200_reduce_device_batch: %s" % lib.wb200_last_error(ctx).decode())
+                for k in range(len(use)):
+                    total_auc += arr[k].auc
+                    if collect:
+                        per_launch.append((int(offs[k][N]), int(arr[k].n_out), arr[k].ms_cursor, arr[k].ms_sweep, int(arr[k].slow_segments), int(arr[k].limbs)))
+                if collect:
+                    kernels += lib.wb200_last_stats(ctx).contents.kernels
+            t = torch.tensor([total_auc], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t)   # whole-genome AUC scalar: the path's only exchange step
+            return t
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        cores = max(1, (os.cpu_count() or 1) // 4)     # the reference scales best on a subset of a large host
-        cpu = cpu_reference_sample(N_TRACKS, 12.0 * (64.0 / N_TRACKS) ** 2, cores)
+        K = args.steps if headline else max(3, min(args.steps, 5))
+        Wm = max(3, args.warmup) if not headline else args.warmup
+        for _ in range(Wm):
+            step(False)
+        barrier()
+        sampler = ClockSampler(local) if headline else None
+        if sampler:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(K):
+            auc_t = step(True)
+        ev1.record()
+        barrier()
+        if sampler:
+            sampler.stop_flag = True
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_per_step = float(t.item()) / K
+        value = genome_bp / 1e6 / (ms_per_step / 1e3)
 
-    if rank == 0:
-        line = {"metric": "Mbp/s, %s over %d tracks" % (BENCH_OP, N_TRACKS), "value": value, "unit": "Mbp/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        # roofline of the dominant kernel: algorithmic bytes 16 B per input interval read + 16 B per
+        # segment written, per launch; duration from CUDA events the library records around each
+        # launch on the launching stream.
+        by = sum(16.0 * i + 16.0 * s for i, s, *_ in per_launch)
+        t_emit = sum(r[3] for r in per_launch) / 1e3
+        t_count = sum(r[2] for r in per_launch) / 1e3
+        achieved = by / t_emit / 1e9 if t_emit > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": dominant_kernel(op), "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak,
+                    "traffic": (traffic_ratio * by / len(per_launch)) if traffic_ratio and per_launch and dominant_kernel(op) == "fastsum_kernel" else None,
+                    "traffic_source": "ncu --set full capture of one launch (profiles/traffic.json): measured dram bytes / algorithmic bytes, times this run's algorithmic bytes per launch",
+                    "peak_source": peak_src, "algorithmic_bytes_per_step": by / K,
+                    "algorithmic_bytes_per_launch": by / max(1, len(per_launch)),
+                    "emit_ms_per_step": 1e3 * t_emit / K, "cursor_ms_per_step": 1e3 * t_count / K,
+                    "path_frac": (by / (t_emit + t_count) / 1e9) / peak if t_emit + t_count > 0 else 0.0,
+                    # exact-sum format the library chose from the value range: 32-bit limbs per position (1: values like
+                    # this generator's; 2: full float32 mantissas; 3: wider), 0 for the statistics without it
+                    "accumulator_limbs": max((r[5] for r in per_launch), default=0)}
+        seg_local = sum(int(arr[k].n_out) for k in range(len(use)))
+        int_local = sum(int(offs[k][N]) for k in range(len(use)))
+        slow = sum(r[4] for r in per_launch) // max(1, K)
+        tot_t = torch.tensor([seg_local, int_local, slow, kernels], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tot_t)
+
+        # parity gate on what the timed region left in HBM: this rank's smallest shard (whole for
+        # N <= 64, its first 8 Mbp otherwise) and, for N <= 64, the last 2 Mbp of its largest one
+        parity, cpu = None, None
+        if checker is not None and use:
+            order = sorted(range(len(use)), key=lambda k: use[k]["L"])
+            regions = []
+            k0 = order[0]
+            L0 = use[k0]["L"]
+            b0 = L0 + 1 if N <= 64 else min(L0 + 1, 1 + int(8e6))
+            regions.append((use[k0], 1, b0, outs[k0][0], outs[k0][1], outs[k0][2], int(arr[k0].n_out)))
+            if N <= 64 and len(use) > 1:
+                k1 = order[-1]
+                L1 = use[k1]["L"]
+                regions.append((use[k1], max(1, L1 + 1 - int(2e6)), L1 + 1, outs[k1][0], outs[k1][1], outs[k1][2], int(arr[k1].n_out)))
+            parity, cpu = checker.check(wl, regions)
+        pk = torch.tensor([1.0 if (parity is None or parity["ok"]) else 0.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(pk, op=dist.ReduceOp.MIN)
+        if parity is not None:
+            parity["all_ranks_ok"] = bool(pk.item() > 0.5)
+
+        line = {"metric": "Mbp/s, %s over %d tracks" % (op, N), "value": value, "unit": "Mbp/s", "n_gpus": world,
+                "steps": K, "warmup": Wm, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(lengths, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": int(launches), "clocks": sampler.summary(),
-                "segments": int(tot[0].item()), "intervals": int(tot[1].item()), "slow_segments": int(slow),
+                "config": workload_config(op, N, wl_lengths, world, wl["f32"]), "roofline": roofline, "parity": parity,
+                "cpu_baseline": cpu, "gpu_launches": int(tot_t[3].item()),
+                "segments": int(tot_t[0].item()), "intervals": int(tot_t[1].item()), "slow_segments": int(tot_t[2].item()),
                 "auc": float(auc_t.item())}
-        if sink is not None:
-            line["sink"] = sink
-        if checksum is not None:
-            line["checksum"] = checksum
-        ph = (C.c_uint64 * 16)()
-        lib.wb200_debug_phases(ctx, ph)
-        if any(ph):                                   # diagnostic builds only
-            names_ = ["clear", "events", "scan", "count", "compact", "lookback", "emit", "window_total", "windows", "lookback_polls", "lookback_steps"]
-            line["phase_cycles_per_window"] = {n: ph[k] / max(1, ph[8]) for k, n in enumerate(names_)}
+        if "config" in wl:
+            line["config"]["baseline_config"] = wl["config"]
+        if sampler:
+            line["clocks"] = sampler.summary()
+        state = dict(use=use, outs=outs, arr=arr, offs=offs, genome_bp=genome_bp, ok=bool(pk.item() > 0.5))
+        return line, state
+
+    lines, all_ok = [], True
+    for wi, wl in enumerate(wls):
+        headline = wi == 0
+        line, st = run_workload(wl, headline)
+        all_ok = all_ok and st["ok"]
+        # end to end through the host-buffer entry point: pinned host tracks -> H2D -> kernels -> D2H of
+        # the segments, every step, timed with the wall clock around synchronous calls (max over ranks)
+        if wl["e2e"] and not args.no_e2e:
+            e2e = run_e2e(torch, dist, lib, ctx, wl, st, dev, world, max(1, args.steps if headline else min(args.steps, 3)))
+            e2e["host_thread_cpus"] = int(local_cpus)     # CPUs local to this rank's GPU the host thread was pinned to (0: not pinned)
+            line["e2e"] = e2e
+        elif not headline:
+            line["e2e"] = None
+        # the device text sink on this rank's smallest shard, outside the timed region:
+        # `write_bg` of the HBM-resident segments, D2H of the text included
+        if headline and rank == 0 and st["use"] and not args.no_e2e and wl["op"] in ("sum", "mean"):
+            line["sink"] = run_sink(torch, lib, ctx, st, names)
+        if headline:
+            ph = (C.c_uint64 * 16)()
+            lib.wb200_debug_phases(ctx, ph)
+            if any(ph):                                   # diagnostic builds only
+                names_ = ["clear", "events", "scan", "count", "compact", "lookback", "emit", "window_total", "windows", "lookback_polls", "lookback_steps"]
+                line["phase_cycles_per_window"] = {n: ph[k] / max(1, ph[8]) for k, n in enumerate(names_)}
+            if os.environ.get("WB200_BENCH_CHECKSUM"):      # development: order-sensitive digest of every output array
+                acc = torch.zeros((), dtype=torch.int64, device=dev)
+                for k in range(len(st["use"])):
+                    S = int(st["arr"][k].n_out)
+                    idx = torch.arange(1, S + 1, device=dev, dtype=torch.int64)
+                    acc += (st["outs"][k][0][:S].long() * idx).sum() * 3 + (st["outs"][k][1][:S].long() * idx).sum() * 5
+                    acc += (st["outs"][k][2][:S].view(torch.int64) * idx).sum()
+                    del idx
+                line["checksum"] = int(acc.item())
+        lines.append(line)
+        del st
+        torch.cuda.empty_cache()
+
+    if checker is not None:
+        checker.close()
+    if rank == 0:
+        line = lines[0]
+        if "e2e" not in line:
+            line["e2e"] = None
+        if len(lines) > 1:
+            line["extra"] = lines[1:]
+        line["parity_gate"] = "passed" if all_ok else "FAILED"
         print(json.dumps(line))
     lib.wb200_destroy(ctx)
     if world > 1:
         dist.destroy_process_group()
+    if not all_ok:
+        sys.exit(1)
 
 
-def run_e2e(torch, dist, lib, ctx, shards, dev, world, genome_bp, steps):
+def run_sink(torch, lib, ctx, st, names):
+    from wiggletools_b200._lib import CSinkState
+    k = min(range(len(st["use"])), key=lambda j: int(st["arr"][j].n_out))
+    sh, S = st["use"][k], int(st["arr"][k].n_out)
+    best = None
+    for rep in range(3):
+        state = CSinkState(0, 0, 0)
+        text, nbytes = C.c_char_p(), C.c_int64(0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rc = lib.wb200_format_device(ctx, 1, names[sh["ci"]].encode(), st["outs"][k][0].data_ptr(), st["outs"][k][1].data_ptr(),
+                                     st["outs"][k][2].data_ptr(), S, C.addressof(state), C.addressof(text), C.addressof(nbytes))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if rc != 0:
+            raise SystemExit("wb200_format_device: %s" % lib.wb200_last_error(ctx).decode())
+        if rep and (best is None or dt < best):
+            best = dt
+    return {"mode": "write_bg", "shard": names[sh["ci"]], "records": int(state.records), "text_bytes": int(nbytes.value),
+            "ms": 1e3 * best, "records_per_s": state.records / best, "d2h_GBps": nbytes.value / best / 1e9,
+            "note": "wb200_format_device on HBM-resident segments, text copied to pinned host memory inside the call"}
+
+
+def run_e2e(torch, dist, lib, ctx, wl, st, dev, world, steps):
     """The call a user of the library makes: wb200_reduce_host_batch on pinned host
     SoA tracks -> pinned host segments (H2D, kernels, D2H all inside the timed region)."""
     from wiggletools_b200._lib import CTrack, CSegments
-    nsh = len(shards)
-    n = len(shards[0]["off"]) - 1 if nsh else 0
+    use, n = st["use"], wl["N"]
+    nsh = len(use)
     arr = (CTrack * max(1, nsh * n))()
     host = []
     h2d = 0
-    for c, sh in enumerate(shards):
-        hs = sh["s"].cpu().pin_memory(); he = sh["e"].cpu().pin_memory(); hv = sh["v"].cpu().pin_memory()
+    for c, sh in enumerate(use):
+        off = st["offs"][c]
+        m = int(off[n])
+        vals = sh["v32"] if wl["f32"] else sh["v"]
+        hs = sh["s"][:m].cpu().pin_memory(); he = sh["e"][:m].cpu().pin_memory(); hv = vals[:m].cpu().pin_memory()
         for i in range(n):
-            a, b = int(sh["off"][i]), int(sh["off"][i + 1])
+            a, b = int(off[i]), int(off[i + 1])
             arr[c * n + i] = CTrack(hs.data_ptr() + 4 * a, he.data_ptr() + 4 * a, hv.data_ptr() + 8 * a, b - a, 0.0)
         host.append((hs, he, hv))
-        h2d += 16 * sh["I"]
+        h2d += 16 * m
     out = (CSegments * max(1, nsh))()
     d2h = 0
 
@@ -447,13 +703,15 @@ def run_e2e(torch, dist, lib, ctx, shards, dev, world, genome_bp, steps):
         nonlocal d2h
         if not nsh:
             return
-        rc = lib.wb200_reduce_host_batch(ctx, 2, nsh, n, n, 0, C.addressof(arr), C.addressof(out))
+        rc = lib.wb200_reduce_host_batch(ctx, OP_CODE[wl["op"]], nsh, n, n, 0, C.addressof(arr), C.addressof(out))
         if rc != 0:
             raise SystemExit("wb200_reduce_host_batch: %s" % lib.wb200_last_error(ctx).decode())
         d2h = sum(16 * out[c].n for c in range(nsh))
 
     one()   # first call sizes the pinned result arena
     one()
+    # the segments that came back over PCIe are the ones the resident run left in HBM
+    same = all(int(out[c].n) == int(st["arr"][c].n_out) for c in range(nsh))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -467,10 +725,14 @@ def run_e2e(torch, dist, lib, ctx, shards, dev, world, genome_bp, steps):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tb)
-    dt = float(t.item())
-    return {"value": genome_bp / 1e6 / (dt / steps), "unit": "Mbp/s", "h2d_bytes_per_step": int(tb[0].item()),
-            "d2h_bytes_per_step": int(tb[1].item()), "steps": steps, "ms_per_step": 1e3 * dt / steps,
-            "api": "wb200_reduce_host_batch (pinned host SoA in, pinned host segments out; staging, kernels and read-back pipelined per chromosome)"}
+    dtm = float(t.item())
+    res = {"value": st["genome_bp"] / 1e6 / (dtm / steps), "unit": "Mbp/s", "h2d_bytes_per_step": int(tb[0].item()),
+           "d2h_bytes_per_step": int(tb[1].item()), "steps": steps, "ms_per_step": 1e3 * dtm / steps,
+           "segments_match_resident_run": bool(same),
+           "this_rank_copy_GBps": (h2d + d2h) / (dt / steps) / 1e9 if dt > 0 else 0.0,
+           "api": "wb200_reduce_host_batch (pinned host SoA in, pinned host segments out; staging, kernels and read-back pipelined per chromosome)"}
+    del host
+    return res
 
 
 if __name__ == "__main__":

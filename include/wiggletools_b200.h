@@ -156,6 +156,31 @@ int wb200_reduce_device(wb200_ctx *ctx, int op, int ntracks, int nset1, int stri
                         int32_t *d_out_start, int32_t *d_out_end, double *d_out_value,
                         int64_t out_cap, int64_t *n_out, double *default_out, double *auc_out);
 
+/* Several HBM-resident chromosome shards in one call (all with the same tracks count and
+ * defaults).  The value samples of all shards are read back with one synchronisation, then the
+ * cursor kernel and the sweep of every shard are queued back to back and all results are read at
+ * the end: two host round trips per call instead of two per chromosome.  Results are identical
+ * to nshards calls of wb200_reduce_device. */
+typedef struct wb200_device_shard {
+	const int32_t *d_start;      /* in: device, all tracks of the shard concatenated */
+	const int32_t *d_end;
+	const double *d_value;
+	const int64_t *h_off;        /* in: host, ntracks+1 offsets */
+	int32_t pos_lo, pos_hi;
+	int32_t *d_out_start;        /* in: device output arrays of out_cap segments */
+	int32_t *d_out_end;
+	double *d_out_value;
+	int64_t out_cap;
+	int64_t n_out;               /* out: S */
+	double auc;                  /* out */
+	int64_t slow_segments;       /* out */
+	float ms_cursor, ms_sweep;   /* out: device time of the two kernels of this shard (CUDA events) */
+	int32_t limbs;               /* out: accumulator limbs of the exact sum path, else 0 */
+	int32_t sweep_kernel;        /* out: 1 = fastsum_kernel ran */
+} wb200_device_shard;
+int wb200_reduce_device_batch(wb200_ctx *ctx, int op, int ntracks, int nset1, int strict, const double *h_defaults,
+                              int nshards, wb200_device_shard *shards, double *default_out);
+
 /* -- whole-genome scalars ------------------------------------------------ */
 /* Pearson correlation of two tracks over one chromosome shard: returns the six
  * running moments so that shards (chromosomes, GPUs) can be merged exactly as

@@ -3,8 +3,8 @@
 #   profiles/kexp.sh [scale] -> gpurun_out/kexp.jsonl (one bench line per variant, tagged)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-export WB200_BENCH_SCALE=${1:-0.25} WB200_BENCH_CHECKSUM=1
-out=gpurun_out/kexp.jsonl
+export WB200_BENCH_SCALE=${1:-0.25} WB200_BENCH_CHECKSUM=1 WB200_BENCH_EXTRAS=0
+out=${KEXP_OUT:-gpurun_out/kexp.jsonl}
 : > $out
 run() {
   tag=$1; shift

@@ -30,6 +30,15 @@ class CStats(C.Structure):
                 ("limbs", C.c_int32), ("sweep_kernel", C.c_int32)]
 
 
+class CDeviceShard(C.Structure):
+    """wb200_device_shard (include/wiggletools_b200.h)."""
+    _fields_ = [("d_start", C.c_void_p), ("d_end", C.c_void_p), ("d_value", C.c_void_p), ("h_off", C.c_void_p),
+                ("pos_lo", C.c_int32), ("pos_hi", C.c_int32),
+                ("d_out_start", C.c_void_p), ("d_out_end", C.c_void_p), ("d_out_value", C.c_void_p), ("out_cap", C.c_int64),
+                ("n_out", C.c_int64), ("auc", C.c_double), ("slow_segments", C.c_int64),
+                ("ms_cursor", C.c_float), ("ms_sweep", C.c_float), ("limbs", C.c_int32), ("sweep_kernel", C.c_int32)]
+
+
 class CMap(C.Structure):
     _fields_ = [("op", C.c_int32), ("reserved", C.c_int32), ("arg", C.c_double)]
 
@@ -70,6 +79,7 @@ def load():
         C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.wb200_reduce_device_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.wb200_pearson_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.wb200_pearson_pair_host.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.wb200_pearson_merge.argtypes = [C.c_void_p, C.c_void_p]
@@ -107,7 +117,7 @@ def load():
 EXPORTS = [
     "wb200_create", "wb200_destroy", "wb200_last_error", "wb200_last_stats", "wb200_set_stream",
     "wb200_set_window", "wb200_bind_host_thread", "wb200_host_alloc", "wb200_host_free", "wb200_reduce_host", "wb200_reduce_host_batch",
-    "wb200_reduce_device", "wb200_pearson_host", "wb200_pearson_pair_host", "wb200_pearson_merge", "wb200_pearson_result",
+    "wb200_reduce_device", "wb200_reduce_device_batch", "wb200_pearson_host", "wb200_pearson_pair_host", "wb200_pearson_merge", "wb200_pearson_result",
     "wb200_tdist_Q", "wb200_bw_open", "wb200_bw_close", "wb200_bw_last_error", "wb200_bw_nchrom", "wb200_bw_chrom_name",
     "wb200_bw_chrom_length", "wb200_bw_set_stretch", "wb200_bw_decode_chrom", "wb200_debug_phases", "wb200_debug_format_value",
     "wb200_format_device", "wb200_format_host", "wb200_reduce_format_host", "wb200_set_input_maps", "wb200_map_default",

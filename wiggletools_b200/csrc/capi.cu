@@ -75,6 +75,10 @@ struct wb200_ctx {
 	HostBuf h_arena;
 	std::vector<cudaEvent_t> pipe_events;
 	unsigned long long diag[16] = {0};      // diagnostic builds: accumulated phase counters
+	// batch device entry (wb200_reduce_device_batch): per-shard tables and result slots
+	DevBuf b_tables, b_small;
+	HostBuf hb_tables, hb_small;
+	std::vector<cudaEvent_t> batch_events;
 	// text sink (wb200_format_*)
 	DevBuf w_certain, w_heads, w_hp, w_tile_count, w_tile_base, w_small, w_bbytes, w_boff, w_text;
 	DevBuf w_in_start, w_in_end, w_in_value;
@@ -167,14 +171,12 @@ bool valid_op(int op) {
 
 int ceil_log2(long long v) { int l = 0; while ((1ll << l) < v) l++; return l; }
 
-// Core: inputs already resident on the device.
-int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
+// Host-side plan of one chromosome shard: argument checks (the reference's arity rules), window
+// size, job geometry.  Buffers are attached by the caller.
+int plan_shard(wb200_ctx *ctx, int op, int N, int &n1, int &strict, const int64_t *h_off, const double *h_dflt,
                const int32_t *d_start, const int32_t *d_end, const double *d_value,
-               const int64_t *h_off, const double *h_dflt, int32_t pos_lo, int32_t pos_hi,
-               int32_t *d_out_start, int32_t *d_out_end, double *d_out_value, int64_t out_cap,
-               int64_t *n_out, double *default_out, double *auc_out, double *moments_out = nullptr, bool force_row = false,
-               int px = 0, int py = 1, int min_limbs = 1) {
-	if (!valid_op(op) && !(op == OP_PEARSON && moments_out && N >= 2)) return fail(ctx, WB200_EINVAL, "unknown op");
+               int32_t pos_lo, int32_t pos_hi, bool moments, int px, int py, Job &job) {
+	if (!valid_op(op) && !(op == OP_PEARSON && moments && N >= 2)) return fail(ctx, WB200_EINVAL, "unknown op");
 	if (N < 1) return fail(ctx, WB200_EINVAL, "need at least one track");
 	const bool setop = (op == OP_TTEST || op == OP_MWU);
 	const bool fill = (op == OP_FILLIN || op == OP_TRIMFILL);
@@ -193,11 +195,6 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 	for (int i = 0; i < N; i++)
 		if (h_off[i + 1] < h_off[i] || h_off[i + 1] - h_off[i] > INT32_MAX)
 			return fail(ctx, WB200_EINVAL, "bad track offsets");
-
-	cudaStream_t s = ctx->stream;
-	wb200_stats &st = ctx->stats;
-	st = wb200_stats{};
-	st.intervals = I;
 
 	// window size
 	int wlog = 12;
@@ -218,7 +215,7 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 	const int64_t span = (int64_t) pos_hi - pos_lo;
 	const int nw = (int) (span >> wlog) + 1;
 
-	Job job{};
+	job = Job{};
 	job.start = d_start; job.end = d_end; job.value = d_value;
 	job.I = I;
 	{
@@ -228,9 +225,105 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 	}
 	job.N = N; job.n1 = n1; job.strict = strict ? 1 : 0; job.op = op;
 	job.p0 = pos_lo; job.wlog = wlog; job.nw = nw;
+	job.cstride = (N + 3) & ~3;
 	job.px = px; job.py = py;
 	{ const char *e = getenv("WB200_LB_WARPS"); job.lb_warps = e ? std::max(1, std::min(WARPS, atoi(e))) : 1; }
+	if (op == OP_MWU) {
+		// integer division in both moments, src/setComparisons.c:386-387
+		job.mwu_mu = (double) (n1 * n2 / 2);
+		job.mwu_sigma = std::sqrt((double) (n1 * n2 * (n1 + n2 + 1) / 12));
+	}
+	return WB200_OK;
+}
+
+// whether the statistic has an exact fixed-point path for these defaults (then the values are sampled)
+bool wants_format(int op, int N, int64_t I, const double *h_dflt, bool force_row) {
+	const bool sum_like = (op == OP_SUM || op == OP_MEAN);
+	const bool moment_like = (op == OP_VAR || op == OP_STDDEV || op == OP_ENTROPY || op == OP_CV);
+	if (!(sum_like || moment_like) || I <= 0 || force_row) return false;
+	for (int i = 0; i < N; i++) if (!std::isfinite(h_dflt[i]) || (moment_like && h_dflt[i] != 0)) return false;
+	return true;
+}
+
+// Fixed-point format of the exact paths from the sampled value range: sets job.fast / fx_*,
+// fills hm_fx[N] (fixed-point defaults) when the sum path is chosen.
+void choose_format(Job &job, int op, int N, const double *h_dflt, double maxabs, long long lsb_key, int min_limbs, int64_t *hm_fx) {
+	const bool sum_like = (op == OP_SUM || op == OP_MEAN);
+	job.fast = 0;
+	for (int i = 0; i < N; i++) maxabs = std::max(maxabs, std::fabs(h_dflt[i]));
+	int emax = 0;
+	if (maxabs > 0) { std::frexp(maxabs, &emax); }   // maxabs < 2^emax
+	const int l2n = ceil_log2(2 * (int64_t) N);
+	const int lw = 32 - l2n;
+	if (sum_like) {
+		// format: |m| < 2^mbits in one, two or three 32-bit limbs per position.
+		//  one  : the sampled values have no bit below 2^q1, q1 = emax + 2 - (29 - l2n): a single
+		//         32-bit accumulator holds every per-position delta sum (integer-like and
+		//         coarse fixed-point data, e.g. read counts);
+		//  two  : float32-grade inputs (24-bit mantissas) over a moderate exponent range;
+		//  three: anything wider.
+		// A value finer than the chosen 2^q poisons its interval; those segments are recomputed
+		// by the fix-up kernel, and a run with too many of them is repeated one format wider.
+		const int cap1 = 29 - l2n;
+		const int cap2 = 29 - l2n + lw;
+		const int cap3 = std::min(29 - l2n + 2 * lw, 62 - ceil_log2(N + 1));
+		const char *env = getenv("WB200_LIMBS");
+		const int forced = env ? atoi(env) : 0;
+		const int lsb_q = lsb_key > 0 ? (int) (2048 - lsb_key) : 4096;          // finest significant bit seen
+		int first = std::max(min_limbs, (forced >= 1 && forced <= 3) ? forced : (cap1 >= 8 && lsb_q >= emax + 2 - cap1 ? 1 : (cap2 >= 40 ? 2 : 3)));
+		bool ok = false;
+		for (int limbs = first; limbs <= 3 && !ok; limbs++) {
+			const int mbits = limbs == 1 ? cap1 : limbs == 2 ? cap2 : cap3;
+			if (mbits < 4) continue;
+			job.fx_mbits = mbits;
+			job.fx_limbs = limbs;
+			job.fx_q = emax + 2 - mbits;           // two bits of headroom above the sampled maximum
+			job.fx_q = std::max(-1000, std::min(1000, job.fx_q));
+			const double inv = std::ldexp(1.0, -job.fx_q), lim = std::ldexp(1.0, mbits);
+			long long base = 0;
+			ok = true;
+			for (int i = 0; i < N && ok; i++) {
+				double t = h_dflt[i] * inv;
+				if (!(std::fabs(t) < lim) || t != std::rint(t)) ok = false;
+				else { hm_fx[i] = (int64_t) t; base += hm_fx[i]; }
+			}
+			if (ok) { job.fast = 1; job.fx_base = base; }
+		}
+	} else {
+		// squares must stay exact in 64 bits: m = v 2^-q with q the finest bit seen in
+		// the sample, |m| < 2^mbits, N m^2 < 2^62.  Finer or larger values poison.
+		const int capm = std::min(30, (61 - ceil_log2(N + 1)) / 2);
+		const int q = lsb_key > 0 ? (int) (2048 - lsb_key) : 0;
+		if (emax - q <= capm && 2 * capm <= 29 - l2n + 2 * lw) {
+			job.fast = 2;
+			job.fx_q = std::max(-1000, std::min(1000, q));
+			job.fx_mbits = capm;
+			job.fx_base = 0;
+		}
+	}
+}
+
+// Core: inputs already resident on the device.
+int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
+               const int32_t *d_start, const int32_t *d_end, const double *d_value,
+               const int64_t *h_off, const double *h_dflt, int32_t pos_lo, int32_t pos_hi,
+               int32_t *d_out_start, int32_t *d_out_end, double *d_out_value, int64_t out_cap,
+               int64_t *n_out, double *default_out, double *auc_out, double *moments_out = nullptr, bool force_row = false,
+               int px = 0, int py = 1, int min_limbs = 1) {
+	Job job{};
+	{
+		int rc = plan_shard(ctx, op, N, n1, strict, h_off, h_dflt, d_start, d_end, d_value, pos_lo, pos_hi, moments_out != nullptr, px, py, job);
+		if (rc != WB200_OK) return rc;
+	}
+	const bool setop = (op == OP_TTEST || op == OP_MWU);
+	const int64_t I = job.I;
+	const int nw = job.nw, wlog = job.wlog;
 	job.out_start = d_out_start; job.out_end = d_out_end; job.out_value = d_out_value; job.out_cap = out_cap;
+
+	cudaStream_t s = ctx->stream;
+	wb200_stats &st = ctx->stats;
+	st = wb200_stats{};
+	st.intervals = I;
 
 	// small tables
 	CK(ctx->off.ensure((N + 1) * sizeof(int64_t)));
@@ -242,7 +335,7 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 	int64_t *hm_fx = (int64_t *) (hm_dflt + N);
 	memcpy(hm_off, h_off, (N + 1) * sizeof(int64_t));
 	memcpy(hm_dflt, h_dflt, N * sizeof(double));
-	CK(ctx->cursor.ensure((size_t) (nw + 1) * N * sizeof(int32_t)));
+	CK(ctx->cursor.ensure((size_t) (nw + 1) * job.cstride * sizeof(int32_t)));
 	CK(ctx->state.ensure((size_t) nw * sizeof(unsigned long long)));
 	CK(ctx->aucp.ensure((size_t) nw * WARPS * sizeof(double)));
 	CK(ctx->small.ensure(256));
@@ -279,87 +372,20 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 	// fixed-point fast paths: sum / mean (one exact accumulator) and var / stddev /
 	// CV (exact sum and sum of squares)
 	job.fast = 0;
-	const bool sum_like = (op == OP_SUM || op == OP_MEAN);
-	const bool moment_like = (op == OP_VAR || op == OP_STDDEV || op == OP_ENTROPY || op == OP_CV);
-	if ((sum_like || moment_like) && I > 0 && !force_row) {
-		bool ok = true;
-		for (int i = 0; i < N; i++) if (!std::isfinite(h_dflt[i]) || (moment_like && h_dflt[i] != 0)) ok = false;
-		if (ok) {
-			int64_t stride = std::max<int64_t>(1, I / (1 << 16));
-			CK(launch_sample_maxabs(d_value, I, stride, d_small, s));
-			st.kernels++;
-			CK(cudaMemcpyAsync(ctx->h_small.p, d_small, 16, cudaMemcpyDeviceToHost, s));
-			CK(cudaStreamSynchronize(s));
-			double maxabs = ctx->h_small.as<double>()[0];
-			const long long lsb_key = ctx->h_small.as<long long>()[1];
-			for (int i = 0; i < N; i++) maxabs = std::max(maxabs, std::fabs(h_dflt[i]));
-			int emax = 0;
-			if (maxabs > 0) { std::frexp(maxabs, &emax); }   // maxabs < 2^emax
-			const int l2n = ceil_log2(2 * (int64_t) N);
-			const int lw = 32 - l2n;
-			if (sum_like) {
-				// format: |m| < 2^mbits in one, two or three 32-bit limbs per position.
-				//  one  : the sampled values have no bit below 2^q1, q1 = emax + 2 - (29 - l2n): a single
-				//         32-bit accumulator holds every per-position delta sum (integer-like and
-				//         coarse fixed-point data, e.g. read counts);
-				//  two  : float32-grade inputs (24-bit mantissas) over a moderate exponent range;
-				//  three: anything wider.
-				// A value finer than the chosen 2^q poisons its interval; those segments are recomputed
-				// by the fix-up kernel, and a run with too many of them is repeated one format wider.
-				const int cap1 = 29 - l2n;
-				const int cap2 = 29 - l2n + lw;
-				const int cap3 = std::min(29 - l2n + 2 * lw, 62 - ceil_log2(N + 1));
-				const char *env = getenv("WB200_LIMBS");
-				const int forced = env ? atoi(env) : 0;
-				const int lsb_q = lsb_key > 0 ? (int) (2048 - lsb_key) : 4096;          // finest significant bit seen
-				int first = std::max(min_limbs, (forced >= 1 && forced <= 3) ? forced : (cap1 >= 8 && lsb_q >= emax + 2 - cap1 ? 1 : (cap2 >= 40 ? 2 : 3)));
-				ok = false;
-				for (int limbs = first; limbs <= 3 && !ok; limbs++) {
-					const int mbits = limbs == 1 ? cap1 : limbs == 2 ? cap2 : cap3;
-					if (mbits < 4) continue;
-					job.fx_mbits = mbits;
-					job.fx_limbs = limbs;
-					job.fx_q = emax + 2 - mbits;           // two bits of headroom above the sampled maximum
-					job.fx_q = std::max(-1000, std::min(1000, job.fx_q));
-					const double inv = std::ldexp(1.0, -job.fx_q), lim = std::ldexp(1.0, mbits);
-					long long base = 0;
-					ok = true;
-					for (int i = 0; i < N && ok; i++) {
-						double t = h_dflt[i] * inv;
-						if (!(std::fabs(t) < lim) || t != std::rint(t)) ok = false;
-						else { hm_fx[i] = (int64_t) t; base += hm_fx[i]; }
-					}
-					if (ok) {
-						job.fast = 1;
-						job.fx_base = base;
-						CK(cudaMemcpyAsync(ctx->dflt_fx.p, hm_fx, N * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-					}
-				}
-			} else {
-				// squares must stay exact in 64 bits: m = v 2^-q with q the finest bit seen in
-				// the sample, |m| < 2^mbits, N m^2 < 2^62.  Finer or larger values poison.
-				const int capm = std::min(30, (61 - ceil_log2(N + 1)) / 2);
-				const int q = lsb_key > 0 ? (int) (2048 - lsb_key) : 0;
-				if (emax - q <= capm && 2 * capm <= 29 - l2n + 2 * lw) {
-					job.fast = 2;
-					job.fx_q = std::max(-1000, std::min(1000, q));
-					job.fx_mbits = capm;
-					job.fx_base = 0;
-				}
-			}
-		}
+	if (wants_format(op, N, I, h_dflt, force_row)) {
+		int64_t stride = std::max<int64_t>(1, I / (1 << 16));
+		CK(launch_sample_maxabs(d_value, I, stride, d_small, s));
+		st.kernels++;
+		CK(cudaMemcpyAsync(ctx->h_small.p, d_small, 16, cudaMemcpyDeviceToHost, s));
+		CK(cudaStreamSynchronize(s));
+		choose_format(job, op, N, h_dflt, ctx->h_small.as<double>()[0], ctx->h_small.as<long long>()[1], min_limbs, hm_fx);
+		if (job.fast == 1) CK(cudaMemcpyAsync(ctx->dflt_fx.p, hm_fx, N * sizeof(int64_t), cudaMemcpyHostToDevice, s));
 	}
 	if (job.fast) {
 		job.slow_cap = std::max<int64_t>(1 << 16, out_cap / 8);
 		CK(ctx->slow_list.ensure((size_t) job.slow_cap * sizeof(long long)));
 		job.slow_list = ctx->slow_list.as<long long>();
 	}
-	if (op == OP_MWU) {
-		// integer division in both moments, src/setComparisons.c:386-387
-		job.mwu_mu = (double) (n1 * n2 / 2);
-		job.mwu_sigma = std::sqrt((double) (n1 * n2 * (n1 + n2 + 1) / 12));
-	}
-
 	size_t need = window_smem_bytes(wlog, N, true, op);
 	if (need > 227 * 1024) return fail(ctx, WB200_EUNSUPPORTED, "window does not fit shared memory; lower WB200_WINDOW");
 
@@ -467,6 +493,8 @@ void wb200_destroy(wb200_ctx *ctx) {
 		ctx->bout_start[k].release(); ctx->bout_end[k].release(); ctx->bout_value[k].release();
 	}
 	for (auto ev : ctx->pipe_events) cudaEventDestroy(ev);
+	for (auto ev : ctx->batch_events) cudaEventDestroy(ev);
+	ctx->b_tables.release(); ctx->b_small.release(); ctx->hb_tables.release(); ctx->hb_small.release();
 	if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
 	if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
 	HostBuf *h[] = {&ctx->h_small, &ctx->h_meta, &ctx->h_start, &ctx->h_end, &ctx->h_value, &ctx->h_arena};
@@ -697,6 +725,161 @@ int wb200_reduce_device(wb200_ctx *ctx, int op, int ntracks, int nset1, int stri
 	cudaSetDevice(ctx->device);
 	return run_device(ctx, op, ntracks, nset1, strict, d_start, d_end, d_value, h_off, h_defaults, pos_lo, pos_hi,
 	                  d_out_start, d_out_end, d_out_value, out_cap, n_out, default_out, auc_out);
+}
+
+// Several chromosome shards resident in HBM, one call: the value samples of all shards are read
+// with ONE synchronisation (one fixed-point format for the whole batch), then cursor kernel and
+// sweep of every shard are queued back to back on the stream and all results are read at the end.
+// Shards the optimistic path cannot finish (segments to fix up, capacity) are repeated one by one.
+int wb200_reduce_device_batch(wb200_ctx *ctx, int op, int ntracks, int nset1, int strict, const double *h_defaults,
+                              int nshards, wb200_device_shard *shards, double *default_out) {
+	if (!ctx || !shards || !h_defaults || nshards < 0) return WB200_EINVAL;
+	cudaSetDevice(ctx->device);
+	if (!ctx->map_nchain.empty()) {
+		ctx->map_chains.clear(); ctx->map_nchain.clear();
+		return fail(ctx, WB200_EUNSUPPORTED, "input maps are not applied by the batch entry points");
+	}
+	const int N = ntracks;
+	cudaStream_t s = ctx->stream;
+	std::vector<Job> jobs(nshards);
+	int64_t max_cursor = 1, max_nw = 1, max_slow = 0;
+	bool sample = nshards > 0;
+	for (int c = 0; c < nshards; c++) {
+		wb200_device_shard &h = shards[c];
+		int n1 = nset1, st_ = strict;
+		int rc = plan_shard(ctx, op, N, n1, st_, h.h_off, h_defaults, h.d_start, h.d_end, h.d_value, h.pos_lo, h.pos_hi, false, 0, 1, jobs[c]);
+		if (rc != WB200_OK) return rc;
+		Job &job = jobs[c];
+		job.out_start = h.d_out_start; job.out_end = h.d_out_end; job.out_value = h.d_out_value; job.out_cap = h.out_cap;
+		max_cursor = std::max<int64_t>(max_cursor, (int64_t) (job.nw + 1) * job.cstride);
+		max_nw = std::max<int64_t>(max_nw, job.nw);
+		max_slow = std::max<int64_t>(max_slow, std::max<int64_t>(1 << 16, h.out_cap / 8));
+		if (!wants_format(op, N, job.I, h_defaults, false)) sample = false;
+		if (window_smem_bytes(job.wlog, N, true, op) > 227 * 1024)
+			return fail(ctx, WB200_EUNSUPPORTED, "window does not fit shared memory; lower WB200_WINDOW");
+		h.n_out = 0; h.auc = 0; h.slow_segments = 0; h.ms_cursor = h.ms_sweep = 0; h.limbs = 0; h.sweep_kernel = 0;
+	}
+	wb200_stats total{};
+	if (nshards == 0) { ctx->stats = total; return WB200_OK; }
+
+	// per-shard tables (offsets | defaults | fixed-point defaults) and result slots, pooled
+	const size_t tbl = ((size_t) (N + 1) * 8 + (size_t) N * 16 + 15) / 16 * 16;
+	CK(ctx->b_tables.ensure(tbl * nshards)); CK(ctx->hb_tables.ensure(tbl * nshards));
+	CK(ctx->b_small.ensure((size_t) 256 * nshards)); CK(ctx->hb_small.ensure((size_t) 256 * nshards));
+	CK(ctx->cursor.ensure((size_t) max_cursor * sizeof(int32_t)));
+	CK(ctx->state.ensure((size_t) max_nw * sizeof(unsigned long long)));
+	CK(ctx->aucp.ensure((size_t) max_nw * WARPS * sizeof(double)));
+	while ((int) ctx->batch_events.size() < 3 * nshards) {
+		cudaEvent_t e;
+		CK(cudaEventCreate(&e));
+		ctx->batch_events.push_back(e);
+	}
+	char *ht = ctx->hb_tables.as<char>(), *dt = ctx->b_tables.as<char>();
+	double *d_small = ctx->b_small.as<double>();
+	CK(cudaMemsetAsync(d_small, 0, (size_t) 256 * nshards, s));
+
+	// 1. one value sample per shard, one synchronisation for all of them
+	double maxabs = 0;
+	long long lsb_key = 0;
+	if (sample) {
+		for (int c = 0; c < nshards; c++) {
+			const int64_t I = jobs[c].I, stride = std::max<int64_t>(1, I / (1 << 16));
+			CK(launch_sample_maxabs(jobs[c].value, I, stride, d_small + 32 * c, s));
+			total.kernels++;
+		}
+		CK(cudaMemcpyAsync(ctx->hb_small.p, d_small, (size_t) 256 * nshards, cudaMemcpyDeviceToHost, s));
+		CK(cudaStreamSynchronize(s));
+		for (int c = 0; c < nshards; c++) {
+			maxabs = std::max(maxabs, ctx->hb_small.as<double>()[32 * c]);
+			lsb_key = std::max(lsb_key, ctx->hb_small.as<long long>()[32 * c + 1]);
+		}
+	}
+	// 2. tables of every shard in one upload
+	for (int c = 0; c < nshards; c++) {
+		Job &job = jobs[c];
+		int64_t *hm_off = (int64_t *) (ht + tbl * c);
+		double *hm_dflt = (double *) (hm_off + N + 1);
+		int64_t *hm_fx = (int64_t *) (hm_dflt + N);
+		memcpy(hm_off, shards[c].h_off, (N + 1) * sizeof(int64_t));
+		memcpy(hm_dflt, h_defaults, N * sizeof(double));
+		memset(hm_fx, 0, N * sizeof(int64_t));
+		if (sample) choose_format(job, op, N, h_defaults, maxabs, lsb_key, 1, hm_fx);
+		job.off = (const int64_t *) (dt + tbl * c);
+		job.dflt = (const double *) (job.off + N + 1);
+		job.dflt_fx = (const int64_t *) (job.dflt + N);
+		job.cursor = ctx->cursor.as<int32_t>(); job.state = ctx->state.as<unsigned long long>();
+		job.auc_partial = ctx->aucp.as<double>();
+		double *sm = d_small + 32 * c;
+		job.slow_count = (unsigned long long *) (sm + 3);
+		job.auc_fix = sm + 10;
+		job.total = (long long *) (sm + 11);
+		job.ticket = (unsigned int *) (sm + 12);
+		job.diag = (unsigned long long *) (sm + 16);
+		if (job.fast) job.slow_cap = max_slow;
+	}
+	if (jobs[0].fast) {
+		CK(ctx->slow_list.ensure((size_t) max_slow * sizeof(long long)));
+		for (auto &job : jobs) job.slow_list = ctx->slow_list.as<long long>();
+	}
+	CK(cudaMemcpyAsync(dt, ht, tbl * nshards, cudaMemcpyHostToDevice, s));
+	// 3. cursor kernel + sweep of every shard, back to back (the scratch tables are reused in stream order)
+	for (int c = 0; c < nshards; c++) {
+		Job &job = jobs[c];
+		cudaEvent_t *ev = ctx->batch_events.data() + 3 * c;
+		int64_t max_len = 0;
+		for (int i = 0; i < N; i++) max_len = std::max<int64_t>(max_len, shards[c].h_off[i + 1] - shards[c].h_off[i]);
+		CK(cudaMemsetAsync(ctx->state.p, 0, (size_t) job.nw * sizeof(unsigned long long), s));
+		CK(cudaEventRecord(ev[0], s));
+		CK(launch_cursor(job, max_len, s));
+		CK(cudaEventRecord(ev[1], s));
+		int auc_per_window = WARPS;
+		CK(launch_emit(job, s, &auc_per_window));
+		CK(cudaEventRecord(ev[2], s));
+		CK(launch_reduce_auc(job.auc_partial, job.nw * auc_per_window, d_small + 32 * c + 2, s));
+		total.kernels += 3;
+		shards[c].sweep_kernel = auc_per_window == 1 ? 1 : 0;
+	}
+	// 4. all results, one synchronisation
+	CK(cudaMemcpyAsync(ctx->hb_small.p, d_small, (size_t) 256 * nshards, cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+	for (int c = 0; c < nshards; c++) {
+		wb200_device_shard &h = shards[c];
+		const Job &job = jobs[c];
+		const int64_t *hs = ctx->hb_small.as<int64_t>() + 32 * c;
+		h.n_out = hs[11];
+		memcpy(&h.auc, hs + 2, 8);
+		h.slow_segments = hs[3];
+		h.limbs = job.fast == 1 ? job.fx_limbs : 0;
+		cudaEvent_t *ev = ctx->batch_events.data() + 3 * c;
+		cudaEventElapsedTime(&h.ms_cursor, ev[0], ev[1]);
+		cudaEventElapsedTime(&h.ms_sweep, ev[1], ev[2]);
+		for (int k = 0; k < 16; k++) ctx->diag[k] += (unsigned long long) hs[16 + k];   // zeros unless built with -DWB_DIAG_PHASES
+	}
+	for (int c = 0; c < nshards; c++) {
+		wb200_device_shard &h = shards[c];
+		const Job &job = jobs[c];
+		if ((job.fast && h.slow_segments > 0) || h.n_out > h.out_cap) {
+			// rare: values outside the fixed-point format or an undersized output -- the single-shard path
+			// (fix-up kernel, wider formats, capacity error) finishes this shard
+			const float msc = h.ms_cursor, mss = h.ms_sweep;
+			double dv = 0;
+			int rc = run_device(ctx, op, N, nset1, strict, h.d_start, h.d_end, h.d_value, h.h_off, h_defaults, h.pos_lo, h.pos_hi,
+			                    h.d_out_start, h.d_out_end, h.d_out_value, h.out_cap, &h.n_out, &dv, &h.auc);
+			if (rc != WB200_OK) return rc;
+			h.slow_segments = ctx->stats.slow_segments; h.limbs = ctx->stats.limbs;
+			h.ms_cursor = msc + ctx->stats.ms_count; h.ms_sweep = mss + ctx->stats.ms_emit;
+			total.kernels += ctx->stats.kernels;
+		}
+		total.intervals += job.I; total.segments += h.n_out; total.windows += job.nw;
+		total.slow_segments += h.slow_segments; total.limbs = std::max(total.limbs, h.limbs);
+		total.ms_count += h.ms_cursor; total.ms_emit += h.ms_sweep;
+		total.fast_path = job.fast; total.sweep_kernel = h.sweep_kernel;
+	}
+	total.ms_total = total.ms_count + total.ms_emit;
+	ctx->stats = total;
+	const bool setop = (op == OP_TTEST || op == OP_MWU);
+	if (default_out) *default_out = setop ? NAN : derived_default(op, N, h_defaults);
+	return WB200_OK;
 }
 
 namespace {

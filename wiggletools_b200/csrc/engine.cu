@@ -1563,7 +1563,7 @@ __global__ void __launch_bounds__(256) cursor_kernel(const Job job) {
 	if ((threadIdx.x & 31) == 0 && j0 > 0) e_prev = end[j0 - 1];
 	int c_prev = j0 > 0 ? cnt(e_prev) : 0;
 	int32_t *col = job.cursor + i;
-	const size_t N = (size_t) job.N;
+	const size_t N = (size_t) job.cstride;
 #pragma unroll
 	for (int k = 0; k < 4; k++) {
 		const int j = j0 + k;
@@ -1601,7 +1601,7 @@ __global__ void __launch_bounds__(THREADS, MODE == MODE_FAST ? (THREADS == 512 ?
 #if WB_LATETICKET
 	int w = blockIdx.x;
 	if (w < job.nw)
-		for (int i = threadIdx.x; i < job.N; i += THREADS) ca[i] = job.cursor[(size_t) w * job.N + i];
+		for (int i = threadIdx.x; i < job.N; i += THREADS) ca[i] = job.cursor[(size_t) w * job.cstride + i];
 	__syncthreads();
 	while (w < job.nw) {
 #ifdef WB_DIAG_PHASES
@@ -1615,7 +1615,7 @@ __global__ void __launch_bounds__(THREADS, MODE == MODE_FAST ? (THREADS == 512 ?
 		w = misc->ticket2;
 		// the drawn window's cursor row travels while the window arrays are cleared
 		if (w < job.nw)
-			for (int i = threadIdx.x; i < job.N; i += THREADS) __pipeline_memcpy_async(&ca[i], &job.cursor[(size_t) w * job.N + i], 4);
+			for (int i = threadIdx.x; i < job.N; i += THREADS) __pipeline_memcpy_async(&ca[i], &job.cursor[(size_t) w * job.cstride + i], 4);
 		__pipeline_commit();
 	}
 	(void) cb;
@@ -1623,7 +1623,7 @@ __global__ void __launch_bounds__(THREADS, MODE == MODE_FAST ? (THREADS == 512 ?
 #else
 	int w = blockIdx.x, w1 = blockIdx.x + gridDim.x;
 	if (w < job.nw)
-		for (int i = threadIdx.x; i < job.N; i += THREADS) ca[i] = job.cursor[(size_t) w * job.N + i];
+		for (int i = threadIdx.x; i < job.N; i += THREADS) ca[i] = job.cursor[(size_t) w * job.cstride + i];
 	__syncthreads();
 	while (w < job.nw) {
 #ifdef WB_DIAG_PHASES
@@ -1633,7 +1633,7 @@ __global__ void __launch_bounds__(THREADS, MODE == MODE_FAST ? (THREADS == 512 ?
 		if (threadIdx.x == 0) t2 = atomicAdd(job.ticket, 1u) + 2u * gridDim.x;   // consumed two windows from now
 		if (w1 < job.nw)
 			for (int i = threadIdx.x; i < job.N; i += THREADS)
-				__pipeline_memcpy_async(&cb[i], &job.cursor[(size_t) w1 * job.N + i], 4);
+				__pipeline_memcpy_async(&cb[i], &job.cursor[(size_t) w1 * job.cstride + i], 4);
 		__pipeline_commit();
 		process_window<MODE, VLOG, LIMBS>(job, w, smem, L, ca, lw, inv_scale, lim, scale);
 		__pipeline_wait_prior(0);
@@ -1769,8 +1769,8 @@ __global__ void fixup_kernel(const Job job, long long count) {
 	const int w = (int) (((long long) bs - job.p0) >> job.wlog);
 	Row row;
 	row.job = &job;
-	row.cur = job.cursor + (size_t) w * job.N;
-	row.nxt = job.cursor + (size_t) (w + 1) * job.N;
+	row.cur = job.cursor + (size_t) w * job.cstride;
+	row.nxt = job.cursor + (size_t) (w + 1) * job.cstride;
 	row.b = bs;
 	const double v = row_eval(row);
 	job.out_value[oi] = v;

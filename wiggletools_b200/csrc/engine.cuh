@@ -50,7 +50,8 @@ struct Job {
 	int wlog;               // log2(window size in bp)
 	int nw;                 // number of windows
 	// scratch
-	int32_t *cursor;        // [(nw+1) * N] first interval of track i with end >= window start (row nw: end of data)
+	int32_t *cursor;        // [(nw+1) * cstride] first interval of track i with end >= window start (row nw: end of data)
+	int cstride;            // row stride of the cursor table: N rounded up to 4 (rows are 16-byte aligned: bulk-copy tiles)
 	unsigned long long *state; // [nw] look-back words: 2 flag bits | segments (aggregate or inclusive prefix)
 	unsigned int *ticket;   // window ticket counter
 	long long *total;       // S, written by the last window

@@ -8,60 +8,67 @@
 // latency-bound phases whose length hardly depends on the window's content, so
 // throughput is (windows in flight per SM) x (window size) / latency.  This
 // kernel therefore uses
-//   * 128 threads per window (32 positions per thread) -> 6 CTAs per SM instead
-//     of 3 at the same register budget;
-//   * 8 or 12 bytes of shared memory per position instead of 13:
-//       cover word  : starts in bits 0..10, ends in bits 11..21 of one int32 -- a
-//                     position is a breakpoint iff the word is non-zero, so the
-//                     separate flag array (and its stores) is gone;
+//   * 128 threads per window (32 positions per thread), 64 registers;
+//   * 6 bytes of shared memory per position (N <= 255, one-limb values) -> 27 KB per
+//     window, 8 windows in flight per SM:
+//       cover field : starts in the low byte, ends in the high byte of a 16-bit field,
+//                     two positions per 32-bit word (the atomics are 32-bit adds of a
+//                     shifted one) -- a position is a breakpoint iff its field is
+//                     non-zero, so there is no flag array.  N > 255: 32-bit fields
+//                     (11 + 11 bits);
 //       value       : one or two 32-bit limbs (host-chosen from the value range);
 //       poison      : NaN / non-representable values are rare and go to a short
 //                     side list instead of a field in every word;
 //   * a scan that never holds the window in registers: pass 1 sums each thread's
 //     32 positions, one block scan stitches the threads, pass 2 re-reads them and
-//     writes the exact prefix back IN PLACE, so the dense breakpoint list is one
-//     32-bit word per breakpoint (position | output rank | flags) over the dead
-//     cover array and the emit phase fetches the value by position.
+//     writes the exact prefix back IN PLACE; the dense breakpoint list is one
+//     16-bit entry per breakpoint (position | keep | slow) over the dead cover
+//     array, the output rank of an entry is a per-32-entries base plus a ballot
+//     popcount, and the emit phase fetches the value by position;
+//   * bulk-async (TMA engine) tiles: the cursor row of a window is one
+//     cp.async.bulk global->shared copy signalled on an mbarrier (UBLKCP), and the
+//     interval slices of the window some CTA will draw next are pulled into L2 with
+//     cp.async.bulk.prefetch.L2 (UBLKPF) -- three instructions per track instead of
+//     a per-lane prefetch loop -- by warps 1..3 while warp 0 runs the look-back.
+// Windows are drawn from a ticket counter from the first one on, so the look-back
+// only ever waits on windows a running CTA owns: no assumption that the whole grid
+// is resident.
 // Output is bit-identical to emit_kernel<MODE_FAST>; anything this kernel does
 // not cover (three limbs, unaligned inputs, other window sizes) stays there.
 #include "engine.cuh"
 #include "device_util.cuh"
-#include <cuda_pipeline.h>
 #include <climits>
 #include <type_traits>
 #include <cstdlib>
+#include <cstdio>
 
 namespace wb {
 namespace fs {
 
-constexpr int MAXWARP = 8;               // CTAs of 128 or 256 threads (one window per CTA at a time)
+constexpr int TH = 128, NWARP = TH / 32;
 #ifndef WB_FS_MINB
-#define WB_FS_MINB 4                  // resident CTAs per SM the 256-thread variant is compiled for
+#define WB_FS_MINB 8                  // resident CTAs per SM the 6 B/position variant is compiled for
 #endif
-constexpr int END_SHIFT = 11;            // cover word: starts | ends << 11 (each <= 1023 per position)
-constexpr uint32_t FIELD = (1u << END_SHIFT) - 1;
 #ifndef WB_FS_LBK
 #define WB_FS_LBK 1
 #endif
-#ifndef WB_FS_LBRELAX
-#define WB_FS_LBRELAX 1               // look-back waits only for the predecessors it sums
-#endif
-#ifndef WB_FS_LATETICKET
-#define WB_FS_LATETICKET 2            // next window drawn: 0 two windows ahead, 1 after the events phase, 2 when the emit phase starts
-#endif
-#ifndef WB_FS_EVPIPE
-#define WB_FS_EVPIPE 1                // events: software-pipelined interval loads
-#endif
 #ifndef WB_FS_LBSLEEP
-#define WB_FS_LBSLEEP 40
+#define WB_FS_LBSLEEP 100             // ns between two polls of the look-back (first wait; doubles up to 8x)
 #endif
 #ifndef WB_FS_PREF
-#define WB_FS_PREF 3                  // next window's intervals: 0 no prefetch, 2 prefetch.L1, 3 prefetch.L2
+#define WB_FS_PREF 1                  // next window's intervals: 0 no prefetch, 1 bulk prefetch into L2
 #endif
+#ifndef WB_FS_EVPIPE
+#define WB_FS_EVPIPE 0                // events: software-pipelined interval loads (two chunks in registers)
+#endif
+#ifndef WB_FS_PREF_IV
+#define WB_FS_PREF_IV 32              // intervals per track the prefetch covers
+#endif
+constexpr int END_SHIFT = 11;            // 32-bit cover field: starts | ends << 11 (each <= 1023 per position)
+constexpr uint32_t FIELD = (1u << END_SHIFT) - 1;
 constexpr int LBK = WB_FS_LBK;           // look-back: 32 * LBK predecessors per step
 constexpr int POIS_CAP = 120;            // poison events kept per window; more -> the whole window takes the fix-up path
-constexpr uint32_t D_KEEP = 1u << 26, D_SLOW = 1u << 27;
-constexpr int D_KID_SHIFT = 13;          // dense word: position (13 bits) | output rank (13 bits) | flags
+constexpr unsigned DN_KEEP = 0x8000, DN_SLOW = 0x4000, DN_POS = 0x1fff;   // dense entry: position | flags
 
 struct PoisEv { uint16_t pos; int16_t delta; };
 
@@ -74,17 +81,20 @@ struct Misc {
 	long long out_base;              // output offset of the window
 	int ticket2;
 	int pad;
-	long long wsum[MAXWARP];
-	int wcov[MAXWARP];
-	int wpack[MAXWARP];
-	double wauc[MAXWARP];
+	unsigned long long bar_cur;      // mbarrier: cursor row of the window being started
+	unsigned long long bar_nxt;      // mbarrier: cursor row of the window prefetched for
+	long long wsum[NWARP];
+	int wcov[NWARP];
+	int wpack[NWARP];
+	double wauc[NWARP];
+	uint16_t kbase[256];             // kept segments before every 32nd dense entry
 	PoisEv pois[POIS_CAP];
 };
-constexpr int MISC_BYTES = 1024;
+constexpr int MISC_BYTES = 1280;
 static_assert(sizeof(Misc) <= MISC_BYTES, "Misc must fit its slot");
 
 struct Layout { size_t off_cur, off_cur2, off_tn, off_toff, off_tmd, off_cov, off_limb, total; };
-__host__ __device__ inline Layout make_layout(int wlog, int N, int limbs) {
+__host__ __device__ inline Layout make_layout(int wlog, int N, int limbs, bool cov16) {
 	Layout L;
 	const size_t W = (size_t) 1 << wlog, nn = (size_t) (N + 4) / 4 * 16;
 	size_t o = MISC_BYTES;
@@ -93,24 +103,55 @@ __host__ __device__ inline Layout make_layout(int wlog, int N, int limbs) {
 	L.off_tn = o;   o += nn;
 	L.off_toff = o; o += 2 * nn;
 	L.off_tmd = o;  o += 2 * nn;
-	L.off_cov = o;  o += 4 * W;
+	L.off_cov = o;  o += (cov16 ? 2 : 4) * W;
 	L.off_limb = o; o += (size_t) limbs * 4 * W;
 	L.total = (o + 15) / 16 * 16;
 	return L;
 }
 
-// Thread t owns the V = 2^VLOG consecutive positions [t*V, t*V+V) and reads them back
-// with 128-bit loads; its V/4 vectors are rotated by a function of t so that the 8
-// lanes of a quarter warp hit 8 different 16-byte bank groups.
-template <int VLOG>
-__device__ __forceinline__ int swz(int t) {
-	constexpr int NV = 1 << (VLOG - 2);
-	return NV >= 8 ? (t & (NV - 1)) : ((t >> (5 - VLOG)) & (NV - 1));
+// ---- bulk-async copies and their mbarriers (PTX; SASS: UBLKCP / UBLKPF / SYNCS) -------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
 }
-template <int VLOG>
-__device__ __forceinline__ int phys(int p) {
-	const int t = p >> VLOG, o = p & ((1 << VLOG) - 1);
-	return (t << VLOG) | (((o >> 2) ^ swz<VLOG>(t)) << 2) | (o & 3);
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+	asm volatile(
+		"{\n"
+		".reg .pred P1;\n"
+		"LAB_WAIT:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+		"@P1 bra DONE;\n"
+		"bra LAB_WAIT;\n"
+		"DONE:\n"
+		"}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one contiguous tile global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
+	asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src), "r"(bytes) : "memory");
+}
+
+// Thread t owns the V = 2^VLOG consecutive positions [t*V, t*V+V) and reads them back
+// with 128-bit loads; its NV 16-byte vectors are rotated by a function of t so that the 8
+// lanes of a quarter warp hit 8 different 16-byte bank groups.
+template <int NV>
+__device__ __forceinline__ int swz(int t) {
+	return NV >= 8 ? (t & (NV - 1)) : NV == 4 ? ((t >> 1) & 3) : NV == 2 ? ((t >> 2) & 1) : 0;
+}
+// the same rotation applied to a position: index of its limb word / of its 16-bit cover field
+template <int VLOG> __device__ __forceinline__ int phys32(int p) { return p ^ ((p >> 3) & (VLOG == 5 ? 0x1c : 0xc)); }
+template <int VLOG> __device__ __forceinline__ int phys16(int p) { return p ^ ((p >> 3) & (VLOG == 5 ? 0x18 : 0x8)); }
+
+template <int VLOG, bool COV16>
+__device__ __forceinline__ void cov_add(uint32_t *cov, int p, bool is_end) {
+	if (COV16) atomicAdd(&cov[phys16<VLOG>(p) >> 1], (is_end ? 0x100u : 1u) << ((p & 1) << 4));
+	else atomicAdd(&cov[phys32<VLOG>(p)], is_end ? (1u << END_SHIFT) : 1u);
 }
 
 struct Chunk {
@@ -119,10 +160,10 @@ struct Chunk {
 	int lo, hi;          // slots lo <= x < hi hold intervals of this track at or after its cursor
 };
 
-// ---- events: +1 start / +1 end per interval in the cover word, +-value in the limbs ----
-template <int TH, int VLOG, int LIMBS>
+// ---- events: +1 start / +1 end per interval in the cover field, +-value in the limbs ----
+template <int VLOG, int LIMBS, bool COV16>
 __device__ __forceinline__ void events(const Job &job, unsigned char *smem, const Layout &L, const int32_t *cur,
-                                       long long w0, int lw, double inv_scale, double lim) {
+                                       int w0i, int lw, double inv_scale, double lim) {
 	constexpr int W = TH << VLOG, G = TH / 8;
 	Misc *misc = (Misc *) smem;
 	const int32_t *tn = (const int32_t *) (smem + L.off_tn);
@@ -132,7 +173,6 @@ __device__ __forceinline__ void events(const Job &job, unsigned char *smem, cons
 	uint32_t *limb = (uint32_t *) (smem + L.off_limb);
 	const int tid = threadIdx.x, lane = tid & 31, gid = tid >> 3, gl = tid & 7, gsh = lane & 24;
 	const int N = job.N;
-	const int w0i = (int) w0;
 	using acc_t = typename std::conditional<LIMBS == 1, int, long long>::type;
 	int in_cov = 0, in_pois = 0, my_next = INT_MAX;
 	acc_t in_val = 0;
@@ -163,9 +203,10 @@ __device__ __forceinline__ void events(const Job &job, unsigned char *smem, cons
 	};
 	auto one = [&](bool valid, int s, int e, double val, long long md) {
 		if (!valid) return;
-		const unsigned xs = (unsigned) (s - w0i), xe = (unsigned) (e - w0i);
-		const bool start_in = xs < (unsigned) W, end_in = xe < (unsigned) W;
-		if (!start_in && s >= w0i) { my_next = min(my_next, s); return; }   // begins at or beyond the window end
+		const int xs = s - w0i;
+		const unsigned xe = (unsigned) (e - w0i);
+		if (xs >= W) { my_next = min(my_next, s); return; }         // begins at or beyond the window end
+		const bool start_in = xs >= 0, end_in = xe < (unsigned) W;
 		acc_t d = 0;
 		bool bad;
 		if (LIMBS == 1) {
@@ -181,15 +222,13 @@ __device__ __forceinline__ void events(const Job &job, unsigned char *smem, cons
 			if (!bad) d = (acc_t) (m - md);
 		}
 		if (start_in) {
-			const int ph = phys<VLOG>((int) xs);
-			atomicAdd(&cov[ph], 1u);
-			if (d != 0) add_limbs_fs<LIMBS, W>(limb, ph, d, lw);
-			if (bad) poison(xs, 1);
+			cov_add<VLOG, COV16>(cov, xs, false);
+			if (d != 0) add_limbs_fs<LIMBS, W>(limb, phys32<VLOG>(xs), d, lw);
+			if (bad) poison((unsigned) xs, 1);
 		} else { in_cov++; in_val += d; in_pois += bad ? 1 : 0; }           // began before the window
 		if (end_in) {
-			const int ph = phys<VLOG>((int) xe);
-			atomicAdd(&cov[ph], 1u << END_SHIFT);
-			if (d != 0) add_limbs_fs<LIMBS, W>(limb, ph, -d, lw);
+			cov_add<VLOG, COV16>(cov, (int) xe, true);
+			if (d != 0) add_limbs_fs<LIMBS, W>(limb, phys32<VLOG>((int) xe), -d, lw);
 			if (bad) poison(xe, -1);
 		} else my_next = min(my_next, e);
 	};
@@ -245,11 +284,26 @@ __device__ __forceinline__ void events(const Job &job, unsigned char *smem, cons
 	}
 }
 
+// the cover fields of four consecutive positions: the 16-byte vector (or half of it) they live in
+template <bool COV16>
+__device__ __forceinline__ void cover4(const uint4 &cv, int half, int st[4], int en[4]) {
+	if (COV16) {
+		const uint32_t a = half ? cv.z : cv.x, b = half ? cv.w : cv.y;
+		st[0] = a & 0xff; en[0] = (a >> 8) & 0xff; st[1] = (a >> 16) & 0xff; en[1] = a >> 24;
+		st[2] = b & 0xff; en[2] = (b >> 8) & 0xff; st[3] = (b >> 16) & 0xff; en[3] = b >> 24;
+	} else {
+		const uint32_t c[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+		for (int j = 0; j < 4; j++) { st[j] = c[j] & FIELD; en[j] = c[j] >> END_SHIFT; }
+	}
+}
+
 // ---- one window ------------------------------------------------------------------------
-template <int TH, int VLOG, int LIMBS>
-__device__ void process_window(const Job &job, int w, unsigned char *smem, const Layout &L, const int32_t *cur,
-                               int32_t *nxt_buf, int w1_early, int lw, double inv_scale, double lim, double scale) {
-	constexpr int V = 1 << VLOG, W = TH << VLOG, NV = V / 4, NWARP = TH / 32;
+template <int VLOG, int LIMBS, bool COV16>
+__device__ void process_window(const Job &job, int w, unsigned char *smem, const Layout &L, int32_t *cur,
+                               int32_t *nxt_buf, unsigned par_cur, unsigned par_nxt, int lw, double inv_scale, double lim, double scale) {
+	constexpr int V = 1 << VLOG, W = TH << VLOG, NVL = V / 4;
+	constexpr int NVC = COV16 ? V / 8 : V / 4;                // 16-byte cover vectors per thread
 	static_assert(V <= 32, "one 32-bit mask per thread");
 	Misc *misc = (Misc *) smem;
 	uint32_t *cov = (uint32_t *) (smem + L.off_cov);
@@ -257,6 +311,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int N = job.N;
 	const long long w0 = job.p0 + ((long long) w << job.wlog);
+	const int w0i = (int) w0;
 	const int thr = job.strict ? N : 1;
 #ifdef WB_DIAG_PHASES
 	long long diag_t = clock64();
@@ -266,53 +321,57 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	{
 		const uint4 z = make_uint4(0, 0, 0, 0);
 		uint4 *zc = (uint4 *) cov;                                   // cov and limbs are contiguous
-		constexpr int n16 = (1 + LIMBS) * W / 4;
+		constexpr int n16 = (COV16 ? W / 8 : W / 4) + LIMBS * W / 4;
 #pragma unroll 4
 		for (int t = tid; t < n16; t += TH) zc[t] = z;
 		if (tid == 0) { misc->next_bp = INT_MAX; misc->base_cov = 0; misc->base_pois = 0; misc->npois = 0; misc->base_val = 0; }
 	}
-#if WB_FS_LATETICKET == 2
-	__pipeline_wait_prior(0);                                  // this window's cursor row, requested before the clear
-#endif
+	mbar_wait(&misc->bar_cur, par_cur);                          // this window's cursor row (bulk copy requested when it was drawn)
 	__syncthreads();
 	WB_PHASE(0);
 
 	// ---- 1. events ---------------------------------------------------------------------
 #ifndef WB_DIAG_SKIP_EVENTS
-	events<TH, VLOG, LIMBS>(job, smem, L, cur, w0, lw, inv_scale, lim);
+	events<VLOG, LIMBS, COV16>(job, smem, L, cur, w0i, lw, inv_scale, lim);
 #endif
 	__syncthreads();
 	WB_PHASE(1);
-	// The look-back of window w waits for every window below w, so the less time passes between
-	// drawing a window and starting it, the less the windows in flight run out of order.
-#if WB_FS_LATETICKET == 1
-	// as late as the draw's own cursor row and interval prefetch allow
-	unsigned next_ticket = 0;
-	if (tid == 0) next_ticket = atomicAdd(job.ticket, 1u) + gridDim.x;
-#endif
 
 	// ---- 2. scan, pass 1: totals of this thread's V positions -------------------------------
-	const int p0 = tid << VLOG, sw = swz<VLOG>(tid);
+	const int p0 = tid << VLOG, swl = swz<NVL>(tid), swc = swz<NVC>(tid);
+	const uint32_t *covt = cov + (COV16 ? p0 >> 1 : p0);         // this thread's cover words
 	using acc_t = typename std::conditional<LIMBS == 1, int, long long>::type;   // one limb: every prefix fits 32 bits
-	unsigned evbits = 0;
 	int ctot = 0;
 	acc_t atot = 0;
+	{
+		if (COV16) {
+			// byte fields summed two positions at a time in 16-bit lanes (<= 16 * 255 each)
+			uint32_t ss = 0, se = 0;
 #pragma unroll
-	for (int k = 0; k < NV; k++) {
-		const int pv = p0 + ((k ^ sw) << 2);
-		const uint4 c = *(const uint4 *) (cov + pv);
-		const uint32_t cw[4] = {c.x, c.y, c.z, c.w};
+			for (int k = 0; k < NVC; k++) {
+				const uint4 c = *(const uint4 *) (covt + ((k ^ swc) << 2));
+				ss += (c.x & 0x00ff00ffu) + (c.y & 0x00ff00ffu) + (c.z & 0x00ff00ffu) + (c.w & 0x00ff00ffu);
+				se += ((c.x >> 8) & 0x00ff00ffu) + ((c.y >> 8) & 0x00ff00ffu) + ((c.z >> 8) & 0x00ff00ffu) + ((c.w >> 8) & 0x00ff00ffu);
+			}
+			ctot = (int) ((ss & 0xffff) + (ss >> 16)) - (int) ((se & 0xffff) + (se >> 16));
+		} else {
 #pragma unroll
-		for (int j = 0; j < 4; j++) {
-			ctot += (int) (cw[j] & FIELD) - (int) (cw[j] >> END_SHIFT);
-			if (cw[j]) evbits |= 1u << (4 * k + j);
+			for (int k = 0; k < NVC; k++) {
+				const uint4 c = *(const uint4 *) (covt + ((k ^ swc) << 2));
+				ctot += (int) ((c.x & FIELD) + (c.y & FIELD) + (c.z & FIELD) + (c.w & FIELD))
+				      - (int) ((c.x >> END_SHIFT) + (c.y >> END_SHIFT) + (c.z >> END_SHIFT) + (c.w >> END_SHIFT));
+			}
 		}
-		const uint4 l = *(const uint4 *) (limb + pv);
-		if (LIMBS == 1) atot += (acc_t) (l.x + l.y + l.z + l.w);
-		else {
-			const uint4 h = *(const uint4 *) (limb + W + pv);
-			atot += (acc_t) ((long long) ((unsigned long long) l.x + l.y + l.z + l.w)
-			      + (((long long) (int32_t) h.x + (int32_t) h.y + (int32_t) h.z + (int32_t) h.w) << lw));
+#pragma unroll
+		for (int k = 0; k < NVL; k++) {
+			const int pv = p0 + ((k ^ swl) << 2);
+			const uint4 l = *(const uint4 *) (limb + pv);
+			if (LIMBS == 1) atot += (acc_t) (l.x + l.y + l.z + l.w);
+			else {
+				const uint4 h = *(const uint4 *) (limb + W + pv);
+				atot += (acc_t) ((long long) ((unsigned long long) l.x + l.y + l.z + l.w)
+				      + (((long long) (int32_t) h.x + (int32_t) h.y + (int32_t) h.z + (int32_t) h.w) << lw));
+			}
 		}
 	}
 	// exclusive block scan of (cover, value)
@@ -336,30 +395,35 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	WB_PHASE(2);
 
 	// ---- pass 2: running state after every position; the exact prefix goes back in place -----
-	unsigned keepbits = 0;
+	unsigned evbits = 0, keepbits = 0;
 	{
 		int c = ec; acc_t a = ea;
+		uint4 cv = make_uint4(0, 0, 0, 0);
 #pragma unroll
-		for (int k = 0; k < NV; k++) {
-			const int pv = p0 + ((k ^ sw) << 2);
-			const uint4 cv = *(const uint4 *) (cov + pv);
-			const uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w};
+		for (int k = 0; k < NVL; k++) {
+			const int pv = p0 + ((k ^ swl) << 2);
+			if (COV16) { if ((k & 1) == 0) cv = *(const uint4 *) (covt + (((k >> 1) ^ swc) << 2)); }
+			else cv = *(const uint4 *) (covt + ((k ^ swc) << 2));
+			int st[4], en[4];
+			cover4<COV16>(cv, k & 1, st, en);
 			uint4 l = *(const uint4 *) (limb + pv);
 			uint32_t lo[4] = {l.x, l.y, l.z, l.w}, hi[4] = {0, 0, 0, 0};
 			if (LIMBS == 2) { const uint4 h = *(const uint4 *) (limb + W + pv); hi[0] = h.x; hi[1] = h.y; hi[2] = h.z; hi[3] = h.w; }
 #pragma unroll
 			for (int j = 0; j < 4; j++) {
-				c += (int) (cw[j] & FIELD) - (int) (cw[j] >> END_SHIFT);
+				c += st[j] - en[j];
 				if (LIMBS == 1) a += (acc_t) lo[j];
 				else a += (acc_t) ((long long) (unsigned long long) lo[j] + ((long long) (int32_t) hi[j] << lw));
-				if (c >= thr) keepbits |= 1u << (4 * k + j);
+				if (st[j] | en[j]) {
+					evbits |= 1u << (4 * k + j);
+					if (c >= thr) keepbits |= 1u << (4 * k + j);
+				}
 				lo[j] = (uint32_t) a;                                  // LIMBS == 1: the sum itself fits 32 bits
 				if (LIMBS == 2) hi[j] = (uint32_t) ((unsigned long long) a >> 32);
 			}
 			*(uint4 *) (limb + pv) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 			if (LIMBS == 2) *(uint4 *) (limb + W + pv) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
 		}
-		keepbits &= evbits;
 	}
 	// rare: segments covering an interval whose value is not representable (fix-up kernel)
 	unsigned slowbits = 0;
@@ -386,9 +450,6 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 #pragma unroll
 		for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(FULL, ip, d); if (lane >= d) ip += v; }
 		if (lane == 31) misc->wpack[warp] = ip;
-#if WB_FS_LATETICKET == 1
-		if (tid == 0) misc->ticket2 = (int) next_ticket;
-#endif
 		__syncthreads();                                       // every thread is past its reads of cov
 		int bp = 0, tp = 0;
 #pragma unroll
@@ -399,62 +460,59 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	}
 	// publish this window's segment count so that later windows can start their look-back
 	if (tid == 0) st_volatile(&job.state[w], LB_AGG | (unsigned long long) kept_total);
-#if WB_FS_LATETICKET
-	// mode 2: the draw happens after the look-back, too late to prefetch for; windows are handed
-	// out in order, so window w + grid starts about one window time after this one did -- its
-	// intervals are pulled into L2 for whichever CTA draws it
-	const int w1 = WB_FS_LATETICKET == 2 ? w + (int) gridDim.x : misc->ticket2;
-	if (w1 < job.nw)
-		for (int i = tid; i < N; i += TH) __pipeline_memcpy_async(&nxt_buf[i], &job.cursor[(size_t) w1 * N + i], 4);
-	__pipeline_commit();
-#else
-	const int w1 = w1_early;
-#endif
-	const int32_t *nxt_cur = w1 < job.nw ? nxt_buf : nullptr;
+	// Windows are handed out in order, so window w + grid starts about one window time after
+	// this one did: its cursor row is fetched now and its intervals are pulled into L2 (below)
+	// for whichever CTA draws it.
+	const int w1 = w + (int) gridDim.x;
+	const bool pref = WB_FS_PREF && w1 < job.nw;
+	if (pref && tid == 0) {
+		const uint32_t bytes = (uint32_t) job.cstride * 4;
+		mbar_expect_tx(&misc->bar_nxt, bytes);
+		bulk_g2s(nxt_buf, job.cursor + (size_t) w1 * job.cstride, bytes, &misc->bar_nxt);
+	}
 	WB_PHASE(3);
 
 	// ---- 3. dense breakpoint list over the dead cover array ---------------------------------
-	uint32_t *dense = cov;
+	uint16_t *dense = (uint16_t *) cov;
 	{
 		unsigned bits = evbits;
 		while (bits) {
 			const int q = __ffs(bits) - 1;
 			bits &= bits - 1;
-			uint32_t d = (uint32_t) (p0 + q);
+			if ((rank & 31) == 0) misc->kbase[rank >> 5] = (uint16_t) kidx;
+			unsigned d = (unsigned) (p0 + q);
 			if ((keepbits >> q) & 1) {
-				d |= D_KEEP | ((uint32_t) kidx++ << D_KID_SHIFT);
-				if ((slowbits >> q) & 1) d |= D_SLOW;
+				d |= DN_KEEP;
+				kidx++;
+				if ((slowbits >> q) & 1) d |= DN_SLOW;
 			}
-			dense[rank++] = d;
+			dense[rank++] = (uint16_t) d;
 		}
 	}
-	__pipeline_wait_prior(0);                                  // this thread's part of the next cursor row has landed
 	__syncthreads();
 	WB_PHASE(4);
-#if WB_FS_PREF >= 2
-	// ask for the next window's intervals now: they travel while this window is emitted
-	if (nxt_cur) {
-		const long long *toff = (const long long *) (smem + L.off_toff);
-		const int32_t *tn = (const int32_t *) (smem + L.off_tn);
-		const int gid = tid >> 3, gl = tid & 7;
-		for (int i = gid; i < N; i += TH / 8) {
-			const long long o = toff[i], first = o + nxt_cur[i];
-			const long long g = (first & ~3ll) + 4 * gl;
-			if (g < o + tn[i] && g + 4 <= job.I) {
-#if WB_FS_PREF == 2
-				asm volatile("prefetch.global.L1 [%0];" :: "l"(job.start + g)); asm volatile("prefetch.global.L1 [%0];" :: "l"(job.end + g));
-				asm volatile("prefetch.global.L1 [%0];" :: "l"(job.value + g)); asm volatile("prefetch.global.L1 [%0];" :: "l"(job.value + g + 2));
-#else
-				asm volatile("prefetch.global.L2 [%0];" :: "l"(job.start + g)); asm volatile("prefetch.global.L2 [%0];" :: "l"(job.end + g));
-				asm volatile("prefetch.global.L2 [%0];" :: "l"(job.value + g)); asm volatile("prefetch.global.L2 [%0];" :: "l"(job.value + g + 2));
-#endif
+
+	if (warp != 0) {
+		// ---- the next window's intervals: bulk prefetch into L2, one lane per track ------------
+		if (pref) {
+			mbar_wait(&misc->bar_nxt, par_nxt);
+			const long long *toff = (const long long *) (smem + L.off_toff);
+			const int32_t *tn = (const int32_t *) (smem + L.off_tn);
+			const long long Iv = job.I & ~3ll;
+			for (int i = tid - 32; i < N; i += TH - 32) {
+				const long long o = toff[i], first = o + nxt_buf[i];
+				const long long g = first & ~3ll;
+				long long cnt = min((long long) WB_FS_PREF_IV, o + tn[i] - g);
+				cnt = min((cnt + 3) & ~3ll, Iv - g);
+				if (cnt > 0) {
+					bulk_prefetch_l2(job.start + g, (uint32_t) cnt * 4);
+					bulk_prefetch_l2(job.end + g, (uint32_t) cnt * 4);
+					bulk_prefetch_l2(job.value + g, (uint32_t) cnt * 8);
+				}
 			}
 		}
-	}
-#endif
-
-	// ---- output offset: decoupled look-back over the preceding windows ----------------------
-	if (warp == 0) {
+	} else {
+		// ---- output offset: decoupled look-back over the preceding windows --------------------
 		// LBK x 32 predecessors per step (the loads of one step are independent: one L2 round
 		// trip), summed back to the nearest window that already knows its inclusive prefix
 		unsigned long long sum = 0;
@@ -466,6 +524,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 		while (!found) {
 			unsigned long long st[LBK];
 			int use = LBK;                                         // groups of 32 states summed in this step
+			unsigned ns = WB_FS_LBSLEEP;
 			while (true) {
 #pragma unroll
 				for (int j = 0; j < LBK; j++) {
@@ -483,16 +542,12 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 				for (int j = 0; j < LBK; j++) {
 					if (j >= use || wait) break;
 					const unsigned nr = __ballot_sync(FULL, (st[j] >> 62) == 0), pm = __ballot_sync(FULL, (st[j] >> 62) == 2);
-#if WB_FS_LBRELAX
 					if (pm != 0 && (nr == 0 || (pm & -pm) < (nr & -nr))) use = j + 1;
 					else if (nr != 0) wait = true;
-#else
-					if (nr != 0) wait = true;
-					else if (pm != 0) use = j + 1;
-#endif
 				}
 				if (!wait) break;
-				__nanosleep(WB_FS_LBSLEEP);
+				__nanosleep(ns);
+				if (ns < 8 * WB_FS_LBSLEEP) ns *= 2;
 			}
 #ifdef WB_DIAG_PHASES
 			diag_steps++;
@@ -520,15 +575,22 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	}
 	__syncthreads();
 	WB_PHASE(5);
-#if WB_FS_LATETICKET == 2
-	unsigned next_ticket = 0;
-	if (tid == 0) next_ticket = atomicAdd(job.ticket, 1u) + gridDim.x;      // lands while this window is emitted
-#endif
+	// The look-back of window w waits for every window below w, so the less time passes between
+	// drawing a window and starting it, the less the windows in flight run out of order: the next
+	// window is drawn now, and its cursor row lands while this window is emitted.
+	if (tid == 0) {
+		const int nw1 = (int) atomicAdd(job.ticket, 1u);
+		misc->ticket2 = nw1;
+		if (nw1 < job.nw) {
+			const uint32_t bytes = (uint32_t) job.cstride * 4;
+			mbar_expect_tx(&misc->bar_cur, bytes);
+			bulk_g2s(cur, job.cursor + (size_t) nw1 * job.cstride, bytes, &misc->bar_cur);
+		}
+	}
 
 	// ---- 4. emit, one breakpoint per thread (coalesced stores) -------------------------------
 	const long long out_base = misc->out_base;
 	const int next_bp = misc->next_bp;
-	const int w0i = (int) w0;
 	int32_t *os = job.out_start + out_base, *oe = job.out_end + out_base;
 	double *ov = job.out_value + out_base;
 	const long long room = job.out_cap - out_base;             // output ranks below this are in range
@@ -537,23 +599,26 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	// sum: x 2^q; mean over a power-of-two N: x 2^q / N is one exact power of two as well
 	const double mul = (mean && npow2) ? scale * (1.0 / N) : scale;
 	const bool div = mean && !npow2;
-	constexpr uint32_t PMASK = (1u << D_KID_SHIFT) - 1;
 	const int32_t fx_base32 = (int32_t) job.fx_base;
 	double auc = 0;
 	// the three output pointers of this window, opaque to the optimiser: one 32-bit
 	// index per store instead of a re-derived 64-bit (out_base + rank) chain
 	asm volatile("" : "+l"(os), "+l"(oe), "+l"(ov));
 	const int room32 = (int) min(room, (long long) INT_MAX);
+	const unsigned lt = (1u << lane) - 1;
 	auto emit_loop = [&](auto div_tag) {
 		constexpr bool DIV = decltype(div_tag)::value;      // mean over a non-power-of-two N: one fp64 division per segment
-#pragma unroll 2
-		for (int r = tid; r < nbp; r += TH) {
-			const uint32_t d = dense[r];
-			if (!(d & D_KEEP)) continue;
-			const int pos = (int) (d & PMASK), kid = (int) ((d >> D_KID_SHIFT) & PMASK);
+		for (int r0 = warp * 32; r0 < nbp; r0 += TH) {
+			const int r = r0 + lane;
+			const unsigned d = r < nbp ? dense[r] : 0u;
+			const bool keep = (d & DN_KEEP) != 0;
+			const unsigned km = __ballot_sync(FULL, keep);
+			if (!keep) continue;
+			const int kid = (int) misc->kbase[r0 >> 5] + __popc(km & lt);
+			const int pos = (int) (d & DN_POS);
 			const int bs = w0i + pos;
-			const int be = (r + 1 < nbp) ? w0i + (int) (dense[r + 1] & PMASK) : next_bp;
-			const int ph = phys<VLOG>(pos);
+			const int be = (r + 1 < nbp) ? w0i + (int) (dense[r + 1] & DN_POS) : next_bp;
+			const int ph = phys32<VLOG>(pos);
 			double v;                                                // correctly rounded exact sum
 			if (LIMBS == 1) v = (double) ((int32_t) limb[ph] + fx_base32) * mul;     // |sum + defaults| < 2^30: one 32-bit conversion
 			else v = (double) ((long long) (((unsigned long long) limb[W + ph] << 32) | limb[ph]) + job.fx_base) * mul;
@@ -562,29 +627,27 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 				os[kid] = bs;
 				oe[kid] = be;
 				ov[kid] = v;
-				if (d & D_SLOW) {
+				if (d & DN_SLOW) {
 					// an input was not representable: the fix-up kernel recomputes this
 					// segment with the reference's own operation order
 					const unsigned long long k = atomicAdd(job.slow_count, 1ull);
 					if (k < (unsigned long long) job.slow_cap) job.slow_list[k] = out_base + kid;
 				}
 			}
-			if (!(d & D_SLOW)) auc += (double) (be - bs) * v;        // v is finite here
+			if (!(d & DN_SLOW)) auc += (double) (be - bs) * v;        // v is finite here
 		}
 	};
 	if (div) emit_loop(std::true_type{}); else emit_loop(std::false_type{});
 	for (int d = 16; d > 0; d >>= 1) auc += __shfl_down_sync(FULL, auc, d);
 	if (lane == 0) misc->wauc[warp] = auc;
-#if WB_FS_LATETICKET == 2
-	if (tid == 0) misc->ticket2 = (int) next_ticket;
-#endif
 	WB_PHASE(6);
 }
 
-template <int TH, int VLOG, int LIMBS>
-__global__ void __launch_bounds__(TH, TH == 128 ? 6 : WB_FS_MINB) fastsum_kernel(const Job job, int lw, double inv_scale, double lim, double scale) {
+template <int VLOG, int LIMBS, bool COV16>
+__global__ void __launch_bounds__(TH, (LIMBS == 1 && COV16) ? WB_FS_MINB : (LIMBS == 1 || COV16) ? 5 : 4)
+fastsum_kernel(const Job job, int lw, double inv_scale, double lim, double scale) {
 	extern __shared__ __align__(16) unsigned char smem[];
-	const Layout L = make_layout(job.wlog, job.N, LIMBS);
+	const Layout L = make_layout(job.wlog, job.N, LIMBS, COV16);
 	int32_t *tn = (int32_t *) (smem + L.off_tn);
 	long long *toff = (long long *) (smem + L.off_toff);
 	long long *tmd = (long long *) (smem + L.off_tmd);
@@ -595,112 +658,83 @@ __global__ void __launch_bounds__(TH, TH == 128 ? 6 : WB_FS_MINB) fastsum_kernel
 		tmd[i] = job.dflt_fx[i];
 	}
 	Misc *misc = (Misc *) smem;
-	int32_t *ca = (int32_t *) (smem + L.off_cur), *cb = (int32_t *) (smem + L.off_cur2);   // current / next cursor rows
-	// Windows are handed out in ascending order (the first two per CTA statically, then a
-	// ticket counter): the look-back only ever waits on windows a resident CTA has drawn.
-#if WB_FS_LATETICKET
-	int w = blockIdx.x;
-	if (w < job.nw)
-		for (int i = threadIdx.x; i < job.N; i += TH) ca[i] = job.cursor[(size_t) w * job.N + i];
+	int32_t *ca = (int32_t *) (smem + L.off_cur), *cb = (int32_t *) (smem + L.off_cur2);   // cursor rows: window being processed / prefetched for
+	// Windows are handed out in ascending order by a ticket counter, the first one included: a CTA
+	// that holds window w is running, and so is (or was) the holder of every window below w.
+	if (threadIdx.x == 0) {
+		mbar_init(&misc->bar_cur, 1);
+		mbar_init(&misc->bar_nxt, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		misc->ticket2 = (int) atomicAdd(job.ticket, 1u);
+	}
 	__syncthreads();
+	int w = misc->ticket2;
+	if (threadIdx.x == 0 && w < job.nw) {
+		const uint32_t bytes = (uint32_t) job.cstride * 4;
+		mbar_expect_tx(&misc->bar_cur, bytes);
+		bulk_g2s(ca, job.cursor + (size_t) w * job.cstride, bytes, &misc->bar_cur);
+	}
+	unsigned par_cur = 0, par_nxt = 0;
 	while (w < job.nw) {
 #ifdef WB_DIAG_PHASES
 		const long long diag_t0 = clock64();
 #endif
-		process_window<TH, VLOG, LIMBS>(job, w, smem, L, ca, cb, 0, lw, inv_scale, lim, scale);
-		__syncthreads();      // dense list consumed, next cursor row landed, AUC partials visible
+		const bool pref = WB_FS_PREF && w + (int) gridDim.x < job.nw;
+		process_window<VLOG, LIMBS, COV16>(job, w, smem, L, ca, cb, par_cur, par_nxt, lw, inv_scale, lim, scale);
+		par_cur ^= 1;
+		if (pref) par_nxt ^= 1;
+		__syncthreads();      // dense list consumed, ticket and AUC partials visible
 		if (threadIdx.x == 0 && job.auc_partial) {
 			double t = 0;
-			for (int k = 0; k < TH / 32; k++) t += misc->wauc[k];
+			for (int k = 0; k < NWARP; k++) t += misc->wauc[k];
 			job.auc_partial[w] = t;
 		}
 #ifdef WB_DIAG_PHASES
 		if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&job.diag[7], (unsigned long long) (t_ - diag_t0)); atomicAdd(&job.diag[8], 1ull); }
 #endif
 		w = misc->ticket2;
-#if WB_FS_LATETICKET == 2
-		// cb only ever holds the row of the window being prefetched for; the row of the window
-		// just drawn travels into ca while the window arrays are cleared
-		if (w < job.nw)
-			for (int i = threadIdx.x; i < job.N; i += TH) __pipeline_memcpy_async(&ca[i], &job.cursor[(size_t) w * job.N + i], 4);
-		__pipeline_commit();
-#else
-		{ int32_t *t = ca; ca = cb; cb = t; }
-#endif
 	}
-#else
-	int w = blockIdx.x, w1 = blockIdx.x + gridDim.x;
-	if (w < job.nw)
-		for (int i = threadIdx.x; i < job.N; i += TH) ca[i] = job.cursor[(size_t) w * job.N + i];
-	__syncthreads();
-	while (w < job.nw) {
-#ifdef WB_DIAG_PHASES
-		const long long diag_t0 = clock64();
-#endif
-		unsigned t2 = 0;
-		if (threadIdx.x == 0) t2 = atomicAdd(job.ticket, 1u) + 2u * gridDim.x;   // consumed two windows from now
-		if (w1 < job.nw)
-			for (int i = threadIdx.x; i < job.N; i += TH)
-				__pipeline_memcpy_async(&cb[i], &job.cursor[(size_t) w1 * job.N + i], 4);
-		__pipeline_commit();
-		process_window<TH, VLOG, LIMBS>(job, w, smem, L, ca, cb, w1, lw, inv_scale, lim, scale);
-		if (threadIdx.x == 0) misc->ticket2 = (int) t2;
-		__syncthreads();      // dense list consumed, next cursor row landed, ticket and AUC partials visible
-		if (threadIdx.x == 0 && job.auc_partial) {
-			double t = 0;
-			for (int k = 0; k < TH / 32; k++) t += misc->wauc[k];
-			job.auc_partial[w] = t;
-		}
-#ifdef WB_DIAG_PHASES
-		if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&job.diag[7], (unsigned long long) (t_ - diag_t0)); atomicAdd(&job.diag[8], 1ull); }
-#endif
-		w = w1; w1 = misc->ticket2;
-		{ int32_t *t = ca; ca = cb; cb = t; }
-	}
-#endif
 }
 
-template <int TH, int VLOG, int LIMBS>
+template <int VLOG, int LIMBS, bool COV16>
 static cudaError_t launch_v(const Job &job, int lw, double inv_scale, double lim, double scale, cudaStream_t s) {
-	size_t smem = make_layout(job.wlog, job.N, LIMBS).total;
+	size_t smem = make_layout(job.wlog, job.N, LIMBS, COV16).total;
 	{ const char *e = getenv("WB200_FS_PAD"); if (e) smem += (size_t) atoi(e) * 1024; }   // development: cap the CTAs per SM
 	int dev = 0, sms = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-	cudaError_t e = cudaFuncSetAttribute(fastsum_kernel<TH, VLOG, LIMBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+	cudaError_t e = cudaFuncSetAttribute(fastsum_kernel<VLOG, LIMBS, COV16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 	if (e != cudaSuccess) return e;
 	int per = 1;
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fastsum_kernel<TH, VLOG, LIMBS>, TH, smem);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fastsum_kernel<VLOG, LIMBS, COV16>, TH, smem);
+	if (getenv("WB200_FS_VERBOSE")) fprintf(stderr, "fastsum_kernel<%d,%d,%d>: %zu B smem, %d CTAs/SM\n", VLOG, LIMBS, (int) COV16, smem, per);
 	const int grid = min(job.nw, sms * max(per, 1));
-	fastsum_kernel<TH, VLOG, LIMBS><<<grid, TH, smem, s>>>(job, lw, inv_scale, lim, scale);
+	fastsum_kernel<VLOG, LIMBS, COV16><<<grid, TH, smem, s>>>(job, lw, inv_scale, lim, scale);
 	return cudaGetLastError();
+}
+
+static bool use_cov16(const Job &job) {
+	const char *e = getenv("WB200_FS_COV16");           // development: 0 forces the 32-bit cover fields
+	return job.N <= 255 && !(e && atoi(e) == 0);
 }
 
 } // namespace fs
 
-// threads per window (development override: WB200_FS_THREADS)
-static int fastsum_threads(const Job &job) {
-	const char *e = getenv("WB200_FS_THREADS");
-	const int th = e ? atoi(e) : 0;
-	return (th == 128 || th == 256) ? th : 128;
-}
-
 // Whether the sum / mean sweep kernel covers this job (else: emit_kernel<MODE_FAST>).
 bool fastsum_supported(const Job &job) {
 	if (job.fast != 1 || !job.vec || job.fx_limbs > 2 || job.N > MAX_TRACKS) return false;
-	const int vlog = job.wlog - (fastsum_threads(job) == 256 ? 8 : 7);
+	const int vlog = job.wlog - 7;
 	if (vlog != 4 && vlog != 5) return false;
-	return fs::make_layout(job.wlog, job.N, job.fx_limbs).total <= 200 * 1024;
+	return fs::make_layout(job.wlog, job.N, job.fx_limbs, fs::use_cov16(job)).total <= 200 * 1024;
 }
 
 cudaError_t launch_fastsum(const Job &job, int lw, double inv_scale, double lim, double scale, cudaStream_t s) {
-	const bool big = fastsum_threads(job) == 256;
-	const int vlog = job.wlog - (big ? 8 : 7);
-	const bool one = job.fx_limbs == 1;
-#define WB_FS(TH, V) (one ? fs::launch_v<TH, V, 1>(job, lw, inv_scale, lim, scale, s) : fs::launch_v<TH, V, 2>(job, lw, inv_scale, lim, scale, s))
-	if (big && vlog == 4) return WB_FS(256, 4);
-	if (!big && vlog == 4) return WB_FS(128, 4);
-	if (!big && vlog == 5) return WB_FS(128, 5);
+	const int vlog = job.wlog - 7;
+	const bool one = job.fx_limbs == 1, c16 = fs::use_cov16(job);
+#define WB_FS(V) (one ? (c16 ? fs::launch_v<V, 1, true>(job, lw, inv_scale, lim, scale, s) : fs::launch_v<V, 1, false>(job, lw, inv_scale, lim, scale, s)) \
+                      : (c16 ? fs::launch_v<V, 2, true>(job, lw, inv_scale, lim, scale, s) : fs::launch_v<V, 2, false>(job, lw, inv_scale, lim, scale, s)))
+	if (vlog == 4) return WB_FS(4);
+	if (vlog == 5) return WB_FS(5);
 #undef WB_FS
 	return cudaErrorInvalidValue;
 }
