@@ -187,6 +187,8 @@ def _region_worker(args):
     """One parity region [a, b) of an exported shard: the reference (oracle/_ref) reduces the
     intervals that overlap [a, b + PAD); the segments that start inside [a, b) come back."""
     kind, path, n_tracks, op, a, b = args
+    # every breakpoint in [a, b + PAD) and every interval covering a position in it is kept, so the
+    # segments that start in [a, b) come out exactly as in the whole-chromosome problem
     from oracle.pyoracle import Oracle, Track
     s = np.load(os.path.join(path, "s.npy"), mmap_mode="r")
     e = np.load(os.path.join(path, "e.npy"), mmap_mode="r")
@@ -195,7 +197,7 @@ def _region_worker(args):
     tracks = []
     for i in range(n_tracks):
         si, ei = s[off[i]:off[i + 1]], e[off[i]:off[i + 1]]
-        lo = int(np.searchsorted(ei, a, side="right"))           # first interval that ends after a
+        lo = int(np.searchsorted(ei, a, side="left"))            # first interval that ends at or after a (an end AT a is a breakpoint at a)
         hi = int(np.searchsorted(si, b + PAD, side="left"))      # first interval that starts at or after b + PAD
         hi = max(hi, lo)
         tracks.append(Track(np.zeros(hi - lo, np.int32), np.array(si[lo:hi]), np.array(ei[lo:hi]),
@@ -327,7 +329,7 @@ class ParityChecker:
             ps, pe, pv, cnt = [], [], [], []
             for i in range(ntr):
                 o0, o1 = int(off[i]), int(off[i + 1])
-                lo = int(torch.searchsorted(sh["e"][o0:o1], a, right=True))
+                lo = int(torch.searchsorted(sh["e"][o0:o1], a))
                 hi = max(lo, int(torch.searchsorted(sh["s"][o0:o1], b + PAD)))
                 ps.append(sh["s"][o0 + lo:o0 + hi]); pe.append(sh["e"][o0 + lo:o0 + hi]); pv.append(vals[o0 + lo:o0 + hi])
                 cnt.append(hi - lo)
@@ -454,7 +456,7 @@ def main():
     checker = None
     if not args.no_cpu:
         ncpu = os.cpu_count() or 1
-        checker = ParityChecker(torch, max(1, min(32, ncpu // (4 * world) if ncpu >= 8 * world else ncpu // world)))
+        checker = ParityChecker(torch, max(1, min(32, ncpu // (2 * world))))
 
     def barrier():
         if world > 1:

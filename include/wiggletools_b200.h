@@ -136,6 +136,15 @@ void wb200_host_free(void *p);
 int wb200_reduce_host(wb200_ctx *ctx, int op, int ntracks, int nset1, int strict,
                       const wb200_track *tracks, wb200_segments *out);
 
+/* Raw multiplexer rows of the chromosome the last wb200_reduce_host() call on the context reduced
+ * (inputs, cursor table and segments are still resident in HBM): for its segments
+ * [first, first+count), values[(k-first)*ntracks + i] is track i's value where it is in play, else its
+ * default_value, and inplay[...] is 1 / 0.  Replaces what popCoreMultiplexer2 leaves in
+ * Multiplexer.values[] / inplay[] (src/multiplexer.c:76-96), read by TeeMultiplexerPop
+ * (src/mWigWriter.c:179-225: mwrite, mwrite_bg, paste) and SelectReductionPop (src/reducers.c:40-65).
+ * values / inplay are host arrays of count*ntracks entries. */
+int wb200_rows_host(wb200_ctx *ctx, int64_t first, int64_t count, double *values, unsigned char *inplay);
+
 /* Same, for several chromosome shards in one call: tracks[c*ntracks + i] is track
  * i on shard c, out[c] receives shard c's segments (all valid until the next
  * call on the context).  H2D staging of shard c+1, the kernels of shard c and the

@@ -6,7 +6,7 @@
  * record by record into the writer thread.
  *
  * /root/reference is read-only here, so the same routing is attached from
- * outside with the linker's --wrap (oracle/Makefile, target `dropin`):
+ * outside with the linker's --wrap (integration/Makefile):
  * calls from src/commandParser.c to TeeWiggleIterator, runWiggleIterator,
  * toFile and toStdout arrive in the __wrap_ functions below; everything that
  * is not a fresh reduction of the library goes on to the reference's own code

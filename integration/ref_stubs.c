@@ -1,7 +1,7 @@
 /* TEST INFRASTRUCTURE ONLY (oracle/): link stubs for the reference reader
  * constructors whose third-party libraries (libBigWig, htslib) are absent from
  * this image; used when linking the reference CLI against the GPU library
- * (oracle/_ref/wiggletools_b200).  Declarations: /root/reference/src/wiggletools.h:36-42,143. */
+ * (integration/_build/wiggletools_b200).  Declarations: /root/reference/src/wiggletools.h:36-42,143. */
 #include <stdio.h>
 #include <stdlib.h>
 #include "wiggletools.h"

@@ -24,9 +24,10 @@ def _built():
     if os.path.isdir("/root/reference/src") and not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libwtrefbw.so")) \
             and os.path.exists(os.path.join(ROOT, "wiggletools_b200", "libwiggletools_b200.so")):
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "refbw"])
-    if os.path.isdir("/root/reference/src") and not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "wiggletools_b200")) \
+    if os.path.isdir("/root/reference/src") and not os.path.exists(os.path.join(ROOT, "integration", "_build", "wiggletools_b200")) \
             and os.path.exists(os.path.join(ROOT, "wiggletools_b200", "libwiggletools_b200.so")):
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "dropin"])
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "integration")])
 
 
 @pytest.fixture(scope="session")

@@ -182,3 +182,71 @@ def test_config0_with_the_reference_itself(tmp_path):
     assert [float(x) for x in out[1:11]] == [.5, 1.5, 1, 3, 2, 4.5, 3, 6, 4, 4.5]
     assert run("pearson", "fixedStep.bw", "variableStep.bw").strip() == "-0.028968"
     assert run("AUC", "mean", "fixedStep.bw", "variableStep.bw").strip() == "30.000000"
+
+
+def test_corrupt_files_fail_cleanly(tmp_path):
+    """Truncated files and corrupted offsets / counts / section types make the decoder report
+    'corrupt BigWig ...' instead of reading past the buffer (the parser trusted every
+    offset in the file; libBigWig fails cleanly on the same inputs)."""
+    import struct
+    path, chroms, per = mixed_file(tmp_path, compress=True)
+    good = open(path, "rb").read()
+
+    def outcome(data):
+        p = tmp_path / "bad.bw"
+        p.write_bytes(data)
+        try:
+            b = BigWig(p)
+        except IOError as e:
+            return str(e)
+        try:
+            for k in range(len(b.chroms)):
+                b.decode(k)
+        except IOError as e:
+            return str(e)
+        return "ok"
+
+    assert outcome(good) == "ok"
+    # truncations at every structural boundary and at many arbitrary lengths
+    for cut in [65, 100, 200, len(good) // 3, len(good) // 2, len(good) - 200, len(good) - 1]:
+        msg = outcome(good[:cut])
+        assert msg == "ok" or "corrupt" in msg or "not in BigWig" in msg, (cut, msg)
+    chrom_tree, = struct.unpack_from("<Q", good, 8)
+    index_off, = struct.unpack_from("<Q", good, 24)
+    # header offsets pointing outside the file
+    for field in (8, 24):
+        bad = bytearray(good)
+        struct.pack_into("<Q", bad, field, len(good) + 12345)
+        assert "corrupt" in outcome(bytes(bad))
+        struct.pack_into("<Q", bad, field, 2 ** 63)
+        assert "corrupt" in outcome(bytes(bad))
+    # a chromosome-tree node claiming 65535 entries, an absurd key size
+    bad = bytearray(good); struct.pack_into("<H", bad, chrom_tree + 32 + 2, 65535)
+    assert "corrupt" in outcome(bytes(bad))
+    bad = bytearray(good); struct.pack_into("<I", bad, chrom_tree + 8, 0x7fffffff)
+    assert "corrupt" in outcome(bytes(bad))
+    # R-tree root: child / block offsets outside the file, a node count that runs off the end
+    bad = bytearray(good); struct.pack_into("<H", bad, index_off + 48 + 2, 65535)
+    assert "corrupt" in outcome(bytes(bad))
+    root_leaf = good[index_off + 48] != 0
+    bad = bytearray(good); struct.pack_into("<Q", bad, index_off + 48 + 4 + 16, len(good) * 4)
+    assert "corrupt" in outcome(bytes(bad))
+    if root_leaf:
+        bad = bytearray(good); struct.pack_into("<Q", bad, index_off + 48 + 4 + 24, 2 ** 62)     # block size
+        assert "corrupt" in outcome(bytes(bad))
+    # an uncompressed file with an unknown section type
+    path2, _, _ = mixed_file(tmp_path, compress=False, seed=9)
+    raw = bytearray(open(path2, "rb").read())
+    index2, = struct.unpack_from("<Q", raw, 24)
+    assert raw[index2 + 48] != 0 or True
+    # find the first data section through the header's full_data_offset (8 bytes count, then sections)
+    data_off, = struct.unpack_from("<Q", raw, 16)
+    raw[data_off + 8 + 20] = 9
+    assert "corrupt" in outcome(bytes(raw))
+    # random single-byte damage must never crash the process
+    rng = np.random.default_rng(1)
+    for _ in range(300):
+        bad = bytearray(good)
+        k = int(rng.integers(0, len(bad)))
+        bad[k] ^= int(rng.integers(1, 256))
+        outcome(bytes(bad))

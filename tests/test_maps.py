@@ -109,12 +109,12 @@ def test_device_maps_everything_dropped_and_errors(engine):
 def test_cli_maps_on_the_device(tmp_path):
     """`mean map ln ...`, `sum map scale ...`, nested maps, a map feeding a host-side operator: the
     reference CLI linked against the library (unary constructors routed to wb200_mapped_iterator
-    by oracle/dropin_binding.c) prints what the unmodified reference CLI prints."""
+    by integration/dropin_binding.c) prints what the unmodified reference CLI prints."""
     import os
     import subprocess
     here = os.path.dirname(os.path.abspath(__file__))
     ref = os.path.join(here, "..", "oracle", "_ref", "wiggletools")
-    exe = os.path.join(here, "..", "oracle", "_ref", "wiggletools_b200")
+    exe = os.path.join(here, "..", "integration", "_build", "wiggletools_b200")
     if not (os.path.exists(ref) and os.path.exists(exe)):
         pytest.skip("oracle/_ref CLIs not built (needs /root/reference at build time)")
     rng = np.random.default_rng(31)

@@ -169,10 +169,10 @@ def test_device_sink_after_reduction(engine, port):
 def test_cli_write_through_device_sink(tmp_path):
     """`write f mean ...`, `write_bg f mean ...`, plain `mean ...` (stdout) and a Tee in the middle of
     a pipeline: the reference CLI linked against the library (device sink routed in by
-    oracle/dropin_binding.c) must print the bytes of the unmodified reference CLI."""
+    integration/dropin_binding.c) must print the bytes of the unmodified reference CLI."""
     import subprocess
     ref = os.path.join(HERE, "..", "oracle", "_ref", "wiggletools")
-    exe = os.path.join(HERE, "..", "oracle", "_ref", "wiggletools_b200")
+    exe = os.path.join(HERE, "..", "integration", "_build", "wiggletools_b200")
     if not (os.path.exists(ref) and os.path.exists(exe)):
         pytest.skip("oracle/_ref CLIs not built (needs /root/reference at build time)")
     rng = np.random.default_rng(21)

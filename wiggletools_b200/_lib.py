@@ -74,6 +74,7 @@ def load():
     lib.wb200_host_alloc.argtypes = [C.c_int64]
     lib.wb200_host_free.argtypes = [C.c_void_p]
     lib.wb200_reduce_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.wb200_rows_host.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
     lib.wb200_reduce_host_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.wb200_reduce_device.argtypes = [
         C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -116,7 +117,7 @@ def load():
 # every symbol include/wiggletools_b200.h declares
 EXPORTS = [
     "wb200_create", "wb200_destroy", "wb200_last_error", "wb200_last_stats", "wb200_set_stream",
-    "wb200_set_window", "wb200_bind_host_thread", "wb200_host_alloc", "wb200_host_free", "wb200_reduce_host", "wb200_reduce_host_batch",
+    "wb200_set_window", "wb200_bind_host_thread", "wb200_host_alloc", "wb200_host_free", "wb200_reduce_host", "wb200_rows_host", "wb200_reduce_host_batch",
     "wb200_reduce_device", "wb200_reduce_device_batch", "wb200_pearson_host", "wb200_pearson_pair_host", "wb200_pearson_merge", "wb200_pearson_result",
     "wb200_tdist_Q", "wb200_bw_open", "wb200_bw_close", "wb200_bw_last_error", "wb200_bw_nchrom", "wb200_bw_chrom_name",
     "wb200_bw_chrom_length", "wb200_bw_set_stretch", "wb200_bw_decode_chrom", "wb200_debug_phases", "wb200_debug_format_value",

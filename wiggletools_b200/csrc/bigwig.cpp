@@ -64,13 +64,26 @@ namespace {
 
 bool fail(wb200_bigwig *bw, const std::string &m) { if (bw) bw->err = m; g_bw_error = m; return false; }
 
-void walk_chrom_tree(const wb200_bigwig *bw, uint64_t node, uint32_t key_size, std::vector<Chrom> &out) {
+// Every offset, count and size in the file is untrusted: reads are bounds-checked against the
+// file size, recursion depth and node counts are capped, and anything out of range makes the walk
+// fail ("corrupt BigWig index") instead of reading past the buffer.
+constexpr int MAX_TREE_DEPTH = 32;
+constexpr size_t MAX_CHROMS = 1u << 24, MAX_BLOCKS = 1u << 28;
+
+inline bool in_file(const wb200_bigwig *bw, uint64_t off, uint64_t len) {
+	return off <= bw->file.size() && len <= bw->file.size() - off;
+}
+
+bool walk_chrom_tree(const wb200_bigwig *bw, uint64_t node, uint32_t key_size, std::vector<Chrom> &out, int depth = 0) {
+	if (depth > MAX_TREE_DEPTH || !in_file(bw, node, 4)) return false;
 	const unsigned char *p = bw->file.data() + node;
 	const bool leaf = p[0] != 0;
 	const uint16_t count = rd<uint16_t>(p + 2);
+	if (!in_file(bw, node + 4, (uint64_t) count * (key_size + 8))) return false;
 	p += 4;
 	for (uint16_t k = 0; k < count; k++) {
 		if (leaf) {
+			if (out.size() >= MAX_CHROMS) return false;
 			Chrom c;
 			c.name.assign((const char *) p, strnlen((const char *) p, key_size));
 			c.id = rd<uint32_t>(p + key_size);
@@ -78,29 +91,37 @@ void walk_chrom_tree(const wb200_bigwig *bw, uint64_t node, uint32_t key_size, s
 			out.push_back(c);
 			p += key_size + 8;
 		} else {
-			walk_chrom_tree(bw, rd<uint64_t>(p + key_size), key_size, out);
+			if (!walk_chrom_tree(bw, rd<uint64_t>(p + key_size), key_size, out, depth + 1)) return false;
 			p += key_size + 8;
 		}
 	}
+	return true;
 }
 
 // data blocks whose chromosome range includes `id`
-void walk_rtree(const wb200_bigwig *bw, uint64_t node, uint32_t id, std::vector<Block> &out) {
+bool walk_rtree(const wb200_bigwig *bw, uint64_t node, uint32_t id, std::vector<Block> &out, int depth = 0) {
+	if (depth > MAX_TREE_DEPTH || !in_file(bw, node, 4)) return false;
 	const unsigned char *p = bw->file.data() + node;
 	const bool leaf = p[0] != 0;
 	const uint16_t count = rd<uint16_t>(p + 2);
+	if (!in_file(bw, node + 4, (uint64_t) count * (leaf ? 32 : 24))) return false;
 	p += 4;
 	for (uint16_t k = 0; k < count; k++) {
 		const uint32_t c0 = rd<uint32_t>(p), c1 = rd<uint32_t>(p + 8);
 		const bool hit = c0 <= id && id <= c1;
 		if (leaf) {
-			if (hit) out.push_back(Block{rd<uint64_t>(p + 16), rd<uint64_t>(p + 24)});
+			if (hit) {
+				const Block b{rd<uint64_t>(p + 16), rd<uint64_t>(p + 24)};
+				if (!in_file(bw, b.offset, b.size) || out.size() >= MAX_BLOCKS) return false;
+				out.push_back(b);
+			}
 			p += 32;
 		} else {
-			if (hit) walk_rtree(bw, rd<uint64_t>(p + 16), id, out);
+			if (hit && !walk_rtree(bw, rd<uint64_t>(p + 16), id, out, depth + 1)) return false;
 			p += 24;
 		}
 	}
+	return true;
 }
 
 struct Raw { std::vector<unsigned char> data; int64_t pieces = 0; bool ok = true; };
@@ -116,13 +137,17 @@ inline int64_t pieces_of(int64_t s, int64_t e, int stretch, int64_t length) {
 	return k1 >= k0 ? k1 - k0 + 1 : 0;
 }
 
+// items of one data section (1 bedGraph, 2 variableStep, 3 fixedStep); false for a section that is
+// truncated or of an unknown type
 template <class F>
-void for_items(const unsigned char *d, size_t n, uint32_t id, F &&f) {
-	if (n < 24) return;
-	if (rd<uint32_t>(d) != id) return;
+bool for_items(const unsigned char *d, size_t n, uint32_t id, F &&f) {
+	if (n < 24) return false;
+	if (rd<uint32_t>(d) != id) return true;           // another chromosome's section: nothing to emit
 	const uint32_t cstart = rd<uint32_t>(d + 4), step = rd<uint32_t>(d + 12), span = rd<uint32_t>(d + 16);
 	const uint8_t type = d[20];
 	const uint16_t count = rd<uint16_t>(d + 22);
+	if (type < 1 || type > 3) return false;
+	if ((size_t) count * (type == 1 ? 12 : type == 2 ? 8 : 4) > n - 24) return false;
 	const unsigned char *p = d + 24;
 	for (uint16_t k = 0; k < count; k++) {
 		int64_t s, e; float v;
@@ -131,6 +156,7 @@ void for_items(const unsigned char *d, size_t n, uint32_t id, F &&f) {
 		else { if (p + 4 > d + n) break; s = (int64_t) cstart + (int64_t) k * step; e = s + span; v = rd<float>(p); p += 4; }
 		f(s + 1, e + 1, v);      // 0-based -> 1-based, bigWiggleReader.c:39-40
 	}
+	return true;
 }
 
 template <class F>
@@ -169,13 +195,20 @@ wb200_bigwig *wb200_bw_open(const char *path) {
 	const uint64_t chrom_tree = rd<uint64_t>(h + 8);
 	bw->index_offset = rd<uint64_t>(h + 24);
 	bw->uncompress_buf = rd<uint32_t>(h + 52);
-	if (rd<uint32_t>(h + chrom_tree) != 0x78CA8C91u || rd<uint32_t>(h + bw->index_offset) != 0x2468ACE0u) {
+	// header offsets are untrusted: B+ tree header (32 bytes) and R-tree header (48 bytes) must lie inside the file
+	if (!in_file(bw, chrom_tree, 32) || !in_file(bw, bw->index_offset, 48) ||
+	    rd<uint32_t>(h + chrom_tree) != 0x78CA8C91u || rd<uint32_t>(h + bw->index_offset) != 0x2468ACE0u) {
 		delete bw;
 		fail(nullptr, "corrupt BigWig index");
 		return nullptr;
 	}
 	const uint32_t key_size = rd<uint32_t>(h + chrom_tree + 8);
-	walk_chrom_tree(bw, chrom_tree + 32, key_size, bw->chroms);
+	if (key_size == 0 || key_size > 4096 || bw->uncompress_buf > (1u << 30) ||
+	    !walk_chrom_tree(bw, chrom_tree + 32, key_size, bw->chroms)) {
+		delete bw;
+		fail(nullptr, "corrupt BigWig index");
+		return nullptr;
+	}
 	std::sort(bw->chroms.begin(), bw->chroms.end(), [](const Chrom &a, const Chrom &b) { return strcmp(a.name.c_str(), b.name.c_str()) < 0; });
 	const char *env = getenv("WB200_BW_THREADS");
 	bw->threads = env ? atoi(env) : (int) std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
@@ -204,7 +237,7 @@ int wb200_bw_decode_chrom(wb200_bigwig *bw, int chrom_index, wb200_track *out) {
 	if (!bw || chrom_index < 0 || chrom_index >= (int) bw->chroms.size() || !out) return WB200_EINVAL;
 	const Chrom &c = bw->chroms[chrom_index];
 	std::vector<Block> blocks;
-	walk_rtree(bw, bw->index_offset + 48, c.id, blocks);
+	if (!walk_rtree(bw, bw->index_offset + 48, c.id, blocks)) { fail(bw, "corrupt BigWig index"); return WB200_EINVAL; }
 	std::sort(blocks.begin(), blocks.end(), [](const Block &a, const Block &b) { return a.offset < b.offset; });
 	const int nb = (int) blocks.size();
 	std::vector<Raw> raw(nb);
@@ -223,7 +256,7 @@ int wb200_bw_decode_chrom(wb200_bigwig *bw, int chrom_index, wb200_track *out) {
 		} else
 			r.data.assign(src, src + blocks[b].size);
 		int64_t cnt = 0;
-		for_items(r.data.data(), r.data.size(), c.id, [&](int64_t s, int64_t e, float) { cnt += pieces_of(s, e, stretch, length); });
+		if (!for_items(r.data.data(), r.data.size(), c.id, [&](int64_t s, int64_t e, float) { cnt += pieces_of(s, e, stretch, length); })) { r.ok = false; return; }
 		r.pieces = cnt;
 	});
 	std::vector<int64_t> off(nb + 1, 0);

@@ -75,6 +75,10 @@ struct wb200_ctx {
 	HostBuf h_arena;
 	std::vector<cudaEvent_t> pipe_events;
 	unsigned long long diag[16] = {0};      // diagnostic builds: accumulated phase counters
+	// raw multiplexer rows of the last single-shard reduction (wb200_rows_host)
+	Job last_job{};
+	int64_t last_S = -1;
+	DevBuf rows_v, rows_p;
 	// batch device entry (wb200_reduce_device_batch): per-shard tables and result slots
 	DevBuf b_tables, b_small;
 	HostBuf hb_tables, hb_small;
@@ -315,6 +319,7 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 		int rc = plan_shard(ctx, op, N, n1, strict, h_off, h_dflt, d_start, d_end, d_value, pos_lo, pos_hi, moments_out != nullptr, px, py, job);
 		if (rc != WB200_OK) return rc;
 	}
+	ctx->last_S = -1;
 	const bool setop = (op == OP_TTEST || op == OP_MWU);
 	const int64_t I = job.I;
 	const int nw = job.nw, wlog = job.wlog;
@@ -439,6 +444,7 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 	cudaEventElapsedTime(&st.ms_count, ctx->ev[1], ctx->ev[2]);
 	cudaEventElapsedTime(&st.ms_emit, ctx->ev[4], ctx->ev[3]);
 	cudaEventElapsedTime(&st.ms_total, ctx->ev[0], ctx->ev[3]);
+	ctx->last_job = job; ctx->last_S = (S > out_cap || !d_out_start) ? -1 : S;      // inputs, cursor table and segments stay resident until the next call
 	if (n_out) *n_out = S;
 	if (auc_out) memcpy(auc_out, h_small + 2, 8);
 	if (default_out) *default_out = setop ? NAN : derived_default(op, N, h_dflt);
@@ -495,6 +501,7 @@ void wb200_destroy(wb200_ctx *ctx) {
 	for (auto ev : ctx->pipe_events) cudaEventDestroy(ev);
 	for (auto ev : ctx->batch_events) cudaEventDestroy(ev);
 	ctx->b_tables.release(); ctx->b_small.release(); ctx->hb_tables.release(); ctx->hb_small.release();
+	ctx->rows_v.release(); ctx->rows_p.release();
 	if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
 	if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
 	HostBuf *h[] = {&ctx->h_small, &ctx->h_meta, &ctx->h_start, &ctx->h_end, &ctx->h_value, &ctx->h_arena};
@@ -760,6 +767,7 @@ int wb200_reduce_device_batch(wb200_ctx *ctx, int op, int ntracks, int nset1, in
 		h.n_out = 0; h.auc = 0; h.slow_segments = 0; h.ms_cursor = h.ms_sweep = 0; h.limbs = 0; h.sweep_kernel = 0;
 	}
 	wb200_stats total{};
+	ctx->last_S = -1;
 	if (nshards == 0) { ctx->stats = total; return WB200_OK; }
 
 	// per-shard tables (offsets | defaults | fixed-point defaults) and result slots, pooled
@@ -977,6 +985,28 @@ int reduce_host_to_device(wb200_ctx *ctx, int op, int ntracks, int nset1, int st
 	return rc;
 }
 } // namespace
+
+// Raw multiplexer rows of the chromosome the last wb200_reduce_host() call on the context reduced
+// (its staged inputs, cursor table and segments are still resident in HBM): for segments
+// [first, first + count), values[(k - first) * ntracks + i] = track i's value where it is in play, else
+// its default, and inplay[...] = 1 / 0 -- Multiplexer.values[] / inplay[] of the reference's sweep
+// (src/multiplexer.c:76-96), which mWigWriter.c:179-225 and SelectReductionPop (reducers.c:40-65) read.
+int wb200_rows_host(wb200_ctx *ctx, int64_t first, int64_t count, double *values, unsigned char *inplay) {
+	if (!ctx || !values || !inplay || first < 0 || count < 0) return WB200_EINVAL;
+	if (ctx->last_S < 0) return fail(ctx, WB200_EINVAL, "wb200_rows_host: no single-chromosome reduction is resident on this context");
+	if (first + count > ctx->last_S) return fail(ctx, WB200_EINVAL, "wb200_rows_host: rows beyond the last reduction's segments");
+	if (count == 0) return WB200_OK;
+	cudaSetDevice(ctx->device);
+	cudaStream_t s = ctx->stream;
+	const size_t n = (size_t) count * ctx->last_job.N;
+	CK(ctx->rows_v.ensure(n * sizeof(double)));
+	CK(ctx->rows_p.ensure(n));
+	CK(launch_rows(ctx->last_job, first, count, ctx->rows_v.as<double>(), ctx->rows_p.as<unsigned char>(), s));
+	CK(cudaMemcpyAsync(values, ctx->rows_v.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+	CK(cudaMemcpyAsync(inplay, ctx->rows_p.p, n, cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+	return WB200_OK;
+}
 
 int wb200_reduce_host(wb200_ctx *ctx, int op, int ntracks, int nset1, int strict,
                       const wb200_track *tracks, wb200_segments *out) {

@@ -386,6 +386,7 @@ void reducer_seek(WiggleIterator *wi, const char *chrom, int start, int finish) 
 	Reducer *r = (Reducer *) wi->data;
 	for (WiggleIterator *it : r->iters) seek(it, chrom, start, finish);
 	r->rs.clear(); r->re.clear(); r->rv.clear(); r->k = 0;
+	r->auc = 0;       // the integral restarts with the sought region (the eager first pop had added the whole first chromosome)
 	pop(wi);
 }
 
@@ -486,7 +487,9 @@ void select_seek(WiggleIterator *wi, const char *chrom, int start, int finish) {
 	pop(wi);
 }
 
-struct StatData { double res; WiggleIterator *source; Reducer *gpu; };
+// popped: area of the records passed through since the last seek; carry: what the reference's never-reset
+// `res` holds from before the last seek (statistics.c:39-43: StatisticSeek does not clear it)
+struct StatData { double res; WiggleIterator *source; Reducer *gpu; double popped, carry; };
 
 void auc_pop(WiggleIterator *wi) {
 	// AUCPop (statistics.c:103-120): pass records through, integrate len*value.
@@ -494,21 +497,26 @@ void auc_pop(WiggleIterator *wi) {
 	// (per-chromosome partials computed on the device, folded in order).
 	StatData *d = (StatData *) wi->data;
 	if (d->source->done) {
-		if (d->gpu) d->res = d->gpu->auc;
+		if (d->gpu) d->res = d->carry + d->gpu->auc;
 		wi->done = true;
 		return;
 	}
 	wi->chrom = d->source->chrom; wi->start = d->source->start; wi->finish = d->source->finish;
 	wi->value = d->source->value;
-	if (!d->gpu && !std::isnan(wi->value)) d->res += (wi->finish - wi->start) * wi->value;
+	if (!std::isnan(wi->value)) {
+		const double area = (wi->finish - wi->start) * wi->value;
+		if (d->gpu) d->popped += area; else d->res += area;
+	}
 	pop(d->source);
 }
 
 void stat_seek(WiggleIterator *wi, const char *chrom, int start, int finish) {
+	// StatisticSeek (statistics.c:39-43): seek the source, pop; the running result is NOT cleared, so
+	// what was integrated before the seek (usually the constructor's first record) stays in it
 	StatData *d = (StatData *) wi->data;
-	seek(d->source, chrom, start, finish);
-	if (d->gpu) d->gpu->auc = 0;
-	d->res = 0;
+	d->carry += d->popped;
+	d->popped = 0;
+	seek(d->source, chrom, start, finish);      // a GPU reduction restarts its own integral here (reducer_seek)
 	pop(wi);
 }
 

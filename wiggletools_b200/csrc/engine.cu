@@ -1783,6 +1783,38 @@ cudaError_t launch_fixup(const Job &job, long long count, cudaStream_t s) {
 	return cudaGetLastError();
 }
 
+// Raw multiplexer rows: what popCoreMultiplexer2 leaves in Multiplexer.values[] / inplay[]
+// (/root/reference/src/multiplexer.c:76-96) for the segments [first, first + count) of the last
+// reduction -- one thread per (segment, track); the covering interval is searched between the
+// cursor rows of the window that holds the segment start.  values: the track's value where it
+// is in play, else its default.
+__global__ void rows_kernel(const Job job, long long first, long long count, double *values, unsigned char *inplay) {
+	const long long idx = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= count * job.N) return;
+	const long long k = idx / job.N;
+	const int i = (int) (idx - k * job.N);
+	const int pos = job.out_start[first + k];
+	const int w = (int) (((long long) pos - job.p0) >> job.wlog);
+	const long long o = job.off[i];
+	const int n = (int) (job.off[i + 1] - o);
+	int lo = job.cursor[(size_t) w * job.cstride + i], hi = min(job.cursor[(size_t) (w + 1) * job.cstride + i], n - 1);
+	int ans = -1;                        // first interval in [lo, hi] whose end lies beyond pos (ends ascend)
+	while (lo <= hi) {
+		const int mid = (lo + hi) >> 1;
+		if (job.end[o + mid] > pos) { ans = mid; hi = mid - 1; } else lo = mid + 1;
+	}
+	const bool in = ans >= 0 && job.start[o + ans] <= pos;
+	values[idx] = in ? job.value[o + ans] : job.dflt[i];
+	inplay[idx] = in ? 1 : 0;
+}
+
+cudaError_t launch_rows(const Job &job, long long first, long long count, double *values, unsigned char *inplay, cudaStream_t s) {
+	if (count <= 0) return cudaSuccess;
+	const long long total = count * job.N;
+	rows_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, s>>>(job, first, count, values, inplay);
+	return cudaGetLastError();
+}
+
 cudaError_t launch_sample_maxabs(const double *value, int64_t n, int64_t stride, double *out2, cudaStream_t s) {
 	cudaError_t e = cudaMemsetAsync(out2, 0, 2 * sizeof(double), s);
 	if (e != cudaSuccess) return e;

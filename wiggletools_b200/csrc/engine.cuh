@@ -115,6 +115,7 @@ cudaError_t launch_emit(const Job &job, cudaStream_t s, int *auc_per_window);
 bool fastsum_supported(const Job &job);
 cudaError_t launch_fastsum(const Job &job, int lw, double inv_scale, double lim, double scale, cudaStream_t s);
 cudaError_t launch_fixup(const Job &job, long long count, cudaStream_t s);
+cudaError_t launch_rows(const Job &job, long long first, long long count, double *values, unsigned char *inplay, cudaStream_t s);
 cudaError_t launch_sample_maxabs(const double *value, int64_t n, int64_t stride, double *out2, cudaStream_t s);
 cudaError_t launch_reduce_auc(const double *partial, int count, double *out, cudaStream_t s);
 cudaError_t launch_reduce_moments(const double *moments, int nw, double *out6, cudaStream_t s);

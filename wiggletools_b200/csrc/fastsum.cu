@@ -25,11 +25,14 @@
 //     16-bit entry per breakpoint (position | keep | slow) over the dead cover
 //     array, the output rank of an entry is a per-32-entries base plus a ballot
 //     popcount, and the emit phase fetches the value by position;
-//   * bulk-async (TMA engine) tiles: the cursor row of a window is one
-//     cp.async.bulk global->shared copy signalled on an mbarrier (UBLKCP), and the
-//     interval slices of the window some CTA will draw next are pulled into L2 with
-//     cp.async.bulk.prefetch.L2 (UBLKPF) -- three instructions per track instead of
-//     a per-lane prefetch loop -- by warps 1..3 while warp 0 runs the look-back.
+//   * a flat, load-balanced events phase: the intervals of a window are read as
+//     16-byte aligned quads (128-bit loads) shared out evenly over the threads by a
+//     block scan + binary search, whatever their distribution over the tracks;
+//   * bulk-async (TMA engine) tiles for the per-window metadata: the two cursor rows
+//     that bound a window's intervals arrive as one cp.async.bulk global->shared copy
+//     signalled on an mbarrier (UBLKCP / SYNCS), requested when the window is drawn;
+//     the interval slices of the window some CTA will draw next are pulled into L2
+//     by warps 1..3 while warp 0 runs the look-back.
 // Windows are drawn from a ticket counter from the first one on, so the look-back
 // only ever waits on windows a running CTA owns: no assumption that the whole grid
 // is resident.
@@ -53,16 +56,19 @@ constexpr int TH = 128, NWARP = TH / 32;
 #define WB_FS_LBK 1
 #endif
 #ifndef WB_FS_LBSLEEP
-#define WB_FS_LBSLEEP 100             // ns between two polls of the look-back (first wait; doubles up to 8x)
+#define WB_FS_LBSLEEP 200             // ns between two polls of the look-back (first wait; doubles up to 8x)
 #endif
 #ifndef WB_FS_PREF
-#define WB_FS_PREF 1                  // next window's intervals: 0 no prefetch, 1 bulk prefetch into L2
+#define WB_FS_PREF 1                  // next window's intervals: 0 no prefetch, 1 prefetch into L2
+#endif
+#ifndef WB_FS_COV16
+#define WB_FS_COV16 1                 // 16-bit cover fields (6 B/position) when N <= 255
+#endif
+#ifndef WB_FS_EMIT2
+#define WB_FS_EMIT2 1                 // emit: two groups of 32 dense entries per warp and step
 #endif
 #ifndef WB_FS_EVPIPE
 #define WB_FS_EVPIPE 0                // events: software-pipelined interval loads (two chunks in registers)
-#endif
-#ifndef WB_FS_PREF_IV
-#define WB_FS_PREF_IV 32              // intervals per track the prefetch covers
 #endif
 constexpr int END_SHIFT = 11;            // 32-bit cover field: starts | ends << 11 (each <= 1023 per position)
 constexpr uint32_t FIELD = (1u << END_SHIFT) - 1;
@@ -87,21 +93,22 @@ struct Misc {
 	int wcov[NWARP];
 	int wpack[NWARP];
 	double wauc[NWARP];
-	uint16_t kbase[256];             // kept segments before every 32nd dense entry
+	uint16_t kbase[128];             // kept segments before every 32nd dense entry (W <= 4096)
 	PoisEv pois[POIS_CAP];
 };
-constexpr int MISC_BYTES = 1280;
+constexpr int MISC_BYTES = 1024;
 static_assert(sizeof(Misc) <= MISC_BYTES, "Misc must fit its slot");
 
-struct Layout { size_t off_cur, off_cur2, off_tn, off_toff, off_tmd, off_cov, off_limb, total; };
+struct Layout { size_t off_cur, off_cur2, off_pre, off_toff, off_tmd, off_cov, off_limb, total; };
+__host__ __device__ inline int quad_table_size(int N) { int p = 2; while (p <= N) p <<= 1; return p; }   // power of two > N
 __host__ __device__ inline Layout make_layout(int wlog, int N, int limbs, bool cov16) {
 	Layout L;
 	const size_t W = (size_t) 1 << wlog, nn = (size_t) (N + 4) / 4 * 16;
 	size_t o = MISC_BYTES;
-	L.off_cur = o;  o += nn;
-	L.off_cur2 = o; o += nn;
-	L.off_tn = o;   o += nn;
-	L.off_toff = o; o += 2 * nn;
+	L.off_cur = o;  o += 2 * nn;                 // cursor rows w and w + 1 (one bulk copy)
+	L.off_cur2 = o; o += nn;                     // cursor row of the window prefetched for
+	L.off_pre = o;  o += (4 * (size_t) quad_table_size(N) + 15) / 16 * 16;   // exclusive prefix of the tracks' quad counts
+	L.off_toff = o; o += 2 * nn;                 // N + 1 track offsets (int64)
 	L.off_tmd = o;  o += 2 * nn;
 	L.off_cov = o;  o += (cov16 ? 2 : 4) * W;
 	L.off_limb = o; o += (size_t) limbs * 4 * W;
@@ -109,7 +116,7 @@ __host__ __device__ inline Layout make_layout(int wlog, int N, int limbs, bool c
 	return L;
 }
 
-// ---- bulk-async copies and their mbarriers (PTX; SASS: UBLKCP / UBLKPF / SYNCS) -------------
+// ---- bulk-async copies and their mbarriers (PTX; SASS: UBLKCP / SYNCS) ----------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
 	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
@@ -133,9 +140,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
 	             :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
-	asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src), "r"(bytes) : "memory");
-}
 
 // Thread t owns the V = 2^VLOG consecutive positions [t*V, t*V+V) and reads them back
 // with 128-bit loads; its NV 16-byte vectors are rotated by a function of t so that the 8
@@ -150,6 +154,9 @@ template <int VLOG> __device__ __forceinline__ int phys16(int p) { return p ^ ((
 
 template <int VLOG, bool COV16>
 __device__ __forceinline__ void cov_add(uint32_t *cov, int p, bool is_end) {
+#ifdef WB_DIAG_NO_COV_ATOM                 // diagnostic builds only (profiles/): cost of the cover atomics
+	if (is_end || p != 0) return;
+#endif
 	if (COV16) atomicAdd(&cov[phys16<VLOG>(p) >> 1], (is_end ? 0x100u : 1u) << ((p & 1) << 4));
 	else atomicAdd(&cov[phys32<VLOG>(p)], is_end ? (1u << END_SHIFT) : 1u);
 }
@@ -161,42 +168,57 @@ struct Chunk {
 };
 
 // ---- events: +1 start / +1 end per interval in the cover field, +-value in the limbs ----
+// The intervals of track i that can touch window w are [cursor[w][i], cursor[w+1][i]] (the last one
+// may begin beyond the window: it only yields the look-ahead breakpoint).  They are read as QUADS,
+// 16-byte aligned groups of four intervals (128-bit loads of start, end and twice value); the
+// quads of all tracks form one flat list that the threads share out evenly: a block scan over
+// the tracks' quad counts, then a binary search per quad.  No lane idles on a track that has
+// fewer intervals than its neighbours, and a track with thousands of intervals in the window
+// costs no more per interval than any other.
 template <int VLOG, int LIMBS, bool COV16>
 __device__ __forceinline__ void events(const Job &job, unsigned char *smem, const Layout &L, const int32_t *cur,
                                        int w0i, int lw, double inv_scale, double lim) {
-	constexpr int W = TH << VLOG, G = TH / 8;
+	constexpr int W = TH << VLOG;
 	Misc *misc = (Misc *) smem;
-	const int32_t *tn = (const int32_t *) (smem + L.off_tn);
 	const long long *toff = (const long long *) (smem + L.off_toff);
 	const long long *tmd = (const long long *) (smem + L.off_tmd);
+	int32_t *pre = (int32_t *) (smem + L.off_pre);
+	auto tn = [&](int i) -> int { return (int) (toff[i + 1] - toff[i]); };     // intervals of track i
 	uint32_t *cov = (uint32_t *) (smem + L.off_cov);
 	uint32_t *limb = (uint32_t *) (smem + L.off_limb);
-	const int tid = threadIdx.x, lane = tid & 31, gid = tid >> 3, gl = tid & 7, gsh = lane & 24;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int N = job.N;
+	const int32_t *nxt = cur + job.cstride;                      // cursor row of window w + 1
 	using acc_t = typename std::conditional<LIMBS == 1, int, long long>::type;
 	int in_cov = 0, in_pois = 0, my_next = INT_MAX;
 	acc_t in_val = 0;
 
-	auto load = [&](int i, int k, Chunk &c) {
-		c.lo = c.hi = 0;
-		if (i >= N) return;
-		const long long o = toff[i], first = o + cur[i];
-		const long long g = (first & ~3ll) + 32 * k + 4 * gl;      // 16-byte aligned index grid
-		c.lo = (int) max(first - g, 0ll);
-		c.hi = (int) min(o + tn[i] - g, 4ll);
-		if (c.hi <= c.lo) { c.lo = c.hi = 0; return; }
-		if (g + 4 <= job.I) {
-			c.s = *(const int4 *) (job.start + g);
-			c.e = *(const int4 *) (job.end + g);
-			const double2 a = *(const double2 *) (job.value + g), b = *(const double2 *) (job.value + g + 2);
-			c.v0 = a.x; c.v1 = a.y; c.v2 = b.x; c.v3 = b.y;
-		} else {                                                   // the last few intervals of the whole array
-			c.s = make_int4(0, 0, 0, 0); c.e = c.s; c.v0 = c.v1 = c.v2 = c.v3 = 0;
-			if (c.lo <= 0 && 0 < c.hi) { c.s.x = job.start[g]; c.e.x = job.end[g]; c.v0 = job.value[g]; }
-			if (c.lo <= 1 && 1 < c.hi) { c.s.y = job.start[g + 1]; c.e.y = job.end[g + 1]; c.v1 = job.value[g + 1]; }
-			if (c.lo <= 2 && 2 < c.hi) { c.s.z = job.start[g + 2]; c.e.z = job.end[g + 2]; c.v2 = job.value[g + 2]; }
-		}
+	// quads of track i: its intervals first..last on the 16-byte aligned index grid
+	auto quads = [&](int i) -> int {
+		const int first = cur[i], last = min(nxt[i], tn(i) - 1);
+		if (last < first) return 0;
+		return (((int) (toff[i] + first) & 3) + (last - first + 1) + 3) >> 2;
 	};
+	const int P2 = quad_table_size(N);
+	{
+		const int K = (N + TH - 1) / TH;                         // consecutive tracks per thread
+		int mine = 0;
+		for (int k = 0; k < K; k++) { const int i = tid * K + k; if (i < N) mine += quads(i); }
+		int inc = mine;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += v; }
+		if (lane == 31) misc->wpack[warp] = inc;
+		__syncthreads();
+		int run = inc - mine;
+#pragma unroll
+		for (int k = 0; k < NWARP; k++) if (k < warp) run += misc->wpack[k];
+		for (int k = 0; k < K; k++) { const int i = tid * K + k; if (i < N) { pre[i] = run; run += quads(i); } }
+		if (tid == TH - 1) pre[N] = run;                         // Q, the number of quads of the window
+		for (int i = N + 1 + tid; i < P2; i += TH) pre[i] = INT_MAX;
+		__syncthreads();
+	}
+	const int Q = pre[N];
+
 	auto poison = [&](unsigned x, int delta) {
 		const int k = atomicAdd(&misc->npois, 1);
 		if (k < POIS_CAP) { PoisEv p; p.pos = (uint16_t) x; p.delta = (int16_t) delta; misc->pois[k] = p; }
@@ -223,51 +245,64 @@ __device__ __forceinline__ void events(const Job &job, unsigned char *smem, cons
 		}
 		if (start_in) {
 			cov_add<VLOG, COV16>(cov, xs, false);
+#ifndef WB_DIAG_NO_LIMB_ATOM               // diagnostic builds only (profiles/): cost of the value atomics
 			if (d != 0) add_limbs_fs<LIMBS, W>(limb, phys32<VLOG>(xs), d, lw);
+#endif
 			if (bad) poison((unsigned) xs, 1);
 		} else { in_cov++; in_val += d; in_pois += bad ? 1 : 0; }           // began before the window
 		if (end_in) {
 			cov_add<VLOG, COV16>(cov, (int) xe, true);
+#ifndef WB_DIAG_NO_LIMB_ATOM
 			if (d != 0) add_limbs_fs<LIMBS, W>(limb, phys32<VLOG>((int) xe), -d, lw);
+#endif
 			if (bad) poison(xe, -1);
 		} else my_next = min(my_next, e);
 	};
-	// returns true when the track may have further intervals in the window
-	auto apply = [&](const Chunk &c, long long md) -> bool {
+	// quad x of the flat list: its track (largest i with pre[i] <= x) and its intervals
+	auto load = [&](int x, Chunk &c, long long &md) {
+		c.lo = c.hi = 0;
+		if (x >= Q) return;
+		int i = 0;
+		for (int st = P2 >> 1; st > 0; st >>= 1) if (pre[i + st] <= x) i += st;
+		const long long o = toff[i], first = o + cur[i], end1 = o + min(nxt[i], tn(i) - 1) + 1;
+		const long long g = (first & ~3ll) + 4ll * (x - pre[i]);    // 16-byte aligned index grid
+		md = tmd[i];
+		c.lo = (int) max(first - g, 0ll);
+		c.hi = (int) min(end1 - g, 4ll);
+		if (g + 4 <= job.I) {
+			c.s = *(const int4 *) (job.start + g);
+			c.e = *(const int4 *) (job.end + g);
+			const double2 a = *(const double2 *) (job.value + g), b = *(const double2 *) (job.value + g + 2);
+			c.v0 = a.x; c.v1 = a.y; c.v2 = b.x; c.v3 = b.y;
+		} else {                                                   // the last few intervals of the whole array
+			c.s = make_int4(0, 0, 0, 0); c.e = c.s; c.v0 = c.v1 = c.v2 = c.v3 = 0;
+			if (c.lo <= 0 && 0 < c.hi) { c.s.x = job.start[g]; c.e.x = job.end[g]; c.v0 = job.value[g]; }
+			if (c.lo <= 1 && 1 < c.hi) { c.s.y = job.start[g + 1]; c.e.y = job.end[g + 1]; c.v1 = job.value[g + 1]; }
+			if (c.lo <= 2 && 2 < c.hi) { c.s.z = job.start[g + 2]; c.e.z = job.end[g + 2]; c.v2 = job.value[g + 2]; }
+		}
+	};
+	auto apply = [&](const Chunk &c, long long md) {
 		one(c.lo <= 0 && 0 < c.hi, c.s.x, c.e.x, c.v0, md);
 		one(c.lo <= 1 && 1 < c.hi, c.s.y, c.e.y, c.v1, md);
 		one(c.lo <= 2 && 2 < c.hi, c.s.z, c.e.z, c.v2, md);
 		one(c.lo <= 3 && 3 < c.hi, c.s.w, c.e.w, c.v3, md);
-		const bool last_in = c.hi == 4 && (unsigned) (c.e.w - w0i) < (unsigned) W;
-		return __shfl_sync(FULL, last_in, gsh + 7);
 	};
 #if WB_FS_EVPIPE
-	// the first chunk of the next round of tracks is requested before this round's events are
-	// applied: one exposed load latency per window instead of one per round
-	Chunk nx;
-	load(gid, 0, nx);
-	for (int rb = 0; rb < N; rb += G) {
-		const int i = rb + gid;
-		const long long md = i < N ? tmd[i] : 0;
-		const Chunk c0 = nx;
-		load(i + G, 0, nx);
-		bool more = apply(c0, md);
-		for (int k = 1; __any_sync(FULL, more); k++) {             // rare: more than ~30 intervals of one track in the window
-			Chunk c;
-			load(more ? i : N, k, c);
-			more = apply(c, md) && more;
-		}
+	// two quads per thread and step: both sets of loads are in flight before the first is applied
+	for (int x = tid; x < Q; x += 2 * TH) {
+		Chunk c0, c1;
+		long long md0 = 0, md1 = 0;
+		load(x, c0, md0);
+		load(x + TH, c1, md1);
+		apply(c0, md0);
+		apply(c1, md1);
 	}
 #else
-	for (int rb = 0; rb < N; rb += G) {
-		const int i = rb + gid;
-		const long long md = i < N ? tmd[i] : 0;
-		bool more = true;
-		for (int k = 0; k == 0 || __any_sync(FULL, more); k++) {   // k > 0 is rare: more than ~30 intervals of one track in the window
-			Chunk c;
-			load(more ? i : N, k, c);
-			more = apply(c, md) && more;
-		}
+	for (int x = tid; x < Q; x += TH) {
+		Chunk c;
+		long long md = 0;
+		load(x, c, md);
+		apply(c, md);
 	}
 #endif
 	// carried-in state and the look-ahead breakpoint: one shared atomic per warp
@@ -493,21 +528,20 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	WB_PHASE(4);
 
 	if (warp != 0) {
-		// ---- the next window's intervals: bulk prefetch into L2, one lane per track ------------
+		// ---- the next window's intervals: L2 prefetch, 8 lanes per track (16 bytes of start and end,
+		// 32 of value each), while warp 0 runs the look-back.  (cp.async.bulk.prefetch.L2 was measured
+		// here: the bulk instruction is issued once per LANE -- a loop over the warp's active lanes --
+		// and cost 10 % of the kernel's instructions; profiles/README.md.)
 		if (pref) {
 			mbar_wait(&misc->bar_nxt, par_nxt);
 			const long long *toff = (const long long *) (smem + L.off_toff);
-			const int32_t *tn = (const int32_t *) (smem + L.off_tn);
-			const long long Iv = job.I & ~3ll;
-			for (int i = tid - 32; i < N; i += TH - 32) {
+			const int gid = (tid - 32) >> 3, gl = tid & 7;
+			for (int i = gid; i < N; i += (TH - 32) / 8) {
 				const long long o = toff[i], first = o + nxt_buf[i];
-				const long long g = first & ~3ll;
-				long long cnt = min((long long) WB_FS_PREF_IV, o + tn[i] - g);
-				cnt = min((cnt + 3) & ~3ll, Iv - g);
-				if (cnt > 0) {
-					bulk_prefetch_l2(job.start + g, (uint32_t) cnt * 4);
-					bulk_prefetch_l2(job.end + g, (uint32_t) cnt * 4);
-					bulk_prefetch_l2(job.value + g, (uint32_t) cnt * 8);
+				const long long g = (first & ~3ll) + 4 * gl;
+				if (g < toff[i + 1] && g + 4 <= job.I) {
+					asm volatile("prefetch.global.L2 [%0];" :: "l"(job.start + g)); asm volatile("prefetch.global.L2 [%0];" :: "l"(job.end + g));
+					asm volatile("prefetch.global.L2 [%0];" :: "l"(job.value + g)); asm volatile("prefetch.global.L2 [%0];" :: "l"(job.value + g + 2));
 				}
 			}
 		}
@@ -582,7 +616,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 		const int nw1 = (int) atomicAdd(job.ticket, 1u);
 		misc->ticket2 = nw1;
 		if (nw1 < job.nw) {
-			const uint32_t bytes = (uint32_t) job.cstride * 4;
+			const uint32_t bytes = (uint32_t) job.cstride * 8;       // rows nw1 and nw1 + 1
 			mbar_expect_tx(&misc->bar_cur, bytes);
 			bulk_g2s(cur, job.cursor + (size_t) nw1 * job.cstride, bytes, &misc->bar_cur);
 		}
@@ -608,21 +642,16 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	const unsigned lt = (1u << lane) - 1;
 	auto emit_loop = [&](auto div_tag) {
 		constexpr bool DIV = decltype(div_tag)::value;      // mean over a non-power-of-two N: one fp64 division per segment
-		for (int r0 = warp * 32; r0 < nbp; r0 += TH) {
-			const int r = r0 + lane;
-			const unsigned d = r < nbp ? dense[r] : 0u;
-			const bool keep = (d & DN_KEEP) != 0;
-			const unsigned km = __ballot_sync(FULL, keep);
-			if (!keep) continue;
-			const int kid = (int) misc->kbase[r0 >> 5] + __popc(km & lt);
-			const int pos = (int) (d & DN_POS);
-			const int bs = w0i + pos;
-			const int be = (r + 1 < nbp) ? w0i + (int) (dense[r + 1] & DN_POS) : next_bp;
+		// value of the segment that starts at position `pos`: correctly rounded exact sum
+		auto value_at = [&](int pos) -> double {
 			const int ph = phys32<VLOG>(pos);
-			double v;                                                // correctly rounded exact sum
+			double v;
 			if (LIMBS == 1) v = (double) ((int32_t) limb[ph] + fx_base32) * mul;     // |sum + defaults| < 2^30: one 32-bit conversion
 			else v = (double) ((long long) (((unsigned long long) limb[W + ph] << 32) | limb[ph]) + job.fx_base) * mul;
 			if (DIV) v = v / N;
+			return v;
+		};
+		auto store = [&](unsigned d, int kid, int bs, int be, double v) {
 			if (kid < room32) {
 				os[kid] = bs;
 				oe[kid] = be;
@@ -635,7 +664,37 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 				}
 			}
 			if (!(d & DN_SLOW)) auc += (double) (be - bs) * v;        // v is finite here
+		};
+#if WB_FS_EMIT2
+		// two groups of 32 dense entries per warp and step: the shared-memory reads of both are in flight together
+		for (int r0 = warp * 32; r0 < nbp; r0 += 2 * TH) {
+			const int ra = r0 + lane, rb = ra + TH;
+			const unsigned da = ra < nbp ? dense[ra] : 0u, db = rb < nbp ? dense[rb] : 0u;
+			const bool ka = (da & DN_KEEP) != 0, kb = (db & DN_KEEP) != 0;
+			const unsigned na = (ka && ra + 1 < nbp) ? dense[ra + 1] : 0u, nb = (kb && rb + 1 < nbp) ? dense[rb + 1] : 0u;
+			const unsigned kma = __ballot_sync(FULL, ka), kmb = __ballot_sync(FULL, kb);
+			const int kida = (int) misc->kbase[r0 >> 5] + __popc(kma & lt);
+			const int kidb = (r0 + TH < nbp ? (int) misc->kbase[(r0 + TH) >> 5] : 0) + __popc(kmb & lt);
+			const int posa = (int) (da & DN_POS), posb = (int) (db & DN_POS);
+			double va = 0, vb = 0;
+			if (ka) va = value_at(posa);
+			if (kb) vb = value_at(posb);
+			if (ka) store(da, kida, w0i + posa, (ra + 1 < nbp) ? w0i + (int) (na & DN_POS) : next_bp, va);
+			if (kb) store(db, kidb, w0i + posb, (rb + 1 < nbp) ? w0i + (int) (nb & DN_POS) : next_bp, vb);
 		}
+#else
+		for (int r0 = warp * 32; r0 < nbp; r0 += TH) {
+			const int r = r0 + lane;
+			const unsigned d = r < nbp ? dense[r] : 0u;
+			const bool keep = (d & DN_KEEP) != 0;
+			const unsigned km = __ballot_sync(FULL, keep);
+			if (!keep) continue;
+			const int kid = (int) misc->kbase[r0 >> 5] + __popc(km & lt);
+			const int pos = (int) (d & DN_POS);
+			const int be = (r + 1 < nbp) ? w0i + (int) (dense[r + 1] & DN_POS) : next_bp;
+			store(d, kid, w0i + pos, be, value_at(pos));
+		}
+#endif
 	};
 	if (div) emit_loop(std::true_type{}); else emit_loop(std::false_type{});
 	for (int d = 16; d > 0; d >>= 1) auc += __shfl_down_sync(FULL, auc, d);
@@ -644,18 +703,15 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 }
 
 template <int VLOG, int LIMBS, bool COV16>
-__global__ void __launch_bounds__(TH, (LIMBS == 1 && COV16) ? WB_FS_MINB : (LIMBS == 1 || COV16) ? 5 : 4)
+__global__ void __launch_bounds__(TH, (LIMBS == 1 && COV16) ? WB_FS_MINB : LIMBS == 1 ? 6 : COV16 ? 5 : 4)
 fastsum_kernel(const Job job, int lw, double inv_scale, double lim, double scale) {
 	extern __shared__ __align__(16) unsigned char smem[];
 	const Layout L = make_layout(job.wlog, job.N, LIMBS, COV16);
-	int32_t *tn = (int32_t *) (smem + L.off_tn);
 	long long *toff = (long long *) (smem + L.off_toff);
 	long long *tmd = (long long *) (smem + L.off_tmd);
-	for (int i = threadIdx.x; i < job.N; i += TH) {
-		const long long o = job.off[i];
-		toff[i] = o;
-		tn[i] = (int) (job.off[i + 1] - o);
-		tmd[i] = job.dflt_fx[i];
+	for (int i = threadIdx.x; i <= job.N; i += TH) {
+		toff[i] = job.off[i];
+		if (i < job.N) tmd[i] = job.dflt_fx[i];
 	}
 	Misc *misc = (Misc *) smem;
 	int32_t *ca = (int32_t *) (smem + L.off_cur), *cb = (int32_t *) (smem + L.off_cur2);   // cursor rows: window being processed / prefetched for
@@ -670,7 +726,7 @@ fastsum_kernel(const Job job, int lw, double inv_scale, double lim, double scale
 	__syncthreads();
 	int w = misc->ticket2;
 	if (threadIdx.x == 0 && w < job.nw) {
-		const uint32_t bytes = (uint32_t) job.cstride * 4;
+		const uint32_t bytes = (uint32_t) job.cstride * 8;           // rows w and w + 1
 		mbar_expect_tx(&misc->bar_cur, bytes);
 		bulk_g2s(ca, job.cursor + (size_t) w * job.cstride, bytes, &misc->bar_cur);
 	}
@@ -714,8 +770,8 @@ static cudaError_t launch_v(const Job &job, int lw, double inv_scale, double lim
 }
 
 static bool use_cov16(const Job &job) {
-	const char *e = getenv("WB200_FS_COV16");           // development: 0 forces the 32-bit cover fields
-	return job.N <= 255 && !(e && atoi(e) == 0);
+	const char *e = getenv("WB200_FS_COV16");           // development override of the compiled default
+	return job.N <= 255 && (e ? atoi(e) != 0 : WB_FS_COV16 != 0);
 }
 
 } // namespace fs
