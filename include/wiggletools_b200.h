@@ -62,7 +62,8 @@ enum wb200_error {
 	WB200_EUNSUPPORTED = -6
 };
 
-#define WB200_MAX_TRACKS 1023  /* per set; cover counters are 10-bit fields */
+#define WB200_MAX_TRACKS 1023  /* per set; cover counters are 10-bit fields.  WB200_MWU: at most 1024 tracks in the two
+                                * sets together (per-warp sort rows in shared memory), else WB200_EUNSUPPORTED */
 
 typedef struct wb200_ctx wb200_ctx;
 
@@ -246,6 +247,37 @@ typedef struct wb200_map { int32_t op; int32_t reserved; double arg; } wb200_map
 int wb200_set_input_maps(wb200_ctx *ctx, int ntracks, const wb200_map *const *maps, const int *nmaps);
 double wb200_map_default(int op, double arg, double default_value);
 
+/* -- regional integrators on the device ------------------ */
+/* `apply` / `apply_paste`: for every region of a sorted BED-like list, the integrators of
+ * src/statistics.c:62-326 over the dataset restricted to the region -- what ApplyMultiplexerPop /
+ * computeApplyValues (src/apply.c:259-321) compute through a per-base buffer
+ * (BufferedWiggleIterator, apply.c:58-160): bases the dataset does not cover count as one run of
+ * its default value (rounded through float, as the buffer keeps it) unless `strict`; NaN records
+ * are skipped by every integrator.  One call per chromosome: the dataset is a sorted, disjoint
+ * segment list (typically a reduction's output still in HBM), regions are 1-based half-open and
+ * may overlap.  out[r*nstats + k] = statistic codes[k] of region r. */
+enum wb200_stat {
+	WB200_STAT_AUC = 1,     /* AUCIntegrator      src/statistics.c:103-127 */
+	WB200_STAT_MEAN = 2,    /* MeanIntegrator     src/statistics.c:62-97 */
+	WB200_STAT_VAR = 3,     /* VarianceIntegrator src/statistics.c:209-268 */
+	WB200_STAT_STDDEV = 4,  /* StandardDeviationIntegrator :270-296 */
+	WB200_STAT_CV = 5,      /* CoefficientOfVariationIntegrator :298-326 */
+	WB200_STAT_MAX = 6,     /* MaxIntegrator      :157-181 */
+	WB200_STAT_MIN = 7,     /* MinIntegrator      :183-207 */
+	WB200_STAT_SPAN = 8     /* SpanIntegrator     :129-155 */
+};
+int wb200_apply_device(wb200_ctx *ctx, const int32_t *d_start, const int32_t *d_end, const double *d_value, int64_t nseg,
+                       double default_value, int64_t nreg, const int32_t *rstart, const int32_t *rend,
+                       int nstats, const int *codes, int strict, double *out);
+/* Same with the dataset's segments in host memory (staged inside the call). */
+int wb200_apply_host(wb200_ctx *ctx, const int32_t *start, const int32_t *end, const double *value, int64_t nseg,
+                     double default_value, int64_t nreg, const int32_t *rstart, const int32_t *rend,
+                     int nstats, const int *codes, int strict, double *out);
+/* Same with the segments of the last wb200_reduce_host() call on the context as the dataset (they are
+ * still resident in HBM): `apply_paste out meanI regions.bed mean a.bw b.bw c.bw` per chromosome. */
+int wb200_apply_last(wb200_ctx *ctx, double default_value, int64_t nreg, const int32_t *rstart, const int32_t *rend,
+                     int nstats, const int *codes, int strict, double *out);
+
 /* -- text sink on the device --------------------------- */
 /* Stands where the reference's default sink works on one host thread: the
  * writer-side CompressionWiggleIterator (src/unaryOps.c:235-263; `write` only),
@@ -288,6 +320,9 @@ int wb200_format_host(wb200_ctx *ctx, int mode, const char *chrom,
 /* Student-t upper tail used by WB200_TTEST (stands where the reference calls
  * gsl_cdf_tdist_Q, src/setComparisons.c:117); exported for tests. */
 double wb200_tdist_Q(double t, double nu);
+
+/* Diagnostic: the same function as the DEVICE evaluates it (one thread per pair): out[i] = Q(t[i], nu[i]). */
+int wb200_debug_tdist_device(wb200_ctx *ctx, int n, const double *t, const double *nu, double *out);
 
 /* Diagnostic: the device formatter's "%lf" compiled for the host (same source function as the
  * kernel's): writes the text of v into out32 (>= 32 bytes), returns its length, -1 for |v| >= 2^63. */

@@ -150,6 +150,15 @@ WiggleIterator *wb200_mapped_iterator(WiggleIterator *i, int op, double arg);
 int wb200_sink_accepts(WiggleIterator *wi);
 void wb200_sink_run(WiggleIterator *wi, FILE *out, wt_bool bedGraph);
 
+/* -- apply.c: ApplyMultiplexer (src/apply.c:340-353) for a dataset that is a fresh reduction of this
+ * library: per run of regions on one chromosome the reduction is sought to the run's span, its
+ * segments stay in HBM and the integrators (WB200_STAT_* of wiggletools_b200.h, one per output
+ * column, standing for the statistics[] constructors of src/statistics.c:62-326) run there as
+ * segmented reductions.  Same row protocol as the reference's (chrom/start/finish = the region,
+ * values[i] = statistic i, first row on display on return).  NULL when the dataset is anything
+ * else: the caller then keeps the reference's ApplyMultiplexer. */
+Multiplexer *wb200_apply_multiplexer(WiggleIterator *regions, const int *stat_codes, int count, WiggleIterator *dataset, wt_bool strict);
+
 #ifdef __cplusplus
 }
 #endif

@@ -127,3 +127,37 @@ WiggleIterator *__wrap_NaturalExpWiggleIterator(WiggleIterator *i) { return wb20
 WiggleIterator *__wrap_PowerWiggleIterator(WiggleIterator *i, double s) { return wb200_mapped_iterator(i, 5, s); }
 WiggleIterator *__wrap_AbsWiggleIterator(WiggleIterator *i) { return wb200_mapped_iterator(i, 6, 0); }
 WiggleIterator *__wrap_DefaultValueWiggleIterator(WiggleIterator *i, double v) { return wb200_mapped_iterator(i, 0, v); }
+
+/* ---- regional integrators (`apply`, `apply_paste`) ---------------------------------
+ * In src/apply.c the edit would be four lines at the top of ApplyMultiplexer (:340):
+ *     Multiplexer * gpu = wb200_apply_multiplexer(regions, codes_of(statistics, count), count, dataset, strict);
+ *     if (gpu) return gpu;
+ * A dataset that is a fresh reduction of the library (`apply_paste out meanI regions.bed mean a.bw b.bw`)
+ * is then sought and reduced per run of regions on the device and the integrators run on the
+ * resident segments; any other dataset, or a statistic the device does not provide, keeps the
+ * reference's per-base buffers. */
+Multiplexer *wb200_apply_multiplexer(WiggleIterator *regions, const int *stat_codes, int count, WiggleIterator *dataset, bool strict);
+Multiplexer *__real_ApplyMultiplexer(WiggleIterator *regions, WiggleIterator *(**statistics)(WiggleIterator *), int count, WiggleIterator *dataset, bool strict);
+WiggleIterator *SpanIntegrator(WiggleIterator *);      /* src/statistics.c:152 (not in wiggletools.h) */
+
+Multiplexer *__wrap_ApplyMultiplexer(WiggleIterator *regions, WiggleIterator *(**statistics)(WiggleIterator *), int count, WiggleIterator *dataset, bool strict) {
+	int codes[64];
+	bool known = statistics != NULL && count >= 1 && count <= 64;
+	for (int i = 0; known && i < count; i++) {
+		WiggleIterator *(*f)(WiggleIterator *) = statistics[i];
+		if (f == &AUCIntegrator) codes[i] = 1;
+		else if (f == &MeanIntegrator) codes[i] = 2;
+		else if (f == &VarianceIntegrator) codes[i] = 3;
+		else if (f == &StandardDeviationIntegrator) codes[i] = 4;
+		else if (f == &CoefficientOfVariationIntegrator) codes[i] = 5;
+		else if (f == &MaxIntegrator) codes[i] = 6;
+		else if (f == &MinIntegrator) codes[i] = 7;
+		else if (f == &SpanIntegrator) codes[i] = 8;
+		else known = false;
+	}
+	if (known) {
+		Multiplexer *gpu = wb200_apply_multiplexer(regions, codes, count, dataset, strict);
+		if (gpu) return gpu;
+	}
+	return __real_ApplyMultiplexer(regions, statistics, count, dataset, strict);
+}

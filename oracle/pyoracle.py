@@ -118,10 +118,10 @@ class Oracle:
         f = self._f("ndpearson")
         f.restype = C.c_double
         f.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        f = self._f("rows")
+        f.restype = C.c_int64
+        f.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         if kind != "dropin":
-            f = self._f("rows")
-            f.restype = C.c_int64
-            f.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
             f = self._f("tdist_Q")
             f.restype = C.c_double
             f.argtypes = [C.c_double, C.c_double]

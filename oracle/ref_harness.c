@@ -224,7 +224,6 @@ double wtref_ndpearson(int n, const wt_track *a, const wt_track *b, int nnames, 
 	return *(double *) wi->data;
 }
 
-#ifndef WB200_DROPIN
 /* Raw multiplexer rows (what mWigWriter sees): values[count] + inplay[count]
  * per segment; row_values/row_inplay hold cap*count entries. */
 int64_t wtref_rows(int ntracks, const wt_track *tracks, int strict, int nnames, char **names,
@@ -248,6 +247,7 @@ int64_t wtref_rows(int ntracks, const wt_track *tracks, int strict, int nnames, 
 	return n;
 }
 
+#ifndef WB200_DROPIN
 /* Writer-side compress (src/unaryOps.c:235-263) applied to a reduction. */
 int64_t wtref_reduce_compressed(int op, int ntracks, const wt_track *tracks, int strict,
                                 int nnames, char **names, wt_out *out) {

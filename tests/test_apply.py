@@ -1,8 +1,8 @@
-"""`apply`: only the ORACLE exists so far -- the restatement of the per-region
+"""`apply`.  CPU tests: the oracle's restatement of the per-region
 integrators (oracle/wt_oracle.c: wto_apply) pinned on the reference's golden vector
 (test/expected/regional_means.txt through test/test.py:101) and bit for bit on the reference's own
-ApplyMultiplexer compiled into oracle/_ref.  The device implementation is round-2 work; these tests
-are what it will be held against."""
+ApplyMultiplexer compiled into oracle/_ref.  GPU tests: the device implementation
+(csrc/apply.cu through wb200_apply_host / wb200_apply_last) against that oracle."""
 import numpy as np
 import pytest
 
@@ -50,3 +50,145 @@ def test_port_matches_reference_apply(port, reference, seed, strict):
     a = port.apply(dataset, regions, STATS, NAMES, strict)
     b = reference.apply(dataset, regions, STATS, NAMES, strict)
     assert np.array_equal(a, b, equal_nan=True), np.argwhere(~((a == b) | (np.isnan(a) & np.isnan(b))))[:5]
+
+
+# ---------------------------------------------------------------------------
+# the device implementation (csrc/apply.cu)
+# ---------------------------------------------------------------------------
+APPLY_RTOL = 1e-10      # north_star's bar for fp64 reductions; sums of exactly representable data are bit-identical
+
+
+def _close(a, b, rtol=APPLY_RTOL):
+    with np.errstate(invalid="ignore"):
+        return (a == b) | (np.isnan(a) & np.isnan(b)) | (np.abs(a - b) <= rtol * np.maximum(np.abs(a), np.abs(b)))
+
+
+@pytest.mark.gpu
+def test_gpu_golden_regional_means(engine):
+    from wiggletools_b200 import api
+    d = api.Track(np.zeros(10, np.int32), np.arange(1, 11, dtype=np.int32), np.arange(2, 12, dtype=np.int32), np.arange(10.0))
+    regions = api.Track(np.array([0, 0, 1], np.int32), np.array([3, 4, 2], np.int32), np.array([7, 9, 5], np.int32), np.ones(3))
+    got = engine.apply(d, regions, ["meanI"], strict=True).ravel()
+    assert got[0] == 3.5 and got[1] == 5.0 and np.isnan(got[2])          # test/expected/regional_means.txt
+    loose = engine.apply(d, regions, ["meanI", "spanI"], strict=False)
+    assert loose[2, 0] == 0.0 and loose[2, 1] == 3.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("strict", [False, True])
+def test_gpu_apply_matches_oracle(engine, port, seed, strict):
+    from wiggletools_b200 import api
+    rng = np.random.default_rng(seed)
+    c, s, e = random_sorted(rng, 4000, 3, 12, 9)
+    default = [0.0, 1.3, 0.0, 2.0, 0.0, 0.7][seed]
+    vals = rng.integers(0, 50, len(s)) / 4.0
+    if seed >= 4:
+        vals = vals + rng.random(len(s))                      # full fp64 mantissas: sums differ from the base-by-base order in the last bits
+        vals[rng.random(len(s)) < 0.02] = np.nan
+    rc, rs, re_ = random_sorted(rng, 300, 3, 150, 60, overlap=bool(seed % 2))
+    want = port.apply(Track(c, s, e, vals, default=default), Track(rc, rs, re_, np.ones(len(rs))), STATS, NAMES, strict)
+    got = engine.apply(api.Track(c, s, e, vals, default=default), api.Track(rc, rs, re_, np.ones(len(rs))), STATS, strict=strict)
+    ok = _close(got, want)
+    assert ok.all(), (np.argwhere(~ok)[:5], got[~ok][:5], want[~ok][:5])
+    # varI / stddevI / CVI replay the reference's own recurrence (its cancellation noise included): bit-identical
+    for k in (2, 3, 4):
+        assert np.array_equal(got[:, k], want[:, k], equal_nan=True), STATS[k]
+    if seed < 4:      # multiples of 1/4 with float-exact defaults: AUC, meanI, maxI, minI, spanI are bit-identical
+        for k in (0, 1, 5, 6, 7):
+            if default in (0.0, 2.0):
+                assert np.array_equal(got[:, k], want[:, k], equal_nan=True), STATS[k]
+
+
+@pytest.mark.gpu
+def test_gpu_apply_on_resident_reduction(engine, port):
+    """`apply meanI regions mean a b c`: the reduction's segments never leave HBM (wb200_apply_last)."""
+    import ctypes as C
+    from wiggletools_b200 import api
+    from wiggletools_b200.synth import make_tracks
+    tr = make_tracks(5, [40000], seed=77, max_len=60, max_gap=50)
+    g = [api.Track(t["chrom"], t["start"], t["end"], t["value"]) for t in tr]
+    o = [Track(t["chrom"], t["start"], t["end"], t["value"]) for t in tr]
+    seg = port.reduce("mean", o, ["chr1"])
+    rng = np.random.default_rng(3)
+    rs = np.sort(rng.integers(1, 39000, 200)).astype(np.int32)
+    re_ = (rs + rng.integers(1, 900, 200)).astype(np.int32)
+    want = port.apply(Track(seg.chrom, seg.start, seg.end, seg.value, default=seg.default),
+                      Track(np.zeros(200, np.int32), rs, re_, np.ones(200)), STATS, ["chr1"], False)
+    gs, ge, gv, gd, _ = engine.reduce_chrom("mean", [(t.start, t.end, t.value, t.default) for t in g])   # wb200_reduce_host: segments stay in HBM
+    assert len(gs) == len(seg) and gd == seg.default
+    codes = np.array([engine.STATS[s_] for s_ in STATS], np.int32)
+    out = np.empty((200, len(STATS)))
+    engine._check(engine.lib.wb200_apply_last(engine.ctx, C.c_double(seg.default), 200, rs.ctypes.data, re_.ctypes.data, len(STATS),
+                                              codes.ctypes.data, 0, out.ctypes.data))
+    ok = _close(out, want)
+    assert ok.all(), (np.argwhere(~ok)[:5], out[~ok][:5], want[~ok][:5])
+
+
+@pytest.mark.gpu
+def test_cli_apply_through_the_device(tmp_path):
+    """`apply_paste` / `apply` through the reference's unmodified front end linked against the library:
+    a dataset that is a GPU reduction takes the device path (wb200_apply_multiplexer, routed in by
+    integration/dropin_binding.c); the text equals what the unmodified reference CLI prints -- the
+    golden test/expected/regional_means.txt first."""
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = os.path.join(here, "..", "integration", "_build", "wiggletools_b200")
+    ref = os.path.join(here, "..", "oracle", "_ref", "wiggletools")
+    if not (os.path.exists(exe) and os.path.exists(ref)):
+        pytest.skip("drop-in / reference CLI not built (needs /root/reference at build time)")
+    (tmp_path / "fixedStep.wig").write_text("fixedStep chrom=chr1 start=1 step=1 span=1\n" + "".join("%d\n" % i for i in range(10)))
+    (tmp_path / "variableStep.wig").write_text("variableStep chrom=chr1 span=1\n" + "".join("%d\t%d\n" % (p, x) for p, x in zip((1, 2, 4, 6, 8), (1, 2, 3, 4, 5))))
+    (tmp_path / "overlapping.bed").write_text("chr1\t2\t6\nchr1\t3\t8\nchr2\t1\t4\n")
+    rng = np.random.default_rng(11)
+    for t in range(3):
+        lines = []
+        for chrom in ("chr1", "chr2"):
+            pos = 0
+            for _ in range(3000):          # contiguous intervals: every track is in play everywhere (see the Q10 note below)
+                ln = int(rng.integers(1, 9))
+                lines.append("%s\t%d\t%d\t%g\n" % (chrom, pos, pos + ln, rng.integers(0, 50) / 4.0))
+                pos += ln
+        (tmp_path / ("t%d.bg" % t)).write_text("".join(lines))
+    reg = []
+    for chrom in ("chr1", "chr2"):
+        starts = np.sort(rng.integers(0, 11000, 150))
+        for s in starts:
+            reg.append("%s\t%d\t%d\n" % (chrom, s, s + int(rng.integers(1, 400))))
+    (tmp_path / "regions.bed").write_text("".join(reg))
+
+    def run(binary, *args):
+        return subprocess.run([binary] + list(args), capture_output=True, text=True, check=True, cwd=tmp_path).stdout
+
+    # the reference's golden vector, through a sum of one track (a GPU reduction as the dataset)
+    got = run(exe, "apply_paste", "-", "meanI", "overlapping.bed", "sum", "fixedStep.wig")
+    assert got == "chr1\t2\t6\t3.500000\nchr1\t3\t8\t5.000000\nchr2\t1\t4\tnan\n" or \
+        [l.split("\t")[-1] for l in got.strip().split("\n")] == ["3.500000", "5.000000", "nan"], got
+    # Multi-track datasets with GAPS are not compared with the reference CLI: it seeks the dataset for every
+    # batch of regions, and seekCoreMultiplexer keeps stale values[] of the tracks that are not in play at the
+    # sought position (quirk Q10, multiplexer.c:130-141) -- e.g. it prints 2.875 for the mean of
+    # mean(fixedStep, variableStep) over chr1:3-7 where the per-base values 1, 3, 2, 4.5 average 2.625.
+    # The engine does not reproduce that staleness (DESIGN.md); tracks without gaps cannot show it.
+    got = run(exe, "apply_paste", "-", "meanI", "overlapping.bed", "mean", "fixedStep.wig", "variableStep.wig")
+    assert [l.split("\t")[-1] for l in got.strip().split("\n")] == ["2.625000", "3.700000", "nan"], got
+    progs = [["apply_paste", "-", "meanI", "overlapping.bed", "sum", "fixedStep.wig", "fixedStep.wig"],
+             ["apply_paste", "-", "AUC", "meanI", "maxI", "minI", "regions.bed", "mean", "t0.bg", "t1.bg", "t2.bg"],
+             ["apply_paste", "-", "AUC", "meanI", "fillIn", "regions.bed", "sum", "t0.bg", "t1.bg"],
+             ["apply_paste", "-", "varI", "stddevI", "CVI", "regions.bed", "mean", "t0.bg", "t1.bg", "t2.bg"]]
+    for prog in progs:
+        want, got = run(ref, *prog), run(exe, *prog)
+        wl, gl = want.strip().split("\n"), got.strip().split("\n")
+        assert len(wl) == len(gl) and len(wl) > 0, prog
+        for a, b in zip(wl, gl):
+            fa, fb = a.split("\t"), b.split("\t")
+            assert fa[:3] == fb[:3], (prog, a, b)
+            for x, y in zip(fa[3:], fb[3:]):
+                if x == y:
+                    continue
+                try:
+                    xv, yv = float(x), float(y)
+                except ValueError:
+                    assert x == y, (prog, a, b)       # the BED file's own columns
+                    continue
+                assert (np.isnan(xv) and np.isnan(yv)) or abs(xv - yv) <= 1.5e-6 * max(1.0, abs(xv)), (prog, a, b)

@@ -97,3 +97,30 @@ def test_config4_mean_512_tracks_sharded(engine, port):
             assert np.array_equal(p[0], res[c][0]) and np.array_equal(p[2], res[c][2])
             auc2 += p[4]
     assert math.isclose(auc2, auc, rel_tol=1e-12)
+
+
+@pytest.mark.parametrize("n", [513, 1023])
+def test_order_statistics_up_to_the_track_limit(engine, port, n):
+    """the shared-memory check rejected median above 512 tracks on sparse data although a
+    smaller window fits.  The window now shrinks until the kernel that actually runs fits: median and
+    max over 513 and 1023 tracks (the documented per-set limit), sparse enough for 4096-bp windows."""
+    tr = make_tracks(n, [6_000, 2_500], seed=21, max_len=300, max_gap=3000, gap_prob=0.9)
+    o, g = both(tr)
+    for op in ("median", "max"):
+        want = port.reduce(op, o, NAMES[:2])
+        got = engine.reduce(op, g, NAMES[:2])
+        assert_segments(got, want.chrom, want.start, want.end, want.value, exact=True, what="%s/%d" % (op, n))
+
+
+def test_wilcoxon_track_limit(engine, port):
+    """wilcoxon sorts the two sets' values per segment in per-warp shared-memory rows: 1024 tracks in
+    total fit (512 + 512), more is refused with WB200_EUNSUPPORTED instead of failing at launch."""
+    tr = make_tracks(1024, [1_500], seed=22, max_len=200, max_gap=2000, gap_prob=0.9)
+    o, g = both(tr)
+    want = port.setcompare("wilcoxon", o[:512], o[512:], NAMES[:1])
+    got = engine.setcompare("wilcoxon", g[:512], g[512:], NAMES[:1])
+    assert_segments(got, want.chrom, want.start, want.end, want.value, what="wilcoxon/512+512")
+    tr = make_tracks(1200, [800], seed=23, max_len=200, max_gap=2000, gap_prob=0.9)
+    _, g = both(tr)
+    with pytest.raises(api.WB200Error, match="1024 tracks"):
+        engine.setcompare("wilcoxon", g[:600], g[600:], NAMES[:1])

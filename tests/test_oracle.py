@@ -159,3 +159,15 @@ def test_tdist_against_high_precision(port):
     for nu in (1.0, 2.5, 4.0, 7.3, 30.0, 254.0, 1022.0, 1e5):
         for t in (1e-3, 0.1, 0.7, 1.96, 3.3, 8.0, 25.0):
             assert math.isclose(port.tdist_Q(t, nu), _tdist_Q_exact(t, nu), rel_tol=5e-12, abs_tol=1e-300), (t, nu)
+
+
+def test_tdist_oracle_on_committed_table(port):
+    """The oracle's Student-t tail on the committed high-precision table (tests/golden/tdist_table.json,
+    mpmath 50 digits, generator beside it): the same table the DEVICE function is pinned on in
+    tests/test_gpu_parity.py, so the t-test p-value is never compared with a copy of itself."""
+    import json
+    import os
+    rows = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "tdist_table.json")))["rows"]
+    assert len(rows) > 300
+    for t, nu, p in rows:
+        assert math.isclose(2 * port.tdist_Q(t, nu), p, rel_tol=1e-10, abs_tol=1e-300), (t, nu)

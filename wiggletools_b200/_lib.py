@@ -108,6 +108,11 @@ def load():
     lib.wb200_format_host.argtypes = lib.wb200_format_device.argtypes
     lib.wb200_reduce_format_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_char_p,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.wb200_apply_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int64,
+                                       C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    lib.wb200_apply_host.argtypes = lib.wb200_apply_device.argtypes
+    lib.wb200_apply_last.argtypes = [C.c_void_p, C.c_double, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    lib.wb200_debug_tdist_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.wb200_tdist_Q.restype = C.c_double
     lib.wb200_tdist_Q.argtypes = [C.c_double, C.c_double]
     _lib = lib
@@ -122,4 +127,5 @@ EXPORTS = [
     "wb200_tdist_Q", "wb200_bw_open", "wb200_bw_close", "wb200_bw_last_error", "wb200_bw_nchrom", "wb200_bw_chrom_name",
     "wb200_bw_chrom_length", "wb200_bw_set_stretch", "wb200_bw_decode_chrom", "wb200_debug_phases", "wb200_debug_format_value",
     "wb200_format_device", "wb200_format_host", "wb200_reduce_format_host", "wb200_set_input_maps", "wb200_map_default",
+    "wb200_apply_device", "wb200_apply_host", "wb200_apply_last", "wb200_debug_tdist_device",
 ]

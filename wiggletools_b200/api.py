@@ -265,6 +265,32 @@ class Engine:
     def auc(self, op, tracks, names=("chr1",), strict=False):
         return self.reduce(op, tracks, names, strict).auc
 
+    # -- regional integrators (apply.c / statistics.c) ---------------------------
+    STATS = {"AUC": 1, "meanI": 2, "varI": 3, "stddevI": 4, "CVI": 5, "maxI": 6, "minI": 7, "spanI": 8}
+
+    def apply(self, dataset, regions, stats, strict=False):
+        """`apply` of a list of integrators (AUC, meanI, varI, stddevI, CVI, maxI, minI, spanI;
+        statistics.c:62-326) over the regions of a sorted BED-like Track, on the segments of
+        `dataset` (a Track or Segments; its `default` fills the bases it does not cover unless
+        strict) -- ApplyMultiplexer (apply.c:340-353), one wb200_apply_host call per chromosome.
+        Returns an array [len(regions), len(stats)]."""
+        codes = np.array([self.STATS[s_] for s_ in stats], np.int32)
+        out = np.full((len(regions.start), len(stats)), np.nan)
+        dchrom, rchrom = np.asarray(dataset.chrom), np.asarray(regions.chrom)
+        default = float(getattr(dataset, "default", 0.0))
+        for c in np.unique(rchrom):
+            ridx = np.flatnonzero(rchrom == c)
+            didx = np.flatnonzero(dchrom == c)
+            s = np.ascontiguousarray(np.asarray(dataset.start)[didx], np.int32); e = np.ascontiguousarray(np.asarray(dataset.end)[didx], np.int32)
+            v = np.ascontiguousarray(np.asarray(dataset.value)[didx], np.float64)
+            rs = np.ascontiguousarray(np.asarray(regions.start)[ridx], np.int32); re_ = np.ascontiguousarray(np.asarray(regions.end)[ridx], np.int32)
+            res = np.empty((len(ridx), len(stats)), np.float64)
+            self._check(self.lib.wb200_apply_host(self.ctx, s.ctypes.data, e.ctypes.data, v.ctypes.data, len(s), default,
+                                                  len(rs), rs.ctypes.data, re_.ctypes.data, len(stats), codes.ctypes.data,
+                                                  int(bool(strict)), res.ctypes.data))
+            out[ridx] = res
+        return out
+
     # -- text sink (wigWriter.c: toFile / toStdout) ------------------------------
     def format_segments(self, seg, names=("chr1",), bedgraph=False):
         """Bytes the reference's default sink prints for a Segments list: `write`

@@ -79,6 +79,9 @@ struct wb200_ctx {
 	Job last_job{};
 	int64_t last_S = -1;
 	DevBuf rows_v, rows_p;
+	// regional integrators (wb200_apply_*)
+	DevBuf ap_rs, ap_re, ap_codes, ap_out;
+	HostBuf hap_out;
 	// batch device entry (wb200_reduce_device_batch): per-shard tables and result slots
 	DevBuf b_tables, b_small;
 	HostBuf hb_tables, hb_small;
@@ -216,6 +219,17 @@ int plan_shard(wb200_ctx *ctx, int op, int N, int &n1, int &strict, const int64_
 		}
 	}
 	wlog = std::min(TLOG + 4, std::max(TLOG + 2, wlog));
+	{
+		// the window must fit shared memory with the kernel that will actually run: sized with that kernel's
+		// limb arrays (var / stddev / CV: up to 6; sum / mean outside the sweep kernel: up to 3; all others: 2)
+		// and shrunk step by step before giving up (median / min / max / wilcoxon carry per-warp sort rows)
+		const bool moment_like = (op == OP_VAR || op == OP_STDDEV || op == OP_ENTROPY || op == OP_CV);
+		const int arrays = moment_like ? 6 : (op == OP_SUM || op == OP_MEAN) ? 3 : 2;
+		while (wlog > TLOG + 2 && window_smem_bytes(wlog, N, true, op, arrays) > 227 * 1024) wlog--;
+		if (window_smem_bytes(wlog, N, true, op, arrays) > 227 * 1024)
+			return fail(ctx, WB200_EUNSUPPORTED, op == OP_MWU ? "wilcoxon over more than 1024 tracks in total does not fit shared memory (per-warp sort rows)"
+			                                                  : "window does not fit shared memory for this many tracks");
+	}
 	const int64_t span = (int64_t) pos_hi - pos_lo;
 	const int nw = (int) (span >> wlog) + 1;
 
@@ -391,8 +405,7 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 		CK(ctx->slow_list.ensure((size_t) job.slow_cap * sizeof(long long)));
 		job.slow_list = ctx->slow_list.as<long long>();
 	}
-	size_t need = window_smem_bytes(wlog, N, true, op);
-	if (need > 227 * 1024) return fail(ctx, WB200_EUNSUPPORTED, "window does not fit shared memory; lower WB200_WINDOW");
+	(void) wlog;      // (shared-memory fit was settled by plan_shard)
 
 	CK(cudaEventRecord(ctx->ev[4], s));
 	int auc_per_window = WARPS;
@@ -502,6 +515,7 @@ void wb200_destroy(wb200_ctx *ctx) {
 	for (auto ev : ctx->batch_events) cudaEventDestroy(ev);
 	ctx->b_tables.release(); ctx->b_small.release(); ctx->hb_tables.release(); ctx->hb_small.release();
 	ctx->rows_v.release(); ctx->rows_p.release();
+	ctx->ap_rs.release(); ctx->ap_re.release(); ctx->ap_codes.release(); ctx->ap_out.release(); ctx->hap_out.release();
 	if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
 	if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
 	HostBuf *h[] = {&ctx->h_small, &ctx->h_meta, &ctx->h_start, &ctx->h_end, &ctx->h_value, &ctx->h_arena};
@@ -671,6 +685,24 @@ double wb200_map_default(int op, double arg, double default_value) {
 	return NAN;
 }
 
+// The Student-t upper tail as the DEVICE evaluates it inside the t-test kernel (same source function
+// as wb200_tdist_Q, compiled for sm_100a): out[i] = Q(t[i], nu[i]).  For tests that pin the device
+// arithmetic on a high-precision table (the reference calls gsl_cdf_tdist_Q, setComparisons.c:117).
+int wb200_debug_tdist_device(wb200_ctx *ctx, int n, const double *t, const double *nu, double *out) {
+	if (!ctx || n < 0 || (n > 0 && (!t || !nu || !out))) return WB200_EINVAL;
+	if (n == 0) return WB200_OK;
+	cudaSetDevice(ctx->device);
+	cudaStream_t s = ctx->stream;
+	CK(ctx->rows_v.ensure((size_t) 3 * n * sizeof(double)));
+	double *d = ctx->rows_v.as<double>();
+	CK(cudaMemcpyAsync(d, t, n * sizeof(double), cudaMemcpyHostToDevice, s));
+	CK(cudaMemcpyAsync(d + n, nu, n * sizeof(double), cudaMemcpyHostToDevice, s));
+	CK(launch_tdist(d, d + n, n, d + 2 * n, s));
+	CK(cudaMemcpyAsync(out, d + 2 * n, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+	return WB200_OK;
+}
+
 // Diagnostic builds (-DWB_DIAG_PHASES): cycles per pipeline phase summed over windows since the
 // last call; all zero in the shipped build.
 void wb200_debug_phases(wb200_ctx *ctx, uint64_t out[16]) {
@@ -762,8 +794,6 @@ int wb200_reduce_device_batch(wb200_ctx *ctx, int op, int ntracks, int nset1, in
 		max_nw = std::max<int64_t>(max_nw, job.nw);
 		max_slow = std::max<int64_t>(max_slow, std::max<int64_t>(1 << 16, h.out_cap / 8));
 		if (!wants_format(op, N, job.I, h_defaults, false)) sample = false;
-		if (window_smem_bytes(job.wlog, N, true, op) > 227 * 1024)
-			return fail(ctx, WB200_EUNSUPPORTED, "window does not fit shared memory; lower WB200_WINDOW");
 		h.n_out = 0; h.auc = 0; h.slow_segments = 0; h.ms_cursor = h.ms_sweep = 0; h.limbs = 0; h.sweep_kernel = 0;
 	}
 	wb200_stats total{};
@@ -985,6 +1015,69 @@ int reduce_host_to_device(wb200_ctx *ctx, int op, int ntracks, int nset1, int st
 	return rc;
 }
 } // namespace
+
+// -- regional integrators ---------------------------------------------------
+// Replaces, per chromosome: ApplyMultiplexerPop / computeApplyValues (src/apply.c:259-321) with the
+// integrator chain AUCIntegrator ... SpanIntegrator (src/statistics.c:62-326) over a buffered region.
+int wb200_apply_device(wb200_ctx *ctx, const int32_t *d_start, const int32_t *d_end, const double *d_value, int64_t nseg,
+                       double default_value, int64_t nreg, const int32_t *rstart, const int32_t *rend,
+                       int nstats, const int *codes, int strict, double *out) {
+	if (!ctx || nseg < 0 || nreg < 0 || nstats < 1 || nstats > 64 || !codes || (nreg > 0 && (!rstart || !rend || !out))) return WB200_EINVAL;
+	for (int k = 0; k < nstats; k++) if (codes[k] < WB200_STAT_AUC || codes[k] > WB200_STAT_SPAN) return fail(ctx, WB200_EINVAL, "unknown regional statistic");
+	if (nreg == 0) return WB200_OK;
+	cudaSetDevice(ctx->device);
+	cudaStream_t s = ctx->stream;
+	const size_t n = (size_t) nreg;
+	CK(ctx->ap_rs.ensure(n * sizeof(int32_t))); CK(ctx->ap_re.ensure(n * sizeof(int32_t)));
+	CK(ctx->ap_codes.ensure(64 * sizeof(int))); CK(ctx->ap_out.ensure(n * nstats * sizeof(double)));
+	CK(ctx->hap_out.ensure(n * nstats * sizeof(double)));
+	CK(cudaMemcpyAsync(ctx->ap_rs.p, rstart, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+	CK(cudaMemcpyAsync(ctx->ap_re.p, rend, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+	CK(cudaMemcpyAsync(ctx->ap_codes.p, codes, nstats * sizeof(int), cudaMemcpyHostToDevice, s));
+	// the buffer's default goes through float (createBufferedWiggleIteratorData keeps it in a float-typed field, apply.c:58-75)
+	const double dflt = (double) (float) default_value;
+	bool var_family = false;
+	for (int k = 0; k < nstats; k++) var_family = var_family || (codes[k] >= WB200_STAT_VAR && codes[k] <= WB200_STAT_CV);
+	CK(launch_apply(d_start, d_end, d_value, nseg, dflt, strict ? 1 : 0, ctx->ap_rs.as<int32_t>(), ctx->ap_re.as<int32_t>(), nreg,
+	                nstats, ctx->ap_codes.as<int>(), ctx->ap_out.as<double>(), var_family, s));
+	CK(cudaMemcpyAsync(ctx->hap_out.p, ctx->ap_out.p, n * nstats * sizeof(double), cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));      // also: the (possibly pageable) region arrays are free again
+	memcpy(out, ctx->hap_out.p, n * nstats * sizeof(double));
+	ctx->stats = wb200_stats{};
+	ctx->stats.segments = nseg; ctx->stats.kernels = 1;
+	ctx->stats.h2d_bytes = (int64_t) n * 8; ctx->stats.d2h_bytes = (int64_t) n * nstats * 8;
+	return WB200_OK;
+}
+
+int wb200_apply_host(wb200_ctx *ctx, const int32_t *start, const int32_t *end, const double *value, int64_t nseg,
+                     double default_value, int64_t nreg, const int32_t *rstart, const int32_t *rend,
+                     int nstats, const int *codes, int strict, double *out) {
+	if (!ctx || nseg < 0 || (nseg > 0 && (!start || !end || !value))) return WB200_EINVAL;
+	cudaSetDevice(ctx->device);
+	cudaStream_t s = ctx->stream;
+	const size_t m = (size_t) std::max<int64_t>(1, nseg);
+	CK(ctx->w_in_start.ensure(m * sizeof(int32_t))); CK(ctx->w_in_end.ensure(m * sizeof(int32_t))); CK(ctx->w_in_value.ensure(m * sizeof(double)));
+	if (nseg > 0) {
+		CK(cudaMemcpyAsync(ctx->w_in_start.p, start, (size_t) nseg * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+		CK(cudaMemcpyAsync(ctx->w_in_end.p, end, (size_t) nseg * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+		CK(cudaMemcpyAsync(ctx->w_in_value.p, value, (size_t) nseg * sizeof(double), cudaMemcpyHostToDevice, s));
+	}
+	int rc = wb200_apply_device(ctx, ctx->w_in_start.as<int32_t>(), ctx->w_in_end.as<int32_t>(), ctx->w_in_value.as<double>(), nseg,
+	                            default_value, nreg, rstart, rend, nstats, codes, strict, out);
+	if (rc == WB200_OK) ctx->stats.h2d_bytes += nseg * 16;
+	return rc;
+}
+
+// the segments of the last wb200_reduce_host() call on the context are the dataset: they never left HBM
+int wb200_apply_last(wb200_ctx *ctx, double default_value, int64_t nreg, const int32_t *rstart, const int32_t *rend,
+                     int nstats, const int *codes, int strict, double *out) {
+	if (!ctx) return WB200_EINVAL;
+	if (ctx->last_S < 0) return fail(ctx, WB200_EINVAL, "wb200_apply_last: no single-chromosome reduction is resident on this context");
+	const Job job = ctx->last_job;
+	const int64_t S = ctx->last_S;
+	int rc = wb200_apply_device(ctx, job.out_start, job.out_end, job.out_value, S, default_value, nreg, rstart, rend, nstats, codes, strict, out);
+	return rc;
+}
 
 // Raw multiplexer rows of the chromosome the last wb200_reduce_host() call on the context reduced
 // (its staged inputs, cursor table and segments are still resident in HBM): for segments

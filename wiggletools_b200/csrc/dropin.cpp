@@ -318,9 +318,8 @@ struct Reducer {
 	// Next chromosome straight into the text sink: reduction and formatting on the device,
 	// only the text comes back (wb200_reduce_format_host).  false = inputs exhausted.
 	bool next_chromosome_to_sink(FILE *out, int mode, wb200_sink_state *state) {
-		std::vector<wb200_track> tracks;
-		std::vector<BwSource *> direct;
-		if (!drain(tracks, direct)) return false;
+		if (!stage()) return false;
+		std::vector<wb200_track> &tracks = st_tracks;
 		const char *text = nullptr;
 		int64_t nbytes = 0, nseg = 0;
 		double a = 0;
@@ -330,15 +329,48 @@ struct Reducer {
 			die(wb200_last_error(engine()));
 		if (nbytes > 0 && fwrite(text, 1, (size_t) nbytes, out) != (size_t) nbytes) die("short write to the output file");
 		auc += a;
-		release(direct);
+		unstage();
 		return true;
+	}
+
+	// A chromosome drained ahead of its reduction (a strict Multiplexer shows its first row at
+	// construction, like the reference's eager pop): the staged inputs wait here until a reduction or
+	// the row server computes on them.
+	bool staged = false;
+	std::vector<wb200_track> st_tracks;
+	std::vector<BwSource *> st_direct;
+
+	bool stage() {
+		if (staged) return true;
+		staged = drain(st_tracks, st_direct);
+		return staged;
+	}
+
+	// the statistic of this Reducer on the staged chromosome (the inputs stay staged)
+	void compute() {
+		const size_t n = iters.size();
+		rs.clear(); re.clear(); rv.clear(); k = 0;
+		wb200_segments out;
+		arm_maps();
+		if (wb200_reduce_host(engine(), op, (int) n, n1, strict ? 1 : 0, st_tracks.data(), &out) != WB200_OK)
+			die(wb200_last_error(engine()));
+		rs.assign(out.start, out.start + out.n);
+		re.assign(out.end, out.end + out.n);
+		rv.assign(out.value, out.value + out.n);
+		last_auc = out.auc;
+	}
+	double last_auc = 0;
+
+	void unstage() {
+		if (!staged) return;
+		release(st_direct);
+		staged = false;
 	}
 
 	// Same as drain(), then run the engine on the chromosome.
 	bool next_chromosome() {
-		std::vector<wb200_track> tracks;
-		std::vector<BwSource *> direct;
-		if (!drain(tracks, direct)) return false;
+		if (!stage()) return false;
+		std::vector<wb200_track> &tracks = st_tracks;
 		const size_t n = iters.size();
 		rs.clear(); re.clear(); rv.clear(); k = 0;
 		if (pearson && nd_rank > 0) {
@@ -347,25 +379,19 @@ struct Reducer {
 				if (wb200_pearson_pair_host(engine(), (int) n, tracks.data(), d, n1 + d, m) != WB200_OK) die(wb200_last_error(engine()));
 				wb200_pearson_merge(nd_moments[d], m);
 			}
-			release(direct);
+			unstage();
 			return true;
 		}
 		if (pearson) {
 			double m[6];
 			if (wb200_pearson_host(engine(), &tracks[0], &tracks[1], m) != WB200_OK) die(wb200_last_error(engine()));
 			wb200_pearson_merge(moments, m);
-			release(direct);
+			unstage();
 			return true;
 		}
-		wb200_segments out;
-		arm_maps();
-		if (wb200_reduce_host(engine(), op, (int) n, n1, strict ? 1 : 0, tracks.data(), &out) != WB200_OK)
-			die(wb200_last_error(engine()));
-		rs.assign(out.start, out.start + out.n);
-		re.assign(out.end, out.end + out.n);
-		rv.assign(out.value, out.value + out.n);
-		auc += out.auc;
-		release(direct);
+		compute();
+		auc += last_auc;
+		unstage();
 		return true;
 	}
 };
@@ -384,6 +410,7 @@ void reducer_pop(WiggleIterator *wi) {
 void reducer_seek(WiggleIterator *wi, const char *chrom, int start, int finish) {
 	// WiggleReducerSeek (reducers.c:25-29): seek every input, then pop
 	Reducer *r = (Reducer *) wi->data;
+	r->staged = false;
 	for (WiggleIterator *it : r->iters) seek(it, chrom, start, finish);
 	r->rs.clear(); r->re.clear(); r->rv.clear(); r->k = 0;
 	r->auc = 0;       // the integral restarts with the sought region (the eager first pop had added the whole first chromosome)
@@ -401,14 +428,20 @@ double host_default(int op, const std::vector<WiggleIterator *> &iters) {
 	return out.default_value;
 }
 
+struct MuxState;
+MuxState *mux_state(Multiplexer *multi);
+// the inputs of a GPU multiplexer pass to a reduction / integrator (with the chromosome a strict
+// multiplexer staged for its first row, if any); the multiplexer itself is spent
+void mux_claim(Multiplexer *multi, Reducer *r);
+
 WiggleIterator *make_reduction(int op, Multiplexer *multi) {
 	if (!is_gpu_multiplexer(multi))
 		die("reducers run on multiplexers built by newMultiplexer(); a custom multiplexer (apply/mwrite) as reducer input is not supported");
 	Reducer *r = new Reducer();
 	r->op = op;
 	r->strict = multi->strict;
-	r->iters.assign(multi->iters, multi->iters + multi->count);
 	r->n1 = multi->count;
+	mux_claim(multi, r);
 	double dflt = host_default(op, r->iters);
 	return newWiggleIterator(r, &reducer_pop, &reducer_seek, dflt, false);
 }
@@ -418,22 +451,163 @@ WiggleIterator *make_setcompare(int op, Multiset *ms) {
 	r->op = op;
 	for (int m = 0; m < 2; m++) {
 		if (!is_gpu_multiplexer(ms->multis[m])) die("set comparisons need multiplexers built by newMultiplexer()");
-		r->iters.insert(r->iters.end(), ms->multis[m]->iters, ms->multis[m]->iters + ms->multis[m]->count);
+		Reducer part;
+		mux_claim(ms->multis[m], &part);
+		if (part.staged) die("set comparisons over strict multiplexers are not supported");   // (the reference's multiset sweeps its children non-strictly)
+		r->iters.insert(r->iters.end(), part.iters.begin(), part.iters.end());
 	}
 	r->n1 = ms->multis[0]->count;
 	return newWiggleIterator(r, &reducer_pop, &reducer_seek, NAN, false);
 }
 
 // ---------------------------------------------------------------------------
-// a GPU-backed Multiplexer is a description of the inputs; rows are not served
+// A GPU-backed Multiplexer is first of all a description of the inputs that a reduction or an
+// integrator takes over.  When somebody POPS it instead (mwrite, mwrite_bg, paste, select, any
+// user of popMultiplexer) it serves rows: per chromosome the union segments come from one
+// reduction on the device and the per-row values[] / inplay[] (multiplexer.c:76-96) from
+// wb200_rows_host, fetched in blocks of 10 000 rows (the multi-writer's own block size,
+// mWigWriter.c:29).  Like the reference's (multiplexer.c:167) it shows its first row on return
+// from newMultiplexer: for a non-strict one that row follows from the inputs' first records and
+// nothing is consumed; a strict one stages its first chromosome on the device (the first row
+// where all inputs are in play can lie anywhere in it).
 // ---------------------------------------------------------------------------
-void gpu_multiplexer_pop(Multiplexer *) {
-	die("this Multiplexer is batch (GPU): per-row values[]/inplay[] are not materialised, "
-	    "so mwrite / paste / raw popMultiplexer are not available on it");
+constexpr size_t ROW_BLOCK = 10000;
+
+struct MuxState {
+	Reducer r;                 // op = SUM: the segments of a sum are the multiplexer's rows
+	bool claimed = false;      // a reduction / integrator took the inputs
+	bool started = false;      // row mode: r holds the segments of the current chromosome
+	bool eager = false;        // the row on display was derived from the inputs' first records
+	long long pops = 0;        // rows the user has moved past
+	size_t row = 0;            // index (in r.rs) of the row on display
+	size_t blk0 = 0, blkn = 0; // rows [blk0, blk0 + blkn) are in vals / inp
+	std::vector<double> vals;
+	std::vector<unsigned char> inp;
+};
+
+MuxState *mux_state(Multiplexer *multi) { return (MuxState *) multi->data; }
+
+void mux_claim(Multiplexer *multi, Reducer *r) {
+	MuxState *ms = mux_state(multi);
+	if (ms->claimed) die("this Multiplexer already feeds another reduction");
+	if (ms->pops > 0) die("this Multiplexer has been popped; a reduction must be built on a fresh one");
+	ms->claimed = true;
+	r->iters = ms->r.iters;
+	if (ms->r.staged) {        // the chromosome staged for the strict first row goes with the inputs
+		r->staged = true;
+		r->st_tracks.swap(ms->r.st_tracks); r->st_direct.swap(ms->r.st_direct);
+		r->s.swap(ms->r.s); r->e.swap(ms->r.e); r->v.swap(ms->r.v); r->chains.swap(ms->r.chains);
+		r->chrom = ms->r.chrom;
+		ms->r.staged = false;
+	}
+}
+
+// the row on display: fields of the Multiplexer, as popCoreMultiplexer2 leaves them
+void mux_show(Multiplexer *m, MuxState *ms) {
+	const size_t n = (size_t) m->count;
+	if (ms->row < ms->blk0 || ms->row >= ms->blk0 + ms->blkn) {
+		ms->blk0 = ms->row;
+		ms->blkn = std::min(ROW_BLOCK, ms->r.rs.size() - ms->row);
+		ms->vals.resize(ms->blkn * n); ms->inp.resize(ms->blkn * n);
+		if (wb200_rows_host(engine(), (int64_t) ms->blk0, (int64_t) ms->blkn, ms->vals.data(), ms->inp.data()) != WB200_OK)
+			die(wb200_last_error(engine()));    // (e.g. another reduction ran on the engine between two blocks of this multiplexer)
+	}
+	const size_t o = (ms->row - ms->blk0) * n;
+	m->chrom = ms->r.chrom; m->start = ms->r.rs[ms->row]; m->finish = ms->r.re[ms->row];
+	int count = 0;
+	for (size_t i = 0; i < n; i++) {
+		m->values[i] = ms->vals[o + i];
+		m->inplay[i] = ms->inp[o + i];
+		count += ms->inp[o + i] ? 1 : 0;
+	}
+	m->inplay_count = count;
+}
+
+// next chromosome of the row server: segments on the device, rows fetched on demand
+bool mux_next_chromosome(MuxState *ms) {
+	while (true) {
+		if (!ms->r.stage()) return false;
+		ms->r.compute();
+		// (the staged inputs stay resident on the device for wb200_rows_host; the sources move on)
+		ms->r.unstage();
+		ms->row = 0; ms->blk0 = ms->blkn = 0;
+		if (!ms->r.rs.empty()) return true;
+	}
+}
+
+void gpu_multiplexer_pop(Multiplexer *m) {
+	MuxState *ms = mux_state(m);
+	if (ms->claimed) die("this Multiplexer feeds a reduction; it cannot be popped as well");
+	ms->pops++;
+	ms->r.unstage();           // a strict multiplexer's first chromosome: its sources move on now (the device keeps the staged copy)
+	if (!ms->started) {
+		// first pop of a non-strict multiplexer: the row on display came from the inputs' first records;
+		// the chromosome is now reduced on the device and its row 0 must be that very row
+		if (!mux_next_chromosome(ms)) { m->done = true; return; }
+		ms->started = true;
+		if (ms->eager && (ms->r.rs[0] != m->start || ms->r.re[0] != m->finish)) die("internal: first multiplexer row differs from the device's");
+		ms->eager = false;
+	}
+	ms->row++;
+	while (ms->row >= ms->r.rs.size())
+		if (!mux_next_chromosome(ms)) { m->done = true; return; }
+	mux_show(m, ms);
+}
+
+// the first row on display after construction / seek (multiplexer.c:157-169, 130-141)
+void mux_first_row(Multiplexer *m) {
+	MuxState *ms = mux_state(m);
+	ms->started = false; ms->eager = false; ms->pops = 0; ms->row = 0; ms->blk0 = ms->blkn = 0;
+	ms->r.staged = false;
+	m->done = false;
+	const int n = m->count;
+	if (m->strict) {
+		// all inputs in play: the first such row can lie anywhere in the chromosome -> stage it now;
+		// a reduction built on this multiplexer takes the staged chromosome over (mux_claim)
+		while (true) {
+			if (!ms->r.stage()) { m->done = true; return; }
+			ms->r.compute();
+			if (!ms->r.rs.empty()) break;
+			ms->r.unstage();
+		}
+		ms->started = true;
+		ms->row = 0; ms->blk0 = ms->blkn = 0;
+		mux_show(m, ms);
+		return;
+	}
+	// non-strict: admit the inputs that start first on the smallest chromosome (multiplexer.c:50-96)
+	const char *best = nullptr;
+	for (int i = 0; i < n; i++) {
+		WiggleIterator *it = m->iters[i];
+		if (!it->done && (!best || strcmp(it->chrom, best) < 0)) best = it->chrom;
+	}
+	if (!best) { m->done = true; return; }
+	int start = 0; bool any = false;
+	for (int i = 0; i < n; i++) {
+		WiggleIterator *it = m->iters[i];
+		if (!it->done && strcmp(it->chrom, best) == 0 && (!any || it->start < start)) { start = it->start; any = true; }
+	}
+	int finish = 0; bool have = false; int count = 0;
+	for (int i = 0; i < n; i++) {
+		WiggleIterator *it = m->iters[i];
+		const bool here = !it->done && strcmp(it->chrom, best) == 0;
+		const bool in = here && it->start == start;
+		m->inplay[i] = in;
+		m->values[i] = in ? it->value : m->default_values[i];
+		count += in ? 1 : 0;
+		if (here) {
+			const int edge = in ? it->finish : it->start;
+			if (!have || edge < finish) { finish = edge; have = true; }
+		}
+	}
+	m->chrom = intern(best); m->start = start; m->finish = finish; m->inplay_count = count;
+	ms->eager = true;
 }
 
 void gpu_multiplexer_seek(Multiplexer *multi, const char *chrom, int start, int finish) {
+	MuxState *ms = mux_state(multi);
 	for (int i = 0; i < multi->count; i++) seek(multi->iters[i], chrom, start, finish);
+	if (!ms->claimed) mux_first_row(multi);       // seekCoreMultiplexer pops once (multiplexer.c:140)
 }
 
 // ---------------------------------------------------------------------------
@@ -616,15 +790,20 @@ Multiplexer *newCoreMultiplexer(void *data, int count, void (*popf)(Multiplexer 
 }
 
 Multiplexer *newMultiplexer(WiggleIterator **iters, int count, wt_bool strict) {
-	Multiplexer *m = newCoreMultiplexer(nullptr, count, &gpu_multiplexer_pop, &gpu_multiplexer_seek);
+	MuxState *ms = new MuxState();
+	Multiplexer *m = newCoreMultiplexer(ms, count, &gpu_multiplexer_pop, &gpu_multiplexer_seek);
 	m->strict = strict;
 	m->iters = (WiggleIterator **) calloc(count, sizeof(WiggleIterator *));
 	for (int i = 0; i < count; i++) {
 		m->iters[i] = NonOverlappingWiggleIterator(iters[i]);
 		m->default_values[i] = m->values[i] = m->iters[i]->default_value;
 	}
-	// The reference pops once here (:167).  A batch multiplexer has no rows to
-	// show; it stays not-done until a reduction or integrator consumes it.
+	ms->r.op = WB200_SUM;
+	ms->r.strict = strict != 0;
+	ms->r.n1 = count;
+	ms->r.iters.assign(m->iters, m->iters + count);
+	// The reference pops once here (multiplexer.c:167): the first row is on display on return.
+	mux_first_row(m);
 	return m;
 }
 
@@ -659,7 +838,6 @@ WiggleIterator *MaxReduction(Multiplexer *m) { return make_reduction(WB200_MAX, 
 WiggleIterator *MedianReduction(Multiplexer *m) { return make_reduction(WB200_MEDIAN, m); }
 
 WiggleIterator *SelectReduction(Multiplexer *multi, int index) {
-	if (is_gpu_multiplexer(multi)) die("select needs multiplexer rows; not available on a batch (GPU) multiplexer");
 	SelectData *d = (SelectData *) calloc(1, sizeof(SelectData));
 	d->multi = multi;
 	d->index = index;
@@ -712,7 +890,7 @@ WiggleIterator *PearsonIntegrator(Multiplexer *multi) {
 	d->res = NAN;
 	d->r = new Reducer();
 	d->r->pearson = true;
-	d->r->iters.assign(multi->iters, multi->iters + 2);
+	mux_claim(multi, d->r);
 	d->r->n1 = 2;
 	WiggleIterator *res = newWiggleIterator(d, &pearson_pop, &pearson_seek, multi->iters[1]->default_value, 0);
 	res->append = multi->iters[1];
@@ -732,11 +910,87 @@ WiggleIterator *NDPearsonIntegrator(Multiset *ms) {
 	d->r->nd_rank = ms->count;     // = 2: the reference's quirk, kept
 	for (int m = 0; m < 2; m++) {
 		if (!is_gpu_multiplexer(ms->multis[m])) die("ndpearson needs multiplexers built by newMultiplexer()");
-		d->r->iters.insert(d->r->iters.end(), ms->multis[m]->iters, ms->multis[m]->iters + ms->multis[m]->count);
+		Reducer part;
+		mux_claim(ms->multis[m], &part);
+		d->r->iters.insert(d->r->iters.end(), part.iters.begin(), part.iters.end());
 	}
 	d->r->n1 = ms->multis[0]->count;
 	WiggleIterator *res = newWiggleIterator(d, &ndpearson_pop, &pearson_seek, 0, 0);
 	res->append = ms->multis[0]->iters[0];
+	return res;
+}
+
+// -- apply.c ----------------------------------------------------------------------------------
+// ApplyMultiplexer (src/apply.c:340-353) for a dataset that is a fresh reduction of this library.
+// The reference seeks the dataset to every batch of regions, copies it into per-base buffers and
+// runs the integrator chain base by base (apply.c:259-321).  Here each run of regions on one
+// chromosome becomes: one seek of the reduction to the span of the run (the segments are
+// computed on the device and stay there), then one wb200_apply_last call -- a segmented
+// reduction per region over the resident segments.  stat_codes: WB200_STAT_* per output column.
+// Returns NULL when the dataset is not a fresh reduction (the caller keeps the reference's path).
+namespace {
+struct ApplyState {
+	WiggleIterator *regions, *dataset;
+	Reducer *r;
+	std::vector<int> codes;
+	bool strict;
+	char *chrom = nullptr;
+	std::vector<int32_t> rs, re;
+	std::vector<double> out;
+	size_t k = 0;
+};
+
+void apply_pop(Multiplexer *m) {
+	ApplyState *st = (ApplyState *) m->data;
+	const int count = m->count;
+	if (st->k >= st->rs.size()) {
+		if (st->regions->done) { m->done = true; return; }
+		// the next run of regions on one chromosome
+		st->chrom = intern(st->regions->chrom);
+		st->rs.clear(); st->re.clear(); st->k = 0;
+		int lo = st->regions->start, hi = st->regions->finish;
+		while (!st->regions->done && strcmp(st->regions->chrom, st->chrom) == 0 && st->rs.size() < (1u << 20)) {
+			st->rs.push_back(st->regions->start); st->re.push_back(st->regions->finish);
+			lo = std::min(lo, st->regions->start); hi = std::max(hi, st->regions->finish);
+			pop(st->regions);
+		}
+		st->out.assign(st->rs.size() * count, NAN);
+		// the dataset over the span of the run: reduced on the device, segments stay resident
+		seek(st->dataset, st->chrom, lo, hi);
+		const bool have = !st->dataset->done && !st->r->rs.empty() && strcmp(st->r->chrom, st->chrom) == 0;
+		int rc;
+		if (have)
+			rc = wb200_apply_last(engine(), st->dataset->default_value, (int64_t) st->rs.size(), st->rs.data(), st->re.data(),
+			                      count, st->codes.data(), st->strict ? 1 : 0, st->out.data());
+		else        // nothing of the dataset in the span: every base is uncovered
+			rc = wb200_apply_host(engine(), nullptr, nullptr, nullptr, 0, st->dataset->default_value, (int64_t) st->rs.size(),
+			                      st->rs.data(), st->re.data(), count, st->codes.data(), st->strict ? 1 : 0, st->out.data());
+		if (rc != WB200_OK) die(wb200_last_error(engine()));
+	}
+	m->chrom = st->chrom; m->start = st->rs[st->k]; m->finish = st->re[st->k];
+	for (int i = 0; i < count; i++) m->values[i] = st->out[st->k * count + i];
+	st->k++;
+}
+
+void apply_seek(Multiplexer *m, const char *chrom, int start, int finish) {
+	ApplyState *st = (ApplyState *) m->data;
+	st->rs.clear(); st->re.clear(); st->k = 0;
+	seek(st->regions, chrom, start, finish);      // ApplyMultiplexerSeek (apply.c:323-333): drop the open targets, seek the regions
+}
+} // namespace
+
+Multiplexer *wb200_apply_multiplexer(WiggleIterator *regions, const int *stat_codes, int count, WiggleIterator *dataset, wt_bool strict) {
+	if (!regions || !dataset || !stat_codes || count < 1 || count > 64) return nullptr;
+	if (dataset->pop != &reducer_pop || dataset->overlaps) return nullptr;
+	Reducer *r = (Reducer *) dataset->data;
+	if (r->pearson) return nullptr;
+	for (int i = 0; i < count; i++) if (stat_codes[i] < WB200_STAT_AUC || stat_codes[i] > WB200_STAT_SPAN) return nullptr;
+	ApplyState *st = new ApplyState();
+	st->regions = regions; st->dataset = dataset; st->r = r; st->strict = strict != 0;
+	st->codes.assign(stat_codes, stat_codes + count);
+	Multiplexer *res = newCoreMultiplexer(st, count, &apply_pop, &apply_seek);
+	for (int i = 0; i < count; i++) res->default_values[i] = NAN;       // apply.c:348-349
+	popMultiplexer(res);                                                // apply.c:350: the first region is on display
 	return res;
 }
 

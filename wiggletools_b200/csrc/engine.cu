@@ -1696,8 +1696,10 @@ static int row_buffer_bytes(int N, int op) {
 	return P * (int) sizeof(SortKey) * WARPS;                                      // one sort buffer per warp
 }
 
-size_t window_smem_bytes(int wlog, int N, bool emit, int op) {
-	return make_layout(wlog, N, emit, 6, emit ? row_buffer_bytes(N, op) : 0).total;
+// shared memory of one emit_kernel CTA: limb_arrays = 32-bit limb arrays per position of the kernel
+// that will run (sum / mean: 1..3; var / stddev / CV: 4 or 6; every other statistic: 2)
+size_t window_smem_bytes(int wlog, int N, bool emit, int op, int limb_arrays) {
+	return make_layout(wlog, N, emit, limb_arrays, emit ? row_buffer_bytes(N, op) : 0).total;
 }
 
 cudaError_t launch_cursor(const Job &job, int64_t max_track_len, cudaStream_t s) {
@@ -1845,6 +1847,17 @@ cudaError_t launch_reduce_moments(const double *moments, int nw, double *out6, c
 
 cudaError_t launch_reduce_auc(const double *partial, int count, double *out, cudaStream_t s) {
 	reduce_auc_kernel<<<1, 1024, 0, s>>>(partial, count, out);
+	return cudaGetLastError();
+}
+
+// the DEVICE build of tdist_Q on n argument pairs (tests pin it on a high-precision table)
+__global__ void tdist_kernel(const double *t, const double *nu, int n, double *out) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = tdist_Q(t[i], nu[i]);
+}
+cudaError_t launch_tdist(const double *t, const double *nu, int n, double *out, cudaStream_t s) {
+	if (n <= 0) return cudaSuccess;
+	tdist_kernel<<<(n + 127) / 128, 128, 0, s>>>(t, nu, n, out);
 	return cudaGetLastError();
 }
 

@@ -107,7 +107,7 @@ __host__ __device__ inline void merge_mom(Mom &a, const Mom &b) {
 }
 
 // launch helpers implemented in engine.cu
-size_t window_smem_bytes(int wlog, int N, bool emit, int op);
+size_t window_smem_bytes(int wlog, int N, bool emit, int op, int limb_arrays);
 cudaError_t launch_cursor(const Job &job, int64_t max_track_len, cudaStream_t s);
 // auc_per_window: how many AUC partials per window the chosen kernel writes to job.auc_partial
 cudaError_t launch_emit(const Job &job, cudaStream_t s, int *auc_per_window);
@@ -115,10 +115,15 @@ cudaError_t launch_emit(const Job &job, cudaStream_t s, int *auc_per_window);
 bool fastsum_supported(const Job &job);
 cudaError_t launch_fastsum(const Job &job, int lw, double inv_scale, double lim, double scale, cudaStream_t s);
 cudaError_t launch_fixup(const Job &job, long long count, cudaStream_t s);
+cudaError_t launch_tdist(const double *t, const double *nu, int n, double *out, cudaStream_t s);
 cudaError_t launch_rows(const Job &job, long long first, long long count, double *values, unsigned char *inplay, cudaStream_t s);
 cudaError_t launch_sample_maxabs(const double *value, int64_t n, int64_t stride, double *out2, cudaStream_t s);
 cudaError_t launch_reduce_auc(const double *partial, int count, double *out, cudaStream_t s);
 cudaError_t launch_reduce_moments(const double *moments, int nw, double *out6, cudaStream_t s);
+// regional integrators over HBM-resident segments (apply.cu)
+cudaError_t launch_apply(const int32_t *start, const int32_t *end, const double *value, long long nseg, double dflt, int strict,
+                         const int32_t *rstart, const int32_t *rend, long long nreg, int nstats, const int *codes, double *out,
+                         bool var_family, cudaStream_t s);
 // element-wise maps on staged inputs (maps.cu)
 constexpr int MAX_MAP_CHAIN = 8;
 enum MapCode : int { MAP_SCALE = 1, MAP_OFFSET = 2, MAP_LOG = 3, MAP_EXP = 4, MAP_POW = 5, MAP_ABS = 6 };
