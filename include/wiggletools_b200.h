@@ -191,6 +191,27 @@ typedef struct wb200_device_shard {
 int wb200_reduce_device_batch(wb200_ctx *ctx, int op, int ntracks, int nset1, int strict, const double *h_defaults,
                               int nshards, wb200_device_shard *shards, double *default_out);
 
+/* -- several GPUs of one box, one process ------------------------ */
+/* Chromosome shards are packed onto the devices (longest processing time first, by interval
+ * count); one host thread per device runs that device's context through wb200_reduce_host_batch
+ * (or wb200_pearson_host).  No per-segment data crosses GPUs.  The whole-genome scalars do, over
+ * NCCL (libnccl.so.2, loaded at run time): the AUC partials with ncclAllReduce(ncclDouble,
+ * ncclSum), the six Pearson moments of every device with ncclAllGather, folded in device order
+ * with wb200_pearson_merge -- what the reference does with one process per genome region
+ * (python/wiggletools/parallelWiggleTools.py:66-68) and a sum of the printed AUCs. */
+typedef struct wb200_multi wb200_multi;
+wb200_multi *wb200_multi_create(int ndev, const int *devices);   /* ndev <= 0: every visible device; devices NULL: 0..ndev-1 */
+void wb200_multi_destroy(wb200_multi *m);
+const char *wb200_multi_last_error(const wb200_multi *m);
+int wb200_multi_ndev(const wb200_multi *m);
+int wb200_multi_owner(const wb200_multi *m, int shard);           /* device index that ran the shard in the last call */
+/* tracks[c*ntracks + i], out[c] as in wb200_reduce_host_batch (out[c]'s arrays belong to the context of the
+ * device that owns shard c, valid until the next call); *auc_total = the NCCL-all-reduced integral. */
+int wb200_multi_reduce_host(wb200_multi *m, int op, int nshards, int ntracks, int nset1, int strict,
+                            const wb200_track *tracks, wb200_segments *out, double *auc_total);
+/* x[c], y[c]: the two tracks on shard c, in chromosome order; moments = the six running moments of the genome. */
+int wb200_multi_pearson_host(wb200_multi *m, int nshards, const wb200_track *x, const wb200_track *y, double moments[6]);
+
 /* -- whole-genome scalars ------------------------------------------------ */
 /* Pearson correlation of two tracks over one chromosome shard: returns the six
  * running moments so that shards (chromosomes, GPUs) can be merged exactly as

@@ -7,7 +7,7 @@ cd "$(dirname "$0")/../wiggletools_b200/csrc"
 V=../../build/variants; O=../../build/obj
 mkdir -p $V $O
 NV="nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC,-Wall,-Wno-unused-function"
-for f in engine.cu writer.cu maps.cu capi.cu dropin.cpp bigwig.cpp apply.cu; do
+for f in engine.cu writer.cu maps.cu capi.cu dropin.cpp bigwig.cpp apply.cu multi.cpp; do
   [ -f $f ] || continue
   [ $O/$f.o -nt $f ] && [ $O/$f.o -nt engine.cuh ] || $NV -c $f -o $O/$f.o &
 done

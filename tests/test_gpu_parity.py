@@ -229,6 +229,27 @@ def test_dropin_api_matches_oracle(port):
         assert same_float(got, want) or math.isclose(got, want, rel_tol=RTOL)
 
 
+def test_unsorted_input_is_refused(engine):
+    """include/wiggletools_b200.h promises WB200_EINVAL for input that breaks the contract (sorted,
+    disjoint, non-empty intervals per track): the cursor kernel checks every interval it reads
+    (such input silently produced wrong segments)."""
+    good = api.Track(np.zeros(4, np.int32), np.array([1, 10, 20, 30], np.int32), np.array([5, 15, 25, 35], np.int32), np.ones(4))
+    other = api.Track(np.zeros(2, np.int32), np.array([3, 40], np.int32), np.array([8, 44], np.int32), np.ones(2))
+    assert len(engine.reduce("sum", [good, other], ["chr1"])) > 0
+    cases = {
+        "unsorted": (np.array([1, 20, 10, 30], np.int32), np.array([5, 25, 15, 35], np.int32)),
+        "overlap": (np.array([1, 10, 14, 30], np.int32), np.array([5, 15, 25, 35], np.int32)),
+        "empty": (np.array([1, 10, 20, 30], np.int32), np.array([5, 10, 25, 35], np.int32)),
+    }
+    for name, (s_, e_) in cases.items():
+        bad = api.Track(np.zeros(4, np.int32), s_, e_, np.ones(4))
+        for op in ("sum", "median", "var"):
+            with pytest.raises(api.WB200Error, match="not sorted|empty interval"):
+                engine.reduce(op, [bad, other], ["chr1"])
+    # the engine is still usable afterwards
+    assert len(engine.reduce("sum", [good, other], ["chr1"])) > 0
+
+
 def test_device_tdist_on_committed_table(engine):
     """The t-test p-value is 2 * Q(t, nu) (src/setComparisons.c:117, gsl_cdf_tdist_Q in the
     reference; GSL is absent here).  The DEVICE build of the engine's tdist_Q -- the function

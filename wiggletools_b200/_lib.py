@@ -113,6 +113,15 @@ def load():
     lib.wb200_apply_host.argtypes = lib.wb200_apply_device.argtypes
     lib.wb200_apply_last.argtypes = [C.c_void_p, C.c_double, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     lib.wb200_debug_tdist_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.wb200_multi_create.restype = C.c_void_p
+    lib.wb200_multi_create.argtypes = [C.c_int, C.c_void_p]
+    lib.wb200_multi_destroy.argtypes = [C.c_void_p]
+    lib.wb200_multi_last_error.restype = C.c_char_p
+    lib.wb200_multi_last_error.argtypes = [C.c_void_p]
+    lib.wb200_multi_ndev.argtypes = [C.c_void_p]
+    lib.wb200_multi_owner.argtypes = [C.c_void_p, C.c_int]
+    lib.wb200_multi_reduce_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.wb200_multi_pearson_host.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.wb200_tdist_Q.restype = C.c_double
     lib.wb200_tdist_Q.argtypes = [C.c_double, C.c_double]
     _lib = lib
@@ -128,4 +137,6 @@ EXPORTS = [
     "wb200_bw_chrom_length", "wb200_bw_set_stretch", "wb200_bw_decode_chrom", "wb200_debug_phases", "wb200_debug_format_value",
     "wb200_format_device", "wb200_format_host", "wb200_reduce_format_host", "wb200_set_input_maps", "wb200_map_default",
     "wb200_apply_device", "wb200_apply_host", "wb200_apply_last", "wb200_debug_tdist_device",
+    "wb200_multi_create", "wb200_multi_destroy", "wb200_multi_last_error", "wb200_multi_ndev", "wb200_multi_owner",
+    "wb200_multi_reduce_host", "wb200_multi_pearson_host",
 ]

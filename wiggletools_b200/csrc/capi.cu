@@ -242,7 +242,7 @@ int plan_shard(wb200_ctx *ctx, int op, int N, int &n1, int &strict, const int64_
 		job.vec = aligned && !(e && atoi(e) == 0);
 	}
 	job.N = N; job.n1 = n1; job.strict = strict ? 1 : 0; job.op = op;
-	job.p0 = pos_lo; job.wlog = wlog; job.nw = nw;
+	job.p0 = pos_lo; job.wlog = wlog; job.nw = nw; job.pos_hi = pos_hi;
 	job.cstride = (N + 3) & ~3;
 	job.px = px; job.py = py;
 	{ const char *e = getenv("WB200_LB_WARPS"); job.lb_warps = e ? std::max(1, std::min(WARPS, atoi(e))) : 1; }
@@ -369,6 +369,7 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 	job.auc_fix = d_small + 10;
 	job.total = (long long *) (d_small + 11);
 	job.ticket = (unsigned int *) (d_small + 12);
+	job.flags = (int *) (d_small + 13);
 	job.diag = (unsigned long long *) (d_small + 16);
 
 	CK(cudaEventRecord(ctx->ev[0], s));
@@ -417,16 +418,15 @@ int run_device(wb200_ctx *ctx, int op, int N, int n1, int strict,
 
 	// S, AUC, slow-path count
 	int64_t *h_small = ctx->h_small.as<int64_t>();
-	CK(cudaMemcpyAsync(h_small, d_small + 11, 8, cudaMemcpyDeviceToHost, s));
-	CK(cudaMemcpyAsync(h_small + 2, d_small + 2, 64, cudaMemcpyDeviceToHost, s));
-#ifdef WB_DIAG_PHASES
-	CK(cudaMemcpyAsync(h_small + 16, d_small + 16, 128, cudaMemcpyDeviceToHost, s));
-#endif
+	CK(cudaMemcpyAsync(h_small, d_small, 256, cudaMemcpyDeviceToHost, s));     // [2] auc [3] slow [4..9] moments [10] auc_fix [11] S [13] flags [16..] diag
 	CK(cudaStreamSynchronize(s));
-	const int64_t S = h_small[0];
-#ifdef WB_DIAG_PHASES
-	for (int k = 0; k < 16; k++) ctx->diag[k] += (unsigned long long) h_small[16 + k];
-#endif
+	const int64_t S = h_small[11];
+	for (int k = 0; k < 16; k++) ctx->diag[k] += (unsigned long long) h_small[16 + k];   // zeros unless built with -DWB_DIAG_PHASES
+	if (const int fl = (int) (h_small[13] & 3)) {
+		ctx->last_S = -1;
+		return fail(ctx, WB200_EINVAL, (fl & 1) ? "a track is not sorted, overlaps itself or holds an empty interval (start >= end)"
+		                                        : "an interval lies outside [pos_lo, pos_hi]");
+	}
 	if (job.fast && h_small[3] > 0) {
 		// segments the fixed-point path could not represent exactly
 		// too many for the fix-up kernel: repeat one accumulator format wider (the sample missed
@@ -852,6 +852,7 @@ int wb200_reduce_device_batch(wb200_ctx *ctx, int op, int ntracks, int nset1, in
 		job.auc_fix = sm + 10;
 		job.total = (long long *) (sm + 11);
 		job.ticket = (unsigned int *) (sm + 12);
+		job.flags = (int *) (sm + 13);
 		job.diag = (unsigned long long *) (sm + 16);
 		if (job.fast) job.slow_cap = max_slow;
 	}
@@ -884,6 +885,9 @@ int wb200_reduce_device_batch(wb200_ctx *ctx, int op, int ntracks, int nset1, in
 		wb200_device_shard &h = shards[c];
 		const Job &job = jobs[c];
 		const int64_t *hs = ctx->hb_small.as<int64_t>() + 32 * c;
+		if (const int fl = (int) (hs[13] & 3))
+			return fail(ctx, WB200_EINVAL, (fl & 1) ? "a track is not sorted, overlaps itself or holds an empty interval (start >= end)"
+			                                        : "an interval lies outside [pos_lo, pos_hi]");
 		h.n_out = hs[11];
 		memcpy(&h.auc, hs + 2, 8);
 		h.slow_segments = hs[3];
@@ -1134,6 +1138,10 @@ int wb200_reduce_host_batch(wb200_ctx *ctx, int op, int nshards, int ntracks, in
                             const wb200_track *tracks, wb200_segments *out) {
 	if (!ctx || !tracks || !out || nshards < 0) return WB200_EINVAL;
 	cudaSetDevice(ctx->device);
+	if (!ctx->map_nchain.empty()) {       // chains armed by wb200_set_input_maps: never left pending for an unrelated call
+		ctx->map_chains.clear(); ctx->map_nchain.clear();
+		return fail(ctx, WB200_EUNSUPPORTED, "input maps are applied by wb200_reduce_host / wb200_reduce_format_host only");
+	}
 	const int N = ntracks;
 	if (N < 1) return fail(ctx, WB200_EINVAL, "need at least one track");
 	if (!ctx->s_h2d) CK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
@@ -1282,6 +1290,10 @@ int wb200_reduce_host_batch(wb200_ctx *ctx, int op, int nshards, int ntracks, in
 
 // moments of tracks px and py over the union cover of all ntracks tracks
 static int pearson_shard(wb200_ctx *ctx, int ntracks, const wb200_track *tracks, int px, int py, double moments[6]) {
+	if (!ctx->map_nchain.empty()) {
+		ctx->map_chains.clear(); ctx->map_nchain.clear();
+		return fail(ctx, WB200_EUNSUPPORTED, "input maps are applied by wb200_reduce_host / wb200_reduce_format_host only");
+	}
 	const int N = ntracks;
 	std::vector<int64_t> off(N + 1, 0);
 	std::vector<double> dflt(N);

@@ -1541,20 +1541,21 @@ __global__ void __launch_bounds__(256) cursor_kernel(const Job job) {
 	// track-relative index of the first of them (negative in the track's first, partial group)
 	const int a = (int) (o & 3);
 	const int j0 = 4 * (int) (blockIdx.x * blockDim.x + threadIdx.x) - a;
-	const int32_t *end = job.end + o;
+	const int32_t *end = job.end + o, *start = job.start + o;
 	// cnt(e) = number of windows that start at or before e; interval j is the cursor of the
 	// windows cnt(end[j-1]) .. cnt(end[j]) - 1, and j = n (one past the last) closes the table
 	const int p0 = (int) job.p0, wlog = job.wlog, rows = job.nw + 1;
 	auto cnt = [&](int e) { return e < p0 ? 0 : (int) (((unsigned) e - (unsigned) p0) >> wlog) + 1; };
-	int ev[4] = {0, 0, 0, 0};
+	int ev[4] = {0, 0, 0, 0}, sv[4] = {0, 0, 0, 0};
 	const bool live = j0 <= n;
 	if (live) {
 		if (job.vec && j0 >= 0 && j0 + 4 <= n) {
-			const int4 v = *(const int4 *) (end + j0);
+			const int4 v = *(const int4 *) (end + j0), u = *(const int4 *) (start + j0);
 			ev[0] = v.x; ev[1] = v.y; ev[2] = v.z; ev[3] = v.w;
+			sv[0] = u.x; sv[1] = u.y; sv[2] = u.z; sv[3] = u.w;
 		} else {
 #pragma unroll
-			for (int k = 0; k < 4; k++) if (j0 + k >= 0 && j0 + k < n) ev[k] = end[j0 + k];
+			for (int k = 0; k < 4; k++) if (j0 + k >= 0 && j0 + k < n) { ev[k] = end[j0 + k]; sv[k] = start[j0 + k]; }
 		}
 	}
 	// the end before this thread's group sits in the previous lane; only lane 0 loads it
@@ -1564,15 +1565,25 @@ __global__ void __launch_bounds__(256) cursor_kernel(const Job job) {
 	int c_prev = j0 > 0 ? cnt(e_prev) : 0;
 	int32_t *col = job.cursor + i;
 	const size_t N = (size_t) job.cstride;
+	// input contract (include/wiggletools_b200.h): within a track start < end and end[j-1] <= start[j]
+	// (sorted, disjoint), all inside [p0, pos_hi] -- what NonOverlappingWiggleIterator guarantees the
+	// reference's sweep (multiplexer.c:163).  Violations raise a flag the host turns into WB200_EINVAL.
+	int bad = 0, pe = e_prev;
 #pragma unroll
 	for (int k = 0; k < 4; k++) {
 		const int j = j0 + k;
 		if (j < 0) continue;
 		if (j > n) break;
+		if (j < n) {
+			if (sv[k] >= ev[k] || (j > 0 && pe > sv[k])) bad |= 1;
+			if (sv[k] < p0 || ev[k] > job.pos_hi) bad |= 2;
+			pe = ev[k];
+		}
 		const int c = j < n ? min(cnt(ev[k]), rows) : rows;
 		for (int w = c_prev; w < c; w++) col[(size_t) w * N] = j;
 		c_prev = c;
 	}
+	if (bad) atomicOr(job.flags, bad);
 }
 
 template <int MODE, int VLOG, int LIMBS>

@@ -75,6 +75,8 @@ struct Job {
 	int fx_limbs;           // sum / mean: 32-bit limbs per position (1..3)
 	int64_t fx_base;        // sum of fixed-point defaults (all tracks absent)
 	unsigned long long *diag; // [16] diagnostic builds: per-phase cycle counters
+	int *flags;             // input validation (cursor kernel): bit 0 unsorted / overlapping / empty interval, bit 1 outside [p0, pos_hi]
+	int pos_hi;             // last position the windows cover
 	double mwu_mu, mwu_sigma; // MWU normal approximation moments (host-computed, integer division quirk)
 };
 
