@@ -23,9 +23,10 @@ def _section(chrom_id, kind, items, span=1, step=1):
     return head + body, cs, ce
 
 
-def write_bigwig(path, chroms, sections, compress=True, rtree_block=4):
+def write_bigwig(path, chroms, sections, compress=True, rtree_block=4, rtree_levels=2):
     """chroms: list of (name, length) -- ids are positions in this list;
-    sections: list of (chrom_id, kind, items, span, step), sorted by (chrom_id, start)."""
+    sections: list of (chrom_id, kind, items, span, step), sorted by (chrom_id, start).
+    rtree_levels=3 puts a layer of inner nodes between the root and the leaf nodes."""
     key_size = max(len(n) for n, _ in chroms) + 1
     out = bytearray(64)
     # chromosome B+ tree: one leaf node
@@ -54,6 +55,22 @@ def write_bigwig(path, chroms, sections, compress=True, rtree_block=4):
         out += struct.pack("<BBH", 1, 0, len(groups[0]))
         for l in groups[0]:
             out += struct.pack("<IIIIQQ", *l)
+    elif rtree_levels >= 3:
+        # root -> inner nodes (rtree_block leaf nodes each) -> leaf nodes
+        supers = [groups[i:i + rtree_block] for i in range(0, len(groups), rtree_block)]
+        root_at = len(out)
+        out += struct.pack("<BBH", 0, 0, len(supers)) + bytes(24 * len(supers))
+        for si, sg in enumerate(supers):
+            inner_at = len(out)
+            out += struct.pack("<BBH", 0, 0, len(sg)) + bytes(24 * len(sg))
+            for gi, g in enumerate(sg):
+                child = len(out)
+                out += struct.pack("<BBH", 1, 0, len(g))
+                for l in g:
+                    out += struct.pack("<IIIIQQ", *l)
+                struct.pack_into("<IIIIQ", out, inner_at + 4 + 24 * gi, g[0][0], g[0][1], g[-1][2], max(x[3] for x in g), child)
+            flat = [l for g in sg for l in g]
+            struct.pack_into("<IIIIQ", out, root_at + 4 + 24 * si, flat[0][0], flat[0][1], flat[-1][2], max(x[3] for x in flat), inner_at)
     else:
         root_at = len(out)
         out += struct.pack("<BBH", 0, 0, len(groups)) + bytes(24 * len(groups))

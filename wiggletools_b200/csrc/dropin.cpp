@@ -11,6 +11,7 @@
 #include "../../include/wiggletools_dropin.h"
 #include "../../include/wiggletools_b200.h"
 
+#include <chrono>
 #include <cmath>
 #include <cstddef>
 #include <cstdio>
@@ -57,6 +58,26 @@ char *intern(const char *name) {
 	return const_cast<char *>(names.insert(name).first->c_str());
 }
 
+// WB200_PROFILE=1: wall time spent decoding BigWig sections, in engine calls (staging + kernels + read-back)
+// and writing text, printed at exit -- where an end-to-end run from files goes
+struct Prof {
+	double decode = 0, engine = 0, write = 0;
+	bool on = false;
+	std::chrono::steady_clock::time_point t0;
+	Prof() { on = getenv("WB200_PROFILE") != nullptr; t0 = std::chrono::steady_clock::now(); }
+	~Prof() {
+		if (!on) return;
+		const double total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+		fprintf(stderr, "wiggletools_b200 profile: total %.3f s, BigWig decode %.3f s, engine calls %.3f s, text write %.3f s\n", total, decode, engine, write);
+	}
+} g_prof;
+struct ProfScope {
+	double &acc;
+	std::chrono::steady_clock::time_point t;
+	explicit ProfScope(double &a) : acc(a), t(std::chrono::steady_clock::now()) {}
+	~ProfScope() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); }
+};
+
 void die(const char *msg) {
 	fprintf(stderr, "wiggletools_b200: %s\n", msg);
 	exit(1);
@@ -86,7 +107,7 @@ struct BwSource {
 	bool load_next_chrom() {
 		if (region) return false;
 		while (++ci < wb200_bw_nchrom(bw)) {
-			if (wb200_bw_decode_chrom(bw, ci, &t) != WB200_OK) die(wb200_bw_last_error(bw));
+			{ ProfScope ps(g_prof.decode); if (wb200_bw_decode_chrom(bw, ci, &t) != WB200_OK) die(wb200_bw_last_error(bw)); }
 			if (t.n > 0) { chrom = intern(wb200_bw_chrom_name(bw, ci)); k = 0; return true; }
 		}
 		t.n = 0; k = 0;
@@ -324,10 +345,13 @@ struct Reducer {
 		int64_t nbytes = 0, nseg = 0;
 		double a = 0;
 		arm_maps();
-		if (wb200_reduce_format_host(engine(), op, (int) tracks.size(), n1, strict ? 1 : 0, tracks.data(), mode, chrom, state,
-		                             &text, &nbytes, &nseg, &a) != WB200_OK)
-			die(wb200_last_error(engine()));
-		if (nbytes > 0 && fwrite(text, 1, (size_t) nbytes, out) != (size_t) nbytes) die("short write to the output file");
+		{
+			ProfScope ps(g_prof.engine);
+			if (wb200_reduce_format_host(engine(), op, (int) tracks.size(), n1, strict ? 1 : 0, tracks.data(), mode, chrom, state,
+			                             &text, &nbytes, &nseg, &a) != WB200_OK)
+				die(wb200_last_error(engine()));
+		}
+		{ ProfScope ps(g_prof.write); if (nbytes > 0 && fwrite(text, 1, (size_t) nbytes, out) != (size_t) nbytes) die("short write to the output file"); }
 		auc += a;
 		unstage();
 		return true;
@@ -352,8 +376,11 @@ struct Reducer {
 		rs.clear(); re.clear(); rv.clear(); k = 0;
 		wb200_segments out;
 		arm_maps();
-		if (wb200_reduce_host(engine(), op, (int) n, n1, strict ? 1 : 0, st_tracks.data(), &out) != WB200_OK)
-			die(wb200_last_error(engine()));
+		{
+			ProfScope ps(g_prof.engine);
+			if (wb200_reduce_host(engine(), op, (int) n, n1, strict ? 1 : 0, st_tracks.data(), &out) != WB200_OK)
+				die(wb200_last_error(engine()));
+		}
 		rs.assign(out.start, out.start + out.n);
 		re.assign(out.end, out.end + out.n);
 		rv.assign(out.value, out.value + out.n);
