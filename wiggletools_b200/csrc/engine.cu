@@ -1537,15 +1537,14 @@ __global__ void __launch_bounds__(256) cursor_kernel(const Job job) {
 	const int i = blockIdx.y;
 	const long long o = job.off[i];
 	const int n = (int) (job.off[i + 1] - o);
-	// four consecutive intervals per thread on a 16-byte aligned grid: one 128-bit load; j0 is the
+	// four consecutive intervals per thread on a 16-byte aligned grid: one 128-bit load per array; j0 is the
 	// track-relative index of the first of them (negative in the track's first, partial group)
-	const int a = (int) (o & 3);
-	const int j0 = 4 * (int) (blockIdx.x * blockDim.x + threadIdx.x) - a;
+	const int j0 = 4 * (int) (blockIdx.x * blockDim.x + threadIdx.x) - (int) (o & 3);
 	const int32_t *end = job.end + o, *start = job.start + o;
-	// cnt(e) = number of windows that start at or before e; interval j is the cursor of the
-	// windows cnt(end[j-1]) .. cnt(end[j]) - 1, and j = n (one past the last) closes the table
+	// cnt(e) = number of windows that start at or before e (capped at the table's row count); interval j is
+	// the cursor of the windows cnt(end[j-1]) .. cnt(end[j]) - 1, and j = n (one past the last) closes the table
 	const int p0 = (int) job.p0, wlog = job.wlog, rows = job.nw + 1;
-	auto cnt = [&](int e) { return e < p0 ? 0 : (int) (((unsigned) e - (unsigned) p0) >> wlog) + 1; };
+	auto cnt = [&](int e) -> int { return e < p0 ? 0 : (int) min((((unsigned) e - (unsigned) p0) >> wlog) + 1u, (unsigned) rows); };
 	int ev[4] = {0, 0, 0, 0}, sv[4] = {0, 0, 0, 0};
 	const bool live = j0 <= n;
 	if (live) {
@@ -1564,24 +1563,29 @@ __global__ void __launch_bounds__(256) cursor_kernel(const Job job) {
 	if ((threadIdx.x & 31) == 0 && j0 > 0) e_prev = end[j0 - 1];
 	int c_prev = j0 > 0 ? cnt(e_prev) : 0;
 	int32_t *col = job.cursor + i;
-	const size_t N = (size_t) job.cstride;
+	const size_t stride = (size_t) job.cstride;
 	// input contract (include/wiggletools_b200.h): within a track start < end and end[j-1] <= start[j]
 	// (sorted, disjoint), all inside [p0, pos_hi] -- what NonOverlappingWiggleIterator guarantees the
 	// reference's sweep (multiplexer.c:163).  Violations raise a flag the host turns into WB200_EINVAL.
-	int bad = 0, pe = e_prev;
+	int bad = 0, pe = j0 > 0 ? e_prev : INT_MIN;
 #pragma unroll
 	for (int k = 0; k < 4; k++) {
 		const int j = j0 + k;
-		if (j < 0) continue;
-		if (j > n) break;
-		if (j < n) {
-			if (sv[k] >= ev[k] || (j > 0 && pe > sv[k])) bad |= 1;
+		if (j >= 0 && j < n) {
+			if (sv[k] >= ev[k] || pe > sv[k]) bad |= 1;
 			if (sv[k] < p0 || ev[k] > job.pos_hi) bad |= 2;
 			pe = ev[k];
+			const int c = cnt(ev[k]);
+			if (c != c_prev) {                         // at most a few windows start inside one interval's reach
+#pragma unroll 1
+				for (int w = c_prev; w < c; w++) col[(size_t) w * stride] = j;
+				c_prev = c;
+			}
 		}
-		const int c = j < n ? min(cnt(ev[k]), rows) : rows;
-		for (int w = c_prev; w < c; w++) col[(size_t) w * N] = j;
-		c_prev = c;
+	}
+	if (n < j0 + 4) {                                  // this group holds index n: the closing rows
+#pragma unroll 1
+		for (int w = c_prev; w < rows; w++) col[(size_t) w * stride] = n;
 	}
 	if (bad) atomicOr(job.flags, bad);
 }
