@@ -611,9 +611,15 @@ def main():
         # end to end through the host-buffer entry point: pinned host tracks -> H2D -> kernels -> D2H of
         # the segments, every step, timed with the wall clock around synchronous calls (max over ranks)
         if wl["e2e"] and not args.no_e2e:
-            e2e = run_e2e(torch, dist, lib, ctx, wl, st, dev, world, max(1, args.steps if headline else min(args.steps, 3)))
+            # `e2e`: the library's narrow PCIe transport (float32 values in, breakpoint-form segments out); `e2e_wide`: fp64 values
+            # in, all three arrays out -- same call, same results (checked against the resident run), 25 % fewer bytes
+            ksteps = max(1, args.steps if headline else min(args.steps, 3))
+            e2e = run_e2e(torch, dist, lib, ctx, wl, st, dev, world, ksteps, narrow=True)
             e2e["host_thread_cpus"] = int(local_cpus)     # CPUs local to this rank's GPU the host thread was pinned to (0: not pinned)
             line["e2e"] = e2e
+            if headline:
+                line["e2e_wide"] = run_e2e(torch, dist, lib, ctx, wl, st, dev, world, ksteps, narrow=False)
+            all_ok = all_ok and e2e["segments_match_resident_run"]
         elif not headline:
             line["e2e"] = None
         # the device text sink on this rank's smallest shard, outside the timed region:
@@ -679,41 +685,68 @@ def run_sink(torch, lib, ctx, st, names):
             "note": "wb200_format_device on HBM-resident segments, text copied to pinned host memory inside the call"}
 
 
-def run_e2e(torch, dist, lib, ctx, wl, st, dev, world, steps):
-    """The call a user of the library makes: wb200_reduce_host_batch on pinned host
-    SoA tracks -> pinned host segments (H2D, kernels, D2H all inside the timed region)."""
+def run_e2e(torch, dist, lib, ctx, wl, st, dev, world, steps, narrow):
+    """The call a user of the library makes: wb200_reduce_host_batch on pinned host SoA tracks ->
+    pinned host segments (H2D, kernels, D2H all inside the timed region).
+    narrow=True is the library's narrow PCIe transport: float32 values in (what BigWig files hold; widened to
+    fp64 on the device) and segments back in breakpoint form (start + value in full, end only where it is
+    not the next start) -- 12 + 12 instead of 16 + 16 bytes per interval / segment; narrow=False moves fp64
+    values in and all three arrays out."""
     from wiggletools_b200._lib import CTrack, CSegments
     use, n = st["use"], wl["N"]
     nsh = len(use)
     arr = (CTrack * max(1, nsh * n))()
     host = []
-    h2d = 0
     for c, sh in enumerate(use):
         off = st["offs"][c]
         m = int(off[n])
         vals = sh["v32"] if wl["f32"] else sh["v"]
-        hs = sh["s"][:m].cpu().pin_memory(); he = sh["e"][:m].cpu().pin_memory(); hv = vals[:m].cpu().pin_memory()
+        hs = sh["s"][:m].cpu().pin_memory(); he = sh["e"][:m].cpu().pin_memory()
+        if narrow:
+            v32 = vals[:m].to(torch.float32)
+            assert bool((v32.to(torch.float64) == vals[:m]).all()), "values are not float32-representable"
+            hv = v32.cpu().pin_memory()
+        else:
+            hv = vals[:m].cpu().pin_memory()
         for i in range(n):
             a, b = int(off[i]), int(off[i + 1])
-            arr[c * n + i] = CTrack(hs.data_ptr() + 4 * a, he.data_ptr() + 4 * a, hv.data_ptr() + 8 * a, b - a, 0.0)
+            if narrow:
+                arr[c * n + i] = CTrack(hs.data_ptr() + 4 * a, he.data_ptr() + 4 * a, None, b - a, 0.0, hv.data_ptr() + 4 * a)
+            else:
+                arr[c * n + i] = CTrack(hs.data_ptr() + 4 * a, he.data_ptr() + 4 * a, hv.data_ptr() + 8 * a, b - a, 0.0)
         host.append((hs, he, hv))
-        h2d += 16 * m
     out = (CSegments * max(1, nsh))()
-    d2h = 0
+    lib.wb200_set_breakpoint_output(ctx, 1 if narrow else 0)
 
     def one():
-        nonlocal d2h
         if not nsh:
             return
         rc = lib.wb200_reduce_host_batch(ctx, OP_CODE[wl["op"]], nsh, n, n, 0, C.addressof(arr), C.addressof(out))
         if rc != 0:
             raise SystemExit("wb200_reduce_host_batch: %s" % lib.wb200_last_error(ctx).decode())
-        d2h = sum(16 * out[c].n for c in range(nsh))
 
     one()   # first call sizes the pinned result arena
     one()
-    # the segments that came back over PCIe are the ones the resident run left in HBM
+    # what came back over PCIe is what the resident run left in HBM: counts for every shard, and all three
+    # arrays (end rebuilt from the breakpoint form) bit for bit on this rank's smallest shard
     same = all(int(out[c].n) == int(st["arr"][c].n_out) for c in range(nsh))
+    if nsh:
+        c = min(range(nsh), key=lambda j: int(out[j].n))
+        S = int(out[c].n)
+        hs_ = np.ctypeslib.as_array(C.cast(out[c].start, C.POINTER(C.c_int32)), (S,))
+        hv_ = np.ctypeslib.as_array(C.cast(out[c].value, C.POINTER(C.c_double)), (S,))
+        if out[c].end:
+            he_ = np.ctypeslib.as_array(C.cast(out[c].end, C.POINTER(C.c_int32)), (S,))
+        else:
+            k = int(out[c].n_ends)
+            he_ = np.empty(S, np.int32)
+            he_[:-1] = hs_[1:]
+            idx = np.ctypeslib.as_array(C.cast(out[c].end_index, C.POINTER(C.c_int32)), (k,))
+            he_[idx] = np.ctypeslib.as_array(C.cast(out[c].end_value, C.POINTER(C.c_int32)), (k,))
+        os_, oe_, ov_ = (t[:S].cpu().numpy() for t in st["outs"][c])
+        same = same and np.array_equal(hs_, os_) and np.array_equal(he_, oe_) and np.array_equal(hv_, ov_, equal_nan=True)
+    stats = lib.wb200_last_stats(ctx).contents
+    h2d, d2h = int(stats.h2d_bytes), int(stats.d2h_bytes)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -722,6 +755,7 @@ def run_e2e(torch, dist, lib, ctx, wl, st, dev, world, steps):
         one()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    lib.wb200_set_breakpoint_output(ctx, 0)
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
     tb = torch.tensor([h2d, d2h], dtype=torch.float64, device=dev)
     if world > 1:
@@ -732,6 +766,8 @@ def run_e2e(torch, dist, lib, ctx, wl, st, dev, world, steps):
            "d2h_bytes_per_step": int(tb[1].item()), "steps": steps, "ms_per_step": 1e3 * dtm / steps,
            "segments_match_resident_run": bool(same),
            "this_rank_copy_GBps": (h2d + d2h) / (dt / steps) / 1e9 if dt > 0 else 0.0,
+           "transport": ("narrow: int32 start/end + float32 value in (widened on the device), start + value + explicit ends only where a gap follows out"
+                         if narrow else "wide: int32 start/end + fp64 value in, int32 start/end + fp64 value out"),
            "api": "wb200_reduce_host_batch (pinned host SoA in, pinned host segments out; staging, kernels and read-back pipelined per chromosome)"}
     del host
     return res

@@ -73,20 +73,28 @@ typedef struct wb200_ctx wb200_ctx;
 typedef struct wb200_track {
 	const int32_t *start;
 	const int32_t *end;
-	const double *value;
+	const double *value;       /* fp64 values, or NULL when value32 is given */
 	int64_t n;
 	double default_value;
+	const float *value32;      /* optional narrow transport: float32 values (what BigWig files hold), widened to fp64
+	                            * on the device -- 12 instead of 16 bytes per interval over PCIe; used when value is NULL
+	                            * (host entry points only) */
 } wb200_track;
 
 /* Segments of one chromosome.  For *_host calls the arrays are owned by the
  * context (pinned host memory) and stay valid until the next call on it. */
 typedef struct wb200_segments {
 	int32_t *start;
-	int32_t *end;
+	int32_t *end;          /* NULL in breakpoint form (see wb200_set_breakpoint_output) */
 	double *value;
 	int64_t n;
 	double default_value;  /* the reducer's derived default (constructor semantics) */
 	double auc;            /* sum over segments of (end-start)*value, NaN skipped (AUCPop, src/statistics.c:103-120) */
+	/* breakpoint form: end[k] = start[k+1] for every segment except the n_ends listed ones (those followed by a gap,
+	 * and the last), whose ends are end_value[r] at segment index end_index[r] (ascending) */
+	int64_t n_ends;
+	const int32_t *end_index;
+	const int32_t *end_value;
 } wb200_segments;
 
 /* Timing / accounting of the last call (for bench.py). */
@@ -116,6 +124,13 @@ const wb200_stats *wb200_last_stats(const wb200_ctx *ctx);
 int wb200_set_stream(wb200_ctx *ctx, void *cuda_stream);
 /* Tuning knobs: window size in bp (power of two, 0 = automatic). */
 int wb200_set_window(wb200_ctx *ctx, int window_bp);
+/* Narrow read-back for wb200_reduce_host_batch: segments come back in BREAKPOINT FORM -- start[] and value[] in full,
+ * end[] only where it is not the next segment's start (a gap follows, or the segment is the last): 12 instead of 16
+ * bytes per segment over PCIe on gap-free data, the layout of a bedGraph-style step function.  The reference's
+ * consumers read one record at a time (pop), so a binding derives `finish` from the next start as it goes; no host
+ * pass over the arrays is needed.  A shard with explicit ends on more than a quarter of its segments is sent in
+ * the full form (end != NULL).  0 (default): always the full form. */
+int wb200_set_breakpoint_output(wb200_ctx *ctx, int on);
 
 /* Pin the calling host thread to the CPUs local to the context's GPU (its PCIe root's NUMA
  * node), so that staging buffers allocated afterwards live in that node's memory: matters

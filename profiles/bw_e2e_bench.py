@@ -32,7 +32,8 @@ with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") els
     for t in range(n_tracks):
         rng = np.random.default_rng([7, t])
         s, e, v = make_chrom_track(rng, length)                       # same generator as bench.py (1-based half-open)
-        items = list(zip((s - 1).tolist(), (e - 1).tolist(), v.astype(np.float32).tolist()))
+        items = np.empty(len(s), dtype=[("s", "<u4"), ("e", "<u4"), ("v", "<f4")])
+        items["s"], items["e"], items["v"] = s - 1, e - 1, v
         sections = [(0, 1, items[k:k + 512], 0, 0) for k in range(0, len(items), 512)]
         path = os.path.join(d, "t%d.bw" % t)
         write_bigwig(path, [("chr1", length + 1)], sections, compress=True, rtree_block=256)

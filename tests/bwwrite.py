@@ -9,7 +9,10 @@ import zlib
 
 def _section(chrom_id, kind, items, span=1, step=1):
     """kind 1: (start,end,value) bedGraph; 2: (start,value) variableStep; 3: fixedStep values from items[0][0]."""
-    if kind == 1:
+    if kind == 1 and hasattr(items, "dtype"):        # numpy structured array (start u4, end u4, value f4): large files
+        cs, ce = int(items["s"][0]), int(items["e"][-1])
+        body = items.tobytes()
+    elif kind == 1:
         cs, ce = items[0][0], items[-1][1]
         body = b"".join(struct.pack("<IIf", s, e, v) for s, e, v in items)
     elif kind == 2:

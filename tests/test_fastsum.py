@@ -159,3 +159,59 @@ def test_unaligned_device_arrays_fall_back(engine):
     a, b = results
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
     assert np.isclose(a[3], b[3], rtol=1e-12)
+
+
+def test_narrow_transport_is_lossless(engine, port):
+    """float32 value inputs (widened on the device) and breakpoint-form read-back (end[] only where it is
+    not the next start) through wb200_reduce_host_batch: the rebuilt arrays equal the wide transport's, for
+    gap-free data (few explicit ends), data with gaps (some) and very sparse data (falls back to the full form)."""
+    import ctypes as C
+    from wiggletools_b200 import _lib
+    from wiggletools_b200.synth import make_tracks
+    lib = engine.lib
+    for seed, kw in ((1, dict(max_len=400, max_gap=200)), (2, dict(max_len=30, max_gap=4000, gap_prob=0.9)), (3, dict(max_len=200, max_gap=1, gap_prob=0.0))):
+        n = 6
+        tr = make_tracks(n, [60_000, 20_000], seed=900 + seed, **kw)
+        shards = []
+        for c in range(2):
+            per = []
+            for t in tr:
+                sel = t["chrom"] == c
+                per.append((np.ascontiguousarray(t["start"][sel]), np.ascontiguousarray(t["end"][sel]), np.ascontiguousarray(t["value"][sel])))
+            shards.append(per)
+        want = engine.reduce_shards("mean", [[(s, e, v, 0.0) for s, e, v in per] for per in shards])
+        keep = []
+        arr = (_lib.CTrack * (2 * n))()
+        for c, per in enumerate(shards):
+            for i, (s, e, v) in enumerate(per):
+                v32 = np.ascontiguousarray(v, np.float32)
+                assert np.array_equal(v32.astype(np.float64), v)
+                keep.append(v32)
+                arr[c * n + i] = _lib.CTrack(s.ctypes.data, e.ctypes.data, None, len(s), 0.0, v32.ctypes.data)
+        out = (_lib.CSegments * 2)()
+        lib.wb200_set_breakpoint_output(engine.ctx, 1)
+        try:
+            engine._check(lib.wb200_reduce_host_batch(engine.ctx, 2, 2, n, n, 0, C.addressof(arr), C.addressof(out)))
+        finally:
+            lib.wb200_set_breakpoint_output(engine.ctx, 0)
+        forms = []
+        for c in range(2):
+            S = int(out[c].n)
+            assert S == len(want[c][0])
+            gs = np.ctypeslib.as_array(C.cast(out[c].start, C.POINTER(C.c_int32)), (S,))
+            gv = np.ctypeslib.as_array(C.cast(out[c].value, C.POINTER(C.c_double)), (S,))
+            if out[c].end:
+                ge = np.ctypeslib.as_array(C.cast(out[c].end, C.POINTER(C.c_int32)), (S,)).copy()
+                forms.append("full")
+            else:
+                k = int(out[c].n_ends)
+                idx = np.ctypeslib.as_array(C.cast(out[c].end_index, C.POINTER(C.c_int32)), (k,))
+                assert np.all(np.diff(idx) > 0) and idx[-1] == S - 1
+                ge = np.empty(S, np.int32); ge[:-1] = gs[1:]
+                ge[idx] = np.ctypeslib.as_array(C.cast(out[c].end_value, C.POINTER(C.c_int32)), (k,))
+                forms.append("breakpoint")
+            assert np.array_equal(gs, want[c][0]) and np.array_equal(ge, want[c][1]) and np.array_equal(gv, want[c][2])
+        if seed == 2:
+            assert "full" in forms          # explicit ends on more than a quarter of the segments: sent in the full form
+        if seed == 3:
+            assert forms == ["breakpoint", "breakpoint"]

@@ -14,12 +14,13 @@ LIB_PATH = os.environ.get("WB200_LIB") or os.path.join(HERE, "libwiggletools_b20
 
 class CTrack(C.Structure):
     _fields_ = [("start", C.c_void_p), ("end", C.c_void_p), ("value", C.c_void_p),
-                ("n", C.c_int64), ("default_value", C.c_double)]
+                ("n", C.c_int64), ("default_value", C.c_double), ("value32", C.c_void_p)]
 
 
 class CSegments(C.Structure):
     _fields_ = [("start", C.c_void_p), ("end", C.c_void_p), ("value", C.c_void_p),
-                ("n", C.c_int64), ("default_value", C.c_double), ("auc", C.c_double)]
+                ("n", C.c_int64), ("default_value", C.c_double), ("auc", C.c_double),
+                ("n_ends", C.c_int64), ("end_index", C.c_void_p), ("end_value", C.c_void_p)]
 
 
 class CStats(C.Structure):
@@ -69,6 +70,7 @@ def load():
     lib.wb200_last_stats.argtypes = [C.c_void_p]
     lib.wb200_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.wb200_set_window.argtypes = [C.c_void_p, C.c_int]
+    lib.wb200_set_breakpoint_output.argtypes = [C.c_void_p, C.c_int]
     lib.wb200_bind_host_thread.argtypes = [C.c_void_p]
     lib.wb200_host_alloc.restype = C.c_void_p
     lib.wb200_host_alloc.argtypes = [C.c_int64]
@@ -131,7 +133,7 @@ def load():
 # every symbol include/wiggletools_b200.h declares
 EXPORTS = [
     "wb200_create", "wb200_destroy", "wb200_last_error", "wb200_last_stats", "wb200_set_stream",
-    "wb200_set_window", "wb200_bind_host_thread", "wb200_host_alloc", "wb200_host_free", "wb200_reduce_host", "wb200_rows_host", "wb200_reduce_host_batch",
+    "wb200_set_window", "wb200_set_breakpoint_output", "wb200_bind_host_thread", "wb200_host_alloc", "wb200_host_free", "wb200_reduce_host", "wb200_rows_host", "wb200_reduce_host_batch",
     "wb200_reduce_device", "wb200_reduce_device_batch", "wb200_pearson_host", "wb200_pearson_pair_host", "wb200_pearson_merge", "wb200_pearson_result",
     "wb200_tdist_Q", "wb200_bw_open", "wb200_bw_close", "wb200_bw_last_error", "wb200_bw_nchrom", "wb200_bw_chrom_name",
     "wb200_bw_chrom_length", "wb200_bw_set_stretch", "wb200_bw_decode_chrom", "wb200_debug_phases", "wb200_debug_format_value",

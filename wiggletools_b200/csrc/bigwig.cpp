@@ -297,7 +297,7 @@ int wb200_bw_decode_chrom(wb200_bigwig *bw, int chrom_index, wb200_track *out) {
 			}
 		});
 	});
-	out->start = S; out->end = E; out->value = V; out->n = total; out->default_value = 0;
+	out->start = S; out->end = E; out->value = V; out->n = total; out->default_value = 0; out->value32 = nullptr;
 	return WB200_OK;
 }
 

@@ -75,6 +75,9 @@ struct wb200_ctx {
 	HostBuf h_arena;
 	std::vector<cudaEvent_t> pipe_events;
 	unsigned long long diag[16] = {0};      // diagnostic builds: accumulated phase counters
+	// narrow transport: float32 value staging and breakpoint-form read-back (wb200_reduce_host_batch)
+	bool breakpoint_out = false;
+	DevBuf bin_value32[2], ends_val[2], ends_idx[2];
 	// raw multiplexer rows of the last single-shard reduction (wb200_rows_host)
 	Job last_job{};
 	int64_t last_S = -1;
@@ -515,6 +518,7 @@ void wb200_destroy(wb200_ctx *ctx) {
 	for (auto ev : ctx->batch_events) cudaEventDestroy(ev);
 	ctx->b_tables.release(); ctx->b_small.release(); ctx->hb_tables.release(); ctx->hb_small.release();
 	ctx->rows_v.release(); ctx->rows_p.release();
+	for (int k = 0; k < 2; k++) { ctx->bin_value32[k].release(); ctx->ends_val[k].release(); ctx->ends_idx[k].release(); }
 	ctx->ap_rs.release(); ctx->ap_re.release(); ctx->ap_codes.release(); ctx->ap_out.release(); ctx->hap_out.release();
 	if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
 	if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
@@ -739,6 +743,12 @@ int wb200_bind_host_thread(wb200_ctx *ctx) {
 	if (count == 0) return 0;
 	if (sched_setaffinity(0, sizeof(set), &set) != 0) return fail(ctx, WB200_EINVAL, "sched_setaffinity failed");
 	return count;
+}
+
+int wb200_set_breakpoint_output(wb200_ctx *ctx, int on) {
+	if (!ctx) return WB200_EINVAL;
+	ctx->breakpoint_out = on != 0;
+	return WB200_OK;
 }
 
 int wb200_set_window(wb200_ctx *ctx, int window_bp) {
@@ -998,7 +1008,15 @@ int reduce_host_to_device(wb200_ctx *ctx, int op, int ntracks, int nset1, int st
 		if (!tracks[i].n) continue;
 		CK(cudaMemcpyAsync(ctx->in_start.as<int32_t>() + off[i], tracks[i].start, tracks[i].n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
 		CK(cudaMemcpyAsync(ctx->in_end.as<int32_t>() + off[i], tracks[i].end, tracks[i].n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-		CK(cudaMemcpyAsync(ctx->in_value.as<double>() + off[i], tracks[i].value, tracks[i].n * sizeof(double), cudaMemcpyHostToDevice, s));
+		if (tracks[i].value)
+			CK(cudaMemcpyAsync(ctx->in_value.as<double>() + off[i], tracks[i].value, tracks[i].n * sizeof(double), cudaMemcpyHostToDevice, s));
+		else if (tracks[i].value32) {
+			// float32 values travel as they are (4 bytes each) into a scratch array and are widened on the device
+			CK(ctx->bin_value32[0].ensure(std::max<int64_t>(1, I) * sizeof(float)));
+			CK(cudaMemcpyAsync(ctx->bin_value32[0].as<float>() + off[i], tracks[i].value32, tracks[i].n * sizeof(float), cudaMemcpyHostToDevice, s));
+			CK(launch_widen(ctx->bin_value32[0].as<float>() + off[i], ctx->in_value.as<double>() + off[i], tracks[i].n, s));
+		} else
+			return fail(ctx, WB200_EINVAL, "a track has neither value nor value32");
 	}
 	const int64_t cap = std::max<int64_t>(1, std::min<int64_t>(2 * I + 1, hi - lo + 1));
 	CK(ctx->out_start.ensure(cap * sizeof(int32_t)));
@@ -1129,6 +1147,7 @@ int wb200_reduce_host(wb200_ctx *ctx, int op, int ntracks, int nset1, int strict
 	out->n = S;
 	out->default_value = dv;
 	out->auc = auc;
+	out->n_ends = 0; out->end_index = nullptr; out->end_value = nullptr;
 	return WB200_OK;
 }
 
@@ -1154,7 +1173,7 @@ int wb200_reduce_host_batch(wb200_ctx *ctx, int op, int nshards, int ntracks, in
 	cudaEvent_t *ev_h2d = ctx->pipe_events.data(), *ev_comp = ev_h2d + nshards, *ev_d2h = ev_comp + nshards;
 	cudaStream_t s = ctx->stream;
 
-	struct Shard { std::vector<int64_t> off; std::vector<double> dflt; int64_t I, lo, hi, cap, S, arena_off; double dv, auc; };
+	struct Shard { std::vector<int64_t> off; std::vector<double> dflt; int64_t I, lo, hi, cap, S, arena_off, h2d = 0, n_ends = -1; double dv, auc; };
 	std::vector<Shard> sh(nshards);
 	int64_t est = 0;
 	for (int c = 0; c < nshards; c++) {
@@ -1170,9 +1189,12 @@ int wb200_reduce_host_batch(wb200_ctx *ctx, int op, int nshards, int ntracks, in
 		h.I = h.off[N];
 		if (h.lo > h.hi) h.lo = h.hi;
 		h.cap = std::max<int64_t>(1, std::min<int64_t>(2 * h.I + 1, h.hi - h.lo + 1));
+		h.h2d = h.I * 16;
 		est += h.I + h.I / 2 + 1024;
 	}
 	CK(ctx->h_arena.ensure((size_t) est * 16));     // first guess S ~ 1.5 I; grown below if needed
+	bool any32 = false;
+	for (int k = 0; k < nshards * N && !any32; k++) any32 = tracks[k].n > 0 && !tracks[k].value && tracks[k].value32;
 
 	// Pipeline order: the first H2D and the last D2H are the only transfers nothing overlaps, so
 	// the small shards go to the two ends and the large ones to the middle.  Results are
@@ -1205,12 +1227,21 @@ int wb200_reduce_host_batch(wb200_ctx *ctx, int op, int nshards, int ntracks, in
 			for (; j < N; j++) {
 				const wb200_track &u = tracks[(size_t) c * N + j];
 				if (!u.n) continue;
-				if (u.start != t.start + n || u.end != t.end + n || u.value != t.value + n) break;
+				if (u.start != t.start + n || u.end != t.end + n) break;
+				if (t.value ? u.value != t.value + n : (u.value != nullptr || u.value32 != t.value32 + n)) break;
 				n += u.n;
 			}
 			CK(cudaMemcpyAsync(ctx->bin_start[b].as<int32_t>() + h.off[i], t.start, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_h2d));
 			CK(cudaMemcpyAsync(ctx->bin_end[b].as<int32_t>() + h.off[i], t.end, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_h2d));
-			CK(cudaMemcpyAsync(ctx->bin_value[b].as<double>() + h.off[i], t.value, n * sizeof(double), cudaMemcpyHostToDevice, ctx->s_h2d));
+			if (t.value)
+				CK(cudaMemcpyAsync(ctx->bin_value[b].as<double>() + h.off[i], t.value, n * sizeof(double), cudaMemcpyHostToDevice, ctx->s_h2d));
+			else if (t.value32) {
+				// narrow transport: 4 bytes per value over PCIe, widened to fp64 on the device (on the copy stream)
+				CK(cudaMemcpyAsync(ctx->bin_value32[b].as<float>() + h.off[i], t.value32, n * sizeof(float), cudaMemcpyHostToDevice, ctx->s_h2d));
+				CK(launch_widen(ctx->bin_value32[b].as<float>() + h.off[i], ctx->bin_value[b].as<double>() + h.off[i], n, ctx->s_h2d));
+				h.h2d -= n * 4;
+			} else
+				return fail(ctx, WB200_EINVAL, "a track has neither value nor value32");
 			i = j;
 		}
 		CK(cudaEventRecord(ev_h2d[k], ctx->s_h2d));
@@ -1225,6 +1256,18 @@ int wb200_reduce_host_batch(wb200_ctx *ctx, int op, int nshards, int ntracks, in
 		CK(ctx->bin_value[b].ensure(maxI * sizeof(double)));
 		CK(ctx->bout_start[b].ensure(maxcap * sizeof(int32_t))); CK(ctx->bout_end[b].ensure(maxcap * sizeof(int32_t)));
 		CK(ctx->bout_value[b].ensure(maxcap * sizeof(double)));
+		if (any32) CK(ctx->bin_value32[b].ensure(maxI * sizeof(float)));
+		if (ctx->breakpoint_out) {
+			CK(ctx->ends_val[b].ensure((size_t) (maxcap / 4 + 1024) * sizeof(int32_t)));
+			CK(ctx->ends_idx[b].ensure((size_t) (maxcap / 4 + 1024) * sizeof(int32_t)));
+		}
+	}
+	if (ctx->breakpoint_out) {
+		// scratch of the explicit-end compaction (the text sink's count / scan / scatter buffers)
+		const int ntiles = sink_tiles(maxcap);
+		CK(ctx->w_heads.ensure((size_t) maxcap)); CK(ctx->w_hp.ensure((size_t) (maxcap + 1) * sizeof(int32_t)));
+		CK(ctx->w_tile_count.ensure((size_t) ntiles * sizeof(int))); CK(ctx->w_tile_base.ensure((size_t) ntiles * sizeof(long long)));
+		CK(ctx->w_small.ensure(64)); CK(ctx->hw_small.ensure(64));
 	}
 
 	int64_t arena_used = 0, h2d = 0, d2h = 0;
@@ -1248,8 +1291,27 @@ int wb200_reduce_host_batch(wb200_ctx *ctx, int op, int nshards, int ntracks, in
 		total.slow_segments += ctx->stats.slow_segments; total.kernels += ctx->stats.kernels; total.fast_path = ctx->stats.fast_path;
 		total.limbs = std::max(total.limbs, ctx->stats.limbs); total.sweep_kernel = ctx->stats.sweep_kernel;
 		total.ms_count += ctx->stats.ms_count; total.ms_emit += ctx->stats.ms_emit; total.ms_total += ctx->stats.ms_total;
+		// breakpoint form: which segments need their end sent (the last one, and those followed by a gap)
+		bool narrow = false;
+		if (ctx->breakpoint_out && h.S > 0) {
+			long long *d_R = (long long *) (ctx->w_small.as<char>() + 16);
+			CK(launch_explicit_ends(ctx->bout_start[b].as<int32_t>(), ctx->bout_end[b].as<int32_t>(), h.S, ctx->w_heads.as<unsigned char>(), s));
+			CK(sink_compact(ctx->w_heads.as<unsigned char>(), h.S, ctx->w_tile_count.as<int>(), ctx->w_tile_base.as<long long>(), d_R,
+			                ctx->w_hp.as<int32_t>(), s));
+			CK(cudaMemcpyAsync(ctx->hw_small.p, d_R, 8, cudaMemcpyDeviceToHost, s));
+			CK(cudaStreamSynchronize(s));
+			h.n_ends = ctx->hw_small.as<long long>()[0];
+			narrow = h.n_ends <= h.S / 4 + 1;
+			if (narrow) {
+				CK(launch_gather_ends(ctx->w_hp.as<int32_t>(), h.n_ends, ctx->bout_end[b].as<int32_t>(), ctx->ends_val[b].as<int32_t>(), s));
+				// the positions leave the shared compaction scratch for this buffer set's own list
+				CK(cudaMemcpyAsync(ctx->ends_idx[b].p, ctx->w_hp.p, (size_t) h.n_ends * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+			} else h.n_ends = -1;
+			CK(cudaEventRecord(ev_comp[k], s));
+			total.kernels += narrow ? 5 : 4;
+		}
 		// host space for this shard's segments
-		const int64_t need = (h.S + 2) * 16;
+		const int64_t need = (h.S + 2) * 16 + (narrow ? (h.n_ends + 2) * 8 : 0);
 		if ((size_t) (arena_used + need) > ctx->h_arena.cap) {
 			CK(cudaStreamSynchronize(ctx->s_d2h));
 			HostBuf bigger;
@@ -1265,10 +1327,15 @@ int wb200_reduce_host_batch(wb200_ctx *ctx, int op, int nshards, int ntracks, in
 		if (h.S > 0) {
 			CK(cudaMemcpyAsync(base, ctx->bout_value[b].p, h.S * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_d2h));
 			CK(cudaMemcpyAsync(base + (h.S + 1) * 8, ctx->bout_start[b].p, h.S * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_d2h));
-			CK(cudaMemcpyAsync(base + (h.S + 1) * 12, ctx->bout_end[b].p, h.S * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_d2h));
+			if (!narrow)
+				CK(cudaMemcpyAsync(base + (h.S + 1) * 12, ctx->bout_end[b].p, h.S * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_d2h));
+			else {
+				CK(cudaMemcpyAsync(base + (h.S + 2) * 16, ctx->ends_idx[b].p, h.n_ends * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_d2h));
+				CK(cudaMemcpyAsync(base + (h.S + 2) * 16 + (h.n_ends + 1) * 4, ctx->ends_val[b].p, h.n_ends * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_d2h));
+			}
 		}
 		CK(cudaEventRecord(ev_d2h[k], ctx->s_d2h));
-		h2d += h.I * 16; d2h += h.S * 16;
+		h2d += h.h2d; d2h += narrow ? h.S * 12 + h.n_ends * 8 : h.S * 16;
 	}
 	CK(cudaStreamSynchronize(ctx->s_d2h));
 	CK(cudaStreamSynchronize(ctx->s_h2d));
@@ -1277,7 +1344,11 @@ int wb200_reduce_host_batch(wb200_ctx *ctx, int op, int nshards, int ntracks, in
 		char *base = (char *) ctx->h_arena.p + h.arena_off;
 		out[c].value = (double *) base;
 		out[c].start = (int32_t *) (base + (h.S + 1) * 8);
-		out[c].end = (int32_t *) (base + (h.S + 1) * 12);
+		const bool narrow = h.n_ends >= 0;
+		out[c].end = narrow ? nullptr : (int32_t *) (base + (h.S + 1) * 12);
+		out[c].n_ends = narrow ? h.n_ends : 0;
+		out[c].end_index = narrow ? (const int32_t *) (base + (h.S + 2) * 16) : nullptr;
+		out[c].end_value = narrow ? (const int32_t *) (base + (h.S + 2) * 16 + (h.n_ends + 1) * 4) : nullptr;
 		out[c].n = h.S;
 		out[c].default_value = h.dv;
 		out[c].auc = h.auc;
@@ -1316,7 +1387,14 @@ static int pearson_shard(wb200_ctx *ctx, int ntracks, const wb200_track *tracks,
 		if (!tracks[i].n) continue;
 		CK(cudaMemcpyAsync(ctx->in_start.as<int32_t>() + off[i], tracks[i].start, tracks[i].n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
 		CK(cudaMemcpyAsync(ctx->in_end.as<int32_t>() + off[i], tracks[i].end, tracks[i].n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-		CK(cudaMemcpyAsync(ctx->in_value.as<double>() + off[i], tracks[i].value, tracks[i].n * sizeof(double), cudaMemcpyHostToDevice, s));
+		if (tracks[i].value)
+			CK(cudaMemcpyAsync(ctx->in_value.as<double>() + off[i], tracks[i].value, tracks[i].n * sizeof(double), cudaMemcpyHostToDevice, s));
+		else if (tracks[i].value32) {
+			CK(ctx->bin_value32[0].ensure(std::max<int64_t>(1, I) * sizeof(float)));
+			CK(cudaMemcpyAsync(ctx->bin_value32[0].as<float>() + off[i], tracks[i].value32, tracks[i].n * sizeof(float), cudaMemcpyHostToDevice, s));
+			CK(launch_widen(ctx->bin_value32[0].as<float>() + off[i], ctx->in_value.as<double>() + off[i], tracks[i].n, s));
+		} else
+			return fail(ctx, WB200_EINVAL, "a track has neither value nor value32");
 	}
 	int rc = run_device(ctx, OP_PEARSON, N, N, 0, ctx->in_start.as<int32_t>(), ctx->in_end.as<int32_t>(),
 	                    ctx->in_value.as<double>(), off.data(), dflt.data(), (int32_t) lo, (int32_t) hi,

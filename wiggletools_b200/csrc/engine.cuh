@@ -135,6 +135,10 @@ cudaError_t launch_map(double *value, const int64_t *d_off, const MapOp *d_chain
 cudaError_t launch_map_gather(const int32_t *hp, const long long *d_R, long long R, const int32_t *s_in, const int32_t *e_in,
                               const double *v_in, int32_t *s_out, int32_t *e_out, double *v_out,
                               const int64_t *d_off, int N, int64_t *d_new_off, cudaStream_t s);
+// narrow transport (maps.cu): float32 -> fp64 widening of staged values; segments whose end is not the next start
+cudaError_t launch_widen(const float *in, double *out, long long n, cudaStream_t s);
+cudaError_t launch_explicit_ends(const int32_t *start, const int32_t *end, long long S, unsigned char *H, cudaStream_t s);
+cudaError_t launch_gather_ends(const int32_t *hp, long long R, const int32_t *end, int32_t *out, cudaStream_t s);
 // positions of the set bytes of H[0..n): hp[0..R), hp[R] = n (count / scan / scatter of writer.cu)
 cudaError_t sink_compact(const unsigned char *H, int64_t n, int *tile_count, long long *tile_base, long long *R, int32_t *hp, cudaStream_t s);
 // text sink (writer.cu): record heads of the compress rule, then the two formatting passes

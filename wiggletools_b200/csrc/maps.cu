@@ -71,7 +71,38 @@ __global__ void bounds_kernel(const int32_t *hp, long long R, const int64_t *off
 	new_off[i] = lo;
 }
 
+// -- narrow transport over PCIe ---------------------------------------------------------------
+// float32 values staged from the host (BigWig payloads are float32) widened to the fp64 the kernels read
+__global__ void widen_kernel(const float *in, double *out, long long n) {
+	for (long long j = blockIdx.x * (long long) blockDim.x + threadIdx.x; j < n; j += (long long) gridDim.x * blockDim.x) out[j] = (double) in[j];
+}
+// H[k] = 1 where segment k's end must be sent explicitly: the last segment, and every segment that is
+// followed by a gap (end[k] != start[k+1]); everywhere else end[k] is start[k+1]
+__global__ void explicit_end_kernel(const int32_t *start, const int32_t *end, long long S, unsigned char *H) {
+	for (long long k = blockIdx.x * (long long) blockDim.x + threadIdx.x; k < S; k += (long long) gridDim.x * blockDim.x)
+		H[k] = (k + 1 == S || end[k] != start[k + 1]) ? 1 : 0;
+}
+__global__ void gather_end_kernel(const int32_t *hp, long long R, const int32_t *end, int32_t *out) {
+	for (long long r = blockIdx.x * (long long) blockDim.x + threadIdx.x; r < R; r += (long long) gridDim.x * blockDim.x) out[r] = end[hp[r]];
+}
+
 } // namespace maps
+
+cudaError_t launch_widen(const float *in, double *out, long long n, cudaStream_t s) {
+	if (n <= 0) return cudaSuccess;
+	maps::widen_kernel<<<(int) std::min<long long>((n + 255) / 256, 148 * 16), 256, 0, s>>>(in, out, n);
+	return cudaGetLastError();
+}
+cudaError_t launch_explicit_ends(const int32_t *start, const int32_t *end, long long S, unsigned char *H, cudaStream_t s) {
+	if (S <= 0) return cudaSuccess;
+	maps::explicit_end_kernel<<<(int) std::min<long long>((S + 255) / 256, 148 * 16), 256, 0, s>>>(start, end, S, H);
+	return cudaGetLastError();
+}
+cudaError_t launch_gather_ends(const int32_t *hp, long long R, const int32_t *end, int32_t *out, cudaStream_t s) {
+	if (R <= 0) return cudaSuccess;
+	maps::gather_end_kernel<<<(int) std::min<long long>((R + 255) / 256, 148 * 16), 256, 0, s>>>(hp, R, end, out);
+	return cudaGetLastError();
+}
 
 cudaError_t launch_map(double *value, const int64_t *d_off, const MapOp *d_chains, const int *d_nchain, int N, int64_t max_len,
                        unsigned char *keep, int *any_dropped, cudaStream_t s) {
