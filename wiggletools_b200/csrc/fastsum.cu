@@ -64,6 +64,9 @@ constexpr int TH = 128, NWARP = TH / 32;
 #ifndef WB_FS_COV16
 #define WB_FS_COV16 1                 // 16-bit cover fields (6 B/position) when N <= 255
 #endif
+#ifndef WB_FS_TICKET_AT_END
+#define WB_FS_TICKET_AT_END 0         // 1: draw the next window after the emit phase instead of at its start (experiment)
+#endif
 #ifndef WB_FS_EMIT2
 #define WB_FS_EMIT2 1                 // emit: two groups of 32 dense entries per warp and step
 #endif
@@ -612,6 +615,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	// The look-back of window w waits for every window below w, so the less time passes between
 	// drawing a window and starting it, the less the windows in flight run out of order: the next
 	// window is drawn now, and its cursor row lands while this window is emitted.
+#if WB_FS_TICKET_AT_END == 0
 	if (tid == 0) {
 		const int nw1 = (int) atomicAdd(job.ticket, 1u);
 		misc->ticket2 = nw1;
@@ -621,6 +625,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 			bulk_g2s(cur, job.cursor + (size_t) nw1 * job.cstride, bytes, &misc->bar_cur);
 		}
 	}
+#endif
 
 	// ---- 4. emit, one breakpoint per thread (coalesced stores) -------------------------------
 	const long long out_base = misc->out_base;
@@ -747,6 +752,20 @@ fastsum_kernel(const Job job, int lw, double inv_scale, double lim, double scale
 		}
 #ifdef WB_DIAG_PHASES
 		if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&job.diag[7], (unsigned long long) (t_ - diag_t0)); atomicAdd(&job.diag[8], 1ull); }
+#endif
+#if WB_FS_TICKET_AT_END
+		// experiment: the next window is drawn only when this one is completely done (its cursor rows then
+		// arrive while the window arrays are cleared)
+		if (threadIdx.x == 0) {
+			const int nw1 = (int) atomicAdd(job.ticket, 1u);
+			misc->ticket2 = nw1;
+			if (nw1 < job.nw) {
+				const uint32_t bytes = (uint32_t) job.cstride * 8;
+				mbar_expect_tx(&misc->bar_cur, bytes);
+				bulk_g2s(ca, job.cursor + (size_t) nw1 * job.cstride, bytes, &misc->bar_cur);
+			}
+		}
+		__syncthreads();
 #endif
 		w = misc->ticket2;
 	}
