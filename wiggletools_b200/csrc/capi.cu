@@ -318,8 +318,13 @@ void choose_format(Job &job, int op, int N, const double *h_dflt, double maxabs,
 		if (emax - q <= capm && 2 * capm <= 29 - l2n + 2 * lw) {
 			job.fast = 2;
 			job.fx_q = std::max(-1000, std::min(1000, q));
-			job.fx_mbits = capm;
+			// |m| < 2^mbits: two bits of headroom above the sampled range instead of the widest format the
+			// arithmetic allows -- the squares then usually fit two limbs instead of three (4 shared atomics
+			// per event instead of 6); a value beyond the range poisons its interval and is fixed up exactly
+			job.fx_mbits = std::max(4, std::min(capm, emax - q + 2));
 			job.fx_base = 0;
+			// every prefix of the plain sum then fits 31 bits: one limb (one shared atomic per event) for it
+			job.sum1 = job.fx_mbits + ceil_log2(N) <= 30 ? 1 : 0;
 		}
 	}
 }

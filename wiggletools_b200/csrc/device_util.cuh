@@ -40,4 +40,28 @@ __device__ __forceinline__ void add_limbs_fs(uint32_t *limb, int ph, long long d
 	atomicAdd(&limb[W + ph], (uint32_t) (d >> lw));
 }
 
+// var / stddev / CV of one segment from exact integer moments of the in-play
+// values: c tracks in play, Sx = sum m, Sxx = sum m^2 with value = m * 2^q.
+// Reference arithmetic being matched (src/reducers.c:428-479, :511-563, :672-725):
+//   mean = (sum over all N of float(x)) / N            -- absent tracks contribute 0 here
+//   var    = sum over in-play (mean - v)^2 / N
+//   stddev = sqrt(sum over all N (mean - x)^2 / N),  CV = stddev / mean
+// The sum of squared deviations is evaluated without cancellation:
+//   sum_C (mean - v)^2 = [ (c Sxx - Sx^2) 2^2q + (c mean - X)^2 ] / c ,  X = Sx 2^q
+// where c Sxx - Sx^2 >= 0 is exact in 128-bit integers.
+__device__ __forceinline__ double moments_stat(int op, int N, int c, long long Sx, long long Sxx, double scale) {
+	if (op == OP_VAR && N < 2) return NAN;
+	const double X = (double) Sx * scale;                  // exact: |Sx| < 2^53
+	const double mean = X / N;
+	if (op == OP_CV && mean == 0) return NAN;
+	const __int128 d1 = (__int128) c * (__int128) Sxx - (__int128) Sx * (__int128) Sx;
+	const double D1 = (double) d1 * scale * scale;
+	const double r = fma((double) c, mean, -X);
+	const double EC = (D1 + r * r) / c;
+	if (op == OP_VAR) return EC / N;
+	const double Eall = EC + (double) (N - c) * mean * mean;
+	const double sd = sqrt(Eall / N);
+	return op == OP_CV ? sd / mean : sd;
+}
+
 } // namespace wb

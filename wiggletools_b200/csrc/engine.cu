@@ -781,6 +781,14 @@ __device__ __forceinline__ void add_limbs(uint32_t *limb, int ph, long long d, i
 	}
 }
 
+// First accumulator (the plain sum) of a position: one 32-bit limb when the job says every prefix fits
+// 31 bits (moments path with a narrow value range: one shared atomic per event instead of LIMBS).
+template <int VLOG, int LIMBS>
+__device__ __forceinline__ void add_sum(const Job &job, uint32_t *limb, int ph, long long d, int lw) {
+	if (job.sum1) atomicAdd(&limb[ph], (uint32_t) d);
+	else add_limbs<VLOG, LIMBS>(limb, ph, d, lw);
+}
+
 // This thread's V positions of one accumulator -> running prefix in registers.
 template <int VLOG, int LIMBS>
 __device__ __forceinline__ long long load_prefix(const uint32_t *limb, int tid, int lw, long long *run) {
@@ -820,29 +828,6 @@ __device__ __forceinline__ long long load_prefix(const uint32_t *limb, int tid, 
 	return a;
 }
 
-// var / stddev / CV of one segment from exact integer moments of the in-play
-// values: c tracks in play, Sx = sum m, Sxx = sum m^2 with value = m * 2^q.
-// Reference arithmetic being matched (src/reducers.c:428-479, :511-563, :672-725):
-//   mean = (sum over all N of float(x)) / N            -- absent tracks contribute 0 here
-//   var    = sum over in-play (mean - v)^2 / N
-//   stddev = sqrt(sum over all N (mean - x)^2 / N),  CV = stddev / mean
-// The sum of squared deviations is evaluated without cancellation:
-//   sum_C (mean - v)^2 = [ (c Sxx - Sx^2) 2^2q + (c mean - X)^2 ] / c ,  X = Sx 2^q
-// where c Sxx - Sx^2 >= 0 is exact in 128-bit integers.
-__device__ __forceinline__ double moments_stat(int op, int N, int c, long long Sx, long long Sxx, double scale) {
-	if (op == OP_VAR && N < 2) return NAN;
-	const double X = (double) Sx * scale;                  // exact: |Sx| < 2^53
-	const double mean = X / N;
-	if (op == OP_CV && mean == 0) return NAN;
-	const __int128 d1 = (__int128) c * (__int128) Sxx - (__int128) Sx * (__int128) Sx;
-	const double D1 = (double) d1 * scale * scale;
-	const double r = fma((double) c, mean, -X);
-	const double EC = (D1 + r * r) / c;
-	if (op == OP_VAR) return EC / N;
-	const double Eall = EC + (double) (N - c) * mean * mean;
-	const double sd = sqrt(Eall / N);
-	return op == OP_CV ? sd / mean : sd;
-}
 
 enum { MODE_FAST = 1, MODE_ROW = 2, MODE_MOMENTS = 3, MODE_WALK = 4 };
 
@@ -941,7 +926,7 @@ __device__ __forceinline__ void events_vec(const Job &job, unsigned char *smem, 
 			atomicAdd(&cov[ph], cd);
 			ev[xs] = 1;
 			if (d != 0) {
-				add_limbs<VLOG, LIMBS>(limb, ph, d, lw);
+				add_sum<VLOG, LIMBS>(job, limb, ph, d, lw);
 				if (NACC == 2) add_limbs<VLOG, LIMBS>(limb + LIMBS * W, ph, d2, lw);
 			}
 		} else { in_cov += cd; in_val += d; in_val2 += d2; }              // began before the window
@@ -950,7 +935,7 @@ __device__ __forceinline__ void events_vec(const Job &job, unsigned char *smem, 
 			atomicAdd(&cov[ph], -cd);
 			ev[xe] = 1;
 			if (d != 0) {
-				add_limbs<VLOG, LIMBS>(limb, ph, -d, lw);
+				add_sum<VLOG, LIMBS>(job, limb, ph, -d, lw);
 				if (NACC == 2) add_limbs<VLOG, LIMBS>(limb + LIMBS * W, ph, -d2, lw);
 			}
 		} else my_next = min(my_next, e);
@@ -1119,7 +1104,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 						atomicAdd(&cov[ph], cd);
 						ev[x] = 1;
 						if (fast && d != 0) {
-							add_limbs<VLOG, LIMBS>(limb, ph, d, lw);
+							add_sum<VLOG, LIMBS>(job, limb, ph, d, lw);
 							if (NACC == 2) add_limbs<VLOG, LIMBS>(limb + LIMBS * W, ph, d2, lw);
 						}
 					} else { in_cov += cd; in_val += d; in_val2 += d2; }   // began before the window
@@ -1128,7 +1113,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 						atomicAdd(&cov[ph], -cd);
 						ev[x] = 1;
 						if (fast && d != 0) {
-							add_limbs<VLOG, LIMBS>(limb, ph, -d, lw);
+							add_sum<VLOG, LIMBS>(job, limb, ph, -d, lw);
 							if (NACC == 2) add_limbs<VLOG, LIMBS>(limb + LIMBS * W, ph, -d2, lw);
 						}
 					}
@@ -1192,7 +1177,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 #pragma unroll
 		for (int q = 0; q < V; q++) { c += cv[q]; c_run[q] = c; }
 		long long a = 0, b = 0;
-		if (fast) a = load_prefix<VLOG, LIMBS>(limb, tid, lw, a_run);
+		if (fast) a = job.sum1 ? load_prefix<VLOG, 1>(limb, tid, lw, a_run) : load_prefix<VLOG, LIMBS>(limb, tid, lw, a_run);
 		else {
 #pragma unroll
 			for (int q = 0; q < V; q++) a_run[q] = 0;

@@ -74,6 +74,7 @@ struct Job {
 	int fx_mbits;           // |m| < 2^fx_mbits
 	int fx_limbs;           // sum / mean: 32-bit limbs per position (1..3)
 	int64_t fx_base;        // sum of fixed-point defaults (all tracks absent)
+	int sum1;               // moments path: the plain sum lives in ONE 32-bit limb (N * 2^fx_mbits < 2^31)
 	unsigned long long *diag; // [16] diagnostic builds: per-phase cycle counters
 	int *flags;             // input validation (cursor kernel): bit 0 unsorted / overlapping / empty interval, bit 1 outside [p0, pos_hi]
 	int pos_hi;             // last position the windows cover

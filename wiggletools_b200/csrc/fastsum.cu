@@ -65,7 +65,7 @@ constexpr int TH = 128, NWARP = TH / 32;
 #define WB_FS_COV16 1                 // 16-bit cover fields (6 B/position) when N <= 255
 #endif
 #ifndef WB_FS_TICKET_AT_END
-#define WB_FS_TICKET_AT_END 0         // 1: draw the next window after the emit phase instead of at its start (experiment)
+#define WB_FS_TICKET_AT_END 1         // the next window is drawn when this one is completely done (0: when its emit phase starts)
 #endif
 #ifndef WB_FS_EMIT2
 #define WB_FS_EMIT2 1                 // emit: two groups of 32 dense entries per warp and step
@@ -87,12 +87,14 @@ struct Misc {
 	int base_pois;                   // of those, tracks whose value is not representable
 	int npois;                       // poison events inside the window
 	unsigned long long base_val;     // fixed-point sum carried into the window
+	unsigned long long base_val2;    // moments: fixed-point sum of squares carried into the window
 	long long out_base;              // output offset of the window
 	int ticket2;
 	int pad;
 	unsigned long long bar_cur;      // mbarrier: cursor row of the window being started
 	unsigned long long bar_nxt;      // mbarrier: cursor row of the window prefetched for
 	long long wsum[NWARP];
+	long long wsum2[NWARP];
 	int wcov[NWARP];
 	int wpack[NWARP];
 	double wauc[NWARP];
@@ -102,9 +104,9 @@ struct Misc {
 constexpr int MISC_BYTES = 1024;
 static_assert(sizeof(Misc) <= MISC_BYTES, "Misc must fit its slot");
 
-struct Layout { size_t off_cur, off_cur2, off_pre, off_toff, off_tmd, off_cov, off_limb, total; };
+struct Layout { size_t off_cur, off_cur2, off_pre, off_toff, off_tmd, off_cov, off_limb, off_cnt, total; };
 __host__ __device__ inline int quad_table_size(int N) { int p = 2; while (p <= N) p <<= 1; return p; }   // power of two > N
-__host__ __device__ inline Layout make_layout(int wlog, int N, int limbs, bool cov16) {
+__host__ __device__ inline Layout make_layout(int wlog, int N, int limbs, bool cov16, bool mom) {
 	Layout L;
 	const size_t W = (size_t) 1 << wlog, nn = (size_t) (N + 4) / 4 * 16;
 	size_t o = MISC_BYTES;
@@ -114,7 +116,8 @@ __host__ __device__ inline Layout make_layout(int wlog, int N, int limbs, bool c
 	L.off_toff = o; o += 2 * nn;                 // N + 1 track offsets (int64)
 	L.off_tmd = o;  o += 2 * nn;
 	L.off_cov = o;  o += (cov16 ? 2 : 4) * W;
-	L.off_limb = o; o += (size_t) limbs * 4 * W;
+	L.off_limb = o; o += (size_t) (mom ? 3 : limbs) * 4 * W;   // moments: sum (one limb), sum of squares (two)
+	L.off_cnt = o;  o += mom ? 2 * W : 0;        // moments: tracks in play at every breakpoint (16 bits)
 	L.total = (o + 15) / 16 * 16;
 	return L;
 }
@@ -178,7 +181,7 @@ struct Chunk {
 // the tracks' quad counts, then a binary search per quad.  No lane idles on a track that has
 // fewer intervals than its neighbours, and a track with thousands of intervals in the window
 // costs no more per interval than any other.
-template <int VLOG, int LIMBS, bool COV16>
+template <int VLOG, int LIMBS, bool COV16, bool MOM>
 __device__ __forceinline__ void events(const Job &job, unsigned char *smem, const Layout &L, const int32_t *cur,
                                        int w0i, int lw, double inv_scale, double lim) {
 	constexpr int W = TH << VLOG;
@@ -195,6 +198,7 @@ __device__ __forceinline__ void events(const Job &job, unsigned char *smem, cons
 	using acc_t = typename std::conditional<LIMBS == 1, int, long long>::type;
 	int in_cov = 0, in_pois = 0, my_next = INT_MAX;
 	acc_t in_val = 0;
+	long long in_val2 = 0;                                       // moments: squares
 
 	// quads of track i: its intervals first..last on the 16-byte aligned index grid
 	auto quads = [&](int i) -> int {
@@ -240,23 +244,31 @@ __device__ __forceinline__ void events(const Job &job, unsigned char *smem, cons
 			const double t = val * inv_scale;
 			const int mi = __double2int_rn(t);
 			bad = !((double) mi == t && fabs(t) < lim && (mi != 0 || val == 0.0));
+			if (MOM) bad = bad || (double) (float) val != val;      // var / stddev / CV: the reference rounds values through float
 			if (!bad) d = (acc_t) (mi - (int) md);
 		} else {
 			long long m;
 			bad = !to_fixed(val, inv_scale, lim, m);
 			if (!bad) d = (acc_t) (m - md);
 		}
+		const long long d2 = MOM ? (long long) d * (long long) d : 0;        // moments: all defaults are 0, d is the value
 		if (start_in) {
 			cov_add<VLOG, COV16>(cov, xs, false);
 #ifndef WB_DIAG_NO_LIMB_ATOM               // diagnostic builds only (profiles/): cost of the value atomics
-			if (d != 0) add_limbs_fs<LIMBS, W>(limb, phys32<VLOG>(xs), d, lw);
+			if (d != 0) {
+				add_limbs_fs<LIMBS, W>(limb, phys32<VLOG>(xs), d, lw);
+				if (MOM) add_limbs_fs<2, W>(limb + W, phys32<VLOG>(xs), d2, lw);
+			}
 #endif
 			if (bad) poison((unsigned) xs, 1);
-		} else { in_cov++; in_val += d; in_pois += bad ? 1 : 0; }           // began before the window
+		} else { in_cov++; in_val += d; in_val2 += d2; in_pois += bad ? 1 : 0; }           // began before the window
 		if (end_in) {
 			cov_add<VLOG, COV16>(cov, (int) xe, true);
 #ifndef WB_DIAG_NO_LIMB_ATOM
-			if (d != 0) add_limbs_fs<LIMBS, W>(limb, phys32<VLOG>((int) xe), -d, lw);
+			if (d != 0) {
+				add_limbs_fs<LIMBS, W>(limb, phys32<VLOG>((int) xe), -d, lw);
+				if (MOM) add_limbs_fs<2, W>(limb + W, phys32<VLOG>((int) xe), -d2, lw);
+			}
 #endif
 			if (bad) poison(xe, -1);
 		} else my_next = min(my_next, e);
@@ -314,11 +326,13 @@ __device__ __forceinline__ void events(const Job &job, unsigned char *smem, cons
 	in_pois = __reduce_add_sync(FULL, in_pois);
 	if (LIMBS == 1) in_val = (acc_t) __reduce_add_sync(FULL, (int) in_val);
 	else for (int d = 16; d > 0; d >>= 1) in_val += __shfl_down_sync(FULL, in_val, d);
+	if (MOM) for (int d = 16; d > 0; d >>= 1) in_val2 += __shfl_down_sync(FULL, in_val2, d);
 	if (lane == 0) {
 		if (my_next != INT_MAX) atomicMin(&misc->next_bp, my_next);
 		if (in_cov) atomicAdd(&misc->base_cov, in_cov);
 		if (in_pois) atomicAdd(&misc->base_pois, in_pois);
 		if (in_val) atomicAdd(&misc->base_val, (unsigned long long) (long long) in_val);
+		if (MOM && in_val2) atomicAdd(&misc->base_val2, (unsigned long long) in_val2);
 	}
 }
 
@@ -337,7 +351,7 @@ __device__ __forceinline__ void cover4(const uint4 &cv, int half, int st[4], int
 }
 
 // ---- one window ------------------------------------------------------------------------
-template <int VLOG, int LIMBS, bool COV16>
+template <int VLOG, int LIMBS, bool COV16, bool MOM>
 __device__ void process_window(const Job &job, int w, unsigned char *smem, const Layout &L, int32_t *cur,
                                int32_t *nxt_buf, unsigned par_cur, unsigned par_nxt, int lw, double inv_scale, double lim, double scale) {
 	constexpr int V = 1 << VLOG, W = TH << VLOG, NVL = V / 4;
@@ -359,10 +373,10 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	{
 		const uint4 z = make_uint4(0, 0, 0, 0);
 		uint4 *zc = (uint4 *) cov;                                   // cov and limbs are contiguous
-		constexpr int n16 = (COV16 ? W / 8 : W / 4) + LIMBS * W / 4;
+		constexpr int n16 = (COV16 ? W / 8 : W / 4) + (MOM ? 3 : LIMBS) * W / 4;
 #pragma unroll 4
 		for (int t = tid; t < n16; t += TH) zc[t] = z;
-		if (tid == 0) { misc->next_bp = INT_MAX; misc->base_cov = 0; misc->base_pois = 0; misc->npois = 0; misc->base_val = 0; }
+		if (tid == 0) { misc->next_bp = INT_MAX; misc->base_cov = 0; misc->base_pois = 0; misc->npois = 0; misc->base_val = 0; misc->base_val2 = 0; }
 	}
 	mbar_wait(&misc->bar_cur, par_cur);                          // this window's cursor row (bulk copy requested when it was drawn)
 	__syncthreads();
@@ -370,7 +384,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 
 	// ---- 1. events ---------------------------------------------------------------------
 #ifndef WB_DIAG_SKIP_EVENTS
-	events<VLOG, LIMBS, COV16>(job, smem, L, cur, w0i, lw, inv_scale, lim);
+	events<VLOG, LIMBS, COV16, MOM>(job, smem, L, cur, w0i, lw, inv_scale, lim);
 #endif
 	__syncthreads();
 	WB_PHASE(1);
@@ -381,6 +395,8 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	using acc_t = typename std::conditional<LIMBS == 1, int, long long>::type;   // one limb: every prefix fits 32 bits
 	int ctot = 0;
 	acc_t atot = 0;
+	long long btot = 0;                                          // moments: squares
+	uint32_t *sq = limb + W;                                     // their two limbs: sq[0..W) low, sq[W..2W) high
 	{
 		if (COV16) {
 			// byte fields summed two positions at a time in 16-bit lanes (<= 16 * 255 each)
@@ -410,32 +426,40 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 				atot += (acc_t) ((long long) ((unsigned long long) l.x + l.y + l.z + l.w)
 				      + (((long long) (int32_t) h.x + (int32_t) h.y + (int32_t) h.z + (int32_t) h.w) << lw));
 			}
+			if (MOM) {
+				const uint4 ql = *(const uint4 *) (sq + pv), qh = *(const uint4 *) (sq + W + pv);
+				btot += (long long) ((unsigned long long) ql.x + ql.y + ql.z + ql.w)
+				      + (((long long) (int32_t) qh.x + (int32_t) qh.y + (int32_t) qh.z + (int32_t) qh.w) << lw);
+			}
 		}
 	}
 	// exclusive block scan of (cover, value)
-	int ec; acc_t ea;
+	int ec; acc_t ea; long long eb = 0;
 	{
-		int ic = ctot; acc_t ia = atot;
+		int ic = ctot; acc_t ia = atot; long long ib = btot;
 #pragma unroll
 		for (int d = 1; d < 32; d <<= 1) {
 			const int vc = __shfl_up_sync(FULL, ic, d);
 			const acc_t va = __shfl_up_sync(FULL, ia, d);
 			if (lane >= d) { ic += vc; ia += va; }
+			if (MOM) { const long long vb = __shfl_up_sync(FULL, ib, d); if (lane >= d) ib += vb; }
 		}
-		if (lane == 31) { misc->wcov[warp] = ic; misc->wsum[warp] = (long long) ia; }
+		if (lane == 31) { misc->wcov[warp] = ic; misc->wsum[warp] = (long long) ia; if (MOM) misc->wsum2[warp] = ib; }
 		__syncthreads();
-		int bc = 0; acc_t ba = 0;
+		int bc = 0; acc_t ba = 0; long long bb = 0;
 #pragma unroll
-		for (int k = 0; k < NWARP; k++) if (k < warp) { bc += misc->wcov[k]; ba += (acc_t) misc->wsum[k]; }
+		for (int k = 0; k < NWARP; k++) if (k < warp) { bc += misc->wcov[k]; ba += (acc_t) misc->wsum[k]; if (MOM) bb += misc->wsum2[k]; }
 		ec = bc + ic - ctot + misc->base_cov;
 		ea = ba + ia - atot + (acc_t) (long long) misc->base_val;
+		if (MOM) eb = bb + ib - btot + (long long) misc->base_val2;
 	}
 	WB_PHASE(2);
 
 	// ---- pass 2: running state after every position; the exact prefix goes back in place -----
 	unsigned evbits = 0, keepbits = 0;
 	{
-		int c = ec; acc_t a = ea;
+		int c = ec; acc_t a = ea; long long b = eb;
+		uint16_t *cnt = (uint16_t *) (smem + L.off_cnt);
 		uint4 cv = make_uint4(0, 0, 0, 0);
 #pragma unroll
 		for (int k = 0; k < NVL; k++) {
@@ -447,20 +471,32 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 			uint4 l = *(const uint4 *) (limb + pv);
 			uint32_t lo[4] = {l.x, l.y, l.z, l.w}, hi[4] = {0, 0, 0, 0};
 			if (LIMBS == 2) { const uint4 h = *(const uint4 *) (limb + W + pv); hi[0] = h.x; hi[1] = h.y; hi[2] = h.z; hi[3] = h.w; }
+			uint32_t ql[4] = {0, 0, 0, 0}, qh[4] = {0, 0, 0, 0};
+			if (MOM) {
+				const uint4 x = *(const uint4 *) (sq + pv), y = *(const uint4 *) (sq + W + pv);
+				ql[0] = x.x; ql[1] = x.y; ql[2] = x.z; ql[3] = x.w; qh[0] = y.x; qh[1] = y.y; qh[2] = y.z; qh[3] = y.w;
+			}
 #pragma unroll
 			for (int j = 0; j < 4; j++) {
 				c += st[j] - en[j];
 				if (LIMBS == 1) a += (acc_t) lo[j];
 				else a += (acc_t) ((long long) (unsigned long long) lo[j] + ((long long) (int32_t) hi[j] << lw));
+				if (MOM) b += (long long) (unsigned long long) ql[j] + ((long long) (int32_t) qh[j] << lw);
 				if (st[j] | en[j]) {
 					evbits |= 1u << (4 * k + j);
 					if (c >= thr) keepbits |= 1u << (4 * k + j);
+					if (MOM) cnt[pv + j] = (uint16_t) c;                   // the statistic needs the tracks in play
 				}
 				lo[j] = (uint32_t) a;                                  // LIMBS == 1: the sum itself fits 32 bits
 				if (LIMBS == 2) hi[j] = (uint32_t) ((unsigned long long) a >> 32);
+				if (MOM) { ql[j] = (uint32_t) b; qh[j] = (uint32_t) ((unsigned long long) b >> 32); }
 			}
 			*(uint4 *) (limb + pv) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 			if (LIMBS == 2) *(uint4 *) (limb + W + pv) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+			if (MOM) {
+				*(uint4 *) (sq + pv) = make_uint4(ql[0], ql[1], ql[2], ql[3]);
+				*(uint4 *) (sq + W + pv) = make_uint4(qh[0], qh[1], qh[2], qh[3]);
+			}
 		}
 	}
 	// rare: segments covering an interval whose value is not representable (fix-up kernel)
@@ -612,10 +648,8 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	}
 	__syncthreads();
 	WB_PHASE(5);
-	// The look-back of window w waits for every window below w, so the less time passes between
-	// drawing a window and starting it, the less the windows in flight run out of order: the next
-	// window is drawn now, and its cursor row lands while this window is emitted.
 #if WB_FS_TICKET_AT_END == 0
+	// (earlier scheme) the next window is drawn now, and its cursor rows land while this window is emitted
 	if (tid == 0) {
 		const int nw1 = (int) atomicAdd(job.ticket, 1u);
 		misc->ticket2 = nw1;
@@ -639,6 +673,8 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	const double mul = (mean && npow2) ? scale * (1.0 / N) : scale;
 	const bool div = mean && !npow2;
 	const int32_t fx_base32 = (int32_t) job.fx_base;
+	const int mom_op = job.op == OP_ENTROPY ? OP_STDDEV : job.op;
+	const uint16_t *cnt16 = (const uint16_t *) (smem + L.off_cnt);
 	double auc = 0;
 	// the three output pointers of this window, opaque to the optimiser: one 32-bit
 	// index per store instead of a re-derived 64-bit (out_base + rank) chain
@@ -651,6 +687,11 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 		auto value_at = [&](int pos) -> double {
 			const int ph = phys32<VLOG>(pos);
 			double v;
+			if (MOM) {
+				// var / stddev / CV from the exact sums (engine.cu: emit_kernel<MODE_MOMENTS> evaluates the same expression)
+				const long long sxx = (long long) (((unsigned long long) sq[W + ph] << 32) | sq[ph]);
+				return moments_stat(mom_op, N, (int) cnt16[ph], (long long) (int32_t) limb[ph], sxx, scale);
+			}
 			if (LIMBS == 1) v = (double) ((int32_t) limb[ph] + fx_base32) * mul;     // |sum + defaults| < 2^30: one 32-bit conversion
 			else v = (double) ((long long) (((unsigned long long) limb[W + ph] << 32) | limb[ph]) + job.fx_base) * mul;
 			if (DIV) v = v / N;
@@ -668,7 +709,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 					if (k < (unsigned long long) job.slow_cap) job.slow_list[k] = out_base + kid;
 				}
 			}
-			if (!(d & DN_SLOW)) auc += (double) (be - bs) * v;        // v is finite here
+			if (!(d & DN_SLOW) && !(MOM && isnan(v))) auc += (double) (be - bs) * v;   // sum / mean: v is finite here
 		};
 #if WB_FS_EMIT2
 		// two groups of 32 dense entries per warp and step: the shared-memory reads of both are in flight together
@@ -707,16 +748,16 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	WB_PHASE(6);
 }
 
-template <int VLOG, int LIMBS, bool COV16>
-__global__ void __launch_bounds__(TH, (LIMBS == 1 && COV16) ? WB_FS_MINB : LIMBS == 1 ? 6 : COV16 ? 5 : 4)
+template <int VLOG, int LIMBS, bool COV16, bool MOM>
+__global__ void __launch_bounds__(TH, MOM ? 4 : (LIMBS == 1 && COV16) ? WB_FS_MINB : LIMBS == 1 ? 6 : COV16 ? 5 : 4)
 fastsum_kernel(const Job job, int lw, double inv_scale, double lim, double scale) {
 	extern __shared__ __align__(16) unsigned char smem[];
-	const Layout L = make_layout(job.wlog, job.N, LIMBS, COV16);
+	const Layout L = make_layout(job.wlog, job.N, LIMBS, COV16, MOM);
 	long long *toff = (long long *) (smem + L.off_toff);
 	long long *tmd = (long long *) (smem + L.off_tmd);
 	for (int i = threadIdx.x; i <= job.N; i += TH) {
 		toff[i] = job.off[i];
-		if (i < job.N) tmd[i] = job.dflt_fx[i];
+		if (i < job.N) tmd[i] = MOM ? 0 : job.dflt_fx[i];          // moments: all defaults are 0 (capi.cu: wants_format)
 	}
 	Misc *misc = (Misc *) smem;
 	int32_t *ca = (int32_t *) (smem + L.off_cur), *cb = (int32_t *) (smem + L.off_cur2);   // cursor rows: window being processed / prefetched for
@@ -741,7 +782,7 @@ fastsum_kernel(const Job job, int lw, double inv_scale, double lim, double scale
 		const long long diag_t0 = clock64();
 #endif
 		const bool pref = WB_FS_PREF && w + (int) gridDim.x < job.nw;
-		process_window<VLOG, LIMBS, COV16>(job, w, smem, L, ca, cb, par_cur, par_nxt, lw, inv_scale, lim, scale);
+		process_window<VLOG, LIMBS, COV16, MOM>(job, w, smem, L, ca, cb, par_cur, par_nxt, lw, inv_scale, lim, scale);
 		par_cur ^= 1;
 		if (pref) par_nxt ^= 1;
 		__syncthreads();      // dense list consumed, ticket and AUC partials visible
@@ -754,8 +795,10 @@ fastsum_kernel(const Job job, int lw, double inv_scale, double lim, double scale
 		if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&job.diag[7], (unsigned long long) (t_ - diag_t0)); atomicAdd(&job.diag[8], 1ull); }
 #endif
 #if WB_FS_TICKET_AT_END
-		// experiment: the next window is drawn only when this one is completely done (its cursor rows then
-		// arrive while the window arrays are cleared)
+		// The look-back of window w waits for every window below w, so the less time passes between drawing a
+		// window and starting it, the less the windows in flight run out of order: the next window is drawn only
+		// now, when this one is completely done (its cursor rows arrive while the window arrays are cleared).
+		// Measured against drawing at the start of the emit phase: look-back 10.7 k -> 9.0 k cycles per window, -2.7 %.
 		if (threadIdx.x == 0) {
 			const int nw1 = (int) atomicAdd(job.ticket, 1u);
 			misc->ticket2 = nw1;
@@ -771,20 +814,20 @@ fastsum_kernel(const Job job, int lw, double inv_scale, double lim, double scale
 	}
 }
 
-template <int VLOG, int LIMBS, bool COV16>
+template <int VLOG, int LIMBS, bool COV16, bool MOM>
 static cudaError_t launch_v(const Job &job, int lw, double inv_scale, double lim, double scale, cudaStream_t s) {
-	size_t smem = make_layout(job.wlog, job.N, LIMBS, COV16).total;
+	size_t smem = make_layout(job.wlog, job.N, LIMBS, COV16, MOM).total;
 	{ const char *e = getenv("WB200_FS_PAD"); if (e) smem += (size_t) atoi(e) * 1024; }   // development: cap the CTAs per SM
 	int dev = 0, sms = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-	cudaError_t e = cudaFuncSetAttribute(fastsum_kernel<VLOG, LIMBS, COV16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+	cudaError_t e = cudaFuncSetAttribute(fastsum_kernel<VLOG, LIMBS, COV16, MOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 	if (e != cudaSuccess) return e;
 	int per = 1;
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fastsum_kernel<VLOG, LIMBS, COV16>, TH, smem);
-	if (getenv("WB200_FS_VERBOSE")) fprintf(stderr, "fastsum_kernel<%d,%d,%d>: %zu B smem, %d CTAs/SM\n", VLOG, LIMBS, (int) COV16, smem, per);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fastsum_kernel<VLOG, LIMBS, COV16, MOM>, TH, smem);
+	if (getenv("WB200_FS_VERBOSE")) fprintf(stderr, "fastsum_kernel<%d,%d,%d,%d>: %zu B smem, %d CTAs/SM\n", VLOG, LIMBS, (int) COV16, (int) MOM, smem, per);
 	const int grid = min(job.nw, sms * max(per, 1));
-	fastsum_kernel<VLOG, LIMBS, COV16><<<grid, TH, smem, s>>>(job, lw, inv_scale, lim, scale);
+	fastsum_kernel<VLOG, LIMBS, COV16, MOM><<<grid, TH, smem, s>>>(job, lw, inv_scale, lim, scale);
 	return cudaGetLastError();
 }
 
@@ -797,17 +840,28 @@ static bool use_cov16(const Job &job) {
 
 // Whether the sum / mean sweep kernel covers this job (else: emit_kernel<MODE_FAST>).
 bool fastsum_supported(const Job &job) {
-	if (job.fast != 1 || !job.vec || job.fx_limbs > 2 || job.N > MAX_TRACKS) return false;
+	if (!job.vec || job.N > MAX_TRACKS) return false;
 	const int vlog = job.wlog - 7;
 	if (vlog != 4 && vlog != 5) return false;
-	return fs::make_layout(job.wlog, job.N, job.fx_limbs, fs::use_cov16(job)).total <= 200 * 1024;
+	if (job.fast == 2) {
+		// var / stddev / CV: the plain sum in one limb, the squares in two (else emit_kernel<MODE_MOMENTS>)
+		int l2n = 0;
+		while ((1ll << l2n) < 2ll * job.N) l2n++;
+		const int lw = 32 - l2n;
+		const char *e = getenv("WB200_FS_MOMENTS");      // development: 0 keeps them on emit_kernel<MODE_MOMENTS>
+		if ((e && atoi(e) == 0) || !job.sum1 || 2 * job.fx_mbits > 30 - l2n + lw || job.N > 65535) return false;
+		return fs::make_layout(job.wlog, job.N, 1, fs::use_cov16(job), true).total <= 200 * 1024;
+	}
+	if (job.fast != 1 || job.fx_limbs > 2) return false;
+	return fs::make_layout(job.wlog, job.N, job.fx_limbs, fs::use_cov16(job), false).total <= 200 * 1024;
 }
 
 cudaError_t launch_fastsum(const Job &job, int lw, double inv_scale, double lim, double scale, cudaStream_t s) {
 	const int vlog = job.wlog - 7;
-	const bool one = job.fx_limbs == 1, c16 = fs::use_cov16(job);
-#define WB_FS(V) (one ? (c16 ? fs::launch_v<V, 1, true>(job, lw, inv_scale, lim, scale, s) : fs::launch_v<V, 1, false>(job, lw, inv_scale, lim, scale, s)) \
-                      : (c16 ? fs::launch_v<V, 2, true>(job, lw, inv_scale, lim, scale, s) : fs::launch_v<V, 2, false>(job, lw, inv_scale, lim, scale, s)))
+	const bool mom = job.fast == 2, one = job.fx_limbs == 1, c16 = fs::use_cov16(job);
+#define WB_FS(V) (mom ? (c16 ? fs::launch_v<V, 1, true, true>(job, lw, inv_scale, lim, scale, s) : fs::launch_v<V, 1, false, true>(job, lw, inv_scale, lim, scale, s)) \
+                : one ? (c16 ? fs::launch_v<V, 1, true, false>(job, lw, inv_scale, lim, scale, s) : fs::launch_v<V, 1, false, false>(job, lw, inv_scale, lim, scale, s)) \
+                      : (c16 ? fs::launch_v<V, 2, true, false>(job, lw, inv_scale, lim, scale, s) : fs::launch_v<V, 2, false, false>(job, lw, inv_scale, lim, scale, s)))
 	if (vlog == 4) return WB_FS(4);
 	if (vlog == 5) return WB_FS(5);
 #undef WB_FS
