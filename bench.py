@@ -70,10 +70,6 @@ def workloads(world):
     return wl
 
 
-def dominant_kernel(op):
-    return "fastsum_kernel" if op in ("sum", "mean") and os.environ.get("WB200_FASTSUM") != "0" else "emit_kernel"
-
-
 def genome():
     names, lengths = sorted_chroms()
     lengths = [max(10000, int(l * SCALE)) for l in lengths]
@@ -512,7 +508,7 @@ def main():
                 for k in range(len(use)):
                     total_auc += arr[k].auc
                     if collect:
-                        per_launch.append((int(offs[k][N]), int(arr[k].n_out), arr[k].ms_cursor, arr[k].ms_sweep, int(arr[k].slow_segments), int(arr[k].limbs)))
+                        per_launch.append((int(offs[k][N]), int(arr[k].n_out), arr[k].ms_cursor, arr[k].ms_sweep, int(arr[k].slow_segments), int(arr[k].limbs), int(arr[k].sweep_kernel)))
                 if collect:
                     kernels += lib.wb200_last_stats(ctx).contents.kernels
             t = torch.tensor([total_auc], dtype=torch.float64, device=dev)
@@ -550,9 +546,12 @@ def main():
         t_emit = sum(r[3] for r in per_launch) / 1e3
         t_count = sum(r[2] for r in per_launch) / 1e3
         achieved = by / t_emit / 1e9 if t_emit > 0 else 0.0
-        roofline = {"bound": "hbm", "kernel": dominant_kernel(op), "achieved": achieved, "peak": peak, "unit": "GB/s",
+        # which kernel ran is the library's own report per launch (sum / mean / var / stddev / CV run on
+        # fastsum_kernel when their fixed-point format allows it, everything else on emit_kernel)
+        kernel = "fastsum_kernel" if per_launch and all(r[6] for r in per_launch) else "emit_kernel"
+        roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak,
-                    "traffic": (traffic_ratio * by / len(per_launch)) if traffic_ratio and per_launch and dominant_kernel(op) == "fastsum_kernel" else None,
+                    "traffic": (traffic_ratio * by / len(per_launch)) if traffic_ratio and per_launch and kernel == "fastsum_kernel" and op in ("sum", "mean") else None,
                     "traffic_source": "ncu --set full capture of one launch (profiles/traffic.json): measured dram bytes / algorithmic bytes, times this run's algorithmic bytes per launch",
                     "peak_source": peak_src, "algorithmic_bytes_per_step": by / K,
                     "algorithmic_bytes_per_launch": by / max(1, len(per_launch)),
@@ -630,7 +629,8 @@ def main():
             ph = (C.c_uint64 * 16)()
             lib.wb200_debug_phases(ctx, ph)
             if any(ph):                                   # diagnostic builds only
-                names_ = ["clear", "events", "scan", "count", "compact", "lookback", "emit", "window_total", "windows", "lookback_polls", "lookback_steps"]
+                names_ = ["clear", "events", "scan", "count", "compact", "lookback", "emit", "window_total", "windows", "lookback_polls", "lookback_steps",
+                          "order_offsets", "order_sort", "order_select", "order_stage", "order_keys"]
                 line["phase_cycles_per_window"] = {n: ph[k] / max(1, ph[8]) for k, n in enumerate(names_)}
             if os.environ.get("WB200_BENCH_CHECKSUM"):      # development: order-sensitive digest of every output array
                 acc = torch.zeros((), dtype=torch.int64, device=dev)

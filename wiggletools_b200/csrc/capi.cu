@@ -217,8 +217,12 @@ int plan_shard(wb200_ctx *ctx, int op, int N, int &n1, int &strict, const int64_
 			// dense data: smaller windows for the kernels that keep a window in registers; the sum / mean
 			// sweep (fastsum.cu) is fastest with the largest window at any density
 			if (density > 0.6 && !(op == OP_SUM || op == OP_MEAN)) wlog = 11;
+			// var / stddev / CV on the sweep kernel: 16 B of shared memory per position, so the smaller window keeps
+			// more windows in flight per SM (measured: N = 64, density 0.5: 6 instead of 3 CTAs per SM)
+			if (density > 0.25 && (op == OP_VAR || op == OP_STDDEV || op == OP_ENTROPY || op == OP_CV)) wlog = 11;
 			// the order-statistic sweep is a serial chain per warp: smaller windows, more CTAs per SM
-			if ((op == OP_MEDIAN || op == OP_MIN || op == OP_MAX) && N <= 512) wlog = N > 128 ? 10 : 11;
+			// (more than 128 tracks: the window's intervals and gaps are sorted once, at most 4096 elements)
+			if ((op == OP_MEDIAN || op == OP_MIN || op == OP_MAX) && N <= 512) wlog = N > 256 ? 9 : N > 128 ? 10 : 11;
 		}
 	}
 	wlog = std::min(TLOG + 4, std::max(TLOG + 2, wlog));

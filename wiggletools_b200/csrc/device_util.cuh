@@ -49,12 +49,15 @@ __device__ __forceinline__ void add_limbs_fs(uint32_t *limb, int ph, long long d
 // The sum of squared deviations is evaluated without cancellation:
 //   sum_C (mean - v)^2 = [ (c Sxx - Sx^2) 2^2q + (c mean - X)^2 ] / c ,  X = Sx 2^q
 // where c Sxx - Sx^2 >= 0 is exact in 128-bit integers.
+// WIDE: the integer type c Sxx and Sx^2 are formed in -- __int128 in general, 64 bits when the
+// caller knows N 2^mbits <= 2^30 (both products are then below 2^60); the result is the same.
+template <typename WIDE = __int128>
 __device__ __forceinline__ double moments_stat(int op, int N, int c, long long Sx, long long Sxx, double scale) {
 	if (op == OP_VAR && N < 2) return NAN;
 	const double X = (double) Sx * scale;                  // exact: |Sx| < 2^53
 	const double mean = X / N;
 	if (op == OP_CV && mean == 0) return NAN;
-	const __int128 d1 = (__int128) c * (__int128) Sxx - (__int128) Sx * (__int128) Sx;
+	const WIDE d1 = (WIDE) c * (WIDE) Sxx - (WIDE) Sx * (WIDE) Sx;
 	const double D1 = (double) d1 * scale * scale;
 	const double r = fma((double) c, mean, -X);
 	const double EC = (D1 + r * r) / c;

@@ -36,6 +36,8 @@
 // the window, so that every window starts independently.
 #include "engine.cuh"
 #include "device_util.cuh"
+#include <cstdio>
+#include <cstdlib>
 #include <cuda_pipeline.h>
 #include <cfloat>
 #include <cstdlib>
@@ -92,7 +94,8 @@ struct Misc {                        // scalars, warp totals
 	int lb_found[WARPS];             // look-back: chunk holds an inclusive prefix
 };
 constexpr int MISC_BYTES = 2048;
-static_assert(sizeof(Misc) <= MISC_BYTES, "Misc must fit its shared-memory slot");
+constexpr int MISC_SCRATCH = 1024;      // the second half of the slot: 1 KB of scratch for whoever needs it between two barriers
+static_assert(sizeof(Misc) <= MISC_SCRATCH, "Misc must fit its shared-memory slot");
 
 constexpr int WALK_MAX_TRACKS = 512;    // order-statistic sweep: N keys per warp in shared memory
 constexpr uint16_t BK_KEEP = 0x8000, BK_SLOW = 0x4000, BK_IDX = 0x3fff;
@@ -643,25 +646,36 @@ __device__ void order_walk(const Job &job, const int32_t *cur, const int32_t *nx
 }
 
 // Shared-memory carve-up of the sweep kernels' row buffer (host and device agree).
+#ifndef WB_SEL_MIN_N
+#define WB_SEL_MIN_N 128                 // fewer tracks: a sorted array per warp (order_walk) instead of sorting the window
+#endif
+constexpr int SEL_PS = 4096;             // bucketed selection: largest universe (64-bit keys), intervals + gaps
 struct WalkLayout {
 	int P;            // pow2 >= N: keys per warp of the sorted-array sweep
-	int P2;           // universe capacity of the rank-bitset sweep (window intervals + N defaults)
-	int cap;          // staged intervals per window (P2 - N)
-	size_t off_tstate, off_keys, off_rank, off_stage, off_tbase, off_bits, total;
+	int P2;           // universe capacity of the rank-bitset sweep (window intervals + N defaults, 16-byte keys)
+	int cap;          // staged intervals per window
+	size_t off_tstate, off_keys, off_rank, off_stage, off_tbase, off_bits, off_rse, total;
+	size_t cnt_bytes; // bucketed selection: room for the bucket counters (over stage | tstate | bits, dead by then)
 };
 __host__ __device__ inline WalkLayout walk_layout(int N) {
 	WalkLayout w;
 	w.P = 1; while (w.P < N) w.P <<= 1;
-	w.P2 = N <= 64 ? 1024 : N <= 256 ? 2048 : 4096;
-	w.cap = w.P2 - N;
+	const bool sel = N > WB_SEL_MIN_N;                         // the window-sorting sweeps are in use
+	w.P2 = N <= 64 ? 1024 : 2048;
+	// staged intervals: what a 1024-bp window of dense coverage data holds (about two intervals per track and
+	// 512 bp, plus the carried-in and the look-ahead one of every track); more than that: order_walk
+	w.cap = !sel ? w.P2 - N : N <= 256 ? (SEL_PS - N) / 2 : 7 * N;
 	size_t o = 0;
-	w.off_tstate = o; o += (size_t) WARPS * N * sizeof(TrackState);
 	const size_t keys = (size_t) w.P2 * sizeof(SortKey), arrs = (size_t) WARPS * w.P * sizeof(SortKey);
-	w.off_keys = o;   o += keys > arrs ? keys : arrs;          // sorted universe | per-warp sorted arrays (fallback)
-	w.off_rank = o;   o += (size_t) w.P2 * 2;
-	w.off_stage = o;  o += (size_t) w.cap * 16 + 16;
+	w.off_keys = o;   o += keys > arrs ? keys : arrs;          // sorted universe (16-byte or 64-bit keys) | per-warp sorted arrays
+	// serial sweeps: rank of every element, state of every track per warp | bucketed: (start, end) of every rank
+	const size_t serial = (size_t) w.P2 * 2 + (size_t) WARPS * N * sizeof(TrackState), rse = sel ? (size_t) SEL_PS * 4 : 0;
+	w.off_rank = o;   w.off_rse = o;  w.off_tstate = o + (size_t) w.P2 * 2;
+	o += serial > rse ? serial : rse;
 	w.off_tbase = o;  o += (size_t) (N + 4) / 4 * 16;
-	w.off_bits = o;   o += (size_t) WARPS * (w.P2 / 32) * 4;
+	w.off_stage = o;  o += (size_t) w.cap * 16 + 16;
+	w.off_bits = o;   o += (size_t) WARPS * (w.P2 / 32) * 4 > (size_t) N * 8 ? (size_t) WARPS * (w.P2 / 32) * 4 : (size_t) N * 8;   // | bucketed: cbase, fa
+	w.cnt_bytes = o - w.off_stage;
 	w.total = (o + 15) / 16 * 16;
 	return w;
 }
@@ -764,6 +778,198 @@ __device__ void bitset_walk(const Job &job, const int32_t *cur, const int32_t *n
 				slow++;
 			}
 		}
+	}
+}
+
+// Bucketed selection (min / max / median), the whole CTA at once, every breakpoint on its own.
+//
+// Universe of a window: its staged intervals plus, per track, the GAPS between them (and before
+// the first / after the last one), each carrying the track's default -- so that at every position
+// exactly one element per track is in play and every element is a plain [start, end).  When all
+// values are float32-exact (what a BigWig / bedGraph reader delivers; no NaN, no -0) an element is
+// one 64-bit key  order-preserving float bits | track | element index  and the universe is sorted
+// once per window with a register-blocked bitonic network.  The ranks are cut into SEL_NB buckets,
+// and a byte counter per (position, bucket) says how many elements of the bucket are in play
+// there: +1 at an element's start, -1 at its end, then a prefix sum along the positions.  Four
+// byte counters share a 32-bit word: the shared atomics add or subtract a shifted one, and since
+// every true count lies in [0, ranks per bucket] <= 255 the 32-bit prefix sums decode byte by
+// byte.  A kept breakpoint finds its bucket from the SEL_NB counters of its position and then the
+// k-th element in play among the bucket's ranks, in rank order.  Ties order by track index, as in
+// the reference's stable sort (src/reducers.c:140-207: qsort of the N current values).
+constexpr int SEL_NB = 32;                                   // buckets (8 words per position)
+__device__ __forceinline__ int sel_word(int p, int c) { return p * (SEL_NB / 4) + (c ^ (((p >> 2) & 1) << 2)); }   // word c of position p
+
+// float32 bits <-> unsigned keys in the same order
+__device__ __forceinline__ uint32_t f32_key(float f) { const uint32_t b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
+__device__ __forceinline__ float key_f32(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+__device__ __forceinline__ bool f32_exact(double v) { return (double) (float) v == v && !(v == 0.0 && signbit(v)); }   // NaN fails too
+
+// Bitonic sort of Ps 64-bit keys in shared memory (Ps a power of two >= 16), ascending, by the
+// whole CTA.  A (virtual) thread holds 16 keys in registers and runs up to four levels of the
+// network on them between two trips to shared memory: the keys whose indices differ in bits
+// b0 .. b0+3 only.  Index -> address is xor-swizzled so that every such gather is spread over
+// the banks.
+__device__ __forceinline__ int sort_phys(int idx) { return idx ^ ((idx >> 4) & 15); }
+// compare-exchange on the high words (the value): which of two equal values comes first is immaterial
+template <bool UP>
+__device__ __forceinline__ void sort_ce(unsigned long long &a, unsigned long long &b) {
+	const uint32_t ha = (uint32_t) (a >> 32), hb = (uint32_t) (b >> 32);
+	const bool sw = UP ? (ha > hb) : (ha < hb);
+	const unsigned long long x = sw ? b : a, y = sw ? a : b;
+	a = x; b = y;
+}
+template <bool UP>
+__device__ __forceinline__ void sort_levels(unsigned long long (&r)[16], int b0, int b) {
+#pragma unroll
+	for (int sft = 3; sft >= 0; sft--)
+		if (b0 + sft <= b) {
+#pragma unroll
+			for (int m = 0; m < 16; m++)
+				if ((m & (1 << sft)) == 0) sort_ce<UP>(r[m], r[m | (1 << sft)]);
+		}
+}
+__device__ void bitonic_u64(unsigned long long *keys, int Ps) {
+	const int tid = threadIdx.x, nvt = Ps >> 4;
+	// k = 2 .. 16: sixteen consecutive keys per thread
+	for (int vt = tid; vt < nvt; vt += THREADS) {
+		unsigned long long r[16];
+		const int base = vt << 4;
+#pragma unroll
+		for (int m = 0; m < 16; m++) r[m] = keys[sort_phys(base | m)];
+#pragma unroll
+		for (int k = 2; k <= 16; k <<= 1)
+#pragma unroll
+			for (int j = k >> 1; j > 0; j >>= 1)
+#pragma unroll
+				for (int m = 0; m < 16; m++)
+					if ((m & j) == 0) {
+						// k < 16: the direction is a compile-time function of m; k = 16: of the thread
+						if (k < 16) { if ((m & k) == 0) sort_ce<true>(r[m], r[m | j]); else sort_ce<false>(r[m], r[m | j]); }
+						else if ((base & 16) == 0) sort_ce<true>(r[m], r[m | j]); else sort_ce<false>(r[m], r[m | j]);
+					}
+#pragma unroll
+		for (int m = 0; m < 16; m++) keys[sort_phys(base | m)] = r[m];
+	}
+	__syncthreads();
+	for (int lk = 5; (1 << lk) <= Ps; lk++) {
+		int b = lk - 1;                                       // levels b .. 0 of this k, four at a time
+		while (b >= 0) {
+			const int b0 = max(b - 3, 0);
+			for (int vt = tid; vt < nvt; vt += THREADS) {
+				unsigned long long r[16];
+				const int base = ((vt >> b0) << (b0 + 4)) | (vt & ((1 << b0) - 1));
+				const bool up = (base & (1 << lk)) == 0;          // bit lk lies above the four levels
+#pragma unroll
+				for (int m = 0; m < 16; m++) r[m] = keys[sort_phys(base | (m << b0))];
+				if (up) sort_levels<true>(r, b0, b); else sort_levels<false>(r, b0, b);
+#pragma unroll
+				for (int m = 0; m < 16; m++) keys[sort_phys(base | (m << b0))] = r[m];
+			}
+			__syncthreads();
+			b = b0 - 1;
+		}
+	}
+}
+
+// One range [h0, h0 + ws) of the window's positions.  val: value of every rank; rse: (start, end) of
+// every rank, window-relative and clipped to the range, (W, W) for the padding; cntw: ws x SEL_NB
+// byte counters, cleared.
+__device__ void bucket_select(const Job &job, Misc *misc, long long w0, int W, int h0, int ws, int nbp, int next_bp,
+                              const uint16_t *bpos, const uint16_t *bkid, long long out_base, const float *val,
+                              const ushort2 *rse, uint32_t *cntw, int Ps, double &auc, unsigned long long &slow) {
+	constexpr int NBW = SEL_NB / 4;
+	const int N = job.N, tid = threadIdx.x;
+	const int sel = job.op == OP_MIN ? 0 : job.op == OP_MAX ? N - 1 : N / 2;
+	int bsh = 0;                                              // ranks per bucket = 2^bsh
+	while ((SEL_NB << bsh) < Ps) bsh++;
+	// events, one rank per thread and step
+	for (int rk = tid; rk < Ps; rk += THREADS) {
+		const ushort2 se = rse[rk];
+		if ((int) se.x >= W) continue;
+		const int b = rk >> bsh;
+		atomicAdd(&cntw[sel_word(se.x - h0, b >> 2)], 1u << ((b & 3) << 3));
+		if ((int) se.y < h0 + ws) atomicSub(&cntw[sel_word(se.y - h0, b >> 2)], 1u << ((b & 3) << 3));
+	}
+	__syncthreads();
+	// prefix sums along the positions: NBW word columns x runs of positions
+	{
+		constexpr int RUNS = THREADS / NBW;
+		const int len = max(1, ws / RUNS), runs = ws / len;     // ws is a power of two
+		const int c = tid % NBW, run = tid / NBW, pa = run * len;
+		uint32_t tot = 0;
+		if (run < runs) {
+#pragma unroll 8
+			for (int p = pa; p < pa + len; p++) tot += cntw[sel_word(p, c)];
+		}
+		uint32_t *rt = (uint32_t *) ((unsigned char *) misc + MISC_SCRATCH);   // RUNS x NBW run totals
+		rt[run * NBW + c] = tot;
+		__syncthreads();
+		if (run < runs) {
+			uint32_t acc = 0;
+			for (int k = 0; k < run; k++) acc += rt[k * NBW + c];
+#pragma unroll 8
+			for (int p = pa; p < pa + len; p++) { const int x = sel_word(p, c); acc += cntw[x]; cntw[x] = acc; }
+		}
+	}
+	__syncthreads();
+	// selection, one kept breakpoint per thread
+	for (int r = tid; r < nbp; r += THREADS) {
+		const uint16_t kd = bkid[r];
+		const int p = bpos[r];
+		if (!(kd & BK_KEEP) || p < h0 || p >= h0 + ws) continue;
+		int k = sel, bucket = SEL_NB - 1;
+		{
+			const uint4 a = *(const uint4 *) (cntw + sel_word(p - h0, 0)), b = *(const uint4 *) (cntw + sel_word(p - h0, 4));
+			const uint32_t wds[NBW] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+			bool found = false;
+#pragma unroll
+			for (int q = 0; q < NBW; q++) {
+				// bytes of one word: whole-word total first, then the byte inside
+				const uint32_t wd = wds[q];
+				const int tot = (int) ((wd & 0xff) + ((wd >> 8) & 0xff) + ((wd >> 16) & 0xff) + (wd >> 24));
+				if (!found) {
+					if (k < tot) {
+						found = true;
+						bool inside = false;
+#pragma unroll
+						for (int j = 0; j < 4; j++) {
+							const int cb = (wd >> (8 * j)) & 0xff;
+							if (!inside) { if (k < cb) { bucket = 4 * q + j; inside = true; } else k -= cb; }
+						}
+					} else k -= tot;
+				}
+			}
+		}
+		// the k-th element in play among the bucket's ranks, in rank order
+		double v = NAN;
+		const int ra = bucket << bsh, rb = ra + (1 << bsh);
+#pragma unroll 2
+		for (int rk = ra; rk < rb; rk += 4) {                  // four ranks per load
+			const uint4 q = *(const uint4 *) (rse + rk);
+			const uint32_t e[4] = {q.x, q.y, q.z, q.w};
+			const unsigned up = (unsigned) p;
+			int in[4], cnt = 0;
+#pragma unroll
+			for (int j = 0; j < 4; j++) { in[j] = ((e[j] & 0xffffu) <= up && up < (e[j] >> 16)) ? 1 : 0; cnt += in[j]; }
+			if (k < cnt) {
+				int hit = 0;
+#pragma unroll
+				for (int j = 0; j < 4; j++) { if (in[j] && k == 0) hit = j; k -= in[j]; }
+				v = (double) val[rk + hit];
+				break;
+			}
+			k -= cnt;
+		}
+		const int bs = (int) (w0 + p);
+		const int be = (r + 1 < nbp) ? (int) (w0 + bpos[r + 1]) : next_bp;
+		const long long oi = out_base + (kd & BK_IDX);
+		if (oi < job.out_cap) {
+			job.out_start[oi] = bs;
+			job.out_end[oi] = be;
+			job.out_value[oi] = v;
+		}
+		auc += (double) (be - bs) * v;                         // no NaN on this path
+		slow++;
 	}
 }
 
@@ -1358,11 +1564,13 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 				__syncthreads();
 			}
 			const int T = run;
+			WB_PHASE(11);
 			const bool staged = T <= wl.cap;
-			const int U = T + N;                              // universe: intervals + one default per track
+			const int U = T + N;                              // universe of the bitset sweep: intervals + one default per track
 			int Ps = 64; while (Ps < U) Ps <<= 1;
 			const bool minmax = (job.op == OP_MIN || job.op == OP_MAX);
-			const bool bitset = staged && N > 128;
+			const bool sorting = staged && N > WB_SEL_MIN_N;  // the window gets sorted (else: a sorted array per warp)
+			bool inexact = false;                             // a value that is not a float32 (NaN, -0 included)
 			if (staged) {
 				const int gid = tid >> 3, gl = tid & 7;
 				for (int i = gid; i < N; i += THREADS / 8) {
@@ -1371,12 +1579,132 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 					for (int j = cur[i] + gl; j <= jl; j += 8) {
 						const double v = job.value[o + j];
 						ss[b + j] = job.start[o + j]; se[b + j] = job.end[o + j]; sv[b + j] = v;
-						if (bitset) { SortKey k; k.v = isnan(v) ? INFINITY : v; k.ord = i; k.pad = b + j; keys[b + j] = k; }
+						inexact |= !f32_exact(v);
 					}
 				}
-				for (int u = T + tid; bitset && u < Ps; u += THREADS) {
+				for (int i = tid; i < N; i += THREADS) inexact |= !f32_exact((minmax && i == 0) ? 0.0 : job.dflt[i]);
+			}
+			// bucketed selection (every breakpoint on its own): float32 values, the universe of intervals and gaps fits
+			WB_PHASE(14);
+			const bool bucketed = sorting && W <= 4096 && !__syncthreads_or(inexact);
+			const bool bitset = sorting && !bucketed && U <= wl.P2;
+			__syncthreads();
+			if (bucketed) {
+				// The window's positions are handled in ranges [h0, h0 + ws): the whole window when its elements
+				// fit the sorted universe, else halves, quarters ... (a range of one position always fits).
+				// Elements of track i in a range: its staged intervals that overlap it -- fa[i] the first of
+				// them, cbase[i] = how many the tracks before i have -- and the gaps around them.
+				unsigned long long *k64 = (unsigned long long *) (rb + wl.off_keys);
+				const size_t keys_bytes = wl.off_rank - wl.off_keys;
+				float *val = (float *) k64;                       // after the sort: value of every rank, over the keys
+				ushort2 *rse = (ushort2 *) (rb + wl.off_rse);
+				int32_t *cbase = (int32_t *) (rb + wl.off_bits), *fa = cbase + N;   // the bitset sweep's rows: not in use on this path
+				int h0 = 0, ws = W;
+				while (h0 < W) {
+					int Tp = 0, Pb = 0;
+					bool in_stage = false;
+					while (true) {
+						const long long ra = w0 + h0, rbnd = ra + ws;
+						Tp = 0;
+						for (int base = 0; base < N; base += THREADS) {
+							const int i = base + tid;
+							int first = 0, cnt = 0;
+							if (i < N) {
+								const int b = tbase[i], L = max(0, min(nxt[i], tn[i] - 1) - cur[i] + 1);
+								int lo = 0, hi = L;                      // first staged interval with end > ra
+								while (lo < hi) { const int mid = (lo + hi) >> 1; if ((long long) se[b + mid] > ra) hi = mid; else lo = mid + 1; }
+								first = lo;
+								hi = L;                                  // first staged interval with start >= rbnd
+								while (lo < hi) { const int mid = (lo + hi) >> 1; if ((long long) ss[b + mid] >= rbnd) hi = mid; else lo = mid + 1; }
+								cnt = lo - first;
+							}
+							int ec, tc;
+							block_scan1(misc, cnt, ec, tc);
+							if (i < N) { cbase[i] = Tp + ec; fa[i] = first; }
+							Tp += tc;
+							__syncthreads();
+						}
+						Pb = 256; while (Pb < 2 * Tp + N) Pb <<= 1;
+						// the counters go over the staging area when this is the last range, else behind the values
+						in_stage = h0 + ws == W && (size_t) ws * SEL_NB <= wl.cnt_bytes;
+						const bool fits = 2 * Tp + N <= SEL_PS && (in_stage || (size_t) Pb * 4 + (size_t) ws * SEL_NB <= keys_bytes);
+						if (fits || ws == 1) break;
+						ws >>= 1;
+					}
+					const long long ra = w0 + h0, rbnd = ra + ws;
+					const int Us = 2 * Tp + N;                        // intervals, then count + 1 gaps per track
+					auto count_of = [&](int i) -> int { return (i + 1 < N ? cbase[i + 1] : Tp) - cbase[i]; };
+					const int gid = tid >> 3, gl = tid & 7;
+					for (int i = gid; i < N; i += THREADS / 8) {
+						const int len = count_of(i), b = tbase[i] + fa[i], cb = cbase[i];
+						const double d = (minmax && i == 0) ? 0.0 : job.dflt[i];     // reducers.c:142-145,209-212
+						const unsigned long long kd = ((unsigned long long) f32_key((float) d) << 32) | ((unsigned long long) i << 16);
+						for (int m = gl; m <= len; m += 8) {
+							if (m < len) {
+								const int u = cb + m;
+								k64[sort_phys(u)] = ((unsigned long long) f32_key((float) sv[b + m]) << 32) | ((unsigned long long) i << 16) | (unsigned) u;
+							}
+							// gap m: from the end of interval m - 1 (the range start) to the start of interval m (the range end)
+							const long long ga = m == 0 ? ra : max((long long) se[b + m - 1], ra);
+							const long long gb = m == len ? rbnd : min((long long) ss[b + m], rbnd);
+							const int u = Tp + cb + i + m;
+							k64[sort_phys(u)] = ga < gb ? (kd | (unsigned) u) : ~0ull;
+						}
+					}
+					for (int u = Us + tid; u < Pb; u += THREADS) k64[sort_phys(u)] = ~0ull;
+					__syncthreads();
+					WB_PHASE(15);
+					bitonic_u64(k64, Pb);
+					WB_PHASE(12);
+					float myv[SEL_PS / THREADS];
+#pragma unroll
+					for (int q = 0; q < SEL_PS / THREADS; q++) {
+						const int rk = tid + q * THREADS;
+						myv[q] = 0;
+						if (rk >= Pb) continue;
+						const unsigned long long key = k64[sort_phys(rk)];
+						ushort2 x; x.x = (uint16_t) W; x.y = (uint16_t) W;   // padding and empty gaps: never in play
+						if (key != ~0ull) {
+							const int u = (int) (key & 0xffff), i = (int) ((key >> 16) & 0xffff);
+							const int b = tbase[i] + fa[i];
+							long long a, e;
+							if (u < Tp) { const int m = u - cbase[i]; a = ss[b + m]; e = se[b + m]; }
+							else {
+								const int m = u - Tp - cbase[i] - i;
+								a = m == 0 ? ra : (long long) se[b + m - 1];
+								e = m == count_of(i) ? rbnd : (long long) ss[b + m];
+							}
+							x.x = (uint16_t) (min(max(a, ra), rbnd) - w0);       // began before the range: in play from its start
+							x.y = (uint16_t) (min(max(e, ra), rbnd) - w0);
+							myv[q] = key_f32((uint32_t) (key >> 32));
+						}
+						rse[rk] = x;
+					}
+					__syncthreads();                                  // every key has been read: the values go over them
+#pragma unroll
+					for (int q = 0; q < SEL_PS / THREADS; q++) { const int rk = tid + q * THREADS; if (rk < Pb) val[rk] = myv[q]; }
+					uint32_t *cntw = in_stage ? (uint32_t *) (rb + wl.off_stage) : (uint32_t *) (rb + wl.off_keys + (size_t) Pb * 4);
+					{
+						const uint4 z = make_uint4(0, 0, 0, 0);
+						uint4 *c4 = (uint4 *) cntw;
+						for (int t = tid; t < max(1, ws * SEL_NB / 16); t += THREADS) c4[t] = z;
+					}
+					__syncthreads();
+					bucket_select(job, misc, w0, W, h0, ws, nbp, next_bp, bpos, bkid, out_base, val, rse, cntw, Pb, auc, slow);
+					__syncthreads();
+					WB_PHASE(13);
+					h0 += ws;
+				}
+			} else if (bitset) {
+				for (int u = tid; u < Ps; u += THREADS) {
 					SortKey k;
-					if (u < U) {
+					if (u < T) {
+						// the track of staged interval u: the last one whose base is <= u
+						int lo = 0, hi = N - 1;
+						while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (tbase[mid] <= u) lo = mid; else hi = mid - 1; }
+						const double v = sv[u];
+						k.v = isnan(v) ? INFINITY : v; k.ord = lo; k.pad = u;
+					} else if (u < U) {
 						const int i = u - T;
 						const double d = (minmax && i == 0) ? 0.0 : job.dflt[i];
 						k.v = isnan(d) ? INFINITY : d; k.ord = i; k.pad = u;
@@ -1384,24 +1712,25 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 					keys[u] = k;
 				}
 				__syncthreads();
-				for (int k = 2; bitset && k <= Ps; k <<= 1)
+				for (int k = 2; k <= Ps; k <<= 1)
 					for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll 4
 						for (int t = tid; t < Ps / 2; t += THREADS) {
-							const int i = ((t / j) * 2 * j) + (t % j), l = i + j;
+							const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i + j;   // j is a power of two
 							const bool up = ((i & k) == 0);
 							const SortKey a = keys[i], b = keys[l];
 							if (up ? key_less(b, a) : key_less(a, b)) { keys[i] = b; keys[l] = a; }
 						}
 						__syncthreads();
 					}
-				for (int pos = tid; bitset && pos < Ps; pos += THREADS) { const int u = keys[pos].pad; if (u < U) rank_of[u] = (uint16_t) pos; }
+				for (int pos = tid; pos < Ps; pos += THREADS) { const int u = keys[pos].pad; if (u < U) rank_of[u] = (uint16_t) pos; }
+				__syncthreads();
 			}
-			__syncthreads();
 			IvAccess iv; iv.job = &job; iv.cur = cur; iv.tbase = staged ? tbase : nullptr; iv.ss = ss; iv.se = se; iv.sv = sv;
 			// each warp sweeps a contiguous share of the window's breakpoints
 			const int chunk = (nbp + WARPS - 1) / WARPS;
 			const int r0 = warp * chunk, r1 = min(nbp, r0 + chunk);
-			if (r0 < r1) {
+			if (r0 < r1 && !bucketed) {
 				if (bitset) {
 					uint32_t *bits = (uint32_t *) (rb + wl.off_bits) + (size_t) warp * (wl.P2 / 32);
 					bitset_walk(job, cur, nxt, w0, r0, r1, nbp, next_bp, bpos, bkid, out_base, keys, rank_of, bits, Ps / 32, T,
@@ -1719,6 +2048,7 @@ static cudaError_t launch_emit_v(const Job &job, int lw, double inv_scale, doubl
 	if (e != cudaSuccess) return e;
 	int per = 1;
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, emit_kernel<MODE, VLOG, LIMBS>, THREADS, smem);
+	if (getenv("WB200_FS_VERBOSE")) fprintf(stderr, "emit_kernel<%d,%d,%d>: %zu B smem, %d CTAs/SM\n", MODE, VLOG, LIMBS, smem, per);
 	int grid = min(job.nw, sms * max(per, 1));
 	emit_kernel<MODE, VLOG, LIMBS><<<grid, THREADS, smem, s>>>(job, lw, inv_scale, lim, scale, rowbuf);
 	return cudaGetLastError();

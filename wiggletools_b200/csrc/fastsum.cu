@@ -52,6 +52,9 @@ constexpr int TH = 128, NWARP = TH / 32;
 #ifndef WB_FS_MINB
 #define WB_FS_MINB 8                  // resident CTAs per SM the 6 B/position variant is compiled for
 #endif
+#ifndef WB_FS_MOM_MINB
+#define WB_FS_MOM_MINB 6              // var / stddev / CV, N <= 255, 2048-bp windows: resident CTAs per SM compiled for
+#endif
 #ifndef WB_FS_LBK
 #define WB_FS_LBK 1
 #endif
@@ -690,7 +693,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 			if (MOM) {
 				// var / stddev / CV from the exact sums (engine.cu: emit_kernel<MODE_MOMENTS> evaluates the same expression)
 				const long long sxx = (long long) (((unsigned long long) sq[W + ph] << 32) | sq[ph]);
-				return moments_stat(mom_op, N, (int) cnt16[ph], (long long) (int32_t) limb[ph], sxx, scale);
+				return moments_stat<long long>(mom_op, N, (int) cnt16[ph], (long long) (int32_t) limb[ph], sxx, scale);   // one-limb sums: 64 bits hold the products
 			}
 			if (LIMBS == 1) v = (double) ((int32_t) limb[ph] + fx_base32) * mul;     // |sum + defaults| < 2^30: one 32-bit conversion
 			else v = (double) ((long long) (((unsigned long long) limb[W + ph] << 32) | limb[ph]) + job.fx_base) * mul;
@@ -749,7 +752,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 }
 
 template <int VLOG, int LIMBS, bool COV16, bool MOM>
-__global__ void __launch_bounds__(TH, MOM ? 4 : (LIMBS == 1 && COV16) ? WB_FS_MINB : LIMBS == 1 ? 6 : COV16 ? 5 : 4)
+__global__ void __launch_bounds__(TH, MOM ? (COV16 && VLOG == 4 ? WB_FS_MOM_MINB : 4) : (LIMBS == 1 && COV16) ? WB_FS_MINB : LIMBS == 1 ? 6 : COV16 ? 5 : 4)
 fastsum_kernel(const Job job, int lw, double inv_scale, double lim, double scale) {
 	extern __shared__ __align__(16) unsigned char smem[];
 	const Layout L = make_layout(job.wlog, job.N, LIMBS, COV16, MOM);
