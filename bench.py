@@ -64,9 +64,12 @@ def workloads(world):
     if world == 1:
         wl += [dict(key="var512", op="var", N=512, f32=False, e2e=False, config="configs[2]"),
                dict(key="stddev512", op="stddev", N=512, f32=False, e2e=False, config="configs[2]"),
-               dict(key="median256", op="median", N=256, f32=False, e2e=False, config="configs[3]",
-                    chroms=os.environ.get("WB200_BENCH_MEDIAN_CHROMS", "chr19,chr20,chr21,chr22").split(",")),
+               dict(key="median256", op="median", N=256, f32=False, e2e=False, config="configs[3]"),
                dict(key="mean64_f32", op="mean", N=64, f32=True, e2e=False, config="configs[1] with float32-mantissa values (two-limb accumulator)")]
+    if os.environ.get("WB200_BENCH_MEDIAN_CHROMS"):     # development: the median line on a few chromosomes only
+        for w in wl:
+            if w["key"] == "median256":
+                w["chroms"] = os.environ["WB200_BENCH_MEDIAN_CHROMS"].split(",")
     return wl
 
 
@@ -629,7 +632,7 @@ def main():
             ph = (C.c_uint64 * 16)()
             lib.wb200_debug_phases(ctx, ph)
             if any(ph):                                   # diagnostic builds only
-                names_ = ["clear", "events", "scan", "count", "compact", "lookback", "emit", "window_total", "windows", "lookback_polls", "lookback_steps",
+                names_ = ["clear", "events", "scan", "count", "compact", "lookback", "emit", "window_total", "windows", "lookback_polls|order_ranks", "lookback_steps|order_counters",
                           "order_offsets", "order_sort", "order_select", "order_stage", "order_keys"]
                 line["phase_cycles_per_window"] = {n: ph[k] / max(1, ph[8]) for k, n in enumerate(names_)}
             if os.environ.get("WB200_BENCH_CHECKSUM"):      # development: order-sensitive digest of every output array

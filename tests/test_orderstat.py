@@ -1,10 +1,10 @@
-"""min / max / median over more than 128 tracks: the window-sorting sweeps of emit_kernel<MODE_WALK>
+"""min / max / median over more than 128 tracks: the window-sorting sweeps of emit_kernel<MODE_SELECT>
 (csrc/engine.cu).  Reference: MedianReductionPop / MinReductionPop / MaxReductionPop,
 /root/reference/src/reducers.c:131-257 (qsort of the N current values, upper median, track 0's
 default read as 0 by min / max).
 
 The bucketed selection handles windows whose values are all float32-exact (one 64-bit key per
-interval and per gap); anything else -- doubles with more mantissa, NaN, -0 -- takes the serial
+interval and per track default); anything else -- doubles with more mantissa, NaN, -0 -- takes the serial
 rank-bitset sweep.  Every value class below must give the oracle's output bit for bit, whichever
 sweep ends up running, including chromosomes where the classes are mixed window by window."""
 import numpy as np
@@ -63,13 +63,15 @@ def test_heavy_ties_and_abutting_intervals(engine, port):
     check(engine, port, tr, ("median", "max"), "ties")
 
 
-def test_double_values_take_the_serial_sweep(engine, port):
-    """Values with more mantissa than a float32: same answers from the rank-bitset sweep."""
-    tr = make_tracks(160, [4_000, 1_500], seed=9)
+@pytest.mark.parametrize("n", [160, 300])
+def test_double_values_take_the_serial_sweep(engine, port, n):
+    """Values with more mantissa than a float32: same answers from the rank-bitset sweep (above 256 tracks
+    half the warps run it)."""
+    tr = make_tracks(n, [4_000, 1_500], seed=9)
     rng = np.random.default_rng(2)
     for t in tr:
         t["value"] = rng.random(len(t["value"])) * 1e-3 + 1.0 / 3.0
-    check(engine, port, tr, ("median", "min"), "f64")
+    check(engine, port, tr, ("median", "min"), "f64/%d" % n)
 
 
 def test_mixed_windows_nan_and_negative_zero(engine, port):
@@ -92,10 +94,10 @@ def test_mixed_windows_nan_and_negative_zero(engine, port):
     check(engine, port, tr, ("median", "min", "max"), "mixed")
 
 
-def test_dense_window_falls_back(engine, port):
-    """More intervals per window than the sorted universe holds (1-bp intervals on every track):
+@pytest.mark.parametrize("n", [160, 300])
+def test_dense_window_falls_back(engine, port, n):
+    """More intervals per window than the staging area holds (1-bp intervals on every track):
     the per-warp sorted arrays take over; results unchanged."""
-    n = 160
     tr = make_tracks(n, [1_500], seed=4, max_len=1, max_gap=1, vmax=9)
     o, g = both(tr)
     want = port.reduce("median", o, ["chr1"])

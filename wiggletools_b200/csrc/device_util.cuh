@@ -12,8 +12,12 @@ namespace wb {
 // accumulated by thread 0 of every CTA into job.diag[phase].
 #ifdef WB_DIAG_PHASES
 #define WB_PHASE(k) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&job.diag[k], (unsigned long long) (t_ - diag_t)); diag_t = t_; } } while (0)
+#define WB_DIAG_PARAM , long long &diag_t          // for device functions that mark phases of their own
+#define WB_DIAG_ARG , diag_t
 #else
 #define WB_PHASE(k) do { } while (0)
+#define WB_DIAG_PARAM
+#define WB_DIAG_ARG
 #endif
 
 // value -> fixed point: m = v * 2^-q exactly, |m| < lim; false for NaN, Inf, values out of

@@ -27,7 +27,8 @@
 // Kernel variants (emit_kernel<MODE,...>):
 //   MODE_FAST    sum / mean from one exact accumulator;
 //   MODE_MOMENTS var / stddev / CV from exact sum and sum of squares;
-//   MODE_WALK    min / max / median from an incrementally maintained sorted array;
+//   MODE_WALK    min / max / median from an incrementally maintained sorted array (up to WB_SEL_MIN_N tracks);
+//   MODE_SELECT  min / max / median from the window's sorted universe (more tracks: bucketed selection, bitset sweep);
 //   MODE_ROW     everything else: row_eval(), a per-segment loop over the N
 //                tracks in index order that mirrors the reference's arithmetic
 //                operation for operation (also the fix-up path for segments whose
@@ -654,6 +655,7 @@ struct WalkLayout {
 	int P;            // pow2 >= N: keys per warp of the sorted-array sweep
 	int P2;           // universe capacity of the rank-bitset sweep (window intervals + N defaults, 16-byte keys)
 	int cap;          // staged intervals per window
+	int warps;        // warps that run the serial sweeps (each needs a sorted array / a state row of its own)
 	size_t off_tstate, off_keys, off_rank, off_stage, off_tbase, off_bits, off_rse, total;
 	size_t cnt_bytes; // bucketed selection: room for the bucket counters (over stage | tstate | bits, dead by then)
 };
@@ -666,15 +668,18 @@ __host__ __device__ inline WalkLayout walk_layout(int N) {
 	// 512 bp, plus the carried-in and the look-ahead one of every track); more than that: order_walk
 	w.cap = !sel ? w.P2 - N : N <= 256 ? (SEL_PS - N) / 2 : 7 * N;
 	size_t o = 0;
-	const size_t keys = (size_t) w.P2 * sizeof(SortKey), arrs = (size_t) WARPS * w.P * sizeof(SortKey);
+	// more than 256 tracks: the serial sweeps are the fallbacks of the bucketed selection, and half the warps
+	// run them -- their rows would otherwise cost the common path a resident CTA
+	w.warps = (sel && N > 256) ? WARPS / 2 : WARPS;
+	const size_t keys = (size_t) w.P2 * sizeof(SortKey), arrs = (size_t) w.warps * w.P * sizeof(SortKey);
 	w.off_keys = o;   o += keys > arrs ? keys : arrs;          // sorted universe (16-byte or 64-bit keys) | per-warp sorted arrays
 	// serial sweeps: rank of every element, state of every track per warp | bucketed: (start, end) of every rank
-	const size_t serial = (size_t) w.P2 * 2 + (size_t) WARPS * N * sizeof(TrackState), rse = sel ? (size_t) SEL_PS * 4 : 0;
+	const size_t serial = (size_t) w.P2 * 2 + (size_t) w.warps * N * sizeof(TrackState), rse = sel ? (size_t) SEL_PS * 4 : 0;
 	w.off_rank = o;   w.off_rse = o;  w.off_tstate = o + (size_t) w.P2 * 2;
 	o += serial > rse ? serial : rse;
 	w.off_tbase = o;  o += (size_t) (N + 4) / 4 * 16;
 	w.off_stage = o;  o += (size_t) w.cap * 16 + 16;
-	w.off_bits = o;   o += (size_t) WARPS * (w.P2 / 32) * 4 > (size_t) N * 8 ? (size_t) WARPS * (w.P2 / 32) * 4 : (size_t) N * 8;   // | bucketed: cbase, fa
+	w.off_bits = o;   o += (size_t) WARPS * (w.P2 / 32) * 4 > (size_t) N * 16 ? (size_t) WARPS * (w.P2 / 32) * 4 : (size_t) N * 16;   // | bucketed: cbase, fa, defaults, gcount
 	w.cnt_bytes = o - w.off_stage;
 	w.total = (o + 15) / 16 * 16;
 	return w;
@@ -804,11 +809,11 @@ __device__ __forceinline__ uint32_t f32_key(float f) { const uint32_t b = __floa
 __device__ __forceinline__ float key_f32(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
 __device__ __forceinline__ bool f32_exact(double v) { return (double) (float) v == v && !(v == 0.0 && signbit(v)); }   // NaN fails too
 
-// Bitonic sort of Ps 64-bit keys in shared memory (Ps a power of two >= 16), ascending, by the
-// whole CTA.  A (virtual) thread holds 16 keys in registers and runs up to four levels of the
-// network on them between two trips to shared memory: the keys whose indices differ in bits
-// b0 .. b0+3 only.  Index -> address is xor-swizzled so that every such gather is spread over
-// the banks.
+// Bitonic sort of Ps 64-bit keys in shared memory (Ps a power of two >= E), ascending by their
+// high words, by the whole CTA.  A (virtual) thread holds E = 2^LE keys in registers and runs up
+// to LE levels of the network on them between two trips to shared memory: the keys whose
+// indices differ in bits b0 .. b0+LE-1 only.  Index -> address is xor-swizzled so that every
+// such gather is spread over the banks.
 __device__ __forceinline__ int sort_phys(int idx) { return idx ^ ((idx >> 4) & 15); }
 // compare-exchange on the high words (the value): which of two equal values comes first is immaterial
 template <bool UP>
@@ -818,52 +823,54 @@ __device__ __forceinline__ void sort_ce(unsigned long long &a, unsigned long lon
 	const unsigned long long x = sw ? b : a, y = sw ? a : b;
 	a = x; b = y;
 }
-template <bool UP>
-__device__ __forceinline__ void sort_levels(unsigned long long (&r)[16], int b0, int b) {
+template <bool UP, int LE>
+__device__ __forceinline__ void sort_levels(unsigned long long (&r)[1 << LE], int b0, int b) {
 #pragma unroll
-	for (int sft = 3; sft >= 0; sft--)
+	for (int sft = LE - 1; sft >= 0; sft--)
 		if (b0 + sft <= b) {
 #pragma unroll
-			for (int m = 0; m < 16; m++)
+			for (int m = 0; m < (1 << LE); m++)
 				if ((m & (1 << sft)) == 0) sort_ce<UP>(r[m], r[m | (1 << sft)]);
 		}
 }
+template <int LE>
 __device__ void bitonic_u64(unsigned long long *keys, int Ps) {
-	const int tid = threadIdx.x, nvt = Ps >> 4;
-	// k = 2 .. 16: sixteen consecutive keys per thread
+	constexpr int E = 1 << LE;
+	const int tid = threadIdx.x, nvt = Ps >> LE;
+	// k = 2 .. E: E consecutive keys per thread
 	for (int vt = tid; vt < nvt; vt += THREADS) {
-		unsigned long long r[16];
-		const int base = vt << 4;
+		unsigned long long r[E];
+		const int base = vt << LE;
 #pragma unroll
-		for (int m = 0; m < 16; m++) r[m] = keys[sort_phys(base | m)];
+		for (int m = 0; m < E; m++) r[m] = keys[sort_phys(base | m)];
 #pragma unroll
-		for (int k = 2; k <= 16; k <<= 1)
+		for (int k = 2; k <= E; k <<= 1)
 #pragma unroll
 			for (int j = k >> 1; j > 0; j >>= 1)
 #pragma unroll
-				for (int m = 0; m < 16; m++)
+				for (int m = 0; m < E; m++)
 					if ((m & j) == 0) {
-						// k < 16: the direction is a compile-time function of m; k = 16: of the thread
-						if (k < 16) { if ((m & k) == 0) sort_ce<true>(r[m], r[m | j]); else sort_ce<false>(r[m], r[m | j]); }
-						else if ((base & 16) == 0) sort_ce<true>(r[m], r[m | j]); else sort_ce<false>(r[m], r[m | j]);
+						// k < E: the direction is a compile-time function of m; k = E: of the thread
+						if (k < E) { if ((m & k) == 0) sort_ce<true>(r[m], r[m | j]); else sort_ce<false>(r[m], r[m | j]); }
+						else if ((base & E) == 0) sort_ce<true>(r[m], r[m | j]); else sort_ce<false>(r[m], r[m | j]);
 					}
 #pragma unroll
-		for (int m = 0; m < 16; m++) keys[sort_phys(base | m)] = r[m];
+		for (int m = 0; m < E; m++) keys[sort_phys(base | m)] = r[m];
 	}
 	__syncthreads();
-	for (int lk = 5; (1 << lk) <= Ps; lk++) {
-		int b = lk - 1;                                       // levels b .. 0 of this k, four at a time
+	for (int lk = LE + 1; (1 << lk) <= Ps; lk++) {
+		int b = lk - 1;                                       // levels b .. 0 of this k, LE at a time
 		while (b >= 0) {
-			const int b0 = max(b - 3, 0);
+			const int b0 = max(b - (LE - 1), 0);
 			for (int vt = tid; vt < nvt; vt += THREADS) {
-				unsigned long long r[16];
-				const int base = ((vt >> b0) << (b0 + 4)) | (vt & ((1 << b0) - 1));
-				const bool up = (base & (1 << lk)) == 0;          // bit lk lies above the four levels
+				unsigned long long r[E];
+				const int base = ((vt >> b0) << (b0 + LE)) | (vt & ((1 << b0) - 1));
+				const bool up = (base & (1 << lk)) == 0;          // bit lk lies above the levels of this trip
 #pragma unroll
-				for (int m = 0; m < 16; m++) r[m] = keys[sort_phys(base | (m << b0))];
-				if (up) sort_levels<true>(r, b0, b); else sort_levels<false>(r, b0, b);
+				for (int m = 0; m < E; m++) r[m] = keys[sort_phys(base | (m << b0))];
+				if (up) sort_levels<true, LE>(r, b0, b); else sort_levels<false, LE>(r, b0, b);
 #pragma unroll
-				for (int m = 0; m < 16; m++) keys[sort_phys(base | (m << b0))] = r[m];
+				for (int m = 0; m < E; m++) keys[sort_phys(base | (m << b0))] = r[m];
 			}
 			__syncthreads();
 			b = b0 - 1;
@@ -876,17 +883,16 @@ __device__ void bitonic_u64(unsigned long long *keys, int Ps) {
 // byte counters, cleared.
 __device__ void bucket_select(const Job &job, Misc *misc, long long w0, int W, int h0, int ws, int nbp, int next_bp,
                               const uint16_t *bpos, const uint16_t *bkid, long long out_base, const float *val,
-                              const ushort2 *rse, uint32_t *cntw, int Ps, double &auc, unsigned long long &slow) {
+                              const ushort2 *rse, uint32_t *cntw, int bs, double &auc, unsigned long long &slow WB_DIAG_PARAM) {
 	constexpr int NBW = SEL_NB / 4;
 	const int N = job.N, tid = threadIdx.x;
 	const int sel = job.op == OP_MIN ? 0 : job.op == OP_MAX ? N - 1 : N / 2;
-	int bsh = 0;                                              // ranks per bucket = 2^bsh
-	while ((SEL_NB << bsh) < Ps) bsh++;
+	const int Ps = bs * SEL_NB;                               // bs ranks per bucket (a multiple of four, <= 255)
 	// events, one rank per thread and step
 	for (int rk = tid; rk < Ps; rk += THREADS) {
 		const ushort2 se = rse[rk];
 		if ((int) se.x >= W) continue;
-		const int b = rk >> bsh;
+		const int b = rk / bs;
 		atomicAdd(&cntw[sel_word(se.x - h0, b >> 2)], 1u << ((b & 3) << 3));
 		if ((int) se.y < h0 + ws) atomicSub(&cntw[sel_word(se.y - h0, b >> 2)], 1u << ((b & 3) << 3));
 	}
@@ -912,6 +918,7 @@ __device__ void bucket_select(const Job &job, Misc *misc, long long w0, int W, i
 		}
 	}
 	__syncthreads();
+	WB_PHASE(10);
 	// selection, one kept breakpoint per thread
 	for (int r = tid; r < nbp; r += THREADS) {
 		const uint16_t kd = bkid[r];
@@ -942,7 +949,7 @@ __device__ void bucket_select(const Job &job, Misc *misc, long long w0, int W, i
 		}
 		// the k-th element in play among the bucket's ranks, in rank order
 		double v = NAN;
-		const int ra = bucket << bsh, rb = ra + (1 << bsh);
+		const int ra = bucket * bs, rb = ra + bs;
 #pragma unroll 2
 		for (int rk = ra; rk < rb; rk += 4) {                  // four ranks per load
 			const uint4 q = *(const uint4 *) (rse + rk);
@@ -1035,7 +1042,7 @@ __device__ __forceinline__ long long load_prefix(const uint32_t *limb, int tid, 
 }
 
 
-enum { MODE_FAST = 1, MODE_ROW = 2, MODE_MOMENTS = 3, MODE_WALK = 4 };
+enum { MODE_FAST = 1, MODE_ROW = 2, MODE_MOMENTS = 3, MODE_WALK = 4, MODE_SELECT = 5 };
 
 // ---------------------------------------------------------------------------
 // events, vectorised (fixed-point modes)
@@ -1504,6 +1511,21 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	// emit phase), not two windows ahead (measured in fastsum.cu: look-back waits 8.5k -> 5k cycles).
 	unsigned next_ticket = 0;
 	if (tid == 0) next_ticket = atomicAdd(job.ticket, 1u) + gridDim.x;
+	if (MODE == MODE_SELECT) {
+		// the selection takes a while: pull the next window's intervals (about eight per track from its cursor
+		// on) into L2 meanwhile -- both its events phase and its staging read them with dependent loads
+		if (tid == 0) misc->ticket1 = (int) next_ticket;
+		__syncthreads();
+		const int wn = misc->ticket1;
+		if (wn < job.nw)
+			for (int i = tid; i < N; i += THREADS) {
+				const long long g = (toff[i] + job.cursor[(size_t) wn * job.cstride + i]) & ~3ll;
+				if (g + 8 <= job.I) {
+					asm volatile("prefetch.global.L2 [%0];" :: "l"(job.start + g)); asm volatile("prefetch.global.L2 [%0];" :: "l"(job.end + g));
+					asm volatile("prefetch.global.L2 [%0];" :: "l"(job.value + g)); asm volatile("prefetch.global.L2 [%0];" :: "l"(job.value + g + 4));
+				}
+			}
+	}
 #endif
 
 	// ---- 4. emit, one breakpoint per thread (coalesced stores) ---------------------------
@@ -1542,7 +1564,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 			}
 			if (!(kd & BK_SLOW) && !isnan(v)) auc += (double) (be - bs) * v;
 		}
-	} else if (MODE == MODE_WALK) {
+	} else if (MODE == MODE_WALK || MODE == MODE_SELECT) {
 		{
 			const WalkLayout wl = walk_layout(N);
 			unsigned char *rb = smem + L.off_rows;
@@ -1569,20 +1591,37 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 			const int U = T + N;                              // universe of the bitset sweep: intervals + one default per track
 			int Ps = 64; while (Ps < U) Ps <<= 1;
 			const bool minmax = (job.op == OP_MIN || job.op == OP_MAX);
-			const bool sorting = staged && N > WB_SEL_MIN_N;  // the window gets sorted (else: a sorted array per warp)
+			const bool sorting = MODE == MODE_SELECT && staged;   // the window gets sorted (else: a sorted array per warp)
 			bool inexact = false;                             // a value that is not a float32 (NaN, -0 included)
+			float *dfl = (float *) (rb + wl.off_bits) + 2 * N;    // bucketed selection: the tracks' defaults as float32
 			if (staged) {
-				const int gid = tid >> 3, gl = tid & 7;
-				for (int i = gid; i < N; i += THREADS / 8) {
-					const long long o = toff[i];
-					const int jl = min(nxt[i], tn[i] - 1), b = tbase[i] - cur[i];
-					for (int j = cur[i] + gl; j <= jl; j += 8) {
-						const double v = job.value[o + j];
-						ss[b + j] = job.start[o + j]; se[b + j] = job.end[o + j]; sv[b + j] = v;
-						inexact |= !f32_exact(v);
+				// one staged slot per thread and step, four steps in flight: the track of a slot is the last one
+				// whose base is not beyond it
+				for (int u0 = 0; u0 < T; u0 += 4 * THREADS) {
+					long long g[4]; bool ok[4];
+#pragma unroll
+					for (int q = 0; q < 4; q++) {
+						const int u = u0 + q * THREADS + tid;
+						ok[q] = u < T;
+						int lo = 0, hi = N - 1;
+						while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (tbase[mid] <= u) lo = mid; else hi = mid - 1; }
+						g[q] = ok[q] ? toff[lo] + cur[lo] + (u - tbase[lo]) : 0;
+					}
+					int s4[4], e4[4]; double v4[4];
+#pragma unroll
+					for (int q = 0; q < 4; q++) if (ok[q]) { s4[q] = job.start[g[q]]; e4[q] = job.end[g[q]]; v4[q] = job.value[g[q]]; }
+#pragma unroll
+					for (int q = 0; q < 4; q++) if (ok[q]) {
+						const int u = u0 + q * THREADS + tid;
+						ss[u] = s4[q]; se[u] = e4[q]; sv[u] = v4[q];
+						inexact |= !f32_exact(v4[q]);
 					}
 				}
-				for (int i = tid; i < N; i += THREADS) inexact |= !f32_exact((minmax && i == 0) ? 0.0 : job.dflt[i]);
+				for (int i = tid; i < N; i += THREADS) {
+					const double d = (minmax && i == 0) ? 0.0 : job.dflt[i];     // reducers.c:142-145,209-212
+					inexact |= !f32_exact(d);
+					if (sorting) dfl[i] = (float) d;
+				}
 			}
 			// bucketed selection (every breakpoint on its own): float32 values, the universe of intervals and gaps fits
 			WB_PHASE(14);
@@ -1599,9 +1638,10 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 				float *val = (float *) k64;                       // after the sort: value of every rank, over the keys
 				ushort2 *rse = (ushort2 *) (rb + wl.off_rse);
 				int32_t *cbase = (int32_t *) (rb + wl.off_bits), *fa = cbase + N;   // the bitset sweep's rows: not in use on this path
+				int32_t *gcount = fa + N + N;                     // (cbase, fa, defaults, gcount: N words each)
 				int h0 = 0, ws = W;
 				while (h0 < W) {
-					int Tp = 0, Pb = 0;
+					int Tp = 0, Pb = 0, Pm = 0;
 					bool in_stage = false;
 					while (true) {
 						const long long ra = w0 + h0, rbnd = ra + ws;
@@ -1620,10 +1660,12 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 							}
 							int ec, tc;
 							block_scan1(misc, cnt, ec, tc);
-							if (i < N) { cbase[i] = Tp + ec; fa[i] = first; }
+							if (i < N) { cbase[i] = Tp + ec; fa[i] = first; gcount[i] = 0; }
 							Tp += tc;
 							__syncthreads();
 						}
+						// sorted: the Tp intervals and one marker per track (its default); ranked: intervals and gaps
+						Pm = 256; while (Pm < Tp + N) Pm <<= 1;
 						Pb = 256; while (Pb < 2 * Tp + N) Pb <<= 1;
 						// the counters go over the staging area when this is the last range, else behind the values
 						in_stage = h0 + ws == W && (size_t) ws * SEL_NB <= wl.cnt_bytes;
@@ -1632,57 +1674,90 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 						ws >>= 1;
 					}
 					const long long ra = w0 + h0, rbnd = ra + ws;
-					const int Us = 2 * Tp + N;                        // intervals, then count + 1 gaps per track
 					auto count_of = [&](int i) -> int { return (i + 1 < N ? cbase[i + 1] : Tp) - cbase[i]; };
+					// gap m of track i (m = 0 .. count): from the end of interval m - 1 (the range start) to the start of
+					// interval m (the range end); b = the track's first staged interval of the range
+					auto gap = [&](int b, int len, int m, long long &ga, long long &gb) {
+						ga = m == 0 ? ra : max((long long) se[b + m - 1], ra);
+						gb = m == len ? rbnd : min((long long) ss[b + m], rbnd);
+					};
 					const int gid = tid >> 3, gl = tid & 7;
 					for (int i = gid; i < N; i += THREADS / 8) {
 						const int len = count_of(i), b = tbase[i] + fa[i], cb = cbase[i];
-						const double d = (minmax && i == 0) ? 0.0 : job.dflt[i];     // reducers.c:142-145,209-212
-						const unsigned long long kd = ((unsigned long long) f32_key((float) d) << 32) | ((unsigned long long) i << 16);
+						int ng = 0;
 						for (int m = gl; m <= len; m += 8) {
 							if (m < len) {
 								const int u = cb + m;
 								k64[sort_phys(u)] = ((unsigned long long) f32_key((float) sv[b + m]) << 32) | ((unsigned long long) i << 16) | (unsigned) u;
 							}
-							// gap m: from the end of interval m - 1 (the range start) to the start of interval m (the range end)
-							const long long ga = m == 0 ? ra : max((long long) se[b + m - 1], ra);
-							const long long gb = m == len ? rbnd : min((long long) ss[b + m], rbnd);
-							const int u = Tp + cb + i + m;
-							k64[sort_phys(u)] = ga < gb ? (kd | (unsigned) u) : ~0ull;
+							long long ga, gb;
+							gap(b, len, m, ga, gb);
+							ng += ga < gb ? 1 : 0;
 						}
+						if (ng) atomicAdd(&gcount[i], ng);              // non-empty gaps of the track
+						if (gl == 0) k64[sort_phys(Tp + i)] = ((unsigned long long) f32_key(dfl[i]) << 32) | ((unsigned long long) i << 16) | (unsigned) (Tp + i);
 					}
-					for (int u = Us + tid; u < Pb; u += THREADS) k64[sort_phys(u)] = ~0ull;
+					for (int u = Tp + N + tid; u < Pm; u += THREADS) k64[sort_phys(u)] = ~0ull;
 					__syncthreads();
 					WB_PHASE(15);
-					bitonic_u64(k64, Pb);
+					if (Pm >= 4096) bitonic_u64<4>(k64, Pm); else bitonic_u64<3>(k64, Pm);
 					WB_PHASE(12);
-					float myv[SEL_PS / THREADS];
+					// ranks: an interval takes one, a marker one per non-empty gap of its track.  Every thread takes
+					// Pm / THREADS consecutive sorted keys, a block scan of the multiplicities gives their first rank.
+					constexpr int KPT = SEL_PS / THREADS;
+					unsigned long long myk[KPT];
+					const int kpt = Pm / THREADS;                     // 1 .. KPT
+					int mine = 0;
 #pragma unroll
-					for (int q = 0; q < SEL_PS / THREADS; q++) {
-						const int rk = tid + q * THREADS;
-						myv[q] = 0;
-						if (rk >= Pb) continue;
-						const unsigned long long key = k64[sort_phys(rk)];
-						ushort2 x; x.x = (uint16_t) W; x.y = (uint16_t) W;   // padding and empty gaps: never in play
-						if (key != ~0ull) {
-							const int u = (int) (key & 0xffff), i = (int) ((key >> 16) & 0xffff);
-							const int b = tbase[i] + fa[i];
-							long long a, e;
-							if (u < Tp) { const int m = u - cbase[i]; a = ss[b + m]; e = se[b + m]; }
-							else {
-								const int m = u - Tp - cbase[i] - i;
-								a = m == 0 ? ra : (long long) se[b + m - 1];
-								e = m == count_of(i) ? rbnd : (long long) ss[b + m];
-							}
-							x.x = (uint16_t) (min(max(a, ra), rbnd) - w0);       // began before the range: in play from its start
-							x.y = (uint16_t) (min(max(e, ra), rbnd) - w0);
-							myv[q] = key_f32((uint32_t) (key >> 32));
-						}
-						rse[rk] = x;
+					for (int q = 0; q < KPT; q++) {
+						myk[q] = ~0ull;
+						if (q < kpt) myk[q] = k64[sort_phys(tid * kpt + q)];
+						if (myk[q] != ~0ull) { const int u = (int) (myk[q] & 0xffff); mine += u < Tp ? 1 : gcount[(myk[q] >> 16) & 0xffff]; }
 					}
-					__syncthreads();                                  // every key has been read: the values go over them
+					int fr, R;
+					block_scan1(misc, mine, fr, R);                   // (ends with every key in registers: the values may go over them)
+					__syncthreads();
 #pragma unroll
-					for (int q = 0; q < SEL_PS / THREADS; q++) { const int rk = tid + q * THREADS; if (rk < Pb) val[rk] = myv[q]; }
+					for (int q = 0; q < KPT; q++) {
+						if (myk[q] == ~0ull) continue;
+						const int u = (int) (myk[q] & 0xffff), i = (int) ((myk[q] >> 16) & 0xffff);
+						const float v = key_f32((uint32_t) (myk[q] >> 32));
+						const int b = tbase[i] + fa[i];
+						if (u < Tp) {
+							const int m = u - cbase[i];
+							ushort2 x;
+							x.x = (uint16_t) (min(max((long long) ss[b + m], ra), rbnd) - w0);   // began before the range: in play from its start
+							x.y = (uint16_t) (min(max((long long) se[b + m], ra), rbnd) - w0);
+							rse[fr] = x; val[fr] = v; fr++;
+						} else { const int g = gcount[i]; gcount[i] = fr; fr += g; }   // a marker: its gaps' first rank, for the pass below
+					}
+					__syncthreads();
+					// the gaps of every track at the ranks of its marker: eight lanes per track
+					for (int i0 = 0; i0 < N; i0 += THREADS / 8) {
+						const int i = i0 + gid;
+						const bool on = i < N;
+						const int len = on ? count_of(i) : -1, b = on ? tbase[i] + fa[i] : 0;
+						int at = on ? gcount[i] : 0;
+						const float v = on ? dfl[i] : 0.f;
+						const int mmax = __reduce_max_sync(FULL, len);
+						for (int m0 = 0; m0 <= mmax; m0 += 8) {
+							const int m = m0 + gl;
+							long long ga = 0, gb = 0;
+							if (m <= len) gap(b, len, m, ga, gb);
+							const unsigned grp = (__ballot_sync(FULL, ga < gb) >> (lane & 24)) & 0xffu;   // this track's lanes
+							if (ga < gb) {
+								const int k = at + __popc(grp & ((1u << gl) - 1));
+								ushort2 x; x.x = (uint16_t) (ga - w0); x.y = (uint16_t) (gb - w0);
+								rse[k] = x; val[k] = v;
+							}
+							at += __popc(grp);
+						}
+					}
+					const int bs = max(4, ((R + SEL_NB - 1) / SEL_NB + 3) & ~3);   // ranks per bucket, a multiple of four; R <= 4096: <= 128
+					const int Pr = bs * SEL_NB;
+					for (int rk = R + tid; rk < Pr; rk += THREADS) { ushort2 x; x.x = (uint16_t) W; x.y = (uint16_t) W; rse[rk] = x; }   // padding: never in play
+					__syncthreads();                                  // (the staging area is dead from here on if this is the last range)
+					WB_PHASE(9);
 					uint32_t *cntw = in_stage ? (uint32_t *) (rb + wl.off_stage) : (uint32_t *) (rb + wl.off_keys + (size_t) Pb * 4);
 					{
 						const uint4 z = make_uint4(0, 0, 0, 0);
@@ -1690,7 +1765,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 						for (int t = tid; t < max(1, ws * SEL_NB / 16); t += THREADS) c4[t] = z;
 					}
 					__syncthreads();
-					bucket_select(job, misc, w0, W, h0, ws, nbp, next_bp, bpos, bkid, out_base, val, rse, cntw, Pb, auc, slow);
+					bucket_select(job, misc, w0, W, h0, ws, nbp, next_bp, bpos, bkid, out_base, val, rse, cntw, bs, auc, slow WB_DIAG_ARG);
 					__syncthreads();
 					WB_PHASE(13);
 					h0 += ws;
@@ -1728,9 +1803,9 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 			}
 			IvAccess iv; iv.job = &job; iv.cur = cur; iv.tbase = staged ? tbase : nullptr; iv.ss = ss; iv.se = se; iv.sv = sv;
 			// each warp sweeps a contiguous share of the window's breakpoints
-			const int chunk = (nbp + WARPS - 1) / WARPS;
+			const int chunk = (nbp + wl.warps - 1) / wl.warps;
 			const int r0 = warp * chunk, r1 = min(nbp, r0 + chunk);
-			if (r0 < r1 && !bucketed) {
+			if (r0 < r1 && !bucketed && warp < wl.warps) {
 				if (bitset) {
 					uint32_t *bits = (uint32_t *) (rb + wl.off_bits) + (size_t) warp * (wl.P2 / 32);
 					bitset_walk(job, cur, nxt, w0, r0, r1, nbp, next_bp, bpos, bkid, out_base, keys, rank_of, bits, Ps / 32, T,
@@ -1831,7 +1906,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	}
 	if (lane == 0) {
 		if (job.auc_partial) job.auc_partial[(size_t) w * WARPS + warp] = auc;
-		if ((MODE == MODE_ROW || MODE == MODE_WALK) && slow && job.slow_count) atomicAdd(job.slow_count, slow);
+		if ((MODE == MODE_ROW || MODE == MODE_WALK || MODE == MODE_SELECT) && slow && job.slow_count) atomicAdd(job.slow_count, slow);
 	}
 	if (MODE == MODE_ROW && job.op == OP_PEARSON) {
 		__syncthreads();
@@ -1905,7 +1980,7 @@ __global__ void __launch_bounds__(256) cursor_kernel(const Job job) {
 }
 
 template <int MODE, int VLOG, int LIMBS>
-__global__ void __launch_bounds__(THREADS, MODE == MODE_FAST ? (THREADS == 512 ? 2 : WB_FAST_MINB) : MODE == MODE_MOMENTS ? 2 : MODE == MODE_WALK ? 3 : 1) emit_kernel(const Job job, int lw, double inv_scale, double lim, double scale, int rowbuf) {
+__global__ void __launch_bounds__(THREADS, MODE == MODE_FAST ? (THREADS == 512 ? 2 : WB_FAST_MINB) : MODE == MODE_MOMENTS ? 2 : MODE == MODE_WALK ? 3 : MODE == MODE_SELECT ? 2 : 1) emit_kernel(const Job job, int lw, double inv_scale, double lim, double scale, int rowbuf) {
 	extern __shared__ __align__(16) unsigned char smem[];
 	const Layout L = make_layout(job.wlog, job.N, true, (MODE == MODE_MOMENTS ? 2 : 1) * LIMBS, rowbuf);
 	int32_t *cur = (int32_t *) (smem + L.off_cur);
@@ -2074,7 +2149,8 @@ cudaError_t launch_emit(const Job &job, cudaStream_t s, int *auc_per_window) {
 	}
 	int rowbuf = row_buffer_bytes(job.N, job.op);
 	const bool walk = (job.op == OP_MEDIAN || job.op == OP_MIN || job.op == OP_MAX) && job.N <= WALK_MAX_TRACKS;
-#define WB_EMIT(V) (walk ? launch_emit_v<MODE_WALK, V, 2>(job, lw, inv_scale, lim, scale, rowbuf, s) \
+#define WB_EMIT(V) (walk ? (job.N > WB_SEL_MIN_N ? launch_emit_v<MODE_SELECT, V, 2>(job, lw, inv_scale, lim, scale, rowbuf, s) \
+                                               : launch_emit_v<MODE_WALK, V, 2>(job, lw, inv_scale, lim, scale, rowbuf, s)) \
                   : !job.fast ? launch_emit_v<MODE_ROW, V, 2>(job, lw, inv_scale, lim, scale, rowbuf, s) \
                   : job.fast == 2 ? (limbs == 2 ? launch_emit_v<MODE_MOMENTS, V, 2>(job, lw, inv_scale, lim, scale, rowbuf, s) \
                                                : launch_emit_v<MODE_MOMENTS, V, 3>(job, lw, inv_scale, lim, scale, rowbuf, s)) \
