@@ -13,6 +13,12 @@ WB200_BENCH_EXTRAS=0 WB200_BENCH_SCALE=0.25 ncu --metrics gpu__time_duration.sum
 # 3. full capture of the two kernels of the path (one launch each, quarter-scale chromosome)
 WB200_BENCH_EXTRAS=0 WB200_BENCH_SCALE=0.25 ncu --set full --clock-control none --import-source on -k regex:'fastsum_kernel|cursor_kernel' -s 60 -c 2 \
   -o gpurun_out/${tag}_prof python bench.py --no-e2e --no-cpu --steps 1 --warmup 1 > /dev/null 2>&1
+# 3b. the same for the other two kernels a bench line reports on: the selection kernel (median over 256 tracks) and the
+#     moments variant of the sweep kernel (var over 512 tracks)
+WB200_BENCH_TRACKS=256 WB200_BENCH_OP=median WB200_BENCH_SCALE=0.25 ncu --set full --clock-control none --import-source on -k regex:'emit_kernel' -s 30 -c 1 \
+  -o gpurun_out/${tag}_prof_median256 python bench.py --no-e2e --no-cpu --steps 1 --warmup 1 > /dev/null 2>&1
+WB200_BENCH_TRACKS=512 WB200_BENCH_OP=var WB200_BENCH_SCALE=0.25 ncu --set full --clock-control none --import-source on -k regex:'fastsum_kernel' -s 30 -c 1 \
+  -o gpurun_out/${tag}_prof_var512 python bench.py --no-e2e --no-cpu --steps 1 --warmup 1 > /dev/null 2>&1
 # 4. BigWig files -> text, end to end: the reference's own pthread pipeline beside the drop-in CLI
 : > gpurun_out/${tag}_bw_e2e.jsonl
 python profiles/bw_e2e_bench.py 8 20 >> gpurun_out/${tag}_bw_e2e.jsonl 2>gpurun_out/${tag}_bw_e2e.err

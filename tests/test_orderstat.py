@@ -1,4 +1,4 @@
-"""min / max / median over more than 128 tracks: the window-sorting sweeps of emit_kernel<MODE_SELECT>
+"""min / max / median over more than 32 tracks: the window-sorting sweeps of emit_kernel<MODE_SELECT>
 (csrc/engine.cu).  Reference: MedianReductionPop / MinReductionPop / MaxReductionPop,
 /root/reference/src/reducers.c:131-257 (qsort of the N current values, upper median, track 0's
 default read as 0 by min / max).
@@ -35,7 +35,7 @@ def check(engine, port, tr, ops, what, defaults=None):
         assert_segments(got, want.chrom, want.start, want.end, want.value, exact=True, what="%s/%s" % (op, what))
 
 
-@pytest.mark.parametrize("n", [129, 200, 256, 300, 512])
+@pytest.mark.parametrize("n", [33, 64, 129, 200, 256, 300, 512])
 def test_float32_values(engine, port, n):
     """Signed, fractional float32 values: the bucketed selection."""
     tr = make_tracks(n, [6_000, 2_500], seed=31 + n)
@@ -63,7 +63,7 @@ def test_heavy_ties_and_abutting_intervals(engine, port):
     check(engine, port, tr, ("median", "max"), "ties")
 
 
-@pytest.mark.parametrize("n", [160, 300])
+@pytest.mark.parametrize("n", [48, 160, 300])
 def test_double_values_take_the_serial_sweep(engine, port, n):
     """Values with more mantissa than a float32: same answers from the rank-bitset sweep (above 256 tracks
     half the warps run it)."""
@@ -94,7 +94,7 @@ def test_mixed_windows_nan_and_negative_zero(engine, port):
     check(engine, port, tr, ("median", "min", "max"), "mixed")
 
 
-@pytest.mark.parametrize("n", [160, 300])
+@pytest.mark.parametrize("n", [48, 160, 300])
 def test_dense_window_falls_back(engine, port, n):
     """More intervals per window than the staging area holds (1-bp intervals on every track):
     the per-warp sorted arrays take over; results unchanged."""
