@@ -803,7 +803,9 @@ __device__ void bitset_walk(const Job &job, const int32_t *cur, const int32_t *n
 // k-th element in play among the bucket's ranks, in rank order.  Ties order by track index, as in
 // the reference's stable sort (src/reducers.c:140-207: qsort of the N current values).
 constexpr int SEL_NB = 32;                                   // buckets (8 words per position)
-__device__ __forceinline__ int sel_word(int p, int c) { return p * (SEL_NB / 4) + (c ^ (((p >> 2) & 1) << 2)); }   // word c of position p
+// word c of position p.  The prefix pass walks runs of 2^lsh positions, four runs per warp: the rows of positions
+// one run apart are rotated into different bank groups (lsh >= 2).
+__device__ __forceinline__ int sel_word(int p, int c, int lsh) { return (p ^ ((p >> lsh) & 3)) * (SEL_NB / 4) + (c ^ (((p >> 2) & 1) << 2)); }
 
 // float32 bits <-> unsigned keys in the same order
 __device__ __forceinline__ uint32_t f32_key(float f) { const uint32_t b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
@@ -815,7 +817,8 @@ __device__ __forceinline__ bool f32_exact(double v) { return (double) (float) v 
 // to LE levels of the network on them between two trips to shared memory: the keys whose
 // indices differ in bits b0 .. b0+LE-1 only.  Index -> address is xor-swizzled so that every
 // such gather is spread over the banks.
-__device__ __forceinline__ int sort_phys(int idx) { return idx ^ ((idx >> 4) & 15); }
+// (le = log2 of the keys per thread the array is sorted with: conflict-free gathers for every trip, checked by enumeration)
+__device__ __forceinline__ int sort_phys(int idx, int le) { return idx ^ ((idx >> le) & 15); }
 // compare-exchange on the high words (the value): which of two equal values comes first is immaterial
 template <bool UP>
 __device__ __forceinline__ void sort_ce(unsigned long long &a, unsigned long long &b) {
@@ -843,7 +846,7 @@ __device__ void bitonic_u64(unsigned long long *keys, int Ps) {
 		unsigned long long r[E];
 		const int base = vt << LE;
 #pragma unroll
-		for (int m = 0; m < E; m++) r[m] = keys[sort_phys(base | m)];
+		for (int m = 0; m < E; m++) r[m] = keys[sort_phys(base | m, LE)];
 #pragma unroll
 		for (int k = 2; k <= E; k <<= 1)
 #pragma unroll
@@ -856,7 +859,7 @@ __device__ void bitonic_u64(unsigned long long *keys, int Ps) {
 						else if ((base & E) == 0) sort_ce<true>(r[m], r[m | j]); else sort_ce<false>(r[m], r[m | j]);
 					}
 #pragma unroll
-		for (int m = 0; m < E; m++) keys[sort_phys(base | m)] = r[m];
+		for (int m = 0; m < E; m++) keys[sort_phys(base | m, LE)] = r[m];
 	}
 	__syncthreads();
 	for (int lk = LE + 1; (1 << lk) <= Ps; lk++) {
@@ -868,10 +871,10 @@ __device__ void bitonic_u64(unsigned long long *keys, int Ps) {
 				const int base = ((vt >> b0) << (b0 + LE)) | (vt & ((1 << b0) - 1));
 				const bool up = (base & (1 << lk)) == 0;          // bit lk lies above the levels of this trip
 #pragma unroll
-				for (int m = 0; m < E; m++) r[m] = keys[sort_phys(base | (m << b0))];
+				for (int m = 0; m < E; m++) r[m] = keys[sort_phys(base | (m << b0), LE)];
 				if (up) sort_levels<true, LE>(r, b0, b); else sort_levels<false, LE>(r, b0, b);
 #pragma unroll
-				for (int m = 0; m < E; m++) keys[sort_phys(base | (m << b0))] = r[m];
+				for (int m = 0; m < E; m++) keys[sort_phys(base | (m << b0), LE)] = r[m];
 			}
 			__syncthreads();
 			b = b0 - 1;
@@ -889,24 +892,26 @@ __device__ void bucket_select(const Job &job, Misc *misc, long long w0, int W, i
 	const int N = job.N, tid = threadIdx.x;
 	const int sel = job.op == OP_MIN ? 0 : job.op == OP_MAX ? N - 1 : N / 2;
 	const int Ps = bs * SEL_NB;                               // bs ranks per bucket (a multiple of four, <= 255)
+	constexpr int RUNS = THREADS / NBW;                       // prefix pass: runs of max(1, ws / RUNS) positions
+	int lsh = 2;
+	while ((RUNS << lsh) < ws) lsh++;
 	// events, one rank per thread and step
 	for (int rk = tid; rk < Ps; rk += THREADS) {
 		const ushort2 se = rse[rk];
 		if ((int) se.x >= W) continue;
 		const int b = rk / bs;
-		atomicAdd(&cntw[sel_word(se.x - h0, b >> 2)], 1u << ((b & 3) << 3));
-		if ((int) se.y < h0 + ws) atomicSub(&cntw[sel_word(se.y - h0, b >> 2)], 1u << ((b & 3) << 3));
+		atomicAdd(&cntw[sel_word(se.x - h0, b >> 2, lsh)], 1u << ((b & 3) << 3));
+		if ((int) se.y < h0 + ws) atomicSub(&cntw[sel_word(se.y - h0, b >> 2, lsh)], 1u << ((b & 3) << 3));
 	}
 	__syncthreads();
 	// prefix sums along the positions: NBW word columns x runs of positions
 	{
-		constexpr int RUNS = THREADS / NBW;
 		const int len = max(1, ws / RUNS), runs = ws / len;     // ws is a power of two
 		const int c = tid % NBW, run = tid / NBW, pa = run * len;
 		uint32_t tot = 0;
 		if (run < runs) {
 #pragma unroll 8
-			for (int p = pa; p < pa + len; p++) tot += cntw[sel_word(p, c)];
+			for (int p = pa; p < pa + len; p++) tot += cntw[sel_word(p, c, lsh)];
 		}
 		uint32_t *rt = (uint32_t *) ((unsigned char *) misc + MISC_SCRATCH);   // RUNS x NBW run totals
 		rt[run * NBW + c] = tot;
@@ -915,7 +920,7 @@ __device__ void bucket_select(const Job &job, Misc *misc, long long w0, int W, i
 			uint32_t acc = 0;
 			for (int k = 0; k < run; k++) acc += rt[k * NBW + c];
 #pragma unroll 8
-			for (int p = pa; p < pa + len; p++) { const int x = sel_word(p, c); acc += cntw[x]; cntw[x] = acc; }
+			for (int p = pa; p < pa + len; p++) { const int x = sel_word(p, c, lsh); acc += cntw[x]; cntw[x] = acc; }
 		}
 	}
 	__syncthreads();
@@ -927,7 +932,7 @@ __device__ void bucket_select(const Job &job, Misc *misc, long long w0, int W, i
 		if (!(kd & BK_KEEP) || p < h0 || p >= h0 + ws) continue;
 		int k = sel, bucket = SEL_NB - 1;
 		{
-			const uint4 a = *(const uint4 *) (cntw + sel_word(p - h0, 0)), b = *(const uint4 *) (cntw + sel_word(p - h0, 4));
+			const uint4 a = *(const uint4 *) (cntw + sel_word(p - h0, 0, lsh)), b = *(const uint4 *) (cntw + sel_word(p - h0, 4, lsh));
 			const uint32_t wds[NBW] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 			bool found = false;
 #pragma unroll
@@ -1566,7 +1571,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 			if (!(kd & BK_SLOW) && !isnan(v)) auc += (double) (be - bs) * v;
 		}
 	} else if (MODE == MODE_WALK || MODE == MODE_SELECT) {
-		{
+		if (kept_total > 0) {                                 // (a window without a kept segment has nothing to select)
 			const WalkLayout wl = walk_layout(N);
 			unsigned char *rb = smem + L.off_rows;
 			TrackState *tstate = (TrackState *) (rb + wl.off_tstate) + (size_t) warp * N;
@@ -1596,16 +1601,21 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 			bool inexact = false;                             // a value that is not a float32 (NaN, -0 included)
 			float *dfl = (float *) (rb + wl.off_bits) + 2 * N;    // bucketed selection: the tracks' defaults as float32
 			if (staged) {
-				// one staged slot per thread and step, four steps in flight: the track of a slot is the last one
-				// whose base is not beyond it
+				// one staged slot per thread and step, four steps in flight; the track of every slot is written
+				// down first (over the key area, free until the keys are built)
+				uint16_t *owner = (uint16_t *) (rb + wl.off_keys);
+				for (int i = tid; i < N; i += THREADS) {
+					const int b = tbase[i], len = max(0, min(nxt[i], tn[i] - 1) - cur[i] + 1);
+					for (int m = 0; m < len; m++) owner[b + m] = (uint16_t) i;
+				}
+				__syncthreads();
 				for (int u0 = 0; u0 < T; u0 += 4 * THREADS) {
 					long long g[4]; bool ok[4];
 #pragma unroll
 					for (int q = 0; q < 4; q++) {
 						const int u = u0 + q * THREADS + tid;
 						ok[q] = u < T;
-						int lo = 0, hi = N - 1;
-						while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (tbase[mid] <= u) lo = mid; else hi = mid - 1; }
+						const int lo = ok[q] ? owner[u] : 0;
 						g[q] = ok[q] ? toff[lo] + cur[lo] + (u - tbase[lo]) : 0;
 					}
 					int s4[4], e4[4]; double v4[4];
@@ -1675,6 +1685,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 						if (fits || ws == 1) break;
 						ws >>= 1;
 					}
+					const int le = Pm >= 4096 ? 4 : 3;                // keys per thread of the sort: 16 or 8
 					const long long ra = w0 + h0, rbnd = ra + ws;
 					auto count_of = [&](int i) -> int { return (i + 1 < N ? cbase[i + 1] : Tp) - cbase[i]; };
 					// gap m of track i (m = 0 .. count): from the end of interval m - 1 (the range start) to the start of
@@ -1690,19 +1701,19 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 						for (int m = gl; m <= len; m += 8) {
 							if (m < len) {
 								const int u = cb + m;
-								k64[sort_phys(u)] = ((unsigned long long) f32_key((float) sv[b + m]) << 32) | ((unsigned long long) i << 16) | (unsigned) u;
+								k64[sort_phys(u, le)] = ((unsigned long long) f32_key((float) sv[b + m]) << 32) | ((unsigned long long) i << 16) | (unsigned) u;
 							}
 							long long ga, gb;
 							gap(b, len, m, ga, gb);
 							ng += ga < gb ? 1 : 0;
 						}
 						if (ng) atomicAdd(&gcount[i], ng);              // non-empty gaps of the track
-						if (gl == 0) k64[sort_phys(Tp + i)] = ((unsigned long long) f32_key(dfl[i]) << 32) | ((unsigned long long) i << 16) | (unsigned) (Tp + i);
+						if (gl == 0) k64[sort_phys(Tp + i, le)] = ((unsigned long long) f32_key(dfl[i]) << 32) | ((unsigned long long) i << 16) | (unsigned) (Tp + i);
 					}
-					for (int u = Tp + N + tid; u < Pm; u += THREADS) k64[sort_phys(u)] = ~0ull;
+					for (int u = Tp + N + tid; u < Pm; u += THREADS) k64[sort_phys(u, le)] = ~0ull;
 					__syncthreads();
 					WB_PHASE(15);
-					if (Pm >= 4096) bitonic_u64<4>(k64, Pm); else bitonic_u64<3>(k64, Pm);
+					if (le == 4) bitonic_u64<4>(k64, Pm); else bitonic_u64<3>(k64, Pm);
 					WB_PHASE(12);
 					// ranks: an interval takes one, a marker one per non-empty gap of its track.  Every thread takes
 					// Pm / THREADS consecutive sorted keys, a block scan of the multiplicities gives their first rank.
@@ -1713,7 +1724,7 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 #pragma unroll
 					for (int q = 0; q < KPT; q++) {
 						myk[q] = ~0ull;
-						if (q < kpt) myk[q] = k64[sort_phys(tid * kpt + q)];
+						if (q < kpt) myk[q] = k64[sort_phys(tid * kpt + q, le)];
 						if (myk[q] != ~0ull) { const int u = (int) (myk[q] & 0xffff); mine += u < Tp ? 1 : gcount[(myk[q] >> 16) & 0xffff]; }
 					}
 					int fr, R;
