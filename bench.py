@@ -116,7 +116,7 @@ def gen_chrom_device(torch, dev, n_tracks, length, seed, n_f32=0):
 
 
 class ClockSampler(threading.Thread):
-    """SM clock and throttle reasons during the timed region (NVML, every few ms;
+    """SM clock and throttle reasons during the timed region (NVML, every 20 ms;
     falls back to polling nvidia-smi)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -150,7 +150,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([str(sm), str(self.max_sm)] + ["Active" if r & b else "Not Active" for _, b in bits])
                 except Exception:
                     pass
-                time.sleep(0.004)
+                time.sleep(0.02)     # NVML queries share driver locks with the launching thread: keep them sparse
             return
         while not self.stop_flag:
             try:

@@ -73,6 +73,16 @@ constexpr int TH = 128, NWARP = TH / 32;
 #ifndef WB_FS_EMIT2
 #define WB_FS_EMIT2 1                 // emit: two groups of 32 dense entries per warp and step
 #endif
+#ifndef WB_FS_MERGE
+#define WB_FS_MERGE 0                 // events: an interval that abuts its predecessor shares its atomics with that one's end.
+                                      // Measured (profiles/r02_kexp8_*): a quarter fewer shared atomics on the generator, and SLOWER --
+                                      // N=64 +8.6 %, N=512 +19 %, var N=512 +20 % kernel time: the held-back end event serialises the
+                                      // four intervals of a quad.  Off; kept for gap-free inputs where half of all events would merge.
+#endif
+#if defined(WB_DIAG_NO_COV_ATOM) || defined(WB_DIAG_NO_LIMB_ATOM)
+#undef WB_FS_MERGE
+#define WB_FS_MERGE 0
+#endif
 #ifndef WB_FS_EVPIPE
 #define WB_FS_EVPIPE 0                // events: software-pipelined interval loads (two chunks in registers)
 #endif
@@ -170,6 +180,13 @@ __device__ __forceinline__ void cov_add(uint32_t *cov, int p, bool is_end) {
 	else atomicAdd(&cov[phys32<VLOG>(p)], is_end ? (1u << END_SHIFT) : 1u);
 }
 
+// an end inside the window and an abutting start: one atomic for both counts
+template <int VLOG, bool COV16>
+__device__ __forceinline__ void cov_add_both(uint32_t *cov, int p) {
+	if (COV16) atomicAdd(&cov[phys16<VLOG>(p) >> 1], 0x101u << ((p & 1) << 4));
+	else atomicAdd(&cov[phys32<VLOG>(p)], (1u << END_SHIFT) | 1u);
+}
+
 struct Chunk {
 	int4 s, e;
 	double v0, v1, v2, v3;
@@ -233,6 +250,24 @@ __device__ __forceinline__ void events(const Job &job, unsigned char *smem, cons
 		const int k = atomicAdd(&misc->npois, 1);
 		if (k < POIS_CAP) { PoisEv p; p.pos = (uint16_t) x; p.delta = (int16_t) delta; misc->pois[k] = p; }
 	};
+	// The end event of an interval is held back until the next interval of the quad is seen: where the two abut
+	// (binned coverage, bedGraph runs) the position gets ONE cover atomic (an end and a start) and ONE value atomic
+	// (the difference of the two deltas; none at all when the values are equal) instead of two of each.
+	bool pend = false;
+	int pend_x = 0;
+	acc_t pend_d = 0;
+	long long pend_d2 = 0;
+	auto flush_end = [&]() {
+		if (!pend) return;
+		pend = false;
+		cov_add<VLOG, COV16>(cov, pend_x, true);
+#ifndef WB_DIAG_NO_LIMB_ATOM
+		if (pend_d != 0) {
+			add_limbs_fs<LIMBS, W>(limb, phys32<VLOG>(pend_x), -pend_d, lw);
+			if (MOM) add_limbs_fs<2, W>(limb + W, phys32<VLOG>(pend_x), -pend_d2, lw);
+		}
+#endif
+	};
 	auto one = [&](bool valid, int s, int e, double val, long long md) {
 		if (!valid) return;
 		const int xs = s - w0i;
@@ -255,24 +290,34 @@ __device__ __forceinline__ void events(const Job &job, unsigned char *smem, cons
 			if (!bad) d = (acc_t) (m - md);
 		}
 		const long long d2 = MOM ? (long long) d * (long long) d : 0;        // moments: all defaults are 0, d is the value
+		bool merged = false;
+		if (WB_FS_MERGE && pend) {
+			if (start_in && xs == pend_x) {
+				pend = false;
+				merged = true;
+				cov_add_both<VLOG, COV16>(cov, xs);
+				const acc_t dd = d - pend_d;
+				if (dd != 0) {
+					add_limbs_fs<LIMBS, W>(limb, phys32<VLOG>(xs), dd, lw);
+					if (MOM && d2 != pend_d2) add_limbs_fs<2, W>(limb + W, phys32<VLOG>(xs), d2 - pend_d2, lw);
+				}
+			} else flush_end();
+		}
 		if (start_in) {
-			cov_add<VLOG, COV16>(cov, xs, false);
+			if (!merged) {
+				cov_add<VLOG, COV16>(cov, xs, false);
 #ifndef WB_DIAG_NO_LIMB_ATOM               // diagnostic builds only (profiles/): cost of the value atomics
-			if (d != 0) {
-				add_limbs_fs<LIMBS, W>(limb, phys32<VLOG>(xs), d, lw);
-				if (MOM) add_limbs_fs<2, W>(limb + W, phys32<VLOG>(xs), d2, lw);
-			}
+				if (d != 0) {
+					add_limbs_fs<LIMBS, W>(limb, phys32<VLOG>(xs), d, lw);
+					if (MOM) add_limbs_fs<2, W>(limb + W, phys32<VLOG>(xs), d2, lw);
+				}
 #endif
+			}
 			if (bad) poison((unsigned) xs, 1);
 		} else { in_cov++; in_val += d; in_val2 += d2; in_pois += bad ? 1 : 0; }           // began before the window
 		if (end_in) {
-			cov_add<VLOG, COV16>(cov, (int) xe, true);
-#ifndef WB_DIAG_NO_LIMB_ATOM
-			if (d != 0) {
-				add_limbs_fs<LIMBS, W>(limb, phys32<VLOG>((int) xe), -d, lw);
-				if (MOM) add_limbs_fs<2, W>(limb + W, phys32<VLOG>((int) xe), -d2, lw);
-			}
-#endif
+			pend = true; pend_x = (int) xe; pend_d = d; pend_d2 = d2;
+			if (!WB_FS_MERGE) flush_end();
 			if (bad) poison(xe, -1);
 		} else my_next = min(my_next, e);
 	};
@@ -304,6 +349,7 @@ __device__ __forceinline__ void events(const Job &job, unsigned char *smem, cons
 		one(c.lo <= 1 && 1 < c.hi, c.s.y, c.e.y, c.v1, md);
 		one(c.lo <= 2 && 2 < c.hi, c.s.z, c.e.z, c.v2, md);
 		one(c.lo <= 3 && 3 < c.hi, c.s.w, c.e.w, c.v3, md);
+		flush_end();
 	};
 #if WB_FS_EVPIPE
 	// two quads per thread and step: both sets of loads are in flight before the first is applied
