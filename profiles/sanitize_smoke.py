@@ -29,3 +29,18 @@ for bg in (False, True):
 # element-wise maps: in-place map, a log that drops records (compaction + rebuilt offsets), nested chains
 r = eng.reduce("mean", g, ["chr1", "chr2"], maps=[[("abs",), ("offset", 0.5), ("ln",)] if i % 2 else [("scale", -1.0), ("log", 2.0)] for i in range(len(g))])
 print("maps", len(r), float(np.nansum(r.value)))
+# round 2: the selection kernel (order statistics over more than 32 tracks: bucketed path, ranges of a window, the
+# bitset and sorted-array fallbacks) and the moments variant of the sweep kernel
+for n, kw, what in ((48, dict(), "f32"), (200, dict(), "f32"), (300, dict(max_len=6, max_gap=4), "dense ranges"), (160, dict(max_len=1, max_gap=1), "staging overflow")):
+    trn = make_tracks(n, [5000], seed=7, vmax=64, **kw)
+    gn = [api.Track(t["chrom"], t["start"], t["end"], t["value"]) for t in trn]
+    for op in ("median", "max"):
+        r = eng.reduce(op, gn, ["chr1"]); print(op, n, what, len(r), float(np.nansum(r.value)))
+trn = make_tracks(160, [5000], seed=8)
+gn = [api.Track(t["chrom"], t["start"], t["end"], t["value"] + 1e-9) for t in trn]
+r = eng.reduce("median", gn, ["chr1"]); print("median 160 doubles (bitset sweep)", len(r), float(np.nansum(r.value)))
+for n in (48, 300):
+    trn = make_tracks(n, [40000], seed=9, vmax=4096)
+    gn = [api.Track(t["chrom"], t["start"], t["end"], t["value"]) for t in trn]
+    for op in ("var", "stddev", "cv"):
+        r = eng.reduce(op, gn, ["chr1"]); print(op, n, len(r), float(np.nansum(r.value)), "sweep kernel" if eng.last_stats[-1]["sweep_kernel"] else "emit kernel")
