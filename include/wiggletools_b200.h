@@ -359,6 +359,9 @@ double wb200_tdist_Q(double t, double nu);
 
 /* Diagnostic: the same function as the DEVICE evaluates it (one thread per pair): out[i] = Q(t[i], nu[i]). */
 int wb200_debug_tdist_device(wb200_ctx *ctx, int n, const double *t, const double *nu, double *out);
+/* Development: dynamic shared memory (bytes) one CTA of emit_kernel requests for `op` over n_tracks with
+ * window_bp-wide windows (csrc/engine.cu: make_layout + walk_layout).  Host arithmetic only. */
+long long wb200_debug_window_smem_bytes(int op, int n_tracks, int window_bp);
 
 /* Diagnostic: the device formatter's "%lf" compiled for the host (same source function as the
  * kernel's): writes the text of v into out32 (>= 32 bytes), returns its length, -1 for |v| >= 2^63. */

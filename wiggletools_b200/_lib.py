@@ -115,6 +115,8 @@ def load():
     lib.wb200_apply_host.argtypes = lib.wb200_apply_device.argtypes
     lib.wb200_apply_last.argtypes = [C.c_void_p, C.c_double, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     lib.wb200_debug_tdist_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.wb200_debug_window_smem_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.wb200_debug_window_smem_bytes.restype = C.c_longlong
     lib.wb200_multi_create.restype = C.c_void_p
     lib.wb200_multi_create.argtypes = [C.c_int, C.c_void_p]
     lib.wb200_multi_destroy.argtypes = [C.c_void_p]
@@ -138,7 +140,7 @@ EXPORTS = [
     "wb200_tdist_Q", "wb200_bw_open", "wb200_bw_close", "wb200_bw_last_error", "wb200_bw_nchrom", "wb200_bw_chrom_name",
     "wb200_bw_chrom_length", "wb200_bw_set_stretch", "wb200_bw_decode_chrom", "wb200_debug_phases", "wb200_debug_format_value",
     "wb200_format_device", "wb200_format_host", "wb200_reduce_format_host", "wb200_set_input_maps", "wb200_map_default",
-    "wb200_apply_device", "wb200_apply_host", "wb200_apply_last", "wb200_debug_tdist_device",
+    "wb200_apply_device", "wb200_apply_host", "wb200_apply_last", "wb200_debug_tdist_device", "wb200_debug_window_smem_bytes",
     "wb200_multi_create", "wb200_multi_destroy", "wb200_multi_last_error", "wb200_multi_ndev", "wb200_multi_owner",
     "wb200_multi_reduce_host", "wb200_multi_pearson_host",
 ]

@@ -702,6 +702,15 @@ double wb200_map_default(int op, double arg, double default_value) {
 // The Student-t upper tail as the DEVICE evaluates it inside the t-test kernel (same source function
 // as wb200_tdist_Q, compiled for sm_100a): out[i] = Q(t[i], nu[i]).  For tests that pin the device
 // arithmetic on a high-precision table (the reference calls gsl_cdf_tdist_Q, setComparisons.c:117).
+// Shared memory one CTA of the window kernel asks for (statistics outside the sum / mean / moments sweep kernel):
+// host arithmetic only, no device needed -- the CPU tests hold the budgets of DESIGN 3b against it.
+long long wb200_debug_window_smem_bytes(int op, int n_tracks, int window_bp) {
+	if (n_tracks < 1 || window_bp < 1) return WB200_EINVAL;
+	const bool moment_like = (op == OP_VAR || op == OP_STDDEV || op == OP_ENTROPY || op == OP_CV);
+	const int arrays = moment_like ? 6 : (op == OP_SUM || op == OP_MEAN) ? 3 : 2;
+	return (long long) window_smem_bytes(ceil_log2(window_bp), n_tracks, true, op, arrays);
+}
+
 int wb200_debug_tdist_device(wb200_ctx *ctx, int n, const double *t, const double *nu, double *out) {
 	if (!ctx || n < 0 || (n > 0 && (!t || !nu || !out))) return WB200_EINVAL;
 	if (n == 0) return WB200_OK;
