@@ -1931,6 +1931,10 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	}
 }
 
+#ifndef WB_CURSOR_GROUPS
+#define WB_CURSOR_GROUPS 2
+#endif
+constexpr int CURSOR_GROUPS = WB_CURSOR_GROUPS;     // groups of four intervals per thread of the cursor kernel
 // cursor kernel: cursor[w][i] = first interval of track i whose end reaches the
 // start of window w.  One thread per interval: interval j is that cursor for every
 // window whose start lies in (end[j-1], end[j]] -- usually none or one.  Reads the
@@ -1939,55 +1943,65 @@ __global__ void __launch_bounds__(256) cursor_kernel(const Job job) {
 	const int i = blockIdx.y;
 	const long long o = job.off[i];
 	const int n = (int) (job.off[i + 1] - o);
-	// four consecutive intervals per thread on a 16-byte aligned grid: one 128-bit load per array; j0 is the
-	// track-relative index of the first of them (negative in the track's first, partial group)
-	const int j0 = 4 * (int) (blockIdx.x * blockDim.x + threadIdx.x) - (int) (o & 3);
 	const int32_t *end = job.end + o, *start = job.start + o;
 	// cnt(e) = number of windows that start at or before e (capped at the table's row count); interval j is
 	// the cursor of the windows cnt(end[j-1]) .. cnt(end[j]) - 1, and j = n (one past the last) closes the table
 	const int p0 = (int) job.p0, wlog = job.wlog, rows = job.nw + 1;
 	auto cnt = [&](int e) -> int { return e < p0 ? 0 : (int) min((((unsigned) e - (unsigned) p0) >> wlog) + 1u, (unsigned) rows); };
-	int ev[4] = {0, 0, 0, 0}, sv[4] = {0, 0, 0, 0};
-	const bool live = j0 <= n;
-	if (live) {
-		if (job.vec && j0 >= 0 && j0 + 4 <= n) {
-			const int4 v = *(const int4 *) (end + j0), u = *(const int4 *) (start + j0);
-			ev[0] = v.x; ev[1] = v.y; ev[2] = v.z; ev[3] = v.w;
-			sv[0] = u.x; sv[1] = u.y; sv[2] = u.z; sv[3] = u.w;
-		} else {
+	// Four consecutive intervals per group on a 16-byte aligned grid: one 128-bit load per array; a thread takes
+	// CURSOR_GROUPS groups one block width apart and has the loads of all of them in flight before it looks at
+	// any (the kernel is a latency chain of one load pair per thread otherwise: 35 % of the DRAM bandwidth).
+	int ev[CURSOR_GROUPS][4], sv[CURSOR_GROUPS][4], j0[CURSOR_GROUPS];
 #pragma unroll
-			for (int k = 0; k < 4; k++) if (j0 + k >= 0 && j0 + k < n) { ev[k] = end[j0 + k]; sv[k] = start[j0 + k]; }
-		}
-	}
-	// the end before this thread's group sits in the previous lane; only lane 0 loads it
-	int e_prev = __shfl_up_sync(FULL, ev[3], 1);
-	if (!live) return;
-	if ((threadIdx.x & 31) == 0 && j0 > 0) e_prev = end[j0 - 1];
-	int c_prev = j0 > 0 ? cnt(e_prev) : 0;
-	int32_t *col = job.cursor + i;
-	const size_t stride = (size_t) job.cstride;
-	// input contract (include/wiggletools_b200.h): within a track start < end and end[j-1] <= start[j]
-	// (sorted, disjoint), all inside [p0, pos_hi] -- what NonOverlappingWiggleIterator guarantees the
-	// reference's sweep (multiplexer.c:163).  Violations raise a flag the host turns into WB200_EINVAL.
-	int bad = 0, pe = j0 > 0 ? e_prev : INT_MIN;
+	for (int g = 0; g < CURSOR_GROUPS; g++) {
+		// j0: track-relative index of the group's first interval (negative in the track's first, partial group)
+		j0[g] = 4 * (int) ((blockIdx.x * CURSOR_GROUPS + g) * blockDim.x + threadIdx.x) - (int) (o & 3);
 #pragma unroll
-	for (int k = 0; k < 4; k++) {
-		const int j = j0 + k;
-		if (j >= 0 && j < n) {
-			if (sv[k] >= ev[k] || pe > sv[k]) bad |= 1;
-			if (sv[k] < p0 || ev[k] > job.pos_hi) bad |= 2;
-			pe = ev[k];
-			const int c = cnt(ev[k]);
-			if (c != c_prev) {                         // at most a few windows start inside one interval's reach
-#pragma unroll 1
-				for (int w = c_prev; w < c; w++) col[(size_t) w * stride] = j;
-				c_prev = c;
+		for (int k = 0; k < 4; k++) { ev[g][k] = 0; sv[g][k] = 0; }
+		if (j0[g] <= n) {
+			if (job.vec && j0[g] >= 0 && j0[g] + 4 <= n) {
+				const int4 v = *(const int4 *) (end + j0[g]), u = *(const int4 *) (start + j0[g]);
+				ev[g][0] = v.x; ev[g][1] = v.y; ev[g][2] = v.z; ev[g][3] = v.w;
+				sv[g][0] = u.x; sv[g][1] = u.y; sv[g][2] = u.z; sv[g][3] = u.w;
+			} else {
+#pragma unroll
+				for (int k = 0; k < 4; k++) if (j0[g] + k >= 0 && j0[g] + k < n) { ev[g][k] = end[j0[g] + k]; sv[g][k] = start[j0[g] + k]; }
 			}
 		}
 	}
-	if (n < j0 + 4) {                                  // this group holds index n: the closing rows
+	int32_t *col = job.cursor + i;
+	const size_t stride = (size_t) job.cstride;
+	int bad = 0;
+#pragma unroll
+	for (int g = 0; g < CURSOR_GROUPS; g++) {
+		// the end before this group sits in the previous lane; only lane 0 loads it
+		int e_prev = __shfl_up_sync(FULL, ev[g][3], 1);
+		if (j0[g] > n) continue;
+		if ((threadIdx.x & 31) == 0 && j0[g] > 0) e_prev = end[j0[g] - 1];
+		int c_prev = j0[g] > 0 ? cnt(e_prev) : 0;
+		// input contract (include/wiggletools_b200.h): within a track start < end and end[j-1] <= start[j]
+		// (sorted, disjoint), all inside [p0, pos_hi] -- what NonOverlappingWiggleIterator guarantees the
+		// reference's sweep (multiplexer.c:163).  Violations raise a flag the host turns into WB200_EINVAL.
+		int pe = j0[g] > 0 ? e_prev : INT_MIN;
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const int j = j0[g] + k;
+			if (j >= 0 && j < n) {
+				if (sv[g][k] >= ev[g][k] || pe > sv[g][k]) bad |= 1;
+				if (sv[g][k] < p0 || ev[g][k] > job.pos_hi) bad |= 2;
+				pe = ev[g][k];
+				const int c = cnt(ev[g][k]);
+				if (c != c_prev) {                     // at most a few windows start inside one interval's reach
 #pragma unroll 1
-		for (int w = c_prev; w < rows; w++) col[(size_t) w * stride] = n;
+					for (int w = c_prev; w < c; w++) col[(size_t) w * stride] = j;
+					c_prev = c;
+				}
+			}
+		}
+		if (n < j0[g] + 4) {                           // this group holds index n: the closing rows
+#pragma unroll 1
+			for (int w = c_prev; w < rows; w++) col[(size_t) w * stride] = n;
+		}
 	}
 	if (bad) atomicOr(job.flags, bad);
 }
@@ -2121,7 +2135,7 @@ size_t window_smem_bytes(int wlog, int N, bool emit, int op, int limb_arrays) {
 
 cudaError_t launch_cursor(const Job &job, int64_t max_track_len, cudaStream_t s) {
 	// max_track_len + 1 intervals (the closing one) + up to 3 slots of alignment, 4 per thread
-	dim3 grid((unsigned) (((max_track_len + 8) / 4 + 255) / 256), (unsigned) job.N);
+	dim3 grid((unsigned) (((max_track_len + 8) / 4 + 256 * CURSOR_GROUPS - 1) / (256 * CURSOR_GROUPS)), (unsigned) job.N);
 	cursor_kernel<<<grid, 256, 0, s>>>(job);
 	return cudaGetLastError();
 }
