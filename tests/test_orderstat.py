@@ -103,3 +103,20 @@ def test_dense_window_falls_back(engine, port, n):
     want = port.reduce("median", o, ["chr1"])
     got = engine.reduce("median", g, ["chr1"])
     assert_segments(got, want.chrom, want.start, want.end, want.value, exact=True, what="median/dense")
+
+
+def test_strict_and_empty_windows(engine, port):
+    """`strict` keeps only the segments every track covers (most windows then have nothing to select and are
+    skipped), and sparse tracks leave whole windows without a breakpoint."""
+    n = 48
+    tr = make_tracks(n, [20_000, 3_000], seed=15, vmax=32, max_len=900, max_gap=120)
+    o, g = both(tr)
+    for strict in (False, True):
+        want = port.reduce("median", o, NAMES, strict)
+        got = engine.reduce("median", g, NAMES, strict=strict)
+        assert_segments(got, want.chrom, want.start, want.end, want.value, exact=True, what="median/strict=%d" % strict)
+    sparse = make_tracks(40, [60_000], seed=16, vmax=8, max_len=30, max_gap=6000, gap_prob=0.9)
+    o, g = both(sparse)
+    want = port.reduce("max", o, ["chr1"])
+    got = engine.reduce("max", g, ["chr1"])
+    assert_segments(got, want.chrom, want.start, want.end, want.value, exact=True, what="max/sparse")

@@ -1271,8 +1271,101 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	__syncthreads();
 	WB_PHASE(0);
 
+	// MODE_WALK / MODE_SELECT: the window's intervals staged in shared memory -- start / end / value of interval j of
+	// track i at tbase[i] + j - cur[i] -- for the sweeps' chains of dependent reads.  One staged slot per thread and
+	// step, four steps in flight; the track of every slot is written down first (over the key area, free until
+	// the keys are built).  with_events: the cover events of the window are taken from the staged intervals on the
+	// way (MODE_SELECT: instead of the track-by-track walk below; needs nxt = cursor row w + 1).
+	int st_T = 0;
+	bool st_done = false, st_ok = false, st_inexact = false;
+	auto stage_window = [&](bool with_events) {
+		const WalkLayout wl = walk_layout(N);
+		unsigned char *rb = smem + L.off_rows;
+		double *sv = (double *) (rb + wl.off_stage);
+		int32_t *ss = (int32_t *) (sv + wl.cap), *se = ss + wl.cap;
+		int32_t *tbase = (int32_t *) (rb + wl.off_tbase);
+		int run = 0;
+		for (int base = 0; base < N; base += THREADS) {
+			const int i = base + tid;
+			const int len = i < N ? max(0, min(nxt[i], tn[i] - 1) - cur[i] + 1) : 0;
+			int ec, tc;
+			block_scan1(misc, len, ec, tc);
+			if (i < N) tbase[i] = run + ec;
+			run += tc;
+			__syncthreads();
+		}
+		st_T = run; st_done = true; st_ok = run <= wl.cap; st_inexact = false;
+		if (!st_ok) return;
+		const int T = run;
+		const bool minmax = (job.op == OP_MIN || job.op == OP_MAX);
+		uint16_t *owner = (uint16_t *) (rb + wl.off_keys);
+		for (int i = tid; i < N; i += THREADS) {
+			const int b = tbase[i], len = max(0, min(nxt[i], tn[i] - 1) - cur[i] + 1);
+			for (int m = 0; m < len; m++) owner[b + m] = (uint16_t) i;
+		}
+		__syncthreads();
+		int in_cov = 0, my_next = INT_MAX;
+		bool inexact = false;
+		for (int u0 = 0; u0 < T; u0 += 4 * THREADS) {
+			long long g[4]; bool ok[4]; int tr[4];
+#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				const int u = u0 + q * THREADS + tid;
+				ok[q] = u < T;
+				tr[q] = ok[q] ? owner[u] : 0;
+				g[q] = ok[q] ? toff[tr[q]] + cur[tr[q]] + (u - tbase[tr[q]]) : 0;
+			}
+			int s4[4], e4[4]; double v4[4];
+#pragma unroll
+			for (int q = 0; q < 4; q++) if (ok[q]) { s4[q] = job.start[g[q]]; e4[q] = job.end[g[q]]; v4[q] = job.value[g[q]]; }
+#pragma unroll
+			for (int q = 0; q < 4; q++) if (ok[q]) {
+				const int u = u0 + q * THREADS + tid;
+				ss[u] = s4[q]; se[u] = e4[q]; sv[u] = v4[q];
+				inexact |= !f32_exact(v4[q]);
+				if (with_events) {
+					// same rules as the walk below: a start inside the window, an end inside the window, the carried-in
+					// cover, and the first breakpoint beyond the window from the interval that leaves it
+					const long long sq = s4[q], eq = e4[q];
+					const int f = (tr[q] < job.n1) ? 1 : (1 << COV_B_SHIFT);
+					if (eq >= w1) my_next = min(my_next, sq < w1 ? e4[q] : s4[q]);
+					if (sq < w1) {
+						if (sq >= w0) { const int x = (int) (sq - w0); atomicAdd(&cov[phys<VLOG>(x)], f); ev[x] = 1; }
+						else in_cov += f;
+						if (eq < w1) { const int x = (int) (eq - w0); atomicAdd(&cov[phys<VLOG>(x)], -f); ev[x] = 1; }
+					}
+				}
+			}
+		}
+		if (MODE == MODE_SELECT) {
+			float *dfl = (float *) (rb + wl.off_bits) + 2 * N;    // bucketed selection: the tracks' defaults as float32
+			for (int i = tid; i < N; i += THREADS) {
+				const double d = (minmax && i == 0) ? 0.0 : job.dflt[i];     // reducers.c:142-145,209-212
+				inexact |= !f32_exact(d);
+				dfl[i] = (float) d;
+			}
+		}
+		st_inexact = inexact;
+		if (with_events) {
+			my_next = __reduce_min_sync(FULL, my_next);
+			in_cov = __reduce_add_sync(FULL, in_cov);
+			if (lane == 0) {
+				if (my_next != INT_MAX) atomicMin(&misc->next_bp, my_next);
+				if (in_cov) atomicAdd(&misc->base_cov, in_cov);
+			}
+		}
+	};
+
 	// ---- 1. events --------------------------------------------------------------
 	bool vec_done = false;
+	if constexpr (MODE == MODE_SELECT) {
+		// the track of window w leaves it at cursor[w + 1] (the first interval whose end reaches the next window's
+		// start): with that row every track's intervals are known without walking them
+		for (int i = tid; i < N; i += THREADS) nxt[i] = job.cursor[(size_t) (w + 1) * job.cstride + i];
+		__syncthreads();
+		stage_window(true);
+		vec_done = st_ok;                                     // more intervals than the staging area holds: the walk below
+	}
 	if constexpr (fast) {
 #ifdef WB_DIAG_SKIP_EVENTS                  // diagnostic builds only (profiles/): time the window skeleton alone
 		vec_done = true;
@@ -1580,60 +1673,17 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 			double *sv = (double *) (rb + wl.off_stage);
 			int32_t *ss = (int32_t *) (sv + wl.cap), *se = ss + wl.cap;
 			int32_t *tbase = (int32_t *) (rb + wl.off_tbase);
-			// stage the window's intervals: the sweep is a chain of dependent reads
-			int run = 0;
-			for (int base = 0; base < N; base += THREADS) {
-				const int i = base + tid;
-				const int len = i < N ? max(0, min(nxt[i], tn[i] - 1) - cur[i] + 1) : 0;
-				int ec, tc;
-				block_scan1(misc, len, ec, tc);
-				if (i < N) tbase[i] = run + ec;
-				run += tc;
-				__syncthreads();
-			}
-			const int T = run;
+			// the window's intervals, staged in shared memory (MODE_SELECT: already there since the events phase)
+			if (!st_done) stage_window(false);
+			const int T = st_T;
 			WB_PHASE(11);
-			const bool staged = T <= wl.cap;
+			const bool staged = st_ok;
 			const int U = T + N;                              // universe of the bitset sweep: intervals + one default per track
 			int Ps = 64; while (Ps < U) Ps <<= 1;
 			const bool minmax = (job.op == OP_MIN || job.op == OP_MAX);
 			const bool sorting = MODE == MODE_SELECT && staged;   // the window gets sorted (else: a sorted array per warp)
-			bool inexact = false;                             // a value that is not a float32 (NaN, -0 included)
+			const bool inexact = st_inexact;                  // a value that is not a float32 (NaN, -0 included)
 			float *dfl = (float *) (rb + wl.off_bits) + 2 * N;    // bucketed selection: the tracks' defaults as float32
-			if (staged) {
-				// one staged slot per thread and step, four steps in flight; the track of every slot is written
-				// down first (over the key area, free until the keys are built)
-				uint16_t *owner = (uint16_t *) (rb + wl.off_keys);
-				for (int i = tid; i < N; i += THREADS) {
-					const int b = tbase[i], len = max(0, min(nxt[i], tn[i] - 1) - cur[i] + 1);
-					for (int m = 0; m < len; m++) owner[b + m] = (uint16_t) i;
-				}
-				__syncthreads();
-				for (int u0 = 0; u0 < T; u0 += 4 * THREADS) {
-					long long g[4]; bool ok[4];
-#pragma unroll
-					for (int q = 0; q < 4; q++) {
-						const int u = u0 + q * THREADS + tid;
-						ok[q] = u < T;
-						const int lo = ok[q] ? owner[u] : 0;
-						g[q] = ok[q] ? toff[lo] + cur[lo] + (u - tbase[lo]) : 0;
-					}
-					int s4[4], e4[4]; double v4[4];
-#pragma unroll
-					for (int q = 0; q < 4; q++) if (ok[q]) { s4[q] = job.start[g[q]]; e4[q] = job.end[g[q]]; v4[q] = job.value[g[q]]; }
-#pragma unroll
-					for (int q = 0; q < 4; q++) if (ok[q]) {
-						const int u = u0 + q * THREADS + tid;
-						ss[u] = s4[q]; se[u] = e4[q]; sv[u] = v4[q];
-						inexact |= !f32_exact(v4[q]);
-					}
-				}
-				for (int i = tid; i < N; i += THREADS) {
-					const double d = (minmax && i == 0) ? 0.0 : job.dflt[i];     // reducers.c:142-145,209-212
-					inexact |= !f32_exact(d);
-					if (sorting) dfl[i] = (float) d;
-				}
-			}
 			// bucketed selection (every breakpoint on its own): float32 values, the universe of intervals and gaps fits
 			WB_PHASE(14);
 			const bool bucketed = sorting && W <= 4096 && !__syncthreads_or(inexact);
