@@ -647,6 +647,9 @@ __device__ void order_walk(const Job &job, const int32_t *cur, const int32_t *nx
 }
 
 // Shared-memory carve-up of the sweep kernels' row buffer (host and device agree).
+#ifndef WB_SEL_TICKET_AT_END
+#define WB_SEL_TICKET_AT_END 1           // selection kernel: draw the next window when the current one is done (0: when its emit phase starts, plus an L2 prefetch)
+#endif
 #ifndef WB_SEL_MIN_N
 #define WB_SEL_MIN_N 32                  // up to this many tracks: a sorted array per warp (order_walk) instead of sorting the window
                                          // (measured, median, 1024-bp windows: 40 tracks 8.9 -> 11.6, 64: 6.2 -> 10.8, 128: 2.0 -> 8.1 Gbp/s)
@@ -1609,8 +1612,8 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	// the order they were drawn: the next one is drawn only now (the atomic lands during the
 	// emit phase), not two windows ahead (measured in fastsum.cu: look-back waits 8.5k -> 5k cycles).
 	unsigned next_ticket = 0;
-	if (tid == 0) next_ticket = atomicAdd(job.ticket, 1u) + gridDim.x;
-	if (MODE == MODE_SELECT) {
+	if (tid == 0 && !(MODE == MODE_SELECT && WB_SEL_TICKET_AT_END)) next_ticket = atomicAdd(job.ticket, 1u) + gridDim.x;
+	if (MODE == MODE_SELECT && !WB_SEL_TICKET_AT_END) {
 		// the selection takes a while: pull the next window's intervals (about eight per track from its cursor
 		// on) into L2 meanwhile -- both its events phase and its staging read them with dependent loads
 		if (tid == 0) misc->ticket1 = (int) next_ticket;
@@ -1712,12 +1715,18 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 							int first = 0, cnt = 0;
 							if (i < N) {
 								const int b = tbase[i], L = max(0, min(nxt[i], tn[i] - 1) - cur[i] + 1);
-								int lo = 0, hi = L;                      // first staged interval with end > ra
-								while (lo < hi) { const int mid = (lo + hi) >> 1; if ((long long) se[b + mid] > ra) hi = mid; else lo = mid + 1; }
-								first = lo;
-								hi = L;                                  // first staged interval with start >= rbnd
-								while (lo < hi) { const int mid = (lo + hi) >> 1; if ((long long) ss[b + mid] >= rbnd) hi = mid; else lo = mid + 1; }
-								cnt = lo - first;
+								if (ws == W) {
+									// the whole window: everything staged but the look-ahead interval (an interval that ends
+									// exactly at the window start stays in as an element that is never in play)
+									cnt = L - ((L > 0 && (long long) ss[b + L - 1] >= rbnd) ? 1 : 0);
+								} else {
+									int lo = 0, hi = L;                  // first staged interval with end > ra
+									while (lo < hi) { const int mid = (lo + hi) >> 1; if ((long long) se[b + mid] > ra) hi = mid; else lo = mid + 1; }
+									first = lo;
+									hi = L;                              // first staged interval with start >= rbnd
+									while (lo < hi) { const int mid = (lo + hi) >> 1; if ((long long) ss[b + mid] >= rbnd) hi = mid; else lo = mid + 1; }
+									cnt = lo - first;
+								}
 							}
 							int ec, tc;
 							block_scan1(misc, cnt, ec, tc);
@@ -1960,6 +1969,9 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 
 	WB_PHASE(6);
 #if WB_LATETICKET
+	// (MODE_SELECT: three quarters of a window are spent after the look-back, so its next window is drawn only here,
+	// when this one is done -- windows then start in the order they were drawn and the look-back waits less)
+	if (tid == 0 && MODE == MODE_SELECT && WB_SEL_TICKET_AT_END) next_ticket = atomicAdd(job.ticket, 1u) + gridDim.x;
 	if (tid == 0) misc->ticket2 = (int) next_ticket;
 #endif
 	// per-warp AUC partials go straight to global memory (fixed order, folded later)
