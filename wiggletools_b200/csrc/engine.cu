@@ -648,7 +648,7 @@ __device__ void order_walk(const Job &job, const int32_t *cur, const int32_t *nx
 
 // Shared-memory carve-up of the sweep kernels' row buffer (host and device agree).
 #ifndef WB_SEL_TICKET_AT_END
-#define WB_SEL_TICKET_AT_END 1           // selection kernel: draw the next window when the current one is done (0: when its emit phase starts, plus an L2 prefetch)
+#define WB_SEL_TICKET_AT_END 1           // per-segment modes (select / walk / row): draw the next window when the current one is done (0: when its emit phase starts)
 #endif
 #ifndef WB_SEL_MIN_N
 #define WB_SEL_MIN_N 32                  // up to this many tracks: a sorted array per warp (order_walk) instead of sorting the window
@@ -1612,7 +1612,8 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 	// the order they were drawn: the next one is drawn only now (the atomic lands during the
 	// emit phase), not two windows ahead (measured in fastsum.cu: look-back waits 8.5k -> 5k cycles).
 	unsigned next_ticket = 0;
-	if (tid == 0 && !(MODE == MODE_SELECT && WB_SEL_TICKET_AT_END)) next_ticket = atomicAdd(job.ticket, 1u) + gridDim.x;
+	constexpr bool long_emit = (MODE == MODE_SELECT || MODE == MODE_WALK || MODE == MODE_ROW) && WB_SEL_TICKET_AT_END;
+	if (tid == 0 && !long_emit) next_ticket = atomicAdd(job.ticket, 1u) + gridDim.x;
 	if (MODE == MODE_SELECT && !WB_SEL_TICKET_AT_END) {
 		// the selection takes a while: pull the next window's intervals (about eight per track from its cursor
 		// on) into L2 meanwhile -- both its events phase and its staging read them with dependent loads
@@ -1969,9 +1970,9 @@ __device__ void process_window(const Job &job, int w, unsigned char *smem, const
 
 	WB_PHASE(6);
 #if WB_LATETICKET
-	// (MODE_SELECT: three quarters of a window are spent after the look-back, so its next window is drawn only here,
-	// when this one is done -- windows then start in the order they were drawn and the look-back waits less)
-	if (tid == 0 && MODE == MODE_SELECT && WB_SEL_TICKET_AT_END) next_ticket = atomicAdd(job.ticket, 1u) + gridDim.x;
+	// (per-segment modes: most of a window is spent after the look-back, so its next window is drawn only here, when
+	// this one is done -- windows then start in the order they were drawn and the look-back waits less)
+	if (tid == 0 && long_emit) next_ticket = atomicAdd(job.ticket, 1u) + gridDim.x;
 	if (tid == 0) misc->ticket2 = (int) next_ticket;
 #endif
 	// per-warp AUC partials go straight to global memory (fixed order, folded later)
