@@ -29,7 +29,7 @@ for bg in (False, True):
 # element-wise maps: in-place map, a log that drops records (compaction + rebuilt offsets), nested chains
 r = eng.reduce("mean", g, ["chr1", "chr2"], maps=[[("abs",), ("offset", 0.5), ("ln",)] if i % 2 else [("scale", -1.0), ("log", 2.0)] for i in range(len(g))])
 print("maps", len(r), float(np.nansum(r.value)))
-# round 2: the selection kernel (order statistics over more than 32 tracks: bucketed path, ranges of a window, the
+# round 2: the selection kernel (order statistics over more than 24 tracks: bucketed path, ranges of a window, the
 # bitset and sorted-array fallbacks) and the moments variant of the sweep kernel
 for n, kw, what in ((48, dict(), "f32"), (200, dict(), "f32"), (300, dict(max_len=6, max_gap=4), "dense ranges"), (160, dict(max_len=1, max_gap=1), "staging overflow")):
     trn = make_tracks(n, [5000], seed=7, vmax=64, **kw)

@@ -59,18 +59,18 @@ def test_dropin_symbols_exported():
 
 
 def test_selection_kernel_shared_memory_budgets():
-    """the bucketed selection (min / max / median over 33..512 tracks, 1024-bp windows) keeps two CTAs
+    """the bucketed selection (min / max / median over 25..512 tracks, 1024-bp windows) keeps two CTAs
     resident per SM up to 300 tracks and always fits one; host arithmetic only (no device)."""
     from wiggletools_b200.api import OPS
     lib = _lib.load()
     sm_total, per_cta_reserved, cta_max = 228 * 1024, 1024, 227 * 1024
     for op in ("median", "min", "max"):
-        for n in (33, 64, 128, 200, 256, 300):
+        for n in (25, 33, 64, 128, 200, 256, 300):
             b = lib.wb200_debug_window_smem_bytes(OPS[op], n, 1024)
             assert 0 < b and 2 * (b + per_cta_reserved) <= sm_total, (op, n, b)
         for n in (301, 400, 512):
             b = lib.wb200_debug_window_smem_bytes(OPS[op], n, 1024)
             assert 0 < b <= cta_max, (op, n, b)
-    # up to 32 tracks: the per-warp sorted arrays, three CTAs per SM at 2048-bp windows
-    b = lib.wb200_debug_window_smem_bytes(OPS["median"], 32, 2048)
+    # up to 24 tracks: the per-warp sorted arrays, three CTAs per SM at 2048-bp windows
+    b = lib.wb200_debug_window_smem_bytes(OPS["median"], 24, 2048)
     assert 0 < b and 3 * (b + per_cta_reserved) <= sm_total, b

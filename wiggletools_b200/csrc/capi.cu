@@ -221,9 +221,9 @@ int plan_shard(wb200_ctx *ctx, int op, int N, int &n1, int &strict, const int64_
 			// more windows in flight per SM (measured: N = 64, density 0.5: 6 instead of 3 CTAs per SM)
 			if (density > 0.25 && (op == OP_VAR || op == OP_STDDEV || op == OP_ENTROPY || op == OP_CV)) wlog = 11;
 			// the order-statistic sweep is a serial chain per warp: smaller windows, more CTAs per SM
-			// (more than 32 tracks: the bucketed selection sorts a window's intervals once and keeps 32 byte counters
+			// (more than 24 tracks: the bucketed selection sorts a window's intervals once and keeps 32 byte counters
 			// per position -- 1024-bp windows)
-			if ((op == OP_MEDIAN || op == OP_MIN || op == OP_MAX) && N <= 512) wlog = N > 32 ? 10 : 11;
+			if ((op == OP_MEDIAN || op == OP_MIN || op == OP_MAX) && N <= 512) wlog = N > 24 ? 10 : 11;
 		}
 	}
 	wlog = std::min(TLOG + 4, std::max(TLOG + 2, wlog));

@@ -27,7 +27,7 @@
 // Kernel variants (emit_kernel<MODE,...>):
 //   MODE_FAST    sum / mean from one exact accumulator;
 //   MODE_MOMENTS var / stddev / CV from exact sum and sum of squares;
-//   MODE_WALK    min / max / median from an incrementally maintained sorted array (up to WB_SEL_MIN_N = 32 tracks);
+//   MODE_WALK    min / max / median from an incrementally maintained sorted array (up to WB_SEL_MIN_N = 24 tracks);
 //   MODE_SELECT  min / max / median from the window's sorted universe (more tracks: bucketed selection, bitset sweep);
 //   MODE_ROW     everything else: row_eval(), a per-segment loop over the N
 //                tracks in index order that mirrors the reference's arithmetic
@@ -651,8 +651,9 @@ __device__ void order_walk(const Job &job, const int32_t *cur, const int32_t *nx
 #define WB_SEL_TICKET_AT_END 1           // per-segment modes (select / walk / row): draw the next window when the current one is done (0: when its emit phase starts)
 #endif
 #ifndef WB_SEL_MIN_N
-#define WB_SEL_MIN_N 32                  // up to this many tracks: a sorted array per warp (order_walk) instead of sorting the window
-                                         // (measured, median, 1024-bp windows: 40 tracks 8.9 -> 11.6, 64: 6.2 -> 10.8, 128: 2.0 -> 8.1 Gbp/s)
+#define WB_SEL_MIN_N 24                  // up to this many tracks: a sorted array per warp (order_walk) instead of sorting the window
+                                         // (measured, median, kernel ms on a tenth of the genome: 16 tracks 13.3 walk / 18.3 select, 24: 18.6 / 18.8,
+                                         // 32: 22.7 / 18.9; 64 tracks 6.2 -> 12.9 Gbp/s, 128: 2.0 -> 8.1)
 #endif
 constexpr int SEL_PS = 4096;             // bucketed selection: largest universe (64-bit keys), intervals + gaps
 struct WalkLayout {
