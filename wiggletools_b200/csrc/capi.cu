@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -809,6 +810,12 @@ int wb200_reduce_device_batch(wb200_ctx *ctx, int op, int ntracks, int nset1, in
 	}
 	const int N = ntracks;
 	cudaStream_t s = ctx->stream;
+	// development: WB200_BATCH_TIMING=1 prints where the host spends a call (ms since entry: planned, samples read,
+	// everything queued, results read)
+	static const bool timing = getenv("WB200_BATCH_TIMING") != nullptr;
+	const auto t_in = std::chrono::steady_clock::now();
+	auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_in).count(); };
+	double t_plan = 0, t_sample = 0, t_queued = 0;
 	std::vector<Job> jobs(nshards);
 	int64_t max_cursor = 1, max_nw = 1, max_slow = 0;
 	bool sample = nshards > 0;
@@ -845,6 +852,7 @@ int wb200_reduce_device_batch(wb200_ctx *ctx, int op, int ntracks, int nset1, in
 	double *d_small = ctx->b_small.as<double>();
 	CK(cudaMemsetAsync(d_small, 0, (size_t) 256 * nshards, s));
 
+	t_plan = since();
 	// 1. one value sample per shard, one synchronisation for all of them
 	double maxabs = 0;
 	long long lsb_key = 0;
@@ -861,6 +869,7 @@ int wb200_reduce_device_batch(wb200_ctx *ctx, int op, int ntracks, int nset1, in
 			lsb_key = std::max(lsb_key, ctx->hb_small.as<long long>()[32 * c + 1]);
 		}
 	}
+	t_sample = since();
 	// 2. tables of every shard in one upload
 	for (int c = 0; c < nshards; c++) {
 		Job &job = jobs[c];
@@ -909,7 +918,9 @@ int wb200_reduce_device_batch(wb200_ctx *ctx, int op, int ntracks, int nset1, in
 	}
 	// 4. all results, one synchronisation
 	CK(cudaMemcpyAsync(ctx->hb_small.p, d_small, (size_t) 256 * nshards, cudaMemcpyDeviceToHost, s));
+	t_queued = since();
 	CK(cudaStreamSynchronize(s));
+	if (timing) fprintf(stderr, "wb200_reduce_device_batch: planned %.3f, samples read %.3f, queued %.3f, results read %.3f ms\n", t_plan, t_sample, t_queued, since());
 	for (int c = 0; c < nshards; c++) {
 		wb200_device_shard &h = shards[c];
 		const Job &job = jobs[c];
