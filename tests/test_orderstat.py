@@ -120,3 +120,22 @@ def test_strict_and_empty_windows(engine, port):
     want = port.reduce("max", o, ["chr1"])
     got = engine.reduce("max", g, ["chr1"])
     assert_segments(got, want.chrom, want.start, want.end, want.value, exact=True, what="max/sparse")
+
+
+def test_infinite_values_are_float32_too(engine, port):
+    """+inf / -inf are float32 values: they stay on the bucketed selection (largest / smallest keys below the
+    padding) and come out as the reference's sort leaves them."""
+    n = 40
+    tr = make_tracks(n, [6_000], seed=23, vmax=16)
+    rng = np.random.default_rng(4)
+    for t in tr:
+        v = t["value"].copy()
+        r = rng.random(len(v))
+        v[r < 0.05] = np.inf
+        v[r > 0.96] = -np.inf
+        t["value"] = v
+    o, g = both(tr)
+    for op in ("median", "min", "max"):
+        want = port.reduce(op, o, ["chr1"])
+        got = engine.reduce(op, g, ["chr1"])
+        assert_segments(got, want.chrom, want.start, want.end, want.value, exact=True, what=op + "/inf")
