@@ -109,3 +109,74 @@ def test_counter_rows(ws):
             for step in range(length):
                 groups = {(rows[(first + j) * length + step]) & 3 for j in range(4)}
                 assert len(groups) == 4, (ws, first, step)
+
+
+# ---- the selection itself, as the kernel organises it ------------------------------------------------------------
+def select_model(tracks, defaults, w0, width, k_sel, nb=32):
+    """Median-like selection at every position of [w0, w0 + width) the way emit_kernel<MODE_SELECT> does it:
+    elements = intervals overlapping the range + the gaps around them (one element per track in play at every
+    position), ranks from one sort by value, byte counters per (position, bucket) packed four to a 32-bit word
+    and accumulated with wrap-around arithmetic, then bucket search + k-th element in play inside the bucket."""
+    import numpy as np
+    ra, rb = w0, w0 + width
+    elems = []                                                  # (value, start, end) clipped to the range
+    for (s, e, v), d in zip(tracks, defaults):
+        lo = int(np.searchsorted(e, ra, side="right"))          # first interval with end > ra
+        hi = int(np.searchsorted(s, rb, side="left"))           # first interval with start >= rb
+        prev = ra
+        for j in range(lo, hi):
+            a, b = max(int(s[j]), ra), min(int(e[j]), rb)
+            if prev < a:
+                elems.append((float(d), prev, a))               # the gap before interval j
+            elems.append((float(v[j]), a, b))
+            prev = b
+        if prev < rb:
+            elems.append((float(d), prev, rb))
+    elems.sort(key=lambda t: t[0])                              # ties: any order gives the same value
+    r = len(elems)
+    bs = max(4, (-(-r // nb) + 3) & ~3)
+    assert bs <= 255
+    words = np.zeros((width, nb // 4), dtype=np.uint32)
+    with np.errstate(over="ignore", under="ignore"):            # the wrap-around is the point
+        for rank, (_, a, b) in enumerate(elems):
+            bk = rank // bs
+            one = np.uint32(1 << (8 * (bk & 3)))
+            words[a - ra, bk >> 2] += one                       # +1 at the start ...
+            if b < rb:
+                words[b - ra, bk >> 2] -= one                   # ... -1 at the end: uint32 wrap-around, as the atomics do
+        words = np.cumsum(words, axis=0, dtype=np.uint32)       # prefix along the positions, still modulo 2^32
+    out = np.empty(width)
+    for p in range(width):
+        counts = [(int(words[p, b >> 2]) >> (8 * (b & 3))) & 0xFF for b in range(nb)]
+        assert sum(counts) == len(tracks)                       # exactly one element per track in play
+        k, bk = k_sel, 0
+        while k >= counts[bk]:
+            k -= counts[bk]
+            bk += 1
+        for val, a, b in elems[bk * bs:(bk + 1) * bs]:
+            if a <= ra + p < b:
+                if k == 0:
+                    out[p] = val
+                    break
+                k -= 1
+    return out
+
+
+@pytest.mark.parametrize("n,seed", [(25, 1), (64, 2), (200, 3)])
+def test_selection_model_against_brute_force(n, seed):
+    import numpy as np
+    from wiggletools_b200.synth import make_tracks
+    tr = make_tracks(n, [3_000], seed=seed, vmax=24, max_len=60, max_gap=40)
+    rng = np.random.default_rng(seed)
+    defaults = rng.integers(-2, 5, n).astype(float)
+    tracks = [(t["start"], t["end"], t["value"]) for t in tr]
+    w0, width = 1024, 512
+    got = select_model(tracks, defaults, w0, width, n // 2)
+    dense = np.tile(defaults[:, None], (1, width))              # brute force: every track's value at every position
+    for i, (s, e, v) in enumerate(tracks):
+        for a, b, x in zip(s, e, v):
+            a, b = max(int(a), w0), min(int(b), w0 + width)
+            if a < b:
+                dense[i, a - w0:b - w0] = x
+    want = np.sort(dense, axis=0)[n // 2]                       # upper median (reducers.c:769-813)
+    assert np.array_equal(got, want)
